@@ -1,0 +1,135 @@
+"""CPU: the oracle restatements (torch and C) against the golden vectors made from the reference's own code
+(oracle/make_golden.py).  This is what pins the oracle; the GPU parity tests then compare CUDA to the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_ref, ss2d_ref, stft_ref
+
+CROSS_TAGS = ["sq", "rect", "odd"]
+SCAN_TAGS = ["n1_full", "n1_nobias", "n1_long", "n2_g1", "n4_nosp"]
+STFT_TAGS = ["48k", "16k", "nfft2048"]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.mark.parametrize("tag", CROSS_TAGS)
+def test_cross_scan_merge_bit_exact(golden_dir, tag):
+    g = _load(golden_dir, "cross_scan_merge.npz")
+    x, xs, gxs, gx = (_t(g[f"{tag}_{k}"]) for k in ("x", "xs", "gxs", "gx"))
+    ys, y, gy, gys = (_t(g[f"{tag}_{k}"]) for k in ("ys", "y", "gy", "gys"))
+    B, C, H, W = x.shape
+    assert torch.equal(ss2d_ref.cross_scan(x), xs)
+    assert torch.equal(ss2d_ref.cross_scan_bwd(gxs, H, W), gx)
+    assert torch.equal(ss2d_ref.cross_merge(ys), y)
+    assert torch.equal(ss2d_ref.cross_merge_bwd(gy, H, W), gys)
+    # C restatement
+    assert np.array_equal(c_ref.cross_scan(x.numpy()), xs.numpy())
+    assert np.array_equal(c_ref.cross_merge(ys.numpy().reshape(B, 4, C, H * W), H, W), y.numpy())
+    assert np.array_equal(c_ref.cross_merge(gxs.numpy(), H, W).reshape(B, C, H, W), gx.numpy())
+
+
+def _scan_case(g, tag):
+    def opt(k):
+        return _t(g[f"{tag}_{k}"]) if f"{tag}_{k}" in g.files else None
+
+    return dict(u=_t(g[f"{tag}_u"]), delta=_t(g[f"{tag}_delta"]), A=_t(g[f"{tag}_A"]), B=_t(g[f"{tag}_B"]),
+                C=_t(g[f"{tag}_C"]), D=opt("D"), bias=opt("bias"), sp=bool(g[f"{tag}_softplus"]))
+
+
+@pytest.mark.parametrize("tag", SCAN_TAGS)
+def test_selective_scan_forward(golden_dir, tag):
+    g = _load(golden_dir, "selective_scan.npz")
+    c = _scan_case(g, tag)
+    out, last = ss2d_ref.selective_scan(c["u"], c["delta"], c["A"], c["B"], c["C"], c["D"], c["bias"], c["sp"],
+                                        return_last_state=True)
+    # same fp32 sequential arithmetic, different op grouping: a few ulp
+    assert torch.allclose(out, _t(g[f"{tag}_out"]), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(last, _t(g[f"{tag}_last"]), rtol=1e-5, atol=1e-5)
+    out64, last64, _ = c_ref.scan_fwd(c["u"], c["delta"], c["A"], c["B"], c["C"], c["D"], c["bias"], c["sp"])
+    assert np.allclose(out64, g[f"{tag}_out"], rtol=2e-5, atol=2e-5)
+    assert np.allclose(last64, g[f"{tag}_last"], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("tag", SCAN_TAGS)
+def test_selective_scan_backward(golden_dir, tag):
+    g = _load(golden_dir, "selective_scan.npz")
+    c = _scan_case(g, tag)
+    gout = _t(g[f"{tag}_gout"])
+    names = ["du", "ddelta", "dA", "dB", "dC", "dD", "dbias"]
+    got_t = ss2d_ref.selective_scan_bwd(c["u"], c["delta"], c["A"], c["B"], c["C"], c["D"], c["bias"], c["sp"], gout)
+    got_c = c_ref.scan_bwd(c["u"], c["delta"], c["A"], c["B"], c["C"], c["D"], c["bias"], c["sp"], gout)
+    for name, a, b in zip(names, got_t, got_c):
+        key = f"{tag}_{name}"
+        if key not in g.files:
+            assert a is None and b is None
+            continue
+        ref = g[key].astype(np.float64)
+        scale = max(np.abs(ref).max(), 1e-6)
+        # the golden gradients are fp32 autograd; ours are fp64 closed form
+        assert np.abs(a.numpy() - ref).max() / scale < 2e-5, name
+        assert np.abs(b - ref).max() / scale < 2e-5, name
+
+
+def test_chunk_state_layout(golden_dir):
+    """(cumulative decay, state) at every chunk end; last chunk == last state (test_selective_scan.py:114)."""
+    g = _load(golden_dir, "selective_scan.npz")
+    c = _scan_case(g, "n1_long")
+    _, last, cs = c_ref.scan_fwd(c["u"], c["delta"], c["A"], c["B"], c["C"], c["D"], c["bias"], c["sp"], chunk=128)
+    assert cs.shape == (1, 4, 3, 2)
+    assert np.allclose(cs[:, :, -1, 1::2], last)
+
+
+@pytest.mark.parametrize("tag", STFT_TAGS)
+def test_stft_istft(golden_dir, tag):
+    g = _load(golden_dir, "stft.npz")
+    n_fft, hop, win = (int(v) for v in g[f"{tag}_params"])
+    wave = _t(g[f"{tag}_wave"])
+    mag, phase = stft_ref.wav2spectro(wave, n_fft, hop, win)
+    gm, gp = g[f"{tag}_mag"].astype(np.float64), g[f"{tag}_phase"].astype(np.float64)
+    assert mag.shape == gm.shape
+    # compare as complex spectra (robust where |X| is tiny), then mag/phase where |X| is not tiny
+    X = np.exp2(mag.numpy()) * np.exp(1j * phase.numpy())
+    Xg = np.exp2(gm) * np.exp(1j * gp)
+    assert np.abs(X - Xg).max() < 1e-5
+    big = np.abs(Xg) > 1e-2
+    assert np.abs(mag.numpy() - gm)[big].max() < 1e-4
+    dphi = np.angle(np.exp(1j * (phase.numpy() - gp)))
+    assert np.abs(dphi)[big].max() < 1e-4
+    # inverse
+    back = stft_ref.spectro2wav(_t(g[f"{tag}_mag2"]), _t(g[f"{tag}_phase2"]), n_fft, hop, win)
+    assert back.shape == g[f"{tag}_wav2"].shape
+    assert np.abs(back.numpy() - g[f"{tag}_wav2"]).max() < 1e-5
+    # round trip of the reference itself is the identity (length hop*(frames-1))
+    assert np.abs(g[f"{tag}_back"] - g[f"{tag}_wave"]).max() < 1e-5
+
+
+@pytest.mark.parametrize("tag", STFT_TAGS)
+def test_istft_gradient(golden_dir, tag):
+    """autograd through the float64 restatement == the reference's autograd through torch.istft."""
+    g = _load(golden_dir, "stft.npz")
+    n_fft, hop, win = (int(v) for v in g[f"{tag}_params"])
+    mag = _t(g[f"{tag}_mag2"]).double().requires_grad_()
+    phase = _t(g[f"{tag}_phase2"]).double().requires_grad_()
+    wav = stft_ref.spectro2wav(mag, phase, n_fft, hop, win)
+    wav.backward(_t(g[f"{tag}_gw"]).double())
+    for got, key in ((mag.grad, "dmag2"), (phase.grad, "dphase2")):
+        ref = g[f"{tag}_{key}"].astype(np.float64)
+        assert np.abs(got.numpy() - ref).max() / np.abs(ref).max() < 1e-5
+
+
+def test_ss2d_core_chain_shapes():
+    torch.manual_seed(0)
+    B, C, H, W, N, R = 2, 4, 6, 5, 1, 1
+    x = torch.randn(B, C, H, W)
+    y = ss2d_ref.ss2d_core(x, torch.randn(4, R + 2 * N, C), torch.randn(4, C, R), torch.rand(4, C),
+                           torch.zeros(4 * C, N), torch.ones(4 * C))
+    assert y.shape == (B, C, H * W) and torch.isfinite(y).all()
