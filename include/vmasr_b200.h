@@ -1,0 +1,141 @@
+/* vmasr_b200 -- C ABI of the B200 (sm_100a) implementation of VM-ASR's SS2D + STFT hot path.
+ *
+ * Everything here is plain C: raw device pointers, sizes, element strides, a CUDA stream handle and an
+ * int return code (0 = ok, non-zero = error; text via vmasr_last_error()).  No torch types cross this
+ * boundary and nothing is thrown across it.  The caller owns every buffer (inputs, outputs, the
+ * chunk-state tensor and the carry workspace); the library allocates nothing and keeps no pointer after
+ * a call returns.  Entry points are re-entrant and never synchronise the device: the reference calls its
+ * forward from the Python main thread and its backward from an autograd worker thread
+ * (model/vmamba.py:325-356), each on torch's current stream.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the VM-ASR tree).
+ */
+#ifndef VMASR_B200_H
+#define VMASR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMASR_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VMASR_API __attribute__((visibility("default")))
+#else
+#define VMASR_API
+#endif
+
+/* element type of u / delta / B / C / out / dout / du / ddelta and of cross-scan maps
+ * (selective_scan.cpp:167-172 accepts exactly these three) */
+enum vmasr_dtype { VMASR_F32 = 0, VMASR_F16 = 1, VMASR_BF16 = 2 };
+
+/* The scan is cut into chunks of this many positions; the chunk-state tensor `x` has
+ * ceil(seqlen / VMASR_SCAN_CHUNK) entries per (batch, channel) -- same figure as selective_scan.cpp:217. */
+#define VMASR_SCAN_CHUNK 2048
+
+VMASR_API int vmasr_abi_version(void);
+/* Message of the last failing call on this host thread ("" if none). */
+VMASR_API const char *vmasr_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Selective scan.  Replaces selective_scan_cuda_core.fwd / .bwd
+ * (kernels/selective_scan/csrc/selective_scan/cus/selective_scan.cpp:157-239, 241-349, pybind :351-354).
+ *
+ *   u, delta, out, dout, du, ddelta : (batch, dim, seqlen), unit stride along seqlen, element type io_dtype
+ *   A                               : (dim, dstate) float
+ *   B, C                            : (batch, ngroups, dstate, seqlen), unit stride along seqlen, io_dtype
+ *   D, delta_bias                   : (dim,) float or NULL
+ *   x                               : (batch, dim, n_chunks, 2*dstate) float, contiguous: per chunk and state
+ *                                     (cumulative decay, state at chunk end) -- written by fwd, read by bwd
+ *   dA (dim,dstate), dD, ddelta_bias (dim,) : float, ACCUMULATED INTO (caller zero-fills, like
+ *                                     selective_scan.cpp:321-327)
+ *   dB, dC                          : (batch, ngroups, dstate, seqlen) float contiguous, accumulated into
+ *                                     (caller zero-fills; the reference casts them to io_dtype afterwards, :347)
+ *   workspace                       : carry-exchange area for the cross-chunk look-back.  At least
+ *                                     vmasr_scan_workspace_bytes() bytes, ZERO-FILLED ONCE when allocated and
+ *                                     then reused call after call (kernels recycle it themselves, so a
+ *                                     captured CUDA graph can replay).  One workspace per stream: two scans
+ *                                     running concurrently must not share one.  May be NULL when
+ *                                     seqlen <= VMASR_SCAN_CHUNK.
+ * Strides are in elements.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vmasr_scan_params {
+    /* forward inputs */
+    const void *u, *delta;
+    const float *A;
+    const void *B, *C;
+    const float *D;          /* nullable */
+    const float *delta_bias; /* nullable */
+    /* forward outputs */
+    void *out;
+    float *x;
+    /* backward input */
+    const void *dout;
+    /* backward outputs */
+    void *du, *ddelta;
+    float *dA, *dB, *dC;
+    float *dD;          /* nullable iff D is NULL */
+    float *ddelta_bias; /* nullable iff delta_bias is NULL */
+    /* carry workspace */
+    void *workspace;
+    uint64_t workspace_bytes;
+    /* sizes */
+    int32_t batch, dim, seqlen, dstate, ngroups;
+    /* strides (elements) */
+    int64_t u_batch_stride, u_d_stride;
+    int64_t delta_batch_stride, delta_d_stride;
+    int64_t A_d_stride, A_dstate_stride;
+    int64_t B_batch_stride, B_group_stride, B_dstate_stride;
+    int64_t C_batch_stride, C_group_stride, C_dstate_stride;
+    int64_t out_batch_stride, out_d_stride;
+    int64_t dout_batch_stride, dout_d_stride;
+    int64_t du_batch_stride, du_d_stride;
+    int64_t ddelta_batch_stride, ddelta_d_stride;
+    /* options */
+    int32_t io_dtype;       /* enum vmasr_dtype */
+    int32_t delta_softplus; /* softplus(delta + delta_bias), identity above 20 (fwd_kernel.cuh:117) */
+    int32_t device;         /* CUDA device ordinal the pointers live on */
+    int32_t reserved;
+    void *stream; /* cudaStream_t */
+} vmasr_scan_params;
+
+VMASR_API uint64_t vmasr_scan_workspace_bytes(int batch, int dim, int seqlen, int dstate);
+VMASR_API int vmasr_scan_fwd(const vmasr_scan_params *p);
+VMASR_API int vmasr_scan_bwd(const vmasr_scan_params *p);
+
+/* ------------------------------------------------------------------------------------------------
+ * 4-direction cross scan / merge.  Replace CrossScan / CrossMerge (model/vmamba.py:27-73) and the Triton
+ * kernels triton_cross_scan / triton_cross_merge (model/csm_triton.py:7-154).
+ *   cross_scan : x (B, C, H, W) contiguous -> xs (B, 4, C, H*W) contiguous; also CrossMerge's backward.
+ *   cross_merge: ys (B, 4, C, H*W) contiguous -> y (B, C, H*W) contiguous, association
+ *                (ys0 + flip ys2) + transpose_back(ys1 + flip ys3) as vmamba.py:55-60; also CrossScan's
+ *                backward.
+ * Bit-exact with the PyTorch versions for all three dtypes.
+ * ---------------------------------------------------------------------------------------------- */
+VMASR_API int vmasr_cross_scan(const void *x, void *xs, int B, int C, int H, int W, int dtype, int device, void *stream);
+VMASR_API int vmasr_cross_merge(const void *ys, void *y, int B, int C, int H, int W, int dtype, int device, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Magnitude/phase STFT and inverse.  Replace wav2spectro / spectro2wav (utils/stft.py:22-68, 71-115),
+ * i.e. torch.stft / torch.istft(normalized=True, center=True, reflect pad, periodic Hann of win_length
+ * zero-padded to n_fft, onesided) fused with log2(|X|+1e-8)/angle and exp2/polar.  float32 only.
+ *   wave  : (B, T) contiguous
+ *   mag, phase : (B, n_fft/2+1, n_frames) contiguous, n_frames = 1 + T/hop
+ *   istft output length = hop*(n_frames-1)
+ *   istft_bwd : d wave -> d mag, d phase (the generator loss flows through spectro2wav, model/model.py:1223)
+ * n_fft must be a power of two in [64, 4096]; win_length <= n_fft.
+ * ---------------------------------------------------------------------------------------------- */
+VMASR_API int vmasr_stft_fwd(const float *wave, float *mag, float *phase, int B, int T, int n_fft, int hop,
+                   int win_length, int device, void *stream);
+VMASR_API int vmasr_istft_fwd(const float *mag, const float *phase, float *wave, int B, int n_frames, int n_fft,
+                    int hop, int win_length, int device, void *stream);
+VMASR_API int vmasr_istft_bwd(const float *mag, const float *phase, const float *dwave, float *dmag, float *dphase,
+                    int B, int n_frames, int n_fft, int hop, int win_length, int device, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMASR_B200_H */

@@ -1,0 +1,111 @@
+"""ctypes binding of ``libvmasr_b200.so`` (C ABI: ``include/vmasr_b200.h``).
+
+There is no fallback: if the CUDA library has not been built, or a tensor is not on a CUDA device, the
+operators raise.  Build with ``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C vm-asr_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libvmasr_b200.so")
+_lib = None
+_lock = threading.Lock()
+
+VMASR_F32, VMASR_F16, VMASR_BF16 = 0, 1, 2
+SCAN_CHUNK = 2048
+DTYPE_CODE = {torch.float32: VMASR_F32, torch.float16: VMASR_F16, torch.bfloat16: VMASR_BF16}
+
+_vp, _i32, _i64, _u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64
+
+
+class ScanParams(ctypes.Structure):
+    """Mirror of ``vmasr_scan_params`` (include/vmasr_b200.h)."""
+
+    _fields_ = (
+        [(n, _vp) for n in ("u", "delta", "A", "B", "C", "D", "delta_bias", "out", "x", "dout", "du", "ddelta",
+                            "dA", "dB", "dC", "dD", "ddelta_bias", "workspace")]
+        + [("workspace_bytes", _u64)]
+        + [(n, _i32) for n in ("batch", "dim", "seqlen", "dstate", "ngroups")]
+        + [(n, _i64) for n in (
+            "u_batch_stride", "u_d_stride", "delta_batch_stride", "delta_d_stride", "A_d_stride", "A_dstate_stride",
+            "B_batch_stride", "B_group_stride", "B_dstate_stride", "C_batch_stride", "C_group_stride", "C_dstate_stride",
+            "out_batch_stride", "out_d_stride", "dout_batch_stride", "dout_d_stride", "du_batch_stride", "du_d_stride",
+            "ddelta_batch_stride", "ddelta_d_stride")]
+        + [(n, _i32) for n in ("io_dtype", "delta_softplus", "device", "reserved")]
+        + [("stream", _vp)]
+    )
+
+
+EXPORTS = {
+    "vmasr_abi_version": (ctypes.c_int, []),
+    "vmasr_last_error": (ctypes.c_char_p, []),
+    "vmasr_scan_workspace_bytes": (_u64, [ctypes.c_int] * 4),
+    "vmasr_scan_fwd": (ctypes.c_int, [ctypes.POINTER(ScanParams)]),
+    "vmasr_scan_bwd": (ctypes.c_int, [ctypes.POINTER(ScanParams)]),
+    "vmasr_cross_scan": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
+    "vmasr_cross_merge": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
+    "vmasr_stft_fwd": (ctypes.c_int, [_vp, _vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
+    "vmasr_istft_fwd": (ctypes.c_int, [_vp, _vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
+    "vmasr_istft_bwd": (ctypes.c_int, [_vp] * 5 + [ctypes.c_int] * 6 + [_vp]),
+}
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def load_library():
+    """Load the shared library once; raise (never fall back) when it is missing."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(_LIB_PATH):
+                    raise RuntimeError(
+                        f"vmasr_b200: CUDA library not built ({_LIB_PATH} missing). Run `make -C vm-asr_b200/csrc` "
+                        "(needs nvcc, sm_100a). There is no CPU or PyTorch fallback for these operators.")
+                lib = ctypes.CDLL(_LIB_PATH)
+                for name, (res, args) in EXPORTS.items():
+                    fn = getattr(lib, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load_library().vmasr_last_error().decode("utf-8", "replace")
+        raise RuntimeError(msg or f"vmasr_b200 call failed with code {rc}")
+
+
+def require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (vmasr_b200 has no CPU path)")
+
+
+def current_stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+# ---- carry workspace of the scan: one per (device, stream), zero-filled once, recycled by the kernels ----
+_workspaces = {}
+
+
+def scan_workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        size = max(int(nbytes), 1 << 20)
+        if ws is not None:
+            size = max(size, 2 * ws.numel())
+        ws = torch.zeros(size, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws

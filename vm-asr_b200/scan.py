@@ -1,0 +1,240 @@
+"""Selective scan: the reference's operator surface on top of ``vmasr_scan_fwd`` / ``vmasr_scan_bwd``.
+
+Mirrors, name for name:
+  * the native module ``selective_scan_cuda_core`` -- ``fwd(u, delta, A, B, C, D, delta_bias, delta_softplus,
+    nrows) -> [out, x]`` and ``bwd(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, nrows) ->
+    [du, ddelta, dA, dB, dC, dD, ddelta_bias]``
+    (kernels/selective_scan/csrc/selective_scan/cus/selective_scan.cpp:157-164, 241-250, 351-354),
+  * ``SelectiveScanCore`` (model/vmamba.py:323-356), the autograd.Function ``SS2D.forward_corev2`` calls,
+  * ``selective_scan_fn`` (kernels/selective_scan/test_selective_scan.py:241-280).
+
+Argument checks raise ``RuntimeError`` for the same conditions the reference's TORCH_CHECKs do
+(selective_scan.cpp:165-215).  No CPU path, no fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ScanParams
+
+
+def _check(cond: bool, msg: str):
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _validate(u, delta, A, B, C, D, delta_bias):
+    _check(u.dtype in _lib.DTYPE_CODE, "selective_scan: input must be float32, float16 or bfloat16")
+    _check(A.dtype == torch.float32, "selective_scan: A must be float32")
+    for name, t in (("delta", delta), ("B", B), ("C", C)):
+        _check(t.dtype == u.dtype, f"selective_scan: {name} must have the dtype of u")
+    for name, t in (("u", u), ("delta", delta), ("A", A), ("B", B), ("C", C)):
+        _lib.require_cuda(t, name)
+    _check(u.dim() == 3, "selective_scan: u must be (batch, dim, seqlen)")
+    batch, dim, seqlen = u.shape
+    _check(A.dim() == 2 and A.shape[0] == dim, "selective_scan: A must be (dim, dstate)")
+    dstate = A.shape[1]
+    _check(B.dim() == 4 and C.dim() == 4, "selective_scan: B and C must be (batch, n_groups, dstate, seqlen)")
+    ngroups = B.shape[1]
+    _check(dim % ngroups == 0, "dims should be dividable by n_groups")
+    _check(dstate <= 256, "selective_scan only supports state dimension <= 256")
+    _check(tuple(delta.shape) == (batch, dim, seqlen), "selective_scan: delta must have the shape of u")
+    _check(tuple(B.shape) == (batch, ngroups, dstate, seqlen), "selective_scan: B has the wrong shape")
+    _check(tuple(C.shape) == (batch, ngroups, dstate, seqlen), "selective_scan: C has the wrong shape")
+    for name, t in (("u", u), ("delta", delta), ("B", B), ("C", C)):
+        _check(t.stride(-1) == 1 or t.size(-1) == 1, f"selective_scan: {name} must have unit stride along seqlen")
+    for name, t in (("D", D), ("delta_bias", delta_bias)):
+        if t is not None:
+            _check(t.dtype == torch.float32, f"selective_scan: {name} must be float32")
+            _lib.require_cuda(t, name)
+            _check(tuple(t.shape) == (dim,), f"selective_scan: {name} must be (dim,)")
+            _check(t.stride(-1) == 1 or t.size(-1) == 1, f"selective_scan: {name} must be contiguous")
+    return batch, dim, seqlen, dstate, ngroups
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _fill_common(p: ScanParams, u, delta, A, B, C, D, delta_bias, dims, delta_softplus):
+    batch, dim, seqlen, dstate, ngroups = dims
+    p.u, p.delta, p.A, p.B, p.C = u.data_ptr(), delta.data_ptr(), A.data_ptr(), B.data_ptr(), C.data_ptr()
+    p.D, p.delta_bias = _ptr(D), _ptr(delta_bias)
+    p.batch, p.dim, p.seqlen, p.dstate, p.ngroups = batch, dim, seqlen, dstate, ngroups
+    p.u_batch_stride, p.u_d_stride = u.stride(0), u.stride(1)
+    p.delta_batch_stride, p.delta_d_stride = delta.stride(0), delta.stride(1)
+    p.A_d_stride, p.A_dstate_stride = A.stride(0), A.stride(1)
+    p.B_batch_stride, p.B_group_stride, p.B_dstate_stride = B.stride(0), B.stride(1), B.stride(2)
+    p.C_batch_stride, p.C_group_stride, p.C_dstate_stride = C.stride(0), C.stride(1), C.stride(2)
+    p.io_dtype = _lib.DTYPE_CODE[u.dtype]
+    p.delta_softplus = 1 if delta_softplus else 0
+    p.device = u.device.index if u.device.index is not None else torch.cuda.current_device()
+    p.stream = _lib.current_stream_ptr(u.device)
+    n_chunks = (seqlen + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
+    if n_chunks > 1:
+        lib = _lib.load_library()
+        need = lib.vmasr_scan_workspace_bytes(batch, dim, seqlen, dstate)
+        ws = _lib.scan_workspace(u.device, need)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    return n_chunks
+
+
+def fwd_out(u, delta, A, B, C, D, delta_bias, delta_softplus, out, x):
+    """Launch the forward into caller-provided ``out`` (like delta) and ``x`` (batch, dim, n_chunks, 2*dstate)
+    float32.  No allocation: usable under CUDA-graph capture (the stream's carry workspace must already exist,
+    i.e. one eager call first)."""
+    lib = _lib.load_library()
+    dims = _validate(u, delta, A, B, C, D, delta_bias)
+    batch, dim, seqlen, dstate, _ = dims
+    n_chunks = (seqlen + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
+    _check(out.dtype == u.dtype and tuple(out.shape) == (batch, dim, seqlen) and (out.stride(-1) == 1 or seqlen == 1),
+           "selective_scan: out must look like delta")
+    _check(x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (batch, dim, n_chunks, 2 * dstate),
+           "selective_scan: x has the wrong shape")
+    p = ScanParams()
+    with torch.cuda.device(u.device):
+        _fill_common(p, u, delta, A, B, C, D, delta_bias, dims, delta_softplus)
+        p.out, p.x = out.data_ptr(), x.data_ptr()
+        p.out_batch_stride, p.out_d_stride = out.stride(0), out.stride(1)
+        _lib.check(lib.vmasr_scan_fwd(ctypes.byref(p)))
+
+
+def fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1):
+    """``selective_scan_cuda_core.fwd``: returns ``[out, x]``.  ``nrows`` is accepted and ignored, like the
+    reference's core kernel does (selective_scan.cpp:163)."""
+    dims = _validate(u, delta, A, B, C, D, delta_bias)
+    batch, dim, seqlen, dstate, _ = dims
+    n_chunks = (seqlen + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
+    out = torch.empty_like(delta)
+    x = torch.empty((batch, dim, n_chunks, 2 * dstate), dtype=torch.float32, device=u.device)
+    fwd_out(u, delta, A, B, C, D, delta_bias, delta_softplus, out, x)
+    return [out, x]
+
+
+def bwd_out(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, du, ddelta, dA, dB, dC, dD, ddelta_bias):
+    """Launch the backward into caller-provided buffers.  ``dA, dB, dC, dD, ddelta_bias`` are float32 and are
+    ACCUMULATED INTO (zero them first); ``dB, dC`` are (batch, n_groups, dstate, seqlen) contiguous."""
+    lib = _lib.load_library()
+    dims = _validate(u, delta, A, B, C, D, delta_bias)
+    batch, dim, seqlen, dstate, ngroups = dims
+    _check(dout.dtype == u.dtype, "selective_scan: dout must have the dtype of u")
+    _lib.require_cuda(dout, "dout")
+    _check(tuple(dout.shape) == (batch, dim, seqlen), "selective_scan: dout has the wrong shape")
+    _check(dout.stride(-1) == 1 or dout.size(-1) == 1, "selective_scan: dout must have unit stride along seqlen")
+    n_chunks = (seqlen + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
+    if n_chunks > 1:
+        _check(x is not None, "selective_scan: x is required when seqlen > 2048")
+    if x is not None:
+        _check(x.dtype == torch.float32 and x.is_cuda and x.is_contiguous(), "selective_scan: x must be contiguous float32 CUDA")
+        _check(tuple(x.shape) == (batch, dim, n_chunks, 2 * dstate), "selective_scan: x has the wrong shape")
+    for name, t in (("dB", dB), ("dC", dC)):
+        _check(t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (batch, ngroups, dstate, seqlen),
+               f"selective_scan: {name} must be contiguous float32 (batch, n_groups, dstate, seqlen)")
+    _check(dA.dtype == torch.float32 and dA.stride() == A.stride(), "selective_scan: dA must look like A")
+    p = ScanParams()
+    with torch.cuda.device(u.device):
+        _fill_common(p, u, delta, A, B, C, D, delta_bias, dims, delta_softplus)
+        p.dout, p.x = dout.data_ptr(), _ptr(x)
+        p.du, p.ddelta, p.dA, p.dB, p.dC = du.data_ptr(), ddelta.data_ptr(), dA.data_ptr(), dB.data_ptr(), dC.data_ptr()
+        p.dD, p.ddelta_bias = _ptr(dD), _ptr(ddelta_bias)
+        p.dout_batch_stride, p.dout_d_stride = dout.stride(0), dout.stride(1)
+        p.du_batch_stride, p.du_d_stride = du.stride(0), du.stride(1)
+        p.ddelta_batch_stride, p.ddelta_d_stride = ddelta.stride(0), ddelta.stride(1)
+        _lib.check(lib.vmasr_scan_bwd(ctypes.byref(p)))
+
+
+def bwd(u, delta, A, B, C, D, delta_bias, dout, x=None, delta_softplus=False, nrows=1):
+    """``selective_scan_cuda_core.bwd``: returns ``[du, ddelta, dA, dB, dC, dD, ddelta_bias]``."""
+    dims = _validate(u, delta, A, B, C, D, delta_bias)
+    batch, dim, seqlen, dstate, ngroups = dims
+    du = torch.empty_like(u)
+    ddelta = torch.empty_like(delta)
+    dA = torch.zeros_like(A)
+    dB = torch.zeros((batch, ngroups, dstate, seqlen), dtype=torch.float32, device=u.device)
+    dC = torch.zeros((batch, ngroups, dstate, seqlen), dtype=torch.float32, device=u.device)
+    dD = torch.zeros_like(D) if D is not None else None
+    dbias = torch.zeros_like(delta_bias) if delta_bias is not None else None
+    bwd_out(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, du, ddelta, dA, dB, dC, dD, dbias)
+    return [du, ddelta, dA, dB.to(B.dtype), dC.to(C.dtype), dD, dbias]
+
+
+class SelectiveScanCore(torch.autograd.Function):
+    """Drop-in for ``model.vmamba.SelectiveScanCore`` (vmamba.py:323-356); same argument list, the trailing
+    ``nrows, backnrows, oflex`` are accepted and ignored exactly as there."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1, backnrows=1, oflex=True):
+        ctx.delta_softplus = delta_softplus
+        out, x = fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, 1)
+        ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, x)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout, *args):
+        u, delta, A, B, C, D, delta_bias, x = ctx.saved_tensors
+        if dout.stride(-1) != 1:
+            dout = dout.contiguous()
+        du, ddelta, dA, dB, dC, dD, ddelta_bias = bwd(u, delta, A, B, C, D, delta_bias, dout, x, ctx.delta_softplus, 1)
+        return (du, ddelta, dA, dB, dC, dD, ddelta_bias, None, None, None, None)
+
+
+class _SelectiveScanFn(torch.autograd.Function):
+    """The functional form with ``return_last_state`` (test_selective_scan.py:24-135)."""
+
+    @staticmethod
+    def forward(ctx, u, delta, A, B, C, D, delta_bias, delta_softplus, return_last_state):
+        if u.stride(-1) != 1:
+            u = u.contiguous()
+        if delta.stride(-1) != 1:
+            delta = delta.contiguous()
+        if B.stride(-1) != 1:
+            B = B.contiguous()
+        if C.stride(-1) != 1:
+            C = C.contiguous()
+        ctx.squeeze_B = B.dim() == 3
+        ctx.squeeze_C = C.dim() == 3
+        if ctx.squeeze_B:
+            B = B.unsqueeze(1)
+        if ctx.squeeze_C:
+            C = C.unsqueeze(1)
+        ctx.d_dtype = None if D is None else D.dtype
+        ctx.bias_dtype = None if delta_bias is None else delta_bias.dtype
+        if D is not None:
+            D = D.float().contiguous()
+        if delta_bias is not None:
+            delta_bias = delta_bias.float().contiguous()
+        ctx.delta_softplus = delta_softplus
+        out, x = fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, 1)
+        ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, x)
+        if return_last_state:
+            last_state = x[:, :, -1, 1::2]
+            ctx.mark_non_differentiable(last_state)
+            return out, last_state
+        return out
+
+    @staticmethod
+    def backward(ctx, dout, *args):
+        u, delta, A, B, C, D, delta_bias, x = ctx.saved_tensors
+        if dout.stride(-1) != 1:
+            dout = dout.contiguous()
+        du, ddelta, dA, dB, dC, dD, dbias = bwd(u, delta, A, B, C, D, delta_bias, dout, x, ctx.delta_softplus, 1)
+        if ctx.squeeze_B:
+            dB = dB.squeeze(1)
+        if ctx.squeeze_C:
+            dC = dC.squeeze(1)
+        if dD is not None and ctx.d_dtype is not None:
+            dD = dD.to(ctx.d_dtype)
+        if dbias is not None and ctx.bias_dtype is not None:
+            dbias = dbias.to(ctx.bias_dtype)
+        return du, ddelta, dA, dB, dC, dD, dbias, None, None
+
+
+def selective_scan_fn(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, return_last_state=False):
+    """``selective_scan_fn(u, delta, A, B, C, D, delta_bias, delta_softplus)`` with its autograd backward.
+    ``B``/``C`` may be (batch, dstate, seqlen) (one group) or (batch, n_groups, dstate, seqlen)."""
+    return _SelectiveScanFn.apply(u, delta, A, B, C, D, delta_bias, delta_softplus, return_last_state)
