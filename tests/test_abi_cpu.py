@@ -40,7 +40,7 @@ def test_workspace_sizing():
     small = lib.vmasr_scan_workspace_bytes(4, 8, 2049, 1)
     big = lib.vmasr_scan_workspace_bytes(4, 8, 262144, 1)
     assert 0 < small < big
-    assert big >= 4 * 8 * 128 * 12                                      # 12 bytes per (b, d, n, chunk) entry
+    assert big >= 4 * 8 * 128 * 16                                      # 16 bytes per (b, d, n, chunk) entry
     assert lib.vmasr_scan_workspace_bytes(0, 8, 4096, 1) == 0
 
 

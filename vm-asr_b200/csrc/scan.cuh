@@ -14,6 +14,8 @@ namespace vmasr {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+struct CarryEntry;
+
 // Device view of one scan call.
 struct ScanArgs {
     const void *u, *delta, *B, *C, *dout;
@@ -22,8 +24,7 @@ struct ScanArgs {
     float *x, *dA, *dB, *dC, *dD, *ddelta_bias;
     // carry exchange
     unsigned *ws_header;  // {ticket, done, epoch, pad}
-    unsigned *ws_flags;
-    float2 *ws_payload;
+    CarryEntry *ws_entries;
     int batch, dim, seqlen, dstate, ngroups;
     int n_chunks;         // ceil(seqlen / chunk)
     int chan_per_group;   // dim / ngroups
@@ -70,50 +71,75 @@ __device__ __forceinline__ Aff warp_scan_down(Aff v, int lane) {
 }
 
 // ---- chunk-carry exchange --------------------------------------------------------------------------
-// One entry per (batch, channel, state, chunk): payload = the chunk's own affine map (p, q), flag = epoch tag.
-// A chunk publishes its map as soon as its local scan is done and never waits before publishing, so there
-// is no dependency chain between chunks.  The state entering chunk i is obtained by composing the maps of
-// ALL chunks before it, always in the same fixed tree (32-entry windows reduced by shuffles, windows folded
-// nearest first).  Reading every predecessor instead of stopping at the first "inclusive" one costs a few
-// hundred bytes per chunk and buys run-to-run bit-reproducible results.
+// One 16-byte entry per (batch, channel, state, chunk): {p, tag, q, tag} -- the chunk's own affine map with
+// the launch's epoch tag repeated in each 8-byte half.  An entry is valid when both tags equal the current
+// tag; 8-byte accesses are single-copy atomic, so a half-written entry can never validate with stale
+// numbers and no fence is needed on either side (the data validates itself, no separate flag to order
+// against).  A chunk publishes its map as soon as its local scan is done and never waits before publishing,
+// so there is no dependency chain between chunks.  The state entering chunk i is obtained by composing the
+// maps of ALL chunks before it, always in the same fixed tree (each lane folds 4 consecutive entries, then
+// a shuffle tree over the lanes, 128 predecessors per round, nearest round first): run-to-run
+// bit-reproducible, one L2 round trip in the common case, and every warp resolves its own copy so no block
+// barrier is involved.
 // The workspace is zero-filled once; every launch that uses it reads the epoch from the header and the
-// last CTA to finish bumps it (and rewinds the ticket counter), so flags of earlier launches are never
-// mistaken for current ones and nothing has to be cleared between launches.
-constexpr int kMaxWindows = 128;  // 32 chunks each: sequences up to 128*32*2048 positions
+// last CTA to finish bumps it, so entries of earlier launches never validate and nothing has to be cleared
+// between launches.
+struct __align__(16) CarryEntry {
+    float p;
+    unsigned tag0;
+    float q;
+    unsigned tag1;
+};
 
 __device__ __forceinline__ void publish(const ScanArgs &a, long long entry, unsigned tag, float p, float q) {
-    st_relaxed_f2(a.ws_payload + entry, make_float2(p, q));
-    st_release_u32(a.ws_flags + entry, tag);
+    asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(a.ws_entries + entry), "r"(__float_as_uint(p)),
+                 "r"(tag), "r"(__float_as_uint(q)), "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 load_entry(const CarryEntry *e) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(e) : "memory");
+    return v;
 }
 
-// Whole warp: composite map of predecessors 32*win+1 .. 32*win+32 (those that exist), nearest = lane 0.
-// `step` is +1 when predecessors are the lower-numbered chunks (forward scan), -1 when they are the
-// higher-numbered ones (adjoint scan).  Result valid in every lane.
-__device__ __forceinline__ Aff window_map(const ScanArgs &a, long long entry0, int chunk, int step, int n_before, int win,
-                                          unsigned tag, int lane) {
-    const int k = win * 32 + lane + 1;
-    Aff v = {1.0f, 0.0f};
-    if (k <= n_before) {
-        const long long e = entry0 + (long long)(chunk - step * k);
-        unsigned f = ld_acquire_u32(a.ws_flags + e);
-        while (f != tag) {
-            __nanosleep(20);
-            f = ld_acquire_u32(a.ws_flags + e);
-        }
-        const float2 pl = ld_relaxed_f2(a.ws_payload + e);
-        v = {pl.x, pl.y};
-    }
-    __syncwarp();
+// Whole warp.  Composite map of all `n_before` predecessor chunks of `chunk`; `step` is +1 when the
+// predecessors are the lower-numbered chunks (forward scan) and -1 when they are the higher-numbered ones
+// (adjoint scan).  `entry0` is the entry of chunk 0 of this (batch, channel, state).  Result in every lane:
+// .q is the state entering the chunk (initial state 0), .p the cumulative decay before it.
+__device__ __forceinline__ Aff carry_in(const ScanArgs &a, long long entry0, int chunk, int step, int n_before, unsigned tag,
+                                        int lane) {
+    Aff acc = {1.0f, 0.0f};
+    for (int base = 0; base < n_before; base += 128) {
+        uint4 e[4];
+        const int k0 = base + 4 * lane + 1;  // nearest predecessor this lane folds
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const float pp = __shfl_down_sync(0xffffffffu, v.p, off);
-        const float pq = __shfl_down_sync(0xffffffffu, v.q, off);
-        if (lane + off < 32) {  // lane+off is farther back: it is applied first
-            v.q = fmaf(v.p, pq, v.q);
-            v.p *= pp;
+        for (int j = 0; j < 4; ++j)
+            if (k0 + j <= n_before) e[j] = load_entry(a.ws_entries + entry0 + (long long)(chunk - step * (k0 + j)));
+        Aff v = {1.0f, 0.0f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (k0 + j <= n_before) {
+                while (e[j].y != tag || e[j].w != tag) {
+                    __nanosleep(20);
+                    e[j] = load_entry(a.ws_entries + entry0 + (long long)(chunk - step * (k0 + j)));
+                }
+                v = compose(Aff{__uint_as_float(e[j].x), __uint_as_float(e[j].z)}, v);  // farther one applies first
+            }
         }
+        __syncwarp();
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const float pp = __shfl_down_sync(0xffffffffu, v.p, off);
+            const float pq = __shfl_down_sync(0xffffffffu, v.q, off);
+            if (lane + off < 32) {  // lane+off holds farther predecessors: applied first
+                v.q = fmaf(v.p, pq, v.q);
+                v.p *= pp;
+            }
+        }
+        const Aff round = {__shfl_sync(0xffffffffu, v.p, 0), __shfl_sync(0xffffffffu, v.q, 0)};
+        acc = compose(round, acc);
     }
-    return {__shfl_sync(0xffffffffu, v.p, 0), __shfl_sync(0xffffffffu, v.q, 0)};
+    return acc;
 }
 
 // Claim a tile.  With more than one chunk per sequence the order in which tiles start matters for forward

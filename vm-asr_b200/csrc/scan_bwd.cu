@@ -51,7 +51,6 @@ __global__ void __launch_bounds__(NT) scan_bwd_kernel(const __grid_constant__ Sc
     __shared__ float s_red[2][ROWS][4];                    // per channel sums: dA, dD, ddelta_bias
     __shared__ float s_dbc[(ROWS > 1) ? 2 * ROWS * TPR * ITEMS : 1];
     __shared__ unsigned s_tile[2];
-    __shared__ float2 s_win[kMaxWindows];
 
     if (threadIdx.x < 2 * ROWS * 4) (&s_red[0][0][0])[threadIdx.x] = 0.0f;
     __syncthreads();
@@ -194,18 +193,7 @@ __global__ void __launch_bounds__(NT) scan_bwd_kernel(const __grid_constant__ Sc
                 const long long entry0 = (((long long)b * a.dim + d) * a.dstate + n) * a.n_chunks;
                 const int n_after = a.n_chunks - 1 - chunk;
                 if (last_warp && lane == 0) publish(a, entry0 + chunk, epoch, total_r.p, total_r.q);
-                const int n_win = (n_after + 31) >> 5;
-                for (int win = warp_in_row; win < n_win; win += WPR) {
-                    const Aff w = window_map(a, entry0, chunk, -1, n_after, win, epoch, lane);
-                    if (lane == 0) s_win[win] = make_float2(w.p, w.q);
-                }
-                __syncthreads();
-                Aff acc = {1.0f, 0.0f};
-                for (int win = 0; win < n_win; ++win) {
-                    const float2 w = s_win[win];
-                    acc = compose(Aff{w.x, w.y}, acc);
-                }
-                g_in = acc.q;
+                g_in = carry_in(a, entry0, chunk, -1, n_after, epoch, lane).q;
             }
 
             // forward states of this thread's positions

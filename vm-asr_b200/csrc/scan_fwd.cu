@@ -13,7 +13,6 @@ __global__ void __launch_bounds__(NT) scan_fwd_kernel(const __grid_constant__ Sc
     constexpr int CHUNK = TPR * ITEMS;
     __shared__ float2 s_tot[2][ROWS][WPR > 1 ? WPR : 1];
     __shared__ unsigned s_tile[2];
-    __shared__ float2 s_win[kMaxWindows];
 
     unsigned tile, epoch;
     claim_tile(a, s_tile, tile, epoch);
@@ -110,17 +109,7 @@ __global__ void __launch_bounds__(NT) scan_fwd_kernel(const __grid_constant__ Sc
             if (a.n_chunks > 1) {
                 const long long entry0 = (((long long)b * a.dim + d) * a.dstate + n) * a.n_chunks;
                 if (last_warp && lane == 0) publish(a, entry0 + chunk, epoch, total.p, total.q);
-                const int n_win = (chunk + 31) >> 5;
-                for (int win = warp_in_row; win < n_win; win += WPR) {
-                    const Aff w = window_map(a, entry0, chunk, +1, chunk, win, epoch, lane);
-                    if (lane == 0) s_win[win] = make_float2(w.p, w.q);
-                }
-                __syncthreads();
-                Aff acc = {1.0f, 0.0f};
-                for (int win = 0; win < n_win; ++win) {
-                    const float2 w = s_win[win];
-                    acc = compose(Aff{w.x, w.y}, acc);
-                }
+                const Aff acc = carry_in(a, entry0, chunk, +1, chunk, epoch, lane);
                 h_in = acc.q;
                 pcum_in = acc.p;
             }

@@ -1,11 +1,15 @@
 // Host side of the selective scan: argument checks (mirroring the TORCH_CHECKs of
 // kernels/selective_scan/csrc/selective_scan/cus/selective_scan.cpp:165-215, 262-317), tile planning, launch.
+#include <cstdlib>
+
 #include "scan.cuh"
 
 namespace vmasr {
 
 int scan_fwd_dispatch(const ScanArgs &a, const ScanPlan &pl, int io_dtype, cudaStream_t stream);
 int scan_bwd_dispatch(const ScanArgs &a, const ScanPlan &pl, int io_dtype, cudaStream_t stream);
+int scan_fwd_tma_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
+constexpr int kMaxTileChannelsHost = 64;  // scan_fwd_tma.cu stages this many channels' parameters per tile
 
 static size_t dtype_size(int dt) { return dt == VMASR_F32 ? 4 : 2; }
 
@@ -32,7 +36,6 @@ static int validate(const vmasr_scan_params *p, bool bwd) {
         if (n_chunks > 1 && !p->x) return fail("selective_scan_bwd: x (chunk states) is required when seqlen > %d", VMASR_SCAN_CHUNK);
     }
     const int n_chunks = (p->seqlen + VMASR_SCAN_CHUNK - 1) / VMASR_SCAN_CHUNK;
-    if (n_chunks > 32 * kMaxWindows) return fail("selective_scan: seqlen %d exceeds the supported maximum %d", p->seqlen, 32 * kMaxWindows * VMASR_SCAN_CHUNK);
     if (n_chunks > 1) {
         if (!p->workspace) return fail("selective_scan: a carry workspace is required when seqlen > %d", VMASR_SCAN_CHUNK);
         const uint64_t need = vmasr_scan_workspace_bytes(p->batch, p->dim, p->seqlen, p->dstate);
@@ -59,6 +62,8 @@ static ScanPlan make_plan(const vmasr_scan_params *p, int n_chunks, int &chan_pe
     const int max_ctiles = (cpg + pl.rows - 1) / pl.rows;
     long long want = (target + base_tiles - 1) / base_tiles;
     if (want < 1) want = 1;
+    const long long min_ctiles = (cpg + kMaxTileChannelsHost - 1) / kMaxTileChannelsHost;
+    if (want < min_ctiles) want = min_ctiles;
     if (want > max_ctiles) want = max_ctiles;
     chan_per_tile = (int)((cpg + want - 1) / want);
     chan_per_tile = ((chan_per_tile + pl.rows - 1) / pl.rows) * pl.rows;
@@ -82,14 +87,10 @@ static ScanArgs make_args(const vmasr_scan_params *p, int n_chunks, int chan_per
     a.out = p->out; a.du = p->du; a.ddelta = p->ddelta;
     a.x = p->x; a.dA = p->dA; a.dB = p->dB; a.dC = p->dC; a.dD = p->dD; a.ddelta_bias = p->ddelta_bias;
     if (p->workspace && n_chunks > 1) {
-        // fixed split of the workspace (independent of this call's sizes, so stale payload bytes can never
-        // be read as flags): [64 B header][flags: cap * 4 B][payload: cap * 8 B]
+        // [64 B header {ticket, done, epoch}][16-byte carry entries]
         char *base = static_cast<char *>(p->workspace);
-        const uint64_t cap = (p->workspace_bytes - 64 - 16) / 12;
         a.ws_header = reinterpret_cast<unsigned *>(base);
-        a.ws_flags = reinterpret_cast<unsigned *>(base + 64);
-        const uint64_t flag_bytes = (cap * 4 + 15) / 16 * 16;
-        a.ws_payload = reinterpret_cast<float2 *>(base + 64 + flag_bytes);
+        a.ws_entries = reinterpret_cast<CarryEntry *>(base + 64);
     }
     a.batch = p->batch; a.dim = p->dim; a.seqlen = p->seqlen; a.dstate = p->dstate; a.ngroups = p->ngroups;
     a.n_chunks = n_chunks;
@@ -129,7 +130,12 @@ static int run(const vmasr_scan_params *p, bool bwd) {
                  mult(p->du_d_stride) && mult(p->ddelta_batch_stride) && mult(p->ddelta_d_stride) && (p->seqlen % 4 == 0);
     }
     cudaStream_t stream = static_cast<cudaStream_t>(p->stream);
-    return bwd ? scan_bwd_dispatch(a, pl, p->io_dtype, stream) : scan_fwd_dispatch(a, pl, p->io_dtype, stream);
+    if (bwd) return scan_bwd_dispatch(a, pl, p->io_dtype, stream);
+    // fast path: fp32, d_state 1, aligned rows -> TMA-staged kernel (VMASR_SCAN_FWD=generic forces the other one)
+    static const bool force_generic = [] { const char *e = getenv("VMASR_SCAN_FWD"); return e && e[0] == 'g'; }();
+    if (!force_generic && p->io_dtype == VMASR_F32 && p->dstate == 1 && pl.vec && a.chan_per_tile <= kMaxTileChannelsHost)
+        return scan_fwd_tma_dispatch(a, pl, stream);
+    return scan_fwd_dispatch(a, pl, p->io_dtype, stream);
 }
 
 }  // namespace vmasr
@@ -139,7 +145,7 @@ extern "C" uint64_t vmasr_scan_workspace_bytes(int batch, int dim, int seqlen, i
     const uint64_t n_chunks = ((uint64_t)seqlen + VMASR_SCAN_CHUNK - 1) / VMASR_SCAN_CHUNK;
     if (n_chunks <= 1) return 0;
     const uint64_t cap = (uint64_t)batch * dim * dstate * n_chunks;
-    const uint64_t bytes = 64 + 16 + 12 * (cap + 4);
+    const uint64_t bytes = 64 + 16 * cap;
     return (bytes + 255) / 256 * 256;
 }
 
