@@ -1,0 +1,169 @@
+// Asynchronous-copy pipeline pieces for the persistent scan kernels (sm_100a): mbarriers, TMA bulk copies
+// (cp.async.bulk -> SASS UBLKCP), a consumer-only named barrier, and the two-level chunk-carry look-back.
+#pragma once
+#include "scan.cuh"
+
+namespace vmasr {
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (TMA), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// barrier among the first `count` threads of the CTA only (the producer warp never joins it)
+template <int ID, int COUNT>
+__device__ __forceinline__ void consumer_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
+
+// position in a ring of NSTAGES buffers and the parity of the mbarrier phase it is in
+template <int NSTAGES>
+struct Ring {
+    int stage = 0;
+    unsigned phase = 0;
+    __device__ __forceinline__ void advance() {
+        if (++stage == NSTAGES) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
+};
+
+// ---- two-level chunk-carry look-back ---------------------------------------------------------------
+// Level 1: one entry per chunk, the chunk's own affine map, published as soon as its local scan is done.
+// Level 2: one entry per GROUP of 16 consecutive chunks (in scan order), the composite map of the group,
+// published by the group's last chunk once it has seen the 15 level-1 entries before it.  The state entering
+// chunk j (scan-order index) is the composition of  level-2 entries of every complete group before it  and
+// the level-1 entries of the chunks before it inside its own group: at most 16 + 15 entries, ONE 16-byte
+// load per lane, combined in a fixed shuffle tree (bit-reproducible run to run).  Publication never waits on
+// anything at level 1 and only on level-1 entries at level 2, so there is no dependency chain along the
+// sequence.  The load is issued at the top of the row (before any arithmetic) and validated after the local
+// scan: in the steady state the predecessors ran a whole wave earlier and the look-back costs no latency.
+struct CarryLook {
+    const CarryEntry *ptr;  // this lane's entry (nullptr: lane holds the identity)
+    uint4 e;
+};
+
+__device__ __forceinline__ CarryLook look_issue(const CarryEntry *l1_row, const CarryEntry *l2_row, int j, int lane) {
+    CarryLook c;
+    const int r = j & 15, gi = j >> 4;
+    c.ptr = nullptr;
+    if (lane < 16) {
+        if (lane < r) c.ptr = l1_row + (j - 1 - lane);
+    } else {
+        const int i = lane - 16;
+        if (i < gi) c.ptr = l2_row + (gi - 1 - i);
+    }
+    c.e = make_uint4(0u, 0u, 0u, 0u);
+    if (c.ptr) c.e = load_entry(c.ptr);
+    return c;
+}
+
+// Whole warp.  Returns the composite map of everything before chunk j in every lane; `ingroup` receives the
+// composite of the level-1 entries before j inside its group (what a group's last chunk folds into level 2).
+__device__ __forceinline__ Aff look_resolve(CarryLook &c, const CarryEntry *l2_row, int j, unsigned tag, int lane, Aff &ingroup) {
+    Aff v = {1.0f, 0.0f};
+    if (c.ptr) {
+        while (c.e.y != tag || c.e.w != tag) {
+            __nanosleep(32);
+            c.e = load_entry(c.ptr);
+        }
+        v = Aff{__uint_as_float(c.e.x), __uint_as_float(c.e.z)};
+    }
+    __syncwarp();
+    // higher lanes hold maps that apply earlier; fold them in first
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const float pp = __shfl_down_sync(0xffffffffu, v.p, off);
+        const float pq = __shfl_down_sync(0xffffffffu, v.q, off);
+        if (lane + off < 32) {
+            v.q = fmaf(v.p, pq, v.q);
+            v.p *= pp;
+        }
+        if (off == 8) ingroup = Aff{__shfl_sync(0xffffffffu, v.p, 0), __shfl_sync(0xffffffffu, v.q, 0)};
+    }
+    Aff acc = {__shfl_sync(0xffffffffu, v.p, 0), __shfl_sync(0xffffffffu, v.q, 0)};
+    // sequences of more than 272 chunks: remaining level-2 entries, 32 per round, nearest round first
+    const int gi = j >> 4;
+    for (int base = 16; base < gi; base += 32) {
+        Aff w = {1.0f, 0.0f};
+        const int i = base + lane;
+        if (i < gi) {
+            const CarryEntry *p = l2_row + (gi - 1 - i);
+            uint4 e = load_entry(p);
+            while (e.y != tag || e.w != tag) {
+                __nanosleep(32);
+                e = load_entry(p);
+            }
+            w = Aff{__uint_as_float(e.x), __uint_as_float(e.z)};
+        }
+        __syncwarp();
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const float pp = __shfl_down_sync(0xffffffffu, w.p, off);
+            const float pq = __shfl_down_sync(0xffffffffu, w.q, off);
+            if (lane + off < 32) {
+                w.q = fmaf(w.p, pq, w.q);
+                w.p *= pp;
+            }
+        }
+        const Aff round = {__shfl_sync(0xffffffffu, w.p, 0), __shfl_sync(0xffffffffu, w.q, 0)};
+        acc = compose(round, acc);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void publish_entry(CarryEntry *e, unsigned tag, float p, float q) {
+    asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(e), "r"(__float_as_uint(p)), "r"(tag),
+                 "r"(__float_as_uint(q)), "r"(tag)
+                 : "memory");
+}
+
+// softplus pieces in the log2 domain: x2 = (delta + bias) * log2(e).  Same accuracy contract as
+// softplus_sig() in common.cuh (relative error < 1e-6 everywhere), fewer instructions: the threshold test
+// of the reference (identity above 20, fwd_kernel.cuh:117) is done on x2.
+constexpr float kSoftplusThr2 = 20.0f * 1.4426950408889634f;
+__device__ __forceinline__ float softplus2(float x2, float x) {
+    const float e = ex2_approx(x2);
+    const float lg = lg2_approx(1.0f + e) * 0.6931471805599453f;
+    const float poly = e * fmaf(-e, fmaf(-e, fmaf(-0.25f, e, 0.33333334f), 0.5f), 1.0f);
+    float sp = (e < 0.03125f) ? poly : lg;
+    return (x2 > kSoftplusThr2) ? x : sp;
+}
+__device__ __forceinline__ float softplus2_sig(float x2, float x, float &sig) {
+    const float e = ex2_approx(x2);
+    const float one_pe = 1.0f + e;
+    const float lg = lg2_approx(one_pe) * 0.6931471805599453f;
+    const float poly = e * fmaf(-e, fmaf(-e, fmaf(-0.25f, e, 0.33333334f), 0.5f), 1.0f);
+    float sp = (e < 0.03125f) ? poly : lg;
+    const bool big = x2 > kSoftplusThr2;
+    sig = big ? 1.0f : __fdividef(e, one_pe);
+    return big ? x : sp;
+}
+
+}  // namespace vmasr

@@ -24,7 +24,9 @@ struct ScanArgs {
     float *x, *dA, *dB, *dC, *dD, *ddelta_bias;
     // carry exchange
     unsigned *ws_header;  // {ticket, done, epoch, pad}
-    CarryEntry *ws_entries;
+    CarryEntry *ws_entries;   // level 1: one entry per (batch, channel, state, chunk)
+    CarryEntry *ws_entries2;  // level 2: one entry per (batch, channel, group of 16 chunks) -- persistent kernels, d_state 1
+    int n_tiles;              // persistent kernels: number of tiles dealt round-robin to the CTAs
     int batch, dim, seqlen, dstate, ngroups;
     int n_chunks;         // ceil(seqlen / chunk)
     int chan_per_group;   // dim / ngroups
