@@ -1,5 +1,5 @@
-// Asynchronous-copy pipeline pieces for the persistent scan kernels (sm_100a): mbarriers, TMA bulk copies
-// (cp.async.bulk -> SASS UBLKCP), a consumer-only named barrier, and the two-level chunk-carry look-back.
+// Pieces shared by the scan kernels (sm_100a): mbarriers and TMA bulk copies (cp.async.bulk -> SASS UBLKCP),
+// the two-level chunk-carry look-back, and the log2-domain softplus.
 #pragma once
 #include "scan.cuh"
 
@@ -35,25 +35,6 @@ __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, 
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// barrier among the first `count` threads of the CTA only (the producer warp never joins it)
-template <int ID, int COUNT>
-__device__ __forceinline__ void consumer_sync() {
-    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
-}
-
-// position in a ring of NSTAGES buffers and the parity of the mbarrier phase it is in
-template <int NSTAGES>
-struct Ring {
-    int stage = 0;
-    unsigned phase = 0;
-    __device__ __forceinline__ void advance() {
-        if (++stage == NSTAGES) {
-            stage = 0;
-            phase ^= 1u;
-        }
-    }
-};
-
 // ---- two-level chunk-carry look-back ---------------------------------------------------------------
 // Level 1: one entry per chunk, the chunk's own affine map, published as soon as its local scan is done.
 // Level 2: one entry per GROUP of 16 consecutive chunks (in scan order), the composite map of the group,
@@ -62,8 +43,8 @@ struct Ring {
 // the level-1 entries of the chunks before it inside its own group: at most 16 + 15 entries, ONE 16-byte
 // load per lane, combined in a fixed shuffle tree (bit-reproducible run to run).  Publication never waits on
 // anything at level 1 and only on level-1 entries at level 2, so there is no dependency chain along the
-// sequence.  The load is issued at the top of the row (before any arithmetic) and validated after the local
-// scan: in the steady state the predecessors ran a whole wave earlier and the look-back costs no latency.
+// sequence.  The TMA forward kernel issues the load at the top of the row (before any arithmetic) and validates
+// it after the local scan.
 struct CarryLook {
     const CarryEntry *ptr;  // this lane's entry (nullptr: lane holds the identity)
     uint4 e;
@@ -84,18 +65,18 @@ __device__ __forceinline__ CarryLook look_issue(const CarryEntry *l1_row, const 
     return c;
 }
 
-// Whole warp.  Returns the composite map of everything before chunk j in every lane; `ingroup` receives the
-// composite of the level-1 entries before j inside its group (what a group's last chunk folds into level 2).
-__device__ __forceinline__ Aff look_resolve(CarryLook &c, const CarryEntry *l2_row, int j, unsigned tag, int lane, Aff &ingroup) {
+// Whole warp.  Shuffle-tree composition of the entries the lanes hold, whatever their state: `ok` tells whether
+// every lane's entry carried the current tag.
+// `ingroup` receives the composite of the level-1 entries before j inside its group (what a group's last chunk
+// folds into level 2); the return value is the composite of all 31 slots (everything before chunk j when j < 272).
+__device__ __forceinline__ Aff look_reduce(const CarryLook &c, unsigned tag, int lane, bool &ok, Aff &ingroup) {
     Aff v = {1.0f, 0.0f};
+    bool mine = true;
     if (c.ptr) {
-        while (c.e.y != tag || c.e.w != tag) {
-            __nanosleep(32);
-            c.e = load_entry(c.ptr);
-        }
+        mine = (c.e.y == tag) && (c.e.w == tag);
         v = Aff{__uint_as_float(c.e.x), __uint_as_float(c.e.z)};
     }
-    __syncwarp();
+    ok = __all_sync(0xffffffffu, mine);
     // higher lanes hold maps that apply earlier; fold them in first
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -107,8 +88,24 @@ __device__ __forceinline__ Aff look_resolve(CarryLook &c, const CarryEntry *l2_r
         }
         if (off == 8) ingroup = Aff{__shfl_sync(0xffffffffu, v.p, 0), __shfl_sync(0xffffffffu, v.q, 0)};
     }
-    Aff acc = {__shfl_sync(0xffffffffu, v.p, 0), __shfl_sync(0xffffffffu, v.q, 0)};
-    // sequences of more than 272 chunks: remaining level-2 entries, 32 per round, nearest round first
+    return Aff{__shfl_sync(0xffffffffu, v.p, 0), __shfl_sync(0xffffffffu, v.q, 0)};
+}
+
+// Slow path, after the chunk's own aggregate is published: wait for the entries that were not there yet, reduce
+// again; then (sequences of more than 272 chunks) the remaining level-2 entries, 32 per round, nearest first.
+__device__ __forceinline__ Aff look_finish(CarryLook &c, Aff acc, bool ok, const CarryEntry *l2_row, int j, unsigned tag, int lane,
+                                           Aff &ingroup) {
+    if (!ok) {
+        if (c.ptr) {
+            while (c.e.y != tag || c.e.w != tag) {
+                __nanosleep(32);
+                c.e = load_entry(c.ptr);
+            }
+        }
+        __syncwarp();
+        bool again;
+        acc = look_reduce(c, tag, lane, again, ingroup);
+    }
     const int gi = j >> 4;
     for (int base = 16; base < gi; base += 32) {
         Aff w = {1.0f, 0.0f};

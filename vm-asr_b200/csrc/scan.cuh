@@ -3,9 +3,9 @@
 // Work decomposition (differs on purpose from the reference's grid=(batch, dim) with a serial chunk loop,
 // selective_scan_fwd_kernel.cuh:80-102): a CTA owns a TILE = (batch b, B/C group g, a range of the group's
 // channels, one chunk of VMASR_SCAN_CHUNK positions).  The sequence axis is therefore split ACROSS CTAs and
-// the carry between chunks travels through a small global exchange area with a decoupled look-back
-// (publish the chunk's aggregate first, then combine the predecessors' aggregates), so one pass over HBM
-// is enough.  Inside a tile every thread owns ITEMS consecutive positions and walks the tile's channels
+// the carry between chunks travels through a small global exchange area with a decoupled two-level look-back
+// (publish the chunk's aggregate first, then combine the predecessors' aggregates; pipe.cuh), so one pass
+// over HBM is enough.  Inside a tile every thread owns ITEMS consecutive positions and walks the tile's channels
 // serially: the positions' B/C values (and, backward, their dB/dC sums) stay in registers across channels.
 #pragma once
 #include "common.cuh"
@@ -25,8 +25,7 @@ struct ScanArgs {
     // carry exchange
     unsigned *ws_header;  // {ticket, done, epoch, pad}
     CarryEntry *ws_entries;   // level 1: one entry per (batch, channel, state, chunk)
-    CarryEntry *ws_entries2;  // level 2: one entry per (batch, channel, group of 16 chunks) -- persistent kernels, d_state 1
-    int n_tiles;              // persistent kernels: number of tiles dealt round-robin to the CTAs
+    CarryEntry *ws_entries2;  // level 2: one entry per (batch, channel, state, group of 16 chunks)
     int batch, dim, seqlen, dstate, ngroups;
     int n_chunks;         // ceil(seqlen / chunk)
     int chan_per_group;   // dim / ngroups
@@ -73,19 +72,13 @@ __device__ __forceinline__ Aff warp_scan_down(Aff v, int lane) {
 }
 
 // ---- chunk-carry exchange --------------------------------------------------------------------------
-// One 16-byte entry per (batch, channel, state, chunk): {p, tag, q, tag} -- the chunk's own affine map with
-// the launch's epoch tag repeated in each 8-byte half.  An entry is valid when both tags equal the current
-// tag; 8-byte accesses are single-copy atomic, so a half-written entry can never validate with stale
-// numbers and no fence is needed on either side (the data validates itself, no separate flag to order
-// against).  A chunk publishes its map as soon as its local scan is done and never waits before publishing,
-// so there is no dependency chain between chunks.  The state entering chunk i is obtained by composing the
-// maps of ALL chunks before it, always in the same fixed tree (each lane folds 4 consecutive entries, then
-// a shuffle tree over the lanes, 128 predecessors per round, nearest round first): run-to-run
-// bit-reproducible, one L2 round trip in the common case, and every warp resolves its own copy so no block
-// barrier is involved.
-// The workspace is zero-filled once; every launch that uses it reads the epoch from the header and the
-// last CTA to finish bumps it, so entries of earlier launches never validate and nothing has to be cleared
-// between launches.
+// 16-byte entries {p, tag, q, tag}: an affine map with the launch's epoch tag repeated in each 8-byte half.
+// An entry is valid when both tags equal the current tag; 8-byte accesses are single-copy atomic, so a
+// half-written entry can never validate with stale numbers and no fence is needed on either side (the data
+// validates itself, there is no separate flag to order against).  The workspace is zero-filled once; every
+// launch that uses it reads the epoch from the header and the last CTA to finish bumps it, so entries of
+// earlier launches never validate and nothing has to be cleared between launches.  How the entries are
+// organised (one per chunk plus one per group of 16 chunks) and combined is in pipe.cuh.
 struct __align__(16) CarryEntry {
     float p;
     unsigned tag0;
@@ -93,55 +86,10 @@ struct __align__(16) CarryEntry {
     unsigned tag1;
 };
 
-__device__ __forceinline__ void publish(const ScanArgs &a, long long entry, unsigned tag, float p, float q) {
-    asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(a.ws_entries + entry), "r"(__float_as_uint(p)),
-                 "r"(tag), "r"(__float_as_uint(q)), "r"(tag)
-                 : "memory");
-}
 __device__ __forceinline__ uint4 load_entry(const CarryEntry *e) {
     uint4 v;
     asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(e) : "memory");
     return v;
-}
-
-// Whole warp.  Composite map of all `n_before` predecessor chunks of `chunk`; `step` is +1 when the
-// predecessors are the lower-numbered chunks (forward scan) and -1 when they are the higher-numbered ones
-// (adjoint scan).  `entry0` is the entry of chunk 0 of this (batch, channel, state).  Result in every lane:
-// .q is the state entering the chunk (initial state 0), .p the cumulative decay before it.
-__device__ __forceinline__ Aff carry_in(const ScanArgs &a, long long entry0, int chunk, int step, int n_before, unsigned tag,
-                                        int lane) {
-    Aff acc = {1.0f, 0.0f};
-    for (int base = 0; base < n_before; base += 128) {
-        uint4 e[4];
-        const int k0 = base + 4 * lane + 1;  // nearest predecessor this lane folds
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (k0 + j <= n_before) e[j] = load_entry(a.ws_entries + entry0 + (long long)(chunk - step * (k0 + j)));
-        Aff v = {1.0f, 0.0f};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (k0 + j <= n_before) {
-                while (e[j].y != tag || e[j].w != tag) {
-                    __nanosleep(20);
-                    e[j] = load_entry(a.ws_entries + entry0 + (long long)(chunk - step * (k0 + j)));
-                }
-                v = compose(Aff{__uint_as_float(e[j].x), __uint_as_float(e[j].z)}, v);  // farther one applies first
-            }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const float pp = __shfl_down_sync(0xffffffffu, v.p, off);
-            const float pq = __shfl_down_sync(0xffffffffu, v.q, off);
-            if (lane + off < 32) {  // lane+off holds farther predecessors: applied first
-                v.q = fmaf(v.p, pq, v.q);
-                v.p *= pp;
-            }
-        }
-        const Aff round = {__shfl_sync(0xffffffffu, v.p, 0), __shfl_sync(0xffffffffu, v.q, 0)};
-        acc = compose(round, acc);
-    }
-    return acc;
 }
 
 // Claim a tile.  With more than one chunk per sequence the order in which tiles start matters for forward

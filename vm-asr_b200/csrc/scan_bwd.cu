@@ -8,7 +8,7 @@
 //   ddelta_l = ddt_l * sigmoid(delta_l + bias)  (softplus on, input <= 20);   ddelta_bias = sum_l ddelta_l
 // The forward states are recomputed per chunk from the chunk-end states `x` the forward saved; the adjoint
 // carry between chunks uses the same look-back exchange as the forward, walking the chunks downwards.
-#include "scan.cuh"
+#include "pipe.cuh"
 
 namespace vmasr {
 
@@ -190,10 +190,23 @@ __global__ void __launch_bounds__(NT) scan_bwd_kernel(const __grid_constant__ Sc
             // adjoint carry from the chunks after this one (n_chunks > 1 implies one row per CTA)
             float g_in = 0.0f;
             if (a.n_chunks > 1) {
-                const long long entry0 = (((long long)b * a.dim + d) * a.dstate + n) * a.n_chunks;
-                const int n_after = a.n_chunks - 1 - chunk;
-                if (last_warp && lane == 0) publish(a, entry0 + chunk, epoch, total_r.p, total_r.q);
-                g_in = carry_in(a, entry0, chunk, -1, n_after, epoch, lane).q;
+                // the adjoint runs right to left: entries are indexed by the chunk's scan-order position j
+                const long long srow = ((long long)b * a.dim + d) * a.dstate + n;
+                const int n_groups16 = (a.n_chunks + 15) >> 4;
+                const int j = a.n_chunks - 1 - chunk;
+                CarryEntry *l1_row = a.ws_entries + srow * a.n_chunks;
+                CarryEntry *l2_row = a.ws_entries2 + srow * n_groups16;
+                if (last_warp && lane == 0) publish_entry(l1_row + j, epoch, total_r.p, total_r.q);
+                CarryLook look = look_issue(l1_row, l2_row, j, lane);
+                bool ok;
+                Aff grp = {1.0f, 0.0f};
+                Aff acc = look_reduce(look, epoch, lane, ok, grp);
+                acc = look_finish(look, acc, ok, l2_row, j, epoch, lane, grp);
+                if (last_warp && lane == 0 && (j & 15) == 15) {
+                    const Aff g16 = compose(grp, total_r);
+                    publish_entry(l2_row + (j >> 4), epoch, g16.p, g16.q);
+                }
+                g_in = acc.q;
             }
 
             // forward states of this thread's positions

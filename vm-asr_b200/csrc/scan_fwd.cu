@@ -2,7 +2,7 @@
 // Replaces selective_scan_fwd_kernel (kernels/selective_scan/csrc/selective_scan/cus/selective_scan_fwd_kernel.cuh:61-172):
 //   dt = softplus(delta + delta_bias);  h_l = exp(dt*A) h_{l-1} + dt*B_l*u_l;  out_l = sum_n C_l h_l + D u_l
 // and writes the per-chunk (cumulative decay, end state) tensor `x` the backward needs.
-#include "scan.cuh"
+#include "pipe.cuh"
 
 namespace vmasr {
 
@@ -107,9 +107,20 @@ __global__ void __launch_bounds__(NT) scan_fwd_kernel(const __grid_constant__ Sc
             // carry from the chunks before this one (n_chunks > 1 implies one row per CTA: TPR == NT)
             float h_in = 0.0f, pcum_in = 1.0f;
             if (a.n_chunks > 1) {
-                const long long entry0 = (((long long)b * a.dim + d) * a.dstate + n) * a.n_chunks;
-                if (last_warp && lane == 0) publish(a, entry0 + chunk, epoch, total.p, total.q);
-                const Aff acc = carry_in(a, entry0, chunk, +1, chunk, epoch, lane);
+                const long long srow = ((long long)b * a.dim + d) * a.dstate + n;
+                const int n_groups16 = (a.n_chunks + 15) >> 4;
+                CarryEntry *l1_row = a.ws_entries + srow * a.n_chunks;
+                CarryEntry *l2_row = a.ws_entries2 + srow * n_groups16;
+                if (last_warp && lane == 0) publish_entry(l1_row + chunk, epoch, total.p, total.q);
+                CarryLook look = look_issue(l1_row, l2_row, chunk, lane);
+                bool ok;
+                Aff grp = {1.0f, 0.0f};
+                Aff acc = look_reduce(look, epoch, lane, ok, grp);
+                acc = look_finish(look, acc, ok, l2_row, chunk, epoch, lane, grp);
+                if (last_warp && lane == 0 && (chunk & 15) == 15) {
+                    const Aff g16 = compose(grp, total);
+                    publish_entry(l2_row + (chunk >> 4), epoch, g16.p, g16.q);
+                }
                 h_in = acc.q;
                 pcum_in = acc.p;
             }

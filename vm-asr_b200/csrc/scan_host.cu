@@ -8,8 +8,8 @@ namespace vmasr {
 
 int scan_fwd_dispatch(const ScanArgs &a, const ScanPlan &pl, int io_dtype, cudaStream_t stream);
 int scan_bwd_dispatch(const ScanArgs &a, const ScanPlan &pl, int io_dtype, cudaStream_t stream);
-int scan_fwd_v2_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
-int scan_bwd_v2_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
+int scan_fwd_tma_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
+constexpr int kMaxTileChannelsHost = 64;  // scan_fwd_tma.cu stages this many channels' parameters per tile
 
 static size_t dtype_size(int dt) { return dt == VMASR_F32 ? 4 : 2; }
 
@@ -47,46 +47,6 @@ static int validate(const vmasr_scan_params *p, bool bwd) {
     return 0;
 }
 
-// Persistent kernels (scan_fwd_v2.cu / scan_bwd_v2.cu): 2 CTAs per SM; as many channels per tile as possible (B/C
-// are loaded once per tile and dB/dC leave once per tile) as long as the tiles still deal evenly over the CTAs.
-static ScanPlan make_plan_persistent(const vmasr_scan_params *p, int n_chunks, int &chan_per_tile, int &n_ctiles, int &n_tiles) {
-    ScanPlan pl;
-    pl.items = 8;
-    pl.threads = 256;
-    const int L = p->seqlen;
-    pl.tpr = L <= 256 ? 32 : L <= 512 ? 64 : L <= 1024 ? 128 : 256;
-    pl.rows = pl.threads / pl.tpr;
-    pl.vec = true;
-    const int cpg = p->dim / p->ngroups;
-    const long long cap = 2LL * sm_count(p->device);
-    const long long base_tiles = (long long)p->batch * p->ngroups * n_chunks;
-    const long long iters = (cpg + pl.rows - 1) / pl.rows;  // row passes per (batch, group, chunk)
-    // row passes per tile: the largest divisor of `iters` (at most 8) that still fills whole waves of CTAs to >= 95 %,
-    // else the one with the best fill
-    long long iters_per_tile = 1;
-    double best_fill = -1.0;
-    for (long long ipt = iters < 8 ? iters : 8; ipt >= 1; --ipt) {
-        if (iters % ipt) continue;
-        const long long tiles = base_tiles * (iters / ipt);
-        const long long waves = (tiles + cap - 1) / cap;
-        const double fill = (double)tiles / (double)(waves * cap);
-        if (fill >= 0.95) {
-            iters_per_tile = ipt;
-            break;
-        }
-        if (fill > best_fill + 1e-9) {
-            best_fill = fill;
-            iters_per_tile = ipt;
-        }
-    }
-    chan_per_tile = (int)(iters_per_tile * pl.rows);
-    n_ctiles = (cpg + chan_per_tile - 1) / chan_per_tile;
-    const long long tiles = base_tiles * n_ctiles;
-    n_tiles = (int)tiles;
-    pl.grid = (int)(tiles < cap ? tiles : cap);
-    return pl;
-}
-
 static ScanPlan make_plan(const vmasr_scan_params *p, int n_chunks, int &chan_per_tile, int &n_ctiles) {
     ScanPlan pl;
     pl.items = 8;
@@ -102,6 +62,8 @@ static ScanPlan make_plan(const vmasr_scan_params *p, int n_chunks, int &chan_pe
     const int max_ctiles = (cpg + pl.rows - 1) / pl.rows;
     long long want = (target + base_tiles - 1) / base_tiles;
     if (want < 1) want = 1;
+    const long long min_ctiles = (cpg + kMaxTileChannelsHost - 1) / kMaxTileChannelsHost;
+    if (want < min_ctiles) want = min_ctiles;
     if (want > max_ctiles) want = max_ctiles;
     chan_per_tile = (int)((cpg + want - 1) / want);
     chan_per_tile = ((chan_per_tile + pl.rows - 1) / pl.rows) * pl.rows;
@@ -169,18 +131,11 @@ static int run(const vmasr_scan_params *p, bool bwd) {
                  mult(p->du_d_stride) && mult(p->ddelta_batch_stride) && mult(p->ddelta_d_stride) && (p->seqlen % 4 == 0);
     }
     cudaStream_t stream = static_cast<cudaStream_t>(p->stream);
-    // fast path: fp32, d_state 1, 16-byte aligned rows -> persistent TMA-fed kernels (VMASR_SCAN=generic forces
-    // the register-IO kernels, which also serve fp16/bf16, d_state > 1 and unaligned or odd-length rows)
-    static const bool force_generic = [] { const char *e = getenv("VMASR_SCAN"); return e && e[0] == 'g'; }();
-    const long long tiles_max = (long long)p->batch * p->dim * n_chunks;
-    if (!force_generic && p->io_dtype == VMASR_F32 && p->dstate == 1 && pl.vec && tiles_max < (1LL << 30)) {
-        int n_tiles = 0;
-        const ScanPlan pp = make_plan_persistent(p, n_chunks, chan_per_tile, n_ctiles, n_tiles);
-        a = make_args(p, n_chunks, chan_per_tile, n_ctiles);
-        a.n_tiles = n_tiles;
-        return bwd ? scan_bwd_v2_dispatch(a, pp, stream) : scan_fwd_v2_dispatch(a, pp, stream);
-    }
     if (bwd) return scan_bwd_dispatch(a, pl, p->io_dtype, stream);
+    // fast path: fp32, d_state 1, 16-byte aligned rows -> TMA-staged kernel (VMASR_SCAN_FWD=generic forces the other one)
+    static const bool force_generic = [] { const char *e = getenv("VMASR_SCAN_FWD"); return e && e[0] == 'g'; }();
+    if (!force_generic && p->io_dtype == VMASR_F32 && p->dstate == 1 && pl.vec && a.chan_per_tile <= kMaxTileChannelsHost)
+        return scan_fwd_tma_dispatch(a, pl, stream);
     return scan_fwd_dispatch(a, pl, p->io_dtype, stream);
 }
 
