@@ -1,10 +1,10 @@
 #!/bin/bash
-# ncu launch list of the bench command + full captures of the two scan kernels on the two biggest shapes.
-# Run under gpurun.  Keeps gpurun_out/ under the 64 MiB merge limit.
+# ncu launch list of the bench command (our kernels only: three full steps = 3 x 68 launches) + full captures of the
+# scan kernels on three shapes.  Run under gpurun.  Keeps gpurun_out/ under the 64 MiB merge limit.
 mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep
 BENCH="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
-timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/launches_run.log 2>&1
+timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:vmasr -c 204 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/launches_run.log 2>&1
 echo "launch list rc=$?"
 for shape in "4 8 262144" "4 64 65536" "4 256 4096"; do
   tag=$(echo $shape | tr ' ' '_')

@@ -66,6 +66,13 @@ static ScanPlan make_plan(const vmasr_scan_params *p, int n_chunks, int &chan_pe
     if (want < min_ctiles) want = min_ctiles;
     if (want > max_ctiles) want = max_ctiles;
     chan_per_tile = (int)((cpg + want - 1) / want);
+    {
+        // A tile walks its channels serially and every channel waits for the carry of the chunk before it, which the
+        // neighbouring CTA publishes at the same point of ITS walk: long walks skew the CTAs of a row against each
+        // other (measured: 4 channels per tile beats both 1 and 16 on every multi-chunk shape of the configs).
+        static const int cap_multi = [] { const char *e = getenv("VMASR_SCAN_CPT"); return e ? atoi(e) : 4; }();
+        if (cap_multi > 0 && n_chunks > 1 && chan_per_tile > cap_multi) chan_per_tile = cap_multi;
+    }
     chan_per_tile = ((chan_per_tile + pl.rows - 1) / pl.rows) * pl.rows;
     n_ctiles = (cpg + chan_per_tile - 1) / chan_per_tile;
     pl.grid = (int)(base_tiles * n_ctiles);
