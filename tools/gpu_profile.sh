@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep
 BENCH="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
-timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:vmasr -c 204 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/launches_run.log 2>&1
+timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -k regex:"scan_|cross_|stft" -c 204 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/launches_run.log 2>&1
 echo "launch list rc=$?"
 for shape in "4 8 262144" "4 64 65536" "4 256 4096"; do
   tag=$(echo $shape | tr ' ' '_')
