@@ -1,37 +1,43 @@
 // Selective-scan forward, fast path for sm_100a: fp32 IO, d_state 1, 16-byte aligned rows.
-// Same maths and same tile decomposition as scan_fwd.cu (see scan.cuh); what changes is how data moves:
-//   * u / delta row segments of the tile's channels are brought in by TMA bulk copies (cp.async.bulk ->
-//     SASS UBLKCP) into a 2-stage shared-memory ring, completion signalled on mbarriers; the copy for
-//     channel c+2 is issued as soon as channel c has been read, so HBM latency is hidden behind a whole
-//     iteration of compute without spending registers on prefetch;
+// Replaces selective_scan_fwd_kernel (kernels/selective_scan/csrc/selective_scan/cus/selective_scan_fwd_kernel.cuh:61-203)
+// for the shapes VM-ASR runs.  Same maths and tile decomposition as scan_fwd.cu (see scan.cuh); what differs:
+//   * u / delta row segments come in by TMA bulk copies (cp.async.bulk -> SASS UBLKCP) into a per-row-segment
+//     shared-memory ring with mbarrier completion; the copy for channel c + STAGES is issued as soon as channel c
+//     has been read, so HBM latency hides behind whole iterations of compute without spending registers on it;
 //   * the B / C segment shared by all channels of the tile is copied once per tile the same way;
-//   * the per-channel parameters (A, D, delta_bias) of the tile are staged once in shared memory;
-//   * full tiles carry no bounds checks; tiles are taken in blockIdx order (chunk-major), so a tile only
-//     ever waits on carries of tiles that were dispatched before it.
+//   * all element-wise arithmetic runs on position pairs with packed fp32x2 instructions (fast.cuh);
+//   * the row segments of a CTA (ROWS = 256 / TPR of them when the sequence is short) are independent pipelines:
+//     own mbarriers, own named barrier, own producer lane -- they never wait on each other;
+//   * the cross-warp combination and the cross-chunk look-back are done by the FIRST WARP of the row segment only,
+//     which hands every warp the state entering it (one float) through shared memory; the other warps spend no
+//     instructions on it;
+//   * full tiles carry no bounds checks; tiles are taken in blockIdx order (chunk-major), so a tile only ever waits
+//     on carries of tiles that were dispatched before it.
 // Outputs go straight from registers to HBM with 128-bit stores.
-#include "pipe.cuh"
+#include <cstdlib>
+
+#include "fast.cuh"
 
 namespace vmasr {
 
 constexpr int kMaxTileChannels = 64;
 
-template <int TPR, bool TAIL>
-__device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned char *smem) {
+template <int TPR, bool TAIL, bool SP, int STAGES>
+__device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned char *smem, const int chunk, const int rg) {
     constexpr int NT = 256, ITEMS = 8;
     constexpr int ROWS = NT / TPR;
     constexpr int WPR = TPR / 32;
     constexpr int SEG = TPR * ITEMS;  // positions per row segment (== chunk when n_chunks > 1)
 
-    // shared memory carve-up
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem);              // [0,1] stages, [2] B/C
-    float2 *s_tot = reinterpret_cast<float2 *>(smem + 32);                                // [2][ROWS][WPR]
-    float *s_par = reinterpret_cast<float *>(smem + 256);                                 // [3][kMaxTileChannels]
-    float *s_bc = reinterpret_cast<float *>(smem + 2048);                                 // [2][SEG]   B, C
-    float *s_stage = s_bc + 2 * SEG;                                                      // [2][2][ROWS*SEG] u, delta
+    // shared memory carve-up (header 2048 bytes)
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem);  // [STAGES][ROWS] stage barriers, then B/C
+    float2 *s_tot = reinterpret_cast<float2 *>(smem + 384);                   // [2][8] warp totals (p, q)
+    float *s_in = reinterpret_cast<float *>(smem + 512);                      // [8] state entering each warp
+    float *s_par = reinterpret_cast<float *>(smem + 1024);                    // [3][kMaxTileChannels]
+    float *s_stage = reinterpret_cast<float *>(smem + 2048);                  // [STAGES][ROWS][2][SEG]  u, delta
+    float *s_bc = s_stage + (size_t)(STAGES - 1) * ROWS * 2 * SEG;            // [2][SEG] B, C: borrowed from the last stage
+    unsigned long long *bar_bc = bars + STAGES * ROWS;
 
-    const int tile = blockIdx.x;
-    const int chunk = tile / a.n_rowgroups;
-    const int rg = tile - chunk * a.n_rowgroups;
     const int ctile = rg % a.n_ctiles;
     const int bg = rg / a.n_ctiles;
     const int g = bg % a.ngroups;
@@ -40,31 +46,30 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
     const int row = threadIdx.x / TPR;
     const int t_in_row = threadIdx.x - row * TPR;
     const int warp_in_row = t_in_row >> 5;
+    const int warp_slot = threadIdx.x >> 5;  // row * WPR + warp_in_row
     const int lane = threadIdx.x & 31;
     const int L = a.seqlen;
     const int seg0 = chunk * SEG;                       // first position of the tile
     const int pos = seg0 + t_in_row * ITEMS;
     const int seg_len = min(SEG, L - seg0);             // valid positions in this tile (multiple of 4)
     const unsigned seg_bytes = (unsigned)seg_len * 4u;
-    const bool last_warp = (warp_in_row == WPR - 1);
     int nvalid = ITEMS;
     if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
 
     const int c_begin = ctile * a.chan_per_tile;
-    const int c_end = min(a.chan_per_group, c_begin + a.chan_per_tile);
-    const int n_chan = c_end - c_begin;
-    const int n_iter = (n_chan + ROWS - 1) / ROWS;
-    const int d0 = g * a.chan_per_group + c_begin;      // first scan channel of the tile
+    const int n_chan = min(a.chan_per_group, c_begin + a.chan_per_tile) - c_begin;
+    const int n_iter = (n_chan - row + ROWS - 1) / ROWS;  // iterations of THIS row segment (may be 0)
+    const int d0 = g * a.chan_per_group + c_begin;        // first scan channel of the tile
 
-    const float *u_base = reinterpret_cast<const float *>(a.u) + b * a.u_bs + (long long)d0 * a.u_ds + seg0;
-    const float *dl_base = reinterpret_cast<const float *>(a.delta) + b * a.delta_bs + (long long)d0 * a.delta_ds + seg0;
+    const float *u_src = reinterpret_cast<const float *>(a.u) + b * a.u_bs + (long long)(d0 + row) * a.u_ds + seg0;
+    const float *dl_src = reinterpret_cast<const float *>(a.delta) + b * a.delta_bs + (long long)(d0 + row) * a.delta_ds + seg0;
     float *out_ptr = reinterpret_cast<float *>(a.out) + b * a.out_bs + (long long)(d0 + row) * a.out_ds + pos;
+    const long long u_step = (long long)ROWS * a.u_ds, dl_step = (long long)ROWS * a.delta_ds, out_step = (long long)ROWS * a.out_ds;
 
     unsigned epoch = 0;
     if (threadIdx.x == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        mbar_init(&bars[2], 1);
+#pragma unroll
+        for (int i = 0; i < STAGES * ROWS + 1; ++i) mbar_init(&bars[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (a.n_chunks > 1) epoch = *reinterpret_cast<volatile unsigned *>(a.ws_header + 2) % 0xfffffffeu + 1u;
@@ -73,153 +78,174 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
         const int which = i / n_chan, cc = i - which * n_chan;
         const int d = d0 + cc;
         float v;
-        if (which == 0) v = __ldg(a.A + d * a.A_ds) * kLog2e;
+        if (which == 0) v = __ldg(a.A + d * a.A_ds);
         else if (which == 1) v = a.D ? __ldg(a.D + d) : 0.0f;
-        else v = a.delta_bias ? __ldg(a.delta_bias + d) : 0.0f;
+        else v = (a.delta_bias ? __ldg(a.delta_bias + d) : 0.0f) * kLog2e;
         s_par[which * kMaxTileChannels + cc] = v;
     }
     __syncthreads();
 
-    auto issue_stage = [&](int it) {
-        // thread 0: bulk copies of iteration `it` into stage it & 1
-        const int s = it & 1;
-        const int rows_here = min(ROWS, n_chan - it * ROWS);
-        mbar_expect_tx(&bars[s], 2u * seg_bytes * (unsigned)rows_here);
-        float *dst_u = s_stage + (size_t)s * 2 * ROWS * SEG;
-        float *dst_d = dst_u + ROWS * SEG;
-        for (int r = 0; r < rows_here; ++r) {
-            const long long ch = (long long)(it * ROWS + r);
-            bulk_load(dst_u + r * SEG, u_base + ch * a.u_ds, seg_bytes, &bars[s]);
-            bulk_load(dst_d + r * SEG, dl_base + ch * a.delta_ds, seg_bytes, &bars[s]);
-        }
+    float *my_stage = s_stage + (size_t)row * 2 * SEG;  // + stage * ROWS * 2 * SEG
+    unsigned long long *my_bars = bars + row;           // + stage * ROWS
+    auto issue_stage = [&](int it) {  // producer lane of the row segment: bulk copies of iteration `it`
+        const int s = it % STAGES;
+        unsigned long long *bar = my_bars + s * ROWS;
+        float *dst = my_stage + (size_t)s * ROWS * 2 * SEG;
+        mbar_expect_tx(bar, 2u * seg_bytes);
+        bulk_load(dst, u_src + it * u_step, seg_bytes, bar);
+        bulk_load(dst + SEG, dl_src + it * dl_step, seg_bytes, bar);
     };
     if (threadIdx.x == 0) {
         const float *Bg = reinterpret_cast<const float *>(a.B) + b * a.B_bs + g * a.B_gs + seg0;
         const float *Cg = reinterpret_cast<const float *>(a.C) + b * a.C_bs + g * a.C_gs + seg0;
-        mbar_expect_tx(&bars[2], 2u * seg_bytes);
-        bulk_load(s_bc, Bg, seg_bytes, &bars[2]);
-        bulk_load(s_bc + SEG, Cg, seg_bytes, &bars[2]);
-        issue_stage(0);
-        if (n_iter > 1) issue_stage(1);
+        mbar_expect_tx(bar_bc, 2u * seg_bytes);
+        bulk_load(s_bc, Bg, seg_bytes, bar_bc);
+        bulk_load(s_bc + SEG, Cg, seg_bytes, bar_bc);
     }
-
-    float Bv[ITEMS], Cv[ITEMS];
-    mbar_wait(&bars[2], 0);
-    {
-        const float4 *pb = reinterpret_cast<const float4 *>(s_bc + t_in_row * ITEMS);
-        const float4 *pc = reinterpret_cast<const float4 *>(s_bc + SEG + t_in_row * ITEMS);
-        const float4 b0 = pb[0], b1 = pb[1], c0 = pc[0], c1 = pc[1];
-        Bv[0] = b0.x; Bv[1] = b0.y; Bv[2] = b0.z; Bv[3] = b0.w; Bv[4] = b1.x; Bv[5] = b1.y; Bv[6] = b1.z; Bv[7] = b1.w;
-        Cv[0] = c0.x; Cv[1] = c0.y; Cv[2] = c0.z; Cv[3] = c0.w; Cv[4] = c1.x; Cv[5] = c1.y; Cv[6] = c1.z; Cv[7] = c1.w;
-    }
-    if (TAIL) {
+    if (t_in_row == 0) {
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i)
-            if (i >= nvalid) { Bv[i] = 0.0f; Cv[i] = 0.0f; }
+        for (int s = 0; s < STAGES - 1; ++s)
+            if (s < n_iter) issue_stage(s);
     }
 
-    const long long entry_stride = a.n_chunks;  // level-1 entries per (b, d)
-    const int n_groups16 = (a.n_chunks + 15) >> 4;
-    for (int it = 0; it < n_iter; ++it) {
-        const int s = it & 1;
-        const int cc = it * ROWS + row;          // channel index inside the tile
-        const bool active = cc < n_chan;
-        const int ccl = active ? cc : 0;
-        const float A2 = s_par[ccl];
-        const float Dv = s_par[kMaxTileChannels + ccl];
-        const float bias = s_par[2 * kMaxTileChannels + ccl];
-        const float bias2 = bias * kLog2e;
+    float2 Bl[4], Cv[4];  // ln2 * B (the scan runs on dt in the log2 domain) and C of this thread's positions
+    mbar_wait(bar_bc, 0);
+    lds8(s_bc + t_in_row * ITEMS, Bl);
+    lds8(s_bc + SEG + t_in_row * ITEMS, Cv);
+    __syncthreads();  // B / C are in registers: the last stage is free for data now
+    if (t_in_row == 0 && STAGES - 1 < n_iter) issue_stage(STAGES - 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Bl[j] = mul2(Bl[j], f2(kLn2));
 
-        // look-back loads first: they fly while the row is computed
-        const long long seq = (long long)b * a.dim + d0 + ccl;
+    const int n_groups16 = (a.n_chunks + 15) >> 4;
+    const bool multi = a.n_chunks > 1;  // then ROWS == 1
+    const bool leader = warp_in_row == 0;
+    for (int it = 0; it < n_iter; ++it) {
+        const int s = it % STAGES;
+        const int cc = it * ROWS + row;  // channel index inside the tile
+        const float Av = s_par[cc];
+        const float Dv = s_par[kMaxTileChannels + cc];
+        const float bias2 = s_par[2 * kMaxTileChannels + cc];
+        const long long seq = (long long)b * a.dim + d0 + cc;
+
+        // look-back loads first (leader warp): they fly while the row is computed
         CarryLook look;
         const CarryEntry *l2_row = nullptr;
-        if (a.n_chunks > 1) {
+        if (multi && leader) {
             l2_row = a.ws_entries2 + seq * n_groups16;
-            look = look_issue(a.ws_entries + seq * entry_stride, l2_row, chunk, lane);
+            look = look_issue(a.ws_entries + seq * a.n_chunks, l2_row, chunk, lane);
         }
-        mbar_wait(&bars[s], (unsigned)((it >> 1) & 1));
-        float uv[ITEMS], dt[ITEMS];
+        mbar_wait(my_bars + s * ROWS, (unsigned)((it / STAGES) & 1));
+        float2 uv[4], av[4], bx[4];
         {
-            const float *su = s_stage + (size_t)s * 2 * ROWS * SEG + (active ? row : 0) * SEG + t_in_row * ITEMS;
-            const float4 *pu = reinterpret_cast<const float4 *>(su);
-            const float4 *pd = reinterpret_cast<const float4 *>(su + ROWS * SEG);
-            const float4 u0 = pu[0], u1 = pu[1], e0 = pd[0], e1 = pd[1];
-            uv[0] = u0.x; uv[1] = u0.y; uv[2] = u0.z; uv[3] = u0.w; uv[4] = u1.x; uv[5] = u1.y; uv[6] = u1.z; uv[7] = u1.w;
-            dt[0] = e0.x; dt[1] = e0.y; dt[2] = e0.z; dt[3] = e0.w; dt[4] = e1.x; dt[5] = e1.y; dt[6] = e1.z; dt[7] = e1.w;
+            const float *su = my_stage + (size_t)s * ROWS * 2 * SEG + t_in_row * ITEMS;
+            float2 dl[4];
+            lds8(su, uv);
+            lds8(su + SEG, dl);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 dt2 = fma2(dl[j], f2(kLog2e), f2(bias2));
+                if (SP) {
+                    float2 e, sp;
+                    dt2 = softplus2_pair(dt2, e, sp);
+                }
+                const float2 da = mul2(dt2, f2(Av));
+                av[j] = make_float2(ex2_approx(da.x), ex2_approx(da.y));
+                bx[j] = mul2(mul2(dt2, Bl[j]), uv[j]);
+            }
         }
-        float av[ITEMS], bx[ITEMS];
+        if (TAIL) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (2 * j >= nvalid) { av[j].x = 1.0f; bx[j].x = 0.0f; }
+                if (2 * j + 1 >= nvalid) { av[j].y = 1.0f; bx[j].y = 0.0f; }
+            }
+        }
         Aff loc = {1.0f, 0.0f};
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const float x = dt[i] + bias;
-            const float d = a.softplus ? softplus2(fmaf(dt[i], kLog2e, bias2), x) : x;
-            av[i] = ex2_approx(d * A2);
-            bx[i] = d * uv[i] * Bv[i];
-            if (TAIL && i >= nvalid) { av[i] = 1.0f; bx[i] = 0.0f; }
-            loc.q = fmaf(av[i], loc.q, bx[i]);
-            loc.p *= av[i];
+        for (int j = 0; j < 4; ++j) {
+            loc.q = fmaf(av[j].x, loc.q, bx[j].x);
+            loc.p *= av[j].x;
+            loc.q = fmaf(av[j].y, loc.q, bx[j].y);
+            loc.p *= av[j].y;
         }
-        Aff inc = warp_scan_up(loc, lane);
-        Aff exc = {__shfl_up_sync(0xffffffffu, inc.p, 1), __shfl_up_sync(0xffffffffu, inc.q, 1)};
-        if (lane == 0) exc = {1.0f, 0.0f};
-        Aff total;
-        if (WPR > 1) {
-            if (lane == 31) s_tot[(s * ROWS + row) * WPR + warp_in_row] = make_float2(inc.p, inc.q);
-        }
-        __syncthreads();  // every thread has consumed stage s (and the warp totals are visible)
-        if (threadIdx.x == 0 && it + 2 < n_iter) issue_stage(it + 2);
-        if (WPR > 1) {
-            Aff before = {1.0f, 0.0f};
-            total = {1.0f, 0.0f};
-#pragma unroll
-            for (int w = 0; w < WPR; ++w) {
-                const float2 t = s_tot[(s * ROWS + row) * WPR + w];
-                if (w == warp_in_row) before = total;
-                total = compose(total, Aff{t.x, t.y});
-            }
-            exc = compose(before, exc);
-        } else {
-            total = {__shfl_sync(0xffffffffu, inc.p, 31), __shfl_sync(0xffffffffu, inc.q, 31)};
-        }
+        const Aff inc = warp_scan_up_fast<32>(loc);
+        const Aff exc = shift_up1(inc, lane);
 
-        float h_in = 0.0f, pcum_in = 1.0f;
-        if (a.n_chunks > 1) {  // one row per CTA in this case
-            if (threadIdx.x == 0) publish_entry(a.ws_entries + seq * entry_stride + chunk, epoch, total.p, total.q);
-            bool ok;
-            Aff grp = {1.0f, 0.0f};
-            Aff acc = look_reduce(look, epoch, lane, ok, grp);
-            acc = look_finish(look, acc, ok, l2_row, chunk, epoch, lane, grp);
-            if (threadIdx.x == 0 && (chunk & 15) == 15) {
-                const Aff g16 = compose(grp, total);
-                publish_entry(a.ws_entries2 + seq * n_groups16 + (chunk >> 4), epoch, g16.p, g16.q);
-            }
-            h_in = acc.q;
-            pcum_in = acc.p;
-        }
-        if (last_warp && lane == 0 && active)
-            reinterpret_cast<float2 *>(a.x)[seq * entry_stride + chunk] = make_float2(total.p * pcum_in, fmaf(total.p, h_in, total.q));
-
-        float h = fmaf(exc.p, h_in, exc.q);
-        float y[ITEMS];
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            h = fmaf(av[i], h, bx[i]);
-            y[i] = fmaf(Cv[i], h, Dv * uv[i]);
-        }
-        if (active) {
-            float *o = out_ptr + (long long)(it * ROWS) * a.out_ds;
-            if (!TAIL || nvalid == ITEMS) {
-                reinterpret_cast<float4 *>(o)[0] = make_float4(y[0], y[1], y[2], y[3]);
-                reinterpret_cast<float4 *>(o)[1] = make_float4(y[4], y[5], y[6], y[7]);
+        float h_warp;  // state entering this warp's first position
+        if (WPR > 1) {
+            float2 *tot = s_tot + (it & 1) * 8;
+            if (lane == 31) tot[warp_slot] = make_float2(inc.p, inc.q);
+            row_barrier(1 + row, TPR);  // stage s consumed by the whole row segment; warp totals visible
+            if (t_in_row == 0 && it + STAGES < n_iter) issue_stage(it + STAGES);
+            if (multi) {
+                if (leader) {
+                    const float2 t = (lane < WPR) ? tot[row * WPR + lane] : make_float2(1.0f, 0.0f);
+                    const Aff cum = warp_scan_up_fast<WPR>(Aff{t.x, t.y});
+                    const Aff before = shift_up1(cum, lane);
+                    const Aff total = {__shfl_sync(0xffffffffu, cum.p, WPR - 1), __shfl_sync(0xffffffffu, cum.q, WPR - 1)};
+                    if (lane == 0) publish_entry(a.ws_entries + seq * a.n_chunks + chunk, epoch, total.p, total.q);
+                    bool ok;
+                    Aff grp = {1.0f, 0.0f};
+                    Aff acc = look_reduce(look, epoch, lane, ok, grp);
+                    acc = look_finish(look, acc, ok, l2_row, chunk, epoch, lane, grp);
+                    if (lane == 0) {
+                        if ((chunk & 15) == 15) {
+                            const Aff g16 = compose(grp, total);
+                            publish_entry(a.ws_entries2 + seq * n_groups16 + (chunk >> 4), epoch, g16.p, g16.q);
+                        }
+                        reinterpret_cast<float2 *>(a.x)[seq * a.n_chunks + chunk] =
+                            make_float2(total.p * acc.p, fmaf(total.p, acc.q, total.q));
+                    }
+                    if (lane < WPR) s_in[row * WPR + lane] = fmaf(before.p, acc.q, before.q);
+                }
+                row_barrier(1 + row, TPR);
+                h_warp = s_in[warp_slot];
             } else {
+                // single chunk: the state entering the sequence is 0; fold the totals of the warps before this one
+                float hq = 0.0f, hp = 1.0f;
 #pragma unroll
-                for (int i = 0; i < ITEMS; ++i)
-                    if (i < nvalid) o[i] = y[i];
+                for (int w = 0; w < WPR - 1; ++w) {
+                    const float2 t = tot[row * WPR + w];
+                    if (w < warp_in_row) {
+                        hq = fmaf(t.x, hq, t.y);
+                        hp *= t.x;
+                    }
+                }
+                h_warp = hq;
+                if (warp_in_row == WPR - 1 && lane == 31)
+                    reinterpret_cast<float2 *>(a.x)[seq] = make_float2(hp * inc.p, fmaf(inc.p, hq, inc.q));
+            }
+        } else {
+            __syncwarp();
+            if (lane == 0 && it + STAGES < n_iter) issue_stage(it + STAGES);
+            h_warp = 0.0f;
+            if (lane == 31) reinterpret_cast<float2 *>(a.x)[seq] = make_float2(inc.p, inc.q);
+        }
+
+        float h = fmaf(exc.p, h_warp, exc.q);
+        float2 y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 hh;
+            h = fmaf(av[j].x, h, bx[j].x);
+            hh.x = h;
+            h = fmaf(av[j].y, h, bx[j].y);
+            hh.y = h;
+            y[j] = fma2(Cv[j], hh, mul2(uv[j], f2(Dv)));
+        }
+        float *o = out_ptr + it * out_step;
+        if (!TAIL || nvalid == ITEMS) {
+            stg8(o, y);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (2 * j < nvalid) o[2 * j] = y[j].x;
+                if (2 * j + 1 < nvalid) o[2 * j + 1] = y[j].y;
             }
         }
     }
-    if (a.n_chunks > 1) {
+    if (multi) {
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -233,42 +259,56 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
     }
 }
 
-template <int TPR>
-__global__ void __launch_bounds__(256) scan_fwd_tma_kernel(const __grid_constant__ ScanArgs a) {
+template <int TPR, bool SP, int STAGES>
+__global__ void __launch_bounds__(256, 3) scan_fwd_tma_kernel(const __grid_constant__ ScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_fwd_tma[];
     constexpr int SEG = TPR * 8;
     const int chunk = blockIdx.x / a.n_rowgroups;
+    const int rg = blockIdx.x - chunk * a.n_rowgroups;
     const bool tail = (chunk + 1) * SEG > a.seqlen;
-    if (tail) scan_fwd_tma_body<TPR, true>(a, smem_fwd_tma);
-    else scan_fwd_tma_body<TPR, false>(a, smem_fwd_tma);
+    if (tail) scan_fwd_tma_body<TPR, true, SP, STAGES>(a, smem_fwd_tma, chunk, rg);
+    else scan_fwd_tma_body<TPR, false, SP, STAGES>(a, smem_fwd_tma, chunk, rg);
 }
 
-size_t scan_fwd_tma_smem(int tpr) {
-    const size_t seg = (size_t)tpr * 8, rows = 256 / tpr;
-    return 2048 + sizeof(float) * (2 * seg + 2 * 2 * rows * seg);
-}
+static size_t scan_fwd_tma_smem(int stages) { return 2048 + sizeof(float) * ((size_t)stages * 2 * 2048); }
 
-template <int TPR>
+template <int TPR, bool SP, int STAGES>
 static int launch_tma(const ScanArgs &a, int grid, cudaStream_t stream) {
-    const size_t smem = scan_fwd_tma_smem(TPR);
+    const size_t smem = scan_fwd_tma_smem(STAGES);
     static bool configured = false;  // attribute is per function; setting it repeatedly is harmless
     if (!configured) {
-        if (int rc = check_cuda(cudaFuncSetAttribute(scan_fwd_tma_kernel<TPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        if (int rc = check_cuda(cudaFuncSetAttribute(scan_fwd_tma_kernel<TPR, SP, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "scan_fwd_tma smem attribute"))
             return rc;
         configured = true;
     }
-    scan_fwd_tma_kernel<TPR><<<grid, 256, smem, stream>>>(a);
+    scan_fwd_tma_kernel<TPR, SP, STAGES><<<grid, 256, smem, stream>>>(a);
     return check_cuda(cudaGetLastError(), "scan_fwd_tma launch");
 }
 
-int scan_fwd_tma_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream) {
+template <bool SP, int STAGES>
+static int dispatch_tpr(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream) {
     switch (pl.tpr) {
-        case 32: return launch_tma<32>(a, pl.grid, stream);
-        case 64: return launch_tma<64>(a, pl.grid, stream);
-        case 128: return launch_tma<128>(a, pl.grid, stream);
-        default: return launch_tma<256>(a, pl.grid, stream);
+        case 32: return launch_tma<32, SP, STAGES>(a, pl.grid, stream);
+        case 64: return launch_tma<64, SP, STAGES>(a, pl.grid, stream);
+        case 128: return launch_tma<128, SP, STAGES>(a, pl.grid, stream);
+        default: return launch_tma<256, SP, STAGES>(a, pl.grid, stream);
     }
+}
+
+template <bool SP>
+static int dispatch_stages(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream) {
+    // depth of the TMA ring: bytes in flight per CTA = STAGES x 16 KB (tuning knob: VMASR_FWD_STAGES = 2 | 3 | 4)
+    static const int stages = [] { const char *e = getenv("VMASR_FWD_STAGES"); return e ? atoi(e) : 4; }();
+    switch (stages) {
+        case 2: return dispatch_tpr<SP, 2>(a, pl, stream);
+        case 3: return dispatch_tpr<SP, 3>(a, pl, stream);
+        default: return dispatch_tpr<SP, 4>(a, pl, stream);
+    }
+}
+
+int scan_fwd_tma_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream) {
+    return a.softplus ? dispatch_stages<true>(a, pl, stream) : dispatch_stages<false>(a, pl, stream);
 }
 
 }  // namespace vmasr

@@ -9,6 +9,7 @@ namespace vmasr {
 int scan_fwd_dispatch(const ScanArgs &a, const ScanPlan &pl, int io_dtype, cudaStream_t stream);
 int scan_bwd_dispatch(const ScanArgs &a, const ScanPlan &pl, int io_dtype, cudaStream_t stream);
 int scan_fwd_tma_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
+int scan_bwd_tma_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
 constexpr int kMaxTileChannelsHost = 64;  // scan_fwd_tma.cu stages this many channels' parameters per tile
 
 static size_t dtype_size(int dt) { return dt == VMASR_F32 ? 4 : 2; }
@@ -138,11 +139,16 @@ static int run(const vmasr_scan_params *p, bool bwd) {
                  mult(p->du_d_stride) && mult(p->ddelta_batch_stride) && mult(p->ddelta_d_stride) && (p->seqlen % 4 == 0);
     }
     cudaStream_t stream = static_cast<cudaStream_t>(p->stream);
-    if (bwd) return scan_bwd_dispatch(a, pl, p->io_dtype, stream);
-    // fast path: fp32, d_state 1, 16-byte aligned rows -> TMA-staged kernel (VMASR_SCAN_FWD=generic forces the other one)
-    static const bool force_generic = [] { const char *e = getenv("VMASR_SCAN_FWD"); return e && e[0] == 'g'; }();
-    if (!force_generic && p->io_dtype == VMASR_F32 && p->dstate == 1 && pl.vec && a.chan_per_tile <= kMaxTileChannelsHost)
-        return scan_fwd_tma_dispatch(a, pl, stream);
+    // fast path: fp32, d_state 1, 16-byte aligned rows -> TMA-staged packed-fp32x2 kernels
+    // (VMASR_SCAN_FWD=generic / VMASR_SCAN_BWD=generic force the generic ones)
+    static const bool fwd_generic = [] { const char *e = getenv("VMASR_SCAN_FWD"); return e && e[0] == 'g'; }();
+    static const bool bwd_generic = [] { const char *e = getenv("VMASR_SCAN_BWD"); return e && e[0] == 'g'; }();
+    const bool fast = p->io_dtype == VMASR_F32 && p->dstate == 1 && pl.vec && a.chan_per_tile <= kMaxTileChannelsHost;
+    if (bwd) {
+        if (fast && !bwd_generic) return scan_bwd_tma_dispatch(a, pl, stream);
+        return scan_bwd_dispatch(a, pl, p->io_dtype, stream);
+    }
+    if (fast && !fwd_generic) return scan_fwd_tma_dispatch(a, pl, stream);
     return scan_fwd_dispatch(a, pl, p->io_dtype, stream);
 }
 
