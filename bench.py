@@ -203,11 +203,16 @@ class DeviceStep:
 
 def time_dominant_kernel(ds: DeviceStep, steps: int):
     """CUDA events around every launch of the dominant kernel (selective-scan backward, 256-thread row variant:
-    every call with seqlen > 1024) on the launching stream.  Returns (avg_ms, avg_algorithmic_bytes)."""
-    idx = [i for i, (c, _, _) in enumerate(ds.calls) if c.L > 1024]
+    every call with seqlen > 1024) on the launching stream.  The whole step is enqueued behind a device-side
+    delay without any host synchronisation in between, so the event pairs bracket kernel time and not the host's
+    launch latency.  Returns (avg_ms, avg_algorithmic_bytes, launches per step)."""
+    idx = {i for i, (c, _, _) in enumerate(ds.calls) if c.L > 1024}
     total_ms, total_bytes, n = 0.0, 0, 0
     B = ds.wl.batch
     for _ in range(steps):
+        pairs = []
+        torch.cuda.synchronize()
+        torch.cuda._sleep(20_000_000)  # ~10 ms of device-side delay: the host gets ahead of the GPU
         ds.arena.zero_()
         for i in range(len(ds.calls)):
             ds.fwd_call(i)
@@ -217,14 +222,15 @@ def time_dominant_kernel(ds: DeviceStep, steps: int):
                 e0.record()
                 ds.bwd_call(i)
                 e1.record()
-                e1.synchronize()
-                c = ds.calls[i][0]
-                total_ms += e0.elapsed_time(e1)
-                total_bytes += 4 * (5 * B * c.D * c.L + 4 * B * 4 * c.L)
-                n += 1
+                pairs.append((i, e0, e1))
             else:
                 ds.bwd_call(i)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        for i, e0, e1 in pairs:
+            c = ds.calls[i][0]
+            total_ms += e0.elapsed_time(e1)
+            total_bytes += 4 * (5 * B * c.D * c.L + 4 * B * 4 * c.L)
+            n += 1
     return total_ms / n, total_bytes / n, n // steps
 
 
@@ -328,6 +334,7 @@ def main():
     ap.add_argument("--cpu-sample-len", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly (profiling aid)")
     args = ap.parse_args()
 
     from vm_asr_b200 import workload as W
@@ -357,6 +364,7 @@ def main():
         return
 
     import torch.distributed as dist
+    from vm_asr_b200 import dist as vdist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
@@ -371,7 +379,11 @@ def main():
                     "ms_per_sample_step": round(ms, 1)}
 
     ds = DeviceStep(wl, device)
-    ds.capture()
+    if args.no_graph:
+        ds.step = ds.run_eager
+        ds.run_eager()
+    else:
+        ds.capture()
     grad_flat = torch.zeros(GEN_PARAMS, dtype=torch.float32, device=device) if world > 1 else None
 
     def one_step():
@@ -406,10 +418,7 @@ def main():
         dist.barrier()
     sampler.stop()
     elapsed_ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = t.item()
+    elapsed_ms = vdist.max_over_ranks(elapsed_ms, device)  # timing rule: max over ranks
     ms_per_step = elapsed_ms / args.steps
     value = world * step_bytes / (ms_per_step * 1e-3) / 1e9
     clocks = sampler.summary(t_wall0, t_wall1)
@@ -437,10 +446,7 @@ def main():
             hs.step()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / args.e2e_steps
-        if world > 1:
-            t = torch.tensor([dt], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = t.item()
+        dt = vdist.max_over_ranks(dt, device)
         e2e = {"value": round(world * step_bytes / dt / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": hs.h2d,
                "d2h_bytes_per_step": hs.d2h, "ms_per_step": round(dt * 1e3, 2), "steps": args.e2e_steps,
                "api": "vm_asr_b200.scan.fwd/bwd (selective_scan_cuda_core surface), pinned host buffers, copies on side streams"}
@@ -456,7 +462,7 @@ def main():
                             f"batch {wl.batch} per GPU, d_state 1, 4 groups",
                 "algorithmic_bytes_per_step": step_bytes, "scan_elements_per_step": wl.scan_elements(),
                 "l2": "inputs larger than L2: every call has its own buffers, ~5.4 GB touched per step vs 126 MB L2",
-                "launch": "one CUDA graph per step", "parallelism": f"dp{world}" if world > 1 else "single",
+                "launch": "eager launches" if args.no_graph else "one CUDA graph per step", "parallelism": f"dp{world}" if world > 1 else "single",
                 "collective": "NCCL all-reduce of a 3.01M-float gradient buffer per step" if world > 1 else "none",
             },
             "frac_of_hbm_peak": round(value / world / peak, 4), "hbm_peak_gbs": peak, "hbm_peak_source": peak_src,
@@ -466,7 +472,7 @@ def main():
             "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic,
-                         "kernel": "scan_bwd_kernel<float,256,256,8,N1,VEC>", "launches_per_step": k_per_step,
+                         "kernel": "scan_bwd_tma_kernel<256,softplus> (csrc/scan_bwd_tma.cu), every backward call with seqlen > 1024", "launches_per_step": k_per_step,
                          "avg_launch_ms": round(k_ms, 5), "avg_algorithmic_bytes_per_launch": int(k_bytes),
                          "peak_source": peak_src},
             "cpu_baseline": cpu_base,
