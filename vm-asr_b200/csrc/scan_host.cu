@@ -10,6 +10,8 @@ int scan_fwd_dispatch(const ScanArgs &a, const ScanPlan &pl, int io_dtype, cudaS
 int scan_bwd_dispatch(const ScanArgs &a, const ScanPlan &pl, int io_dtype, cudaStream_t stream);
 int scan_fwd_tma_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
 int scan_bwd_tma_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
+int scan_fwd_pipe_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
+int scan_bwd_pipe_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
 constexpr int kMaxTileChannelsHost = 64;  // scan_fwd_tma.cu stages this many channels' parameters per tile
 
 static size_t dtype_size(int dt) { return dt == VMASR_F32 ? 4 : 2; }
@@ -145,10 +147,19 @@ static int run(const vmasr_scan_params *p, bool bwd) {
     static const bool bwd_generic = [] { const char *e = getenv("VMASR_SCAN_BWD"); return e && e[0] == 'g'; }();
     const bool fast = p->io_dtype == VMASR_F32 && p->dstate == 1 && pl.vec && a.chan_per_tile <= kMaxTileChannelsHost;
     if (bwd) {
-        if (fast && !bwd_generic) return scan_bwd_tma_dispatch(a, pl, stream);
+        static const bool bwd_nopipe = [] { const char *e = getenv("VMASR_SCAN_BWD"); return e && e[0] == 't'; }();
+        if (fast && !bwd_generic) {
+            if (n_chunks > 1 && !bwd_nopipe) return scan_bwd_pipe_dispatch(a, pl, stream);
+            return scan_bwd_tma_dispatch(a, pl, stream);
+        }
         return scan_bwd_dispatch(a, pl, p->io_dtype, stream);
     }
-    if (fast && !fwd_generic) return scan_fwd_tma_dispatch(a, pl, stream);
+    static const bool fwd_nopipe = [] { const char *e = getenv("VMASR_SCAN_FWD"); return e && e[0] == 't'; }();
+    if (fast && !fwd_generic) {
+        // more than one chunk: the software-pipelined kernel (no CTA-wide barrier around the carry exchange)
+        if (n_chunks > 1 && !fwd_nopipe) return scan_fwd_pipe_dispatch(a, pl, stream);
+        return scan_fwd_tma_dispatch(a, pl, stream);
+    }
     return scan_fwd_dispatch(a, pl, p->io_dtype, stream);
 }
 
