@@ -5,45 +5,49 @@
 //   dA = sum g_l dt_l a_l h_{l-1};  dB_l += g_l dt_l u_l;  dC_l += dout_l h_l;  dD = sum dout u;
 //   ddelta_l = ddt_l sigmoid(delta_l + bias);  ddelta_bias = sum ddelta_l;          a_l h_{l-1} = h_l - dt_l B_l u_l
 //
-// Same software pipeline as scan_fwd_pipe.cu -- no CTA-wide barrier in the channel loop:
-//   P1(j)    u / delta / dout of channel j arrive by TMA; softplus, decay, the thread's aggregates of BOTH recurrences
-//            (forward state h left to right, adjoint g right to left), two interleaved warp scans, warp aggregates to
-//            shared memory, ARRIVE on mbarrier tot[j].  The only per-position value kept is dt (log2 domain), parked in
-//            delta's slot of the ring; four registers hold the thread's warp-exclusive prefixes.
-//   leader   (first warp) waits on tot[j], publishes the chunk's adjoint aggregate of channel j; finishes the look-back of
-//            channel j - 1 (loads issued an iteration earlier), combines it with the forward state entering the chunk
-//            (from the `x` tensor the forward saved) into the two states entering every warp, arrives on in[j - 1];
-//            issues the look-back loads of channel j; refills the ring slot all warps are done with; flushes the
-//            per-channel sums of channel j - 2.
-//   P2(j-1)  waits on in[j - 1]; re-reads u, dt, dout from the ring, recomputes the decay (one ex2) and the sigmoid
-//            (1 - 2^-dt, one ex2) instead of carrying them in registers across the exchange, walks both recurrences,
-//            forms the gradients, 128-bit stores of du / ddelta, dB / dC accumulated in registers over the tile's channels.
+// Same structure as scan_fwd_pipe.cu -- the tile (<= 4 channels x 2048 positions x {u, delta, dout}, 96 KB) is resident in
+// shared memory, no CTA-wide barrier around the carry exchange; 8 compute warps (8 positions per thread) + 1 exchange warp:
+//   compute warps:
+//     P1(j), j = 0..n-1   u / delta / dout of channel j arrive by TMA (all issued at kernel start); softplus, decay, the
+//                thread's aggregates of BOTH recurrences (forward state h left to right, adjoint g right to left), two
+//                interleaved warp scans, warp aggregates to shared memory, ARRIVE on mbarrier tot[j].  The only
+//                per-position value kept is dt (log2 domain), parked in delta's slot; four registers per channel hold
+//                the thread's warp-exclusive prefixes.
+//     P2(j), j = 0..n-1   waits on mbarrier in[j]; re-reads u, dt, dout, recomputes the decay (one ex2) and the sigmoid
+//                (1 - 2^-dt, one ex2) instead of carrying them in registers across the exchange, walks both recurrences,
+//                forms the gradients; 128-bit stores of du / ddelta; dB / dC accumulate in registers over the channels.
+//   exchange warp:
+//     sweep A    per channel: waits on tot[j], combines the 8 warp aggregates, publishes the chunk's adjoint aggregate,
+//                issues the look-back loads over the chunks to the right (pipe.cuh) and the load of the forward state
+//                entering the chunk (from the `x` tensor the forward saved);
+//     sweep B    per channel: reduces the look-back, writes the two states entering every warp, arrives on in[j].
+//     Finally it adds the per-channel sums (dA, dD, ddelta_bias) the compute warps left in shared memory to global memory.
 #include <cstdlib>
 
 #include "fast.cuh"
 
 namespace vmasr {
 
-constexpr int kBPipeStages = 3;        // TMA ring depth (u + delta + dout, 24 KB per stage)
-constexpr int kBPipeSlots = 4;         // depth of the warp-total / entering-state / channel-sum exchange areas
-constexpr int kBPipeMaxChannels = 64;  // channels whose parameters are staged per tile
+constexpr int kBPipeStages = 4;        // channels per tile = resident stages (u + delta + dout, 24 KB per channel)
+constexpr int kBPipeThreads = 288;     // 8 compute warps + the exchange warp
 
 template <bool TAIL, bool SP>
 __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned char *smem, const int chunk, const int rg,
                                                    const unsigned epoch) {
-    constexpr int NT = 256, ITEMS = 8, WPR = 8, SEG = NT * ITEMS, STAGES = kBPipeStages, SLOTS = kBPipeSlots;
+    constexpr int NC = 256, ITEMS = 8, WPR = 8, SEG = NC * ITEMS, STAGES = kBPipeStages;
 
     // shared memory carve-up (header 2048 bytes; [1016, 1024) is the tile ticket of the kernel wrapper)
     unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(smem);  // [STAGES] TMA completion
     unsigned long long *bar_bc = bar_full + STAGES;                               // B / C segment
-    unsigned long long *bar_tot = bar_bc + 1;                                     // [SLOTS] 8 arrivals
-    unsigned long long *bar_in = bar_tot + SLOTS;                                 // [SLOTS] 1 arrival
-    float4 *s_tot = reinterpret_cast<float4 *>(smem + 128);                       // [SLOTS][8] warp totals {p, q fwd, q adjoint, -}
-    float2 *s_in = reinterpret_cast<float2 *>(smem + 640);                        // [SLOTS][8] {h, g} entering each warp
-    float *s_red = reinterpret_cast<float *>(smem + 896);                         // [SLOTS][4] channel sums dA, dD, dbias
-    float *s_par = reinterpret_cast<float *>(smem + 1024);                        // [3][kBPipeMaxChannels]
-    float *s_bc = reinterpret_cast<float *>(smem + 2048);                         // [2][SEG]   B, C
-    float *s_stage = s_bc + 2 * SEG;                                              // [STAGES][3][SEG]  u, delta -> dt, dout
+    unsigned long long *bar_tot = bar_bc + 1;                                     // [STAGES] 8 arrivals
+    unsigned long long *bar_in = bar_tot + STAGES;                                // [STAGES] 1 arrival
+    float4 *s_tot = reinterpret_cast<float4 *>(smem + 128);                       // [STAGES][8] warp totals {p, q fwd, q adjoint, -}
+    float2 *s_in = reinterpret_cast<float2 *>(smem + 640);                        // [STAGES][8] {h, g} entering each warp
+    float *s_red = reinterpret_cast<float *>(smem + 896);                         // [STAGES][4] channel sums dA, dD, dbias
+    float *s_par = reinterpret_cast<float *>(smem + 960);                         // [3][STAGES]
+    float *s_c = reinterpret_cast<float *>(smem + 2048);                          // [SEG]   C
+    float *s_stage = s_c + SEG;                                                   // [STAGES][3][SEG]  u, delta -> dt, dout
+    float *s_b = s_stage + (size_t)(STAGES - 1) * 3 * SEG;                        // B: borrowed from the last stage
 
     const int ctile = rg % a.n_ctiles;
     const int bg = rg / a.n_ctiles;
@@ -52,332 +56,327 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const bool leader = warp == 0;
+    const bool exchange = warp == WPR;
     const int L = a.seqlen;
     const int seg0 = chunk * SEG;
-    const int pos = seg0 + threadIdx.x * ITEMS;
     const int seg_len = min(SEG, L - seg0);
     const unsigned seg_bytes = (unsigned)seg_len * 4u;
-    int nvalid = ITEMS;
-    if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
 
     const int c_begin = ctile * a.chan_per_tile;
-    const int n_iter = min(a.chan_per_group, c_begin + a.chan_per_tile) - c_begin;
+    const int n_iter = min(a.chan_per_group, c_begin + a.chan_per_tile) - c_begin;  // <= STAGES
     const int d0 = g * a.chan_per_group + c_begin;
 
     const float *u_src = reinterpret_cast<const float *>(a.u) + b * a.u_bs + (long long)d0 * a.u_ds + seg0;
     const float *dl_src = reinterpret_cast<const float *>(a.delta) + b * a.delta_bs + (long long)d0 * a.delta_ds + seg0;
     const float *dy_src = reinterpret_cast<const float *>(a.dout) + b * a.dout_bs + (long long)d0 * a.dout_ds + seg0;
-    float *du_ptr = reinterpret_cast<float *>(a.du) + b * a.du_bs + (long long)d0 * a.du_ds + pos;
-    float *dd_ptr = reinterpret_cast<float *>(a.ddelta) + b * a.ddelta_bs + (long long)d0 * a.ddelta_ds + pos;
 
-    if (threadIdx.x == 0) {
+    auto issue_stage = [&](int it) {  // lane 0 of the exchange warp only
+        float *dst = s_stage + (size_t)it * 3 * SEG;
+        mbar_expect_tx(&bar_full[it], 3u * seg_bytes);
+        bulk_load(dst, u_src + it * a.u_ds, seg_bytes, &bar_full[it]);
+        bulk_load(dst + SEG, dl_src + it * a.delta_ds, seg_bytes, &bar_full[it]);
+        bulk_load(dst + 2 * SEG, dy_src + it * a.dout_ds, seg_bytes, &bar_full[it]);
+    };
+    // the bulk copies go out first: they do not depend on the per-channel parameters staged below
+    if (threadIdx.x == NC) {
 #pragma unroll
         for (int i = 0; i < STAGES + 1; ++i) mbar_init(&bar_full[i], 1);
 #pragma unroll
-        for (int i = 0; i < SLOTS; ++i) {
+        for (int i = 0; i < STAGES; ++i) {
             mbar_init(&bar_tot[i], WPR);
             mbar_init(&bar_in[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // the bulk copies go out first: they do not depend on the per-channel parameters staged below
-    auto issue_stage = [&](int it) {  // thread 0 only
-        const int s = it % STAGES;
-        float *dst = s_stage + (size_t)s * 3 * SEG;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slot was written through the generic proxy (dt)
-        mbar_expect_tx(&bar_full[s], 3u * seg_bytes);
-        bulk_load(dst, u_src + it * a.u_ds, seg_bytes, &bar_full[s]);
-        bulk_load(dst + SEG, dl_src + it * a.delta_ds, seg_bytes, &bar_full[s]);
-        bulk_load(dst + 2 * SEG, dy_src + it * a.dout_ds, seg_bytes, &bar_full[s]);
-    };
-    if (threadIdx.x == 0) {
         const float *Bg = reinterpret_cast<const float *>(a.B) + b * a.B_bs + g * a.B_gs + seg0;
         const float *Cg = reinterpret_cast<const float *>(a.C) + b * a.C_bs + g * a.C_gs + seg0;
         mbar_expect_tx(bar_bc, 2u * seg_bytes);
-        bulk_load(s_bc, Bg, seg_bytes, bar_bc);
-        bulk_load(s_bc + SEG, Cg, seg_bytes, bar_bc);
+        bulk_load(s_b, Bg, seg_bytes, bar_bc);
+        bulk_load(s_c, Cg, seg_bytes, bar_bc);
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s)
+        for (int s = 0; s < STAGES - 1; ++s)
             if (s < n_iter) issue_stage(s);
     }
-
-    if (threadIdx.x < SLOTS * 4) s_red[threadIdx.x] = 0.0f;
-    for (int i = threadIdx.x; i < 3 * n_iter; i += NT) {
+    if (threadIdx.x < STAGES * 4) s_red[threadIdx.x] = 0.0f;
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + 3 * n_iter) {
+        const int i = threadIdx.x - 32;
         const int which = i / n_iter, cc = i - which * n_iter;
         const int d = d0 + cc;
         float v;
         if (which == 0) v = __ldg(a.A + d * a.A_ds);
         else if (which == 1) v = a.D ? __ldg(a.D + d) : 0.0f;
         else v = (a.delta_bias ? __ldg(a.delta_bias + d) : 0.0f) * kLog2e;
-        s_par[which * kBPipeMaxChannels + cc] = v;
+        s_par[which * STAGES + cc] = v;
     }
     __syncthreads();
 
-    float2 Bv[4], dBacc[4], dCacc[4];
-    float *sC = s_bc + SEG + threadIdx.x * ITEMS;  // this thread's C values (only this thread touches them)
-    mbar_wait(bar_bc, 0);
-    lds8(s_bc + threadIdx.x * ITEMS, Bv);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        dBacc[k] = f2(0.0f);
-        dCacc[k] = f2(0.0f);
-    }
-    if (TAIL) {  // positions past the end contribute nothing and stay finite
-        float2 Cv[4];
-        lds8(sC, Cv);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (2 * k >= nvalid) { Bv[k].x = 0.0f; Cv[k].x = 0.0f; }
-            if (2 * k + 1 >= nvalid) { Bv[k].y = 0.0f; Cv[k].y = 0.0f; }
-        }
-        stg8(sC, Cv);
-    }
-
-    const int n_groups16 = (a.n_chunks + 15) >> 4;
-    const int jrev = a.n_chunks - 1 - chunk;  // position of this chunk in the adjoint's scan order
     const long long seq0 = (long long)b * a.dim + d0;
-    CarryLook look;
-    look.ptr = nullptr;
-    look.e = make_uint4(0u, 0u, 0u, 0u);
-    float h_chunk = 0.0f;  // leader: forward state entering the chunk, channel j - 1
-    Aff excf_prev = {1.0f, 0.0f}, excr_prev = {1.0f, 0.0f};
-
-    auto flush_sums = [&](int c) {  // leader lanes 0..2: channel sums of channel c -> global
-        float *red = s_red + (c & (SLOTS - 1)) * 4;
-        const float v = red[lane];
-        red[lane] = 0.0f;
-        const int d = d0 + c;
-        if (lane == 0) atomicAdd(a.dA + d * a.A_ds, v);
-        else if (lane == 1) { if (a.dD) atomicAdd(a.dD + d, v); }
-        else { if (a.ddelta_bias) atomicAdd(a.ddelta_bias + d, v); }
-    };
-
-    for (int j = 0; j <= n_iter; ++j) {
-        Aff excf_cur = {1.0f, 0.0f}, excr_cur = {1.0f, 0.0f};
-        if (j < n_iter) {
-            // ---- P1(j) ----
-            const int s = j % STAGES;
-            const float Av = s_par[j];
-            const float bias2 = s_par[2 * kBPipeMaxChannels + j];
-            float *su = s_stage + (size_t)s * 3 * SEG + threadIdx.x * ITEMS;
-            mbar_wait(&bar_full[s], (unsigned)((j / STAGES) & 1));
-            float2 uv[4], dl[4], dy[4], Cv[4], dts[4];
-            lds8(su, uv);
-            lds8(su + SEG, dl);
-            lds8(su + 2 * SEG, dy);
-            lds8(sC, Cv);
-            if (TAIL) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (2 * k >= nvalid) { uv[k].x = 0.0f; dl[k].x = 0.0f; dy[k].x = 0.0f; }
-                    if (2 * k + 1 >= nvalid) { uv[k].y = 0.0f; dl[k].y = 0.0f; dy[k].y = 0.0f; }
-                }
-                stg8(su, uv);  // park the cleaned values for P2
-                stg8(su + 2 * SEG, dy);
-            }
-            float p = 1.0f, q = 0.0f, qr = 0.0f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float2 dt2 = fma2(dl[k], f2(kLog2e), f2(bias2));
-                if (SP) {
-                    float2 e, sp;
-                    dt2 = softplus2_pair(dt2, e, sp);
-                }
-                dts[k] = dt2;
-                const float2 da = mul2(dt2, f2(Av));
-                const float2 av = make_float2(ex2_approx(da.x), ex2_approx(da.y));
-                const float2 bx = mul2(mul2(dt2, f2(kLn2)), mul2(Bv[k], uv[k]));
-                const float2 cdy = mul2(Cv[k], dy[k]);
-                // local aggregates of both recurrences in one left-to-right walk:
-                //   forward  s -> p s + q;   adjoint (entering from the right)  G -> p G + qr,  qr = sum_i (prod_{m<=i} a_m) C_i dout_i
-                q = fmaf(av.x, q, bx.x);
-                p *= av.x;
-                qr = fmaf(p, cdy.x, qr);
-                q = fmaf(av.y, q, bx.y);
-                p *= av.y;
-                qr = fmaf(p, cdy.y, qr);
-            }
-            stg8(su + SEG, dts);
-            // two independent warp scans, interleaved level by level (each level is shuffle-latency bound)
-            Aff inc_f = {p, q}, inc_r = {p, qr};
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                scan_step_up(inc_f.p, inc_f.q, off);
-                scan_step_down(inc_r.p, inc_r.q, off);
-            }
-            excf_cur = shift_up1(inc_f, lane);
-            excr_cur = shift_down1(inc_r, lane);
-            float4 *tot = s_tot + (j & (SLOTS - 1)) * WPR + warp;
-            const float qr0 = __shfl_sync(0xffffffffu, inc_r.q, 0);
-            if (lane == 31) *tot = make_float4(inc_f.p, inc_f.q, qr0, 0.0f);
-            __syncwarp();
-            if (lane == 31) mbar_arrive(&bar_tot[j & (SLOTS - 1)]);
+    if (exchange) {
+        // ================= exchange warp =================
+        mbar_wait(bar_bc, 0);
+        __syncthreads();  // the compute warps hold B in registers: the last stage is free for data now
+        if (lane == 0 && STAGES - 1 < n_iter) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_stage(STAGES - 1);
         }
-        if (leader) {
-            if (j < n_iter) {
-                // ---- La(j): adjoint aggregate of the chunk, channel j -> global ----
-                mbar_wait(&bar_tot[j & (SLOTS - 1)], (unsigned)((j / SLOTS) & 1));
-                if (j >= 2) {
-                    // every warp is past P2(j - 2): its ring slot and its channel sums are free
-                    if (lane == 0 && j - 2 + STAGES < n_iter) issue_stage(j - 2 + STAGES);
-                    if (lane < 3) flush_sums(j - 2);
-                }
-                float4 t = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
-                if (lane < WPR) t = s_tot[(j & (SLOTS - 1)) * WPR + lane];
-                const Aff cum_r = warp_scan_down_fast<WPR>(Aff{t.x, t.z});
-                if (lane == 0) publish_entry(a.ws_entries + (seq0 + j) * a.n_chunks + jrev, epoch, cum_r.p, cum_r.q);
+        const int n_groups16 = (a.n_chunks + 15) >> 4;
+        const int jrev = a.n_chunks - 1 - chunk;  // position of this chunk in the adjoint's scan order
+        CarryLook look[STAGES];
+        Aff cum_f[STAGES], cum_r[STAGES];
+        float h_chunk[STAGES];
+        // per channel: publish the chunk's adjoint aggregate as soon as it exists and start its look-back; finish the
+        // look-back of the channel before (its loads have been in flight for one P1 sweep of the compute warps)
+        auto finish = [&](int j, const CarryLook &lk, const Aff &cf, const Aff &cr, float hc) {
+            CarryEntry *l2_row = a.ws_entries2 + (seq0 + j) * n_groups16;
+            const Aff before_f = shift_up1(cf, lane);
+            const Aff before_r = shift_down1(cr, lane);
+            const Aff total_r = {__shfl_sync(0xffffffffu, cr.p, 0), __shfl_sync(0xffffffffu, cr.q, 0)};
+            bool ok;
+            Aff grp = {1.0f, 0.0f};
+            CarryLook l = lk;
+            Aff acc = look_reduce(l, epoch, lane, ok, grp);
+            acc = look_finish(l, acc, ok, l2_row, jrev, epoch, lane, grp);
+            if (lane == 0 && (jrev & 15) == 15) {
+                const Aff g16 = compose(grp, total_r);
+                publish_entry(l2_row + (jrev >> 4), epoch, g16.p, g16.q);
             }
-            if (j >= 1) {
-                // ---- Lb(j - 1) ----
-                const int c = j - 1;
-                const long long seq = seq0 + c;
-                CarryEntry *l2_row = a.ws_entries2 + seq * n_groups16;
-                float4 t = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
-                if (lane < WPR) t = s_tot[(c & (SLOTS - 1)) * WPR + lane];
-                Aff cum_f = {t.x, t.y}, cum_r = {t.x, t.z};
+            if (lane < WPR)
+                s_in[j * WPR + lane] = make_float2(fmaf(before_f.p, hc, before_f.q), fmaf(before_r.p, acc.q, before_r.q));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_in[j]);
+        };
 #pragma unroll
-                for (int off = 1; off < WPR; off <<= 1) {
-                    scan_step_up(cum_f.p, cum_f.q, off);
-                    scan_step_down(cum_r.p, cum_r.q, off);
-                }
-                const Aff before_f = shift_up1(cum_f, lane);
-                const Aff before_r = shift_down1(cum_r, lane);
-                const Aff total_r = {__shfl_sync(0xffffffffu, cum_r.p, 0), __shfl_sync(0xffffffffu, cum_r.q, 0)};
-                bool ok;
-                Aff grp = {1.0f, 0.0f};
-                Aff acc = look_reduce(look, epoch, lane, ok, grp);
-                acc = look_finish(look, acc, ok, l2_row, jrev, epoch, lane, grp);
-                if (lane == 0 && (jrev & 15) == 15) {
-                    const Aff g16 = compose(grp, total_r);
-                    publish_entry(l2_row + (jrev >> 4), epoch, g16.p, g16.q);
-                }
-                if (lane < WPR)
-                    s_in[(c & (SLOTS - 1)) * WPR + lane] =
-                        make_float2(fmaf(before_f.p, h_chunk, before_f.q), fmaf(before_r.p, acc.q, before_r.q));
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_in[c & (SLOTS - 1)]);
-            }
+        for (int j = 0; j < STAGES; ++j) {
             if (j < n_iter) {
                 const long long seq = seq0 + j;
-                look = look_issue(a.ws_entries + seq * a.n_chunks, a.ws_entries2 + seq * n_groups16, jrev, lane);
-                h_chunk = (chunk > 0) ? __ldg(a.x + (seq * a.n_chunks + (chunk - 1)) * 2 + 1) : 0.0f;
+                CarryEntry *l1_row = a.ws_entries + seq * a.n_chunks;
+                h_chunk[j] = (chunk > 0) ? __ldg(a.x + (seq * a.n_chunks + (chunk - 1)) * 2 + 1) : 0.0f;
+                mbar_wait(&bar_tot[j], 0);
+                float4 t = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+                if (lane < WPR) t = s_tot[j * WPR + lane];
+                cum_f[j] = Aff{t.x, t.y};
+                cum_r[j] = Aff{t.x, t.z};
+#pragma unroll
+                for (int off = 1; off < WPR; off <<= 1) {
+                    scan_step_down(cum_r[j].p, cum_r[j].q, off);
+                    scan_step_up(cum_f[j].p, cum_f[j].q, off);
+                }
+                if (lane == 0) publish_entry(l1_row + jrev, epoch, cum_r[j].p, cum_r[j].q);
+                look[j] = look_issue(l1_row, a.ws_entries2 + seq * n_groups16, jrev, lane);
+                if (j >= 1) finish(j - 1, look[j - 1], cum_f[j - 1], cum_r[j - 1], h_chunk[j - 1]);
             }
         }
-        if (j >= 1) {
-            // ---- P2(j - 1) ----
-            const int c = j - 1;
-            const float Av = s_par[c];
-            const float Dv = s_par[kBPipeMaxChannels + c];
-            mbar_wait(&bar_in[c & (SLOTS - 1)], (unsigned)((c / SLOTS) & 1));
-            const float2 in = s_in[(c & (SLOTS - 1)) * WPR + warp];
-            const float *su = s_stage + (size_t)(c % STAGES) * 3 * SEG + threadIdx.x * ITEMS;
-            float2 uv[4], dts[4], dy[4], Cv[4];
-            lds8(su, uv);
-            lds8(su + SEG, dts);
-            lds8(su + 2 * SEG, dy);
-            lds8(sC, Cv);
-            float2 av[4], bu[4], dtn[4], hs[4], gl[4];
-            // forward states of this thread's positions
-            {
-                float h = fmaf(excf_prev.p, in.x, excf_prev.q);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float2 da = mul2(dts[k], f2(Av));
-                    av[k] = make_float2(ex2_approx(da.x), ex2_approx(da.y));
-                    dtn[k] = mul2(dts[k], f2(kLn2));
-                    bu[k] = mul2(Bv[k], uv[k]);
-                    const float2 bx = mul2(dtn[k], bu[k]);
-                    h = fmaf(av[k].x, h, bx.x);
-                    hs[k].x = h;
-                    h = fmaf(av[k].y, h, bx.y);
-                    hs[k].y = h;
-                }
-            }
-            // adjoint walk, right to left
-            {
-                float G = fmaf(excr_prev.p, in.y, excr_prev.q);
-#pragma unroll
-                for (int k = 3; k >= 0; --k) {
-                    const float2 cdy = mul2(Cv[k], dy[k]);
-                    gl[k].y = cdy.y + G;
-                    G = av[k].y * gl[k].y;
-                    gl[k].x = cdy.x + G;
-                    G = av[k].x * gl[k].x;
-                }
-            }
-            // gradients, position pairs
-            float2 du[4], ddl[4];
-            float2 sA = f2(0.0f), sD = f2(0.0f), sB = f2(0.0f);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 carried = fma2(mul2(dtn[k], bu[k]), f2(-1.0f), hs[k]);  // a_l h_{l-1}
-                const float2 w = mul2(gl[k], dtn[k]);
-                du[k] = fma2(w, Bv[k], mul2(dy[k], f2(Dv)));
-                const float2 gc = mul2(gl[k], carried);
-                const float2 ddt = fma2(gl[k], bu[k], mul2(gc, f2(Av)));
-                if (SP) {
-                    // sigmoid(delta + bias) = 1 - exp(-softplus) = 1 - 2^(-dt2); exactly 1 above the reference's threshold
-                    float2 sig = make_float2(1.0f - ex2_approx(-dts[k].x), 1.0f - ex2_approx(-dts[k].y));
-                    if (dts[k].x > kSoftplusThr2) sig.x = 1.0f;
-                    if (dts[k].y > kSoftplusThr2) sig.y = 1.0f;
-                    ddl[k] = mul2(ddt, sig);
-                } else {
-                    ddl[k] = ddt;
-                }
-                sA = fma2(w, carried, sA);
-                dBacc[k] = fma2(w, uv[k], dBacc[k]);
-                dCacc[k] = fma2(dy[k], hs[k], dCacc[k]);
-                sD = fma2(dy[k], uv[k], sD);
-                sB = add2(sB, ddl[k]);
-            }
-            {
-                float *o_du = du_ptr + (long long)c * a.du_ds;
-                float *o_dd = dd_ptr + (long long)c * a.ddelta_ds;
-                if (!TAIL || nvalid == ITEMS) {
-                    stg8(o_du, du);
-                    stg8(o_dd, ddl);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (2 * k < nvalid) { o_du[2 * k] = du[k].x; o_dd[2 * k] = ddl[k].x; }
-                        if (2 * k + 1 < nvalid) { o_du[2 * k + 1] = du[k].y; o_dd[2 * k + 1] = ddl[k].y; }
-                    }
-                }
-            }
-            // per-channel sums: dA, dD, ddelta_bias (lanes 0, 8, 16 hold them after the reduction)
-            const float r = warp_sum3(sA.x + sA.y, sD.x + sD.y, sB.x + sB.y, lane);
-            if ((lane & 7) == 0 && lane < 24) atomicAdd(s_red + (c & (SLOTS - 1)) * 4 + (lane >> 3), r);
+        for (int j = 0; j < STAGES; ++j)
+            if (j == n_iter - 1) finish(j, look[j], cum_f[j], cum_r[j], h_chunk[j]);
+        __syncthreads();  // every compute warp is done: the channel sums are complete
+        if (lane < 3 * n_iter) {
+            const int c = lane / 3, which = lane - 3 * c;
+            const float v = s_red[c * 4 + which];
+            const int d = d0 + c;
+            if (which == 0) atomicAdd(a.dA + d * a.A_ds, v);
+            else if (which == 1) { if (a.dD) atomicAdd(a.dD + d, v); }
+            else { if (a.ddelta_bias) atomicAdd(a.ddelta_bias + d, v); }
         }
-        excf_prev = excf_cur;
-        excr_prev = excr_cur;
-    }
-    __syncthreads();
-    if (leader && lane < 3) {
-        if (n_iter >= 2) flush_sums(n_iter - 2);
-        flush_sums(n_iter - 1);
-    }
-
-    // dB / dC of this tile's positions, summed over the tile's channels
-    float *dBg = a.dB + ((long long)b * a.ngroups + g) * (long long)L;
-    float *dCg = a.dC + ((long long)b * a.ngroups + g) * (long long)L;
-    if (!TAIL || nvalid == ITEMS) {
-        atomicAdd(reinterpret_cast<float4 *>(dBg + pos), make_float4(dBacc[0].x, dBacc[0].y, dBacc[1].x, dBacc[1].y));
-        atomicAdd(reinterpret_cast<float4 *>(dBg + pos + 4), make_float4(dBacc[2].x, dBacc[2].y, dBacc[3].x, dBacc[3].y));
-        atomicAdd(reinterpret_cast<float4 *>(dCg + pos), make_float4(dCacc[0].x, dCacc[0].y, dCacc[1].x, dCacc[1].y));
-        atomicAdd(reinterpret_cast<float4 *>(dCg + pos + 4), make_float4(dCacc[2].x, dCacc[2].y, dCacc[3].x, dCacc[3].y));
     } else {
+        // ================= compute warps =================
+        const int pos = seg0 + threadIdx.x * ITEMS;
+        int nvalid = ITEMS;
+        if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
+        float *du_ptr = reinterpret_cast<float *>(a.du) + b * a.du_bs + (long long)d0 * a.du_ds + pos;
+        float *dd_ptr = reinterpret_cast<float *>(a.ddelta) + b * a.ddelta_bs + (long long)d0 * a.ddelta_ds + pos;
+
+        float2 Bv[4], dBacc[4], dCacc[4];
+        float *sC = s_c + threadIdx.x * ITEMS;  // this thread's C values (only this thread touches them)
+        mbar_wait(bar_bc, 0);
+        lds8(s_b + threadIdx.x * ITEMS, Bv);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (2 * k < nvalid) { atomicAdd(dBg + pos + 2 * k, dBacc[k].x); atomicAdd(dCg + pos + 2 * k, dCacc[k].x); }
-            if (2 * k + 1 < nvalid) { atomicAdd(dBg + pos + 2 * k + 1, dBacc[k].y); atomicAdd(dCg + pos + 2 * k + 1, dCacc[k].y); }
+            dBacc[k] = f2(0.0f);
+            dCacc[k] = f2(0.0f);
+        }
+        if (TAIL) {  // positions past the end contribute nothing and stay finite
+            float2 Cv[4];
+            lds8(sC, Cv);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (2 * k >= nvalid) { Bv[k].x = 0.0f; Cv[k].x = 0.0f; }
+                if (2 * k + 1 >= nvalid) { Bv[k].y = 0.0f; Cv[k].y = 0.0f; }
+            }
+            stg8(sC, Cv);
+        }
+        __syncthreads();
+
+        Aff excf[STAGES], excr[STAGES];
+#pragma unroll
+        for (int j = 0; j < STAGES; ++j) {
+            if (j < n_iter) {
+                // ---- P1(j) ----
+                const float Av = s_par[j];
+                const float bias2 = s_par[2 * STAGES + j];
+                float *su = s_stage + (size_t)j * 3 * SEG + threadIdx.x * ITEMS;
+                mbar_wait(&bar_full[j], 0);
+                float2 uv[4], dl[4], dy[4], Cv[4], dts[4];
+                lds8(su, uv);
+                lds8(su + SEG, dl);
+                lds8(su + 2 * SEG, dy);
+                lds8(sC, Cv);
+                if (TAIL) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (2 * k >= nvalid) { uv[k].x = 0.0f; dl[k].x = 0.0f; dy[k].x = 0.0f; }
+                        if (2 * k + 1 >= nvalid) { uv[k].y = 0.0f; dl[k].y = 0.0f; dy[k].y = 0.0f; }
+                    }
+                    stg8(su, uv);  // park the cleaned values for P2
+                    stg8(su + 2 * SEG, dy);
+                }
+                float p = 1.0f, q = 0.0f, qr = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float2 dt2 = fma2(dl[k], f2(kLog2e), f2(bias2));
+                    if (SP) {
+                        float2 e, sp;
+                        dt2 = softplus2_pair(dt2, e, sp);
+                    }
+                    dts[k] = dt2;
+                    const float2 da = mul2(dt2, f2(Av));
+                    const float2 av = make_float2(ex2_approx(da.x), ex2_approx(da.y));
+                    const float2 bx = mul2(mul2(dt2, f2(kLn2)), mul2(Bv[k], uv[k]));
+                    const float2 cdy = mul2(Cv[k], dy[k]);
+                    // local aggregates of both recurrences in one left-to-right walk:
+                    //   forward  s -> p s + q;   adjoint (entering from the right)  G -> p G + qr,  qr = sum_i (prod_{m<=i} a_m) C_i dout_i
+                    q = fmaf(av.x, q, bx.x);
+                    p *= av.x;
+                    qr = fmaf(p, cdy.x, qr);
+                    q = fmaf(av.y, q, bx.y);
+                    p *= av.y;
+                    qr = fmaf(p, cdy.y, qr);
+                }
+                stg8(su + SEG, dts);
+                // two independent warp scans, interleaved level by level (each level is shuffle-latency bound)
+                Aff inc_f = {p, q}, inc_r = {p, qr};
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    scan_step_up(inc_f.p, inc_f.q, off);
+                    scan_step_down(inc_r.p, inc_r.q, off);
+                }
+                excf[j] = shift_up1(inc_f, lane);
+                excr[j] = shift_down1(inc_r, lane);
+                const float qr0 = __shfl_sync(0xffffffffu, inc_r.q, 0);
+                if (lane == 31) s_tot[j * WPR + warp] = make_float4(inc_f.p, inc_f.q, qr0, 0.0f);
+                __syncwarp();
+                if (lane == 31) mbar_arrive(&bar_tot[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < STAGES; ++j) {
+            if (j < n_iter) {
+                // ---- P2(j) ----
+                const float Av = s_par[j];
+                const float Dv = s_par[STAGES + j];
+                mbar_wait(&bar_in[j], 0);
+                const float2 in = s_in[j * WPR + warp];
+                const float *su = s_stage + (size_t)j * 3 * SEG + threadIdx.x * ITEMS;
+                float2 uv[4], dts[4], dy[4], Cv[4];
+                lds8(su, uv);
+                lds8(su + SEG, dts);
+                lds8(su + 2 * SEG, dy);
+                lds8(sC, Cv);
+                float2 av[4], bu[4], dtn[4], hs[4], gl[4];
+                // forward states of this thread's positions
+                {
+                    float h = fmaf(excf[j].p, in.x, excf[j].q);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 da = mul2(dts[k], f2(Av));
+                        av[k] = make_float2(ex2_approx(da.x), ex2_approx(da.y));
+                        dtn[k] = mul2(dts[k], f2(kLn2));
+                        bu[k] = mul2(Bv[k], uv[k]);
+                        const float2 bx = mul2(dtn[k], bu[k]);
+                        h = fmaf(av[k].x, h, bx.x);
+                        hs[k].x = h;
+                        h = fmaf(av[k].y, h, bx.y);
+                        hs[k].y = h;
+                    }
+                }
+                // adjoint walk, right to left
+                {
+                    float G = fmaf(excr[j].p, in.y, excr[j].q);
+#pragma unroll
+                    for (int k = 3; k >= 0; --k) {
+                        const float2 cdy = mul2(Cv[k], dy[k]);
+                        gl[k].y = cdy.y + G;
+                        G = av[k].y * gl[k].y;
+                        gl[k].x = cdy.x + G;
+                        G = av[k].x * gl[k].x;
+                    }
+                }
+                // gradients, position pairs
+                float2 du[4], ddl[4];
+                float2 sA = f2(0.0f), sD = f2(0.0f), sB = f2(0.0f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 carried = fma2(mul2(dtn[k], bu[k]), f2(-1.0f), hs[k]);  // a_l h_{l-1}
+                    const float2 w = mul2(gl[k], dtn[k]);
+                    du[k] = fma2(w, Bv[k], mul2(dy[k], f2(Dv)));
+                    const float2 gc = mul2(gl[k], carried);
+                    const float2 ddt = fma2(gl[k], bu[k], mul2(gc, f2(Av)));
+                    if (SP) {
+                        // sigmoid(delta + bias) = 1 - exp(-softplus) = 1 - 2^(-dt2); exactly 1 above the reference's threshold
+                        float2 sig = make_float2(1.0f - ex2_approx(-dts[k].x), 1.0f - ex2_approx(-dts[k].y));
+                        if (dts[k].x > kSoftplusThr2) sig.x = 1.0f;
+                        if (dts[k].y > kSoftplusThr2) sig.y = 1.0f;
+                        ddl[k] = mul2(ddt, sig);
+                    } else {
+                        ddl[k] = ddt;
+                    }
+                    sA = fma2(w, carried, sA);
+                    dBacc[k] = fma2(w, uv[k], dBacc[k]);
+                    dCacc[k] = fma2(dy[k], hs[k], dCacc[k]);
+                    sD = fma2(dy[k], uv[k], sD);
+                    sB = add2(sB, ddl[k]);
+                }
+                {
+                    float *o_du = du_ptr + (long long)j * a.du_ds;
+                    float *o_dd = dd_ptr + (long long)j * a.ddelta_ds;
+                    if (!TAIL || nvalid == ITEMS) {
+                        stg8(o_du, du);
+                        stg8(o_dd, ddl);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (2 * k < nvalid) { o_du[2 * k] = du[k].x; o_dd[2 * k] = ddl[k].x; }
+                            if (2 * k + 1 < nvalid) { o_du[2 * k + 1] = du[k].y; o_dd[2 * k + 1] = ddl[k].y; }
+                        }
+                    }
+                }
+                // per-channel sums: dA, dD, ddelta_bias (lanes 0, 8, 16 hold them after the reduction)
+                const float r = warp_sum3(sA.x + sA.y, sD.x + sD.y, sB.x + sB.y, lane);
+                if ((lane & 7) == 0 && lane < 24) atomicAdd(s_red + j * 4 + (lane >> 3), r);
+            }
+        }
+        __syncthreads();
+
+        // dB / dC of this tile's positions, summed over the tile's channels
+        float *dBg = a.dB + ((long long)b * a.ngroups + g) * (long long)L;
+        float *dCg = a.dC + ((long long)b * a.ngroups + g) * (long long)L;
+        if (!TAIL || nvalid == ITEMS) {
+            atomicAdd(reinterpret_cast<float4 *>(dBg + pos), make_float4(dBacc[0].x, dBacc[0].y, dBacc[1].x, dBacc[1].y));
+            atomicAdd(reinterpret_cast<float4 *>(dBg + pos + 4), make_float4(dBacc[2].x, dBacc[2].y, dBacc[3].x, dBacc[3].y));
+            atomicAdd(reinterpret_cast<float4 *>(dCg + pos), make_float4(dCacc[0].x, dCacc[0].y, dCacc[1].x, dCacc[1].y));
+            atomicAdd(reinterpret_cast<float4 *>(dCg + pos + 4), make_float4(dCacc[2].x, dCacc[2].y, dCacc[3].x, dCacc[3].y));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (2 * k < nvalid) { atomicAdd(dBg + pos + 2 * k, dBacc[k].x); atomicAdd(dCg + pos + 2 * k, dCacc[k].x); }
+                if (2 * k + 1 < nvalid) { atomicAdd(dBg + pos + 2 * k + 1, dBacc[k].y); atomicAdd(dCg + pos + 2 * k + 1, dCacc[k].y); }
+            }
         }
     }
     retire_tile(a);
 }
 
 template <bool SP>
-__global__ void __launch_bounds__(256, 2) scan_bwd_pipe_kernel(const __grid_constant__ ScanArgs a) {
+__global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const __grid_constant__ ScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_bwd_pipe[];
     unsigned tile, epoch;
     claim_tile(a, reinterpret_cast<unsigned *>(smem_bwd_pipe + 1016), tile, epoch);
@@ -390,7 +389,7 @@ __global__ void __launch_bounds__(256, 2) scan_bwd_pipe_kernel(const __grid_cons
 
 template <bool SP>
 static int launch_bwd_pipe(const ScanArgs &a, int grid, cudaStream_t stream) {
-    const size_t smem = 2048 + sizeof(float) * (2 * 2048 + (size_t)kBPipeStages * 3 * 2048);
+    const size_t smem = 2048 + sizeof(float) * (2048 + (size_t)kBPipeStages * 3 * 2048);
     static bool configured = false;
     if (!configured) {
         if (int rc = check_cuda(cudaFuncSetAttribute(scan_bwd_pipe_kernel<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -398,12 +397,13 @@ static int launch_bwd_pipe(const ScanArgs &a, int grid, cudaStream_t stream) {
             return rc;
         configured = true;
     }
-    scan_bwd_pipe_kernel<SP><<<grid, 256, smem, stream>>>(a);
+    scan_bwd_pipe_kernel<SP><<<grid, kBPipeThreads, smem, stream>>>(a);
     return check_cuda(cudaGetLastError(), "scan_bwd_pipe launch");
 }
 
-// n_chunks > 1 only (then a row segment is the whole 2048-position chunk, one row per CTA)
+// n_chunks > 1 and at most kBPipeStages channels per tile (scan_host.cu plans it so)
 int scan_bwd_pipe_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream) {
+    if (a.chan_per_tile > kBPipeStages) return fail("scan_bwd_pipe: %d channels per tile (max %d)", a.chan_per_tile, kBPipeStages);
     return a.softplus ? launch_bwd_pipe<true>(a, pl.grid, stream) : launch_bwd_pipe<false>(a, pl.grid, stream);
 }
 

@@ -2,47 +2,49 @@
 // Replaces selective_scan_fwd_kernel (kernels/selective_scan/csrc/selective_scan/cus/selective_scan_fwd_kernel.cuh:61-203),
 // whose CTA walks the chunks of a row serially (:102); here every chunk is its own CTA (see scan.cuh / pipe.cuh).
 //
-// What this kernel adds to scan_fwd_tma.cu (which keeps the single-chunk shapes): the channel loop is SOFTWARE-PIPELINED
-// around the carry exchange, and no CTA-wide barrier is left in it.  ncu on the barrier version showed the warps of a
-// CTA parked on `bar.sync` for most of every channel iteration while the first warp resolved the cross-chunk look-back
-// (stall_barrier 7-13 cycles per issue, issue slots 20-30 % busy).  Here an iteration j does, per warp:
+// What this kernel adds to scan_fwd_tma.cu (which keeps the single-chunk shapes): no CTA-wide barrier around the carry
+// exchange, and the exchange runs on a warp of its own.  ncu on the barrier version showed the warps of a CTA parked on
+// `bar.sync` for most of every channel iteration while the first warp resolved the cross-chunk look-back (stall_barrier
+// 7-13 cycles per issue, issue slots 20-30 % busy); a first pipelined version (outputs of channel j - 1 after the local
+// scan of channel j) still had 30 % of its stall samples on the hand-off, because the aggregate a chunk needs from its
+// left neighbour is published by a CTA running in lock-step with it, one cross-SM round trip (> 1 us) away.
+// So the whole tile (<= 4 channels x 2048 positions, 64 KB) is RESIDENT in shared memory and the work is two sweeps:
 //
-//   P1(j)    wait for channel j's u / delta (TMA ring), element-wise work, in-thread scan, warp scan; the warp's
-//            aggregate goes to shared memory and the warp ARRIVES on mbarrier tot[j] -- it does not wait for anything.
-//            Because every output is affine in the state entering the thread,  y_l = Y0_l + Y1_l * h_in,  P1 leaves
-//            just the two arrays Y0 = C (local state) + D u  and  Y1 = C (local decay product)  in place of u / delta
-//            in the ring, plus two registers (the warp-exclusive prefix of the thread).
-//   leader   (first warp only) waits on tot[j], combines the 8 warp aggregates, PUBLISHES the chunk's aggregate of
-//            channel j, then finishes the look-back of channel j - 1 -- whose loads were issued one iteration ago, right
-//            after that channel's publish, so they have had a whole iteration to land -- writes the state entering
-//            each warp to shared memory and arrives on mbarrier in[j - 1]; then issues the look-back loads of channel j
-//            and refills the ring slot every warp is done with.
-//   P2(j-1)  wait on in[j - 1] (normally already complete), y = Y0 + Y1 * h_in straight from shared memory, 128-bit stores.
+//   compute warps (8; one thread owns 8 positions):
+//     P1(j), j = 0..n-1   wait for channel j's u / delta (TMA bulk copies, all issued at kernel start), element-wise work,
+//                in-thread scan, warp scan; the warp's aggregate goes to shared memory and the warp ARRIVES on mbarrier
+//                tot[j] -- it waits for nothing.  Every output is affine in the state entering the thread,
+//                y_l = Y0_l + Y1_l * h_in,  so P1 leaves just the two arrays  Y0 = C (local state) + D u  and
+//                Y1 = C (local decay product)  in place of u / delta, plus two registers (the thread's warp-exclusive prefix).
+//     P2(j), j = 0..n-1   wait on mbarrier in[j], y = Y0 + Y1 * h_in straight from shared memory, 128-bit stores.
+//   exchange warp:
+//     sweep A    per channel: wait on tot[j], combine the 8 warp aggregates, PUBLISH the chunk's aggregate, issue the
+//                look-back loads (pipe.cuh) -- the loads of all channels are in flight together;
+//     sweep B    per channel: reduce the look-back, write the chunk-end state to `x`, write the state entering each warp
+//                to shared memory, arrive on in[j].
 //
-// Only the leader ever waits on the other warps, and only through an mbarrier it is itself an arriver of.
+// By the time a CTA asks for its neighbours' aggregates (sweep B) it has published all of its own, and so have they.
 #include <cstdlib>
 
 #include "fast.cuh"
 
 namespace vmasr {
 
-constexpr int kPipeStages = 4;        // TMA ring depth (u + delta, 16 KB per stage)
-constexpr int kPipeSlots = 4;         // depth of the warp-total / entering-state exchange areas
-constexpr int kPipeMaxChannels = 64;  // channels whose parameters are staged per tile
-
+constexpr int kPipeStages = 4;        // channels per tile = resident stages (u + delta, 16 KB per channel)
+constexpr int kPipeThreads = 288;     // 8 compute warps + the exchange warp
 
 template <bool TAIL, bool SP>
 __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned char *smem, const int chunk, const int rg) {
-    constexpr int NT = 256, ITEMS = 8, WPR = 8, SEG = NT * ITEMS, STAGES = kPipeStages, SLOTS = kPipeSlots;
+    constexpr int NC = 256, ITEMS = 8, WPR = 8, SEG = NC * ITEMS, STAGES = kPipeStages;
 
     // shared memory carve-up (header 2048 bytes)
     unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(smem);  // [STAGES] TMA completion
     unsigned long long *bar_bc = bar_full + STAGES;                               // B / C segment
-    unsigned long long *bar_tot = bar_bc + 1;                                     // [SLOTS] 8 arrivals: warp totals written
-    unsigned long long *bar_in = bar_tot + SLOTS;                                 // [SLOTS] 1 arrival: entering states written
-    float2 *s_tot = reinterpret_cast<float2 *>(smem + 256);                       // [SLOTS][8] warp totals (p, q)
-    float *s_in = reinterpret_cast<float *>(smem + 512);                          // [SLOTS][8] state entering each warp
-    float *s_par = reinterpret_cast<float *>(smem + 1024);                        // [3][kPipeMaxChannels]
+    unsigned long long *bar_tot = bar_bc + 1;                                     // [STAGES] 8 arrivals: warp totals written
+    unsigned long long *bar_in = bar_tot + STAGES;                                // [STAGES] 1 arrival: entering states written
+    float2 *s_tot = reinterpret_cast<float2 *>(smem + 256);                       // [STAGES][8] warp totals (p, q)
+    float *s_in = reinterpret_cast<float *>(smem + 512);                          // [STAGES][8] state entering each warp
+    float *s_par = reinterpret_cast<float *>(smem + 1024);                        // [3][STAGES]
     float *s_stage = reinterpret_cast<float *>(smem + 2048);                      // [STAGES][2][SEG]
     float *s_bc = s_stage + (size_t)(STAGES - 1) * 2 * SEG;                       // B, C: borrowed from the last stage
 
@@ -53,43 +55,35 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const bool leader = warp == 0;
+    const bool exchange = warp == WPR;  // the ninth warp
     const int L = a.seqlen;
     const int seg0 = chunk * SEG;
-    const int pos = seg0 + threadIdx.x * ITEMS;
     const int seg_len = min(SEG, L - seg0);  // multiple of 4
     const unsigned seg_bytes = (unsigned)seg_len * 4u;
-    int nvalid = ITEMS;
-    if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
 
     const int c_begin = ctile * a.chan_per_tile;
-    const int n_iter = min(a.chan_per_group, c_begin + a.chan_per_tile) - c_begin;  // channels of this tile
+    const int n_iter = min(a.chan_per_group, c_begin + a.chan_per_tile) - c_begin;  // channels of this tile (<= STAGES)
     const int d0 = g * a.chan_per_group + c_begin;
 
     const float *u_src = reinterpret_cast<const float *>(a.u) + b * a.u_bs + (long long)d0 * a.u_ds + seg0;
     const float *dl_src = reinterpret_cast<const float *>(a.delta) + b * a.delta_bs + (long long)d0 * a.delta_ds + seg0;
-    float *out_ptr = reinterpret_cast<float *>(a.out) + b * a.out_bs + (long long)d0 * a.out_ds + pos;
 
-    if (threadIdx.x == 0) {
+    auto issue_stage = [&](int it) {  // lane 0 of the exchange warp only
+        float *dst = s_stage + (size_t)it * 2 * SEG;
+        mbar_expect_tx(&bar_full[it], 2u * seg_bytes);
+        bulk_load(dst, u_src + it * a.u_ds, seg_bytes, &bar_full[it]);
+        bulk_load(dst + SEG, dl_src + it * a.delta_ds, seg_bytes, &bar_full[it]);
+    };
+    // the bulk copies go out first: they do not depend on the per-channel parameters staged below
+    if (threadIdx.x == NC) {
 #pragma unroll
         for (int i = 0; i < STAGES + 1; ++i) mbar_init(&bar_full[i], 1);
 #pragma unroll
-        for (int i = 0; i < SLOTS; ++i) {
+        for (int i = 0; i < STAGES; ++i) {
             mbar_init(&bar_tot[i], WPR);
             mbar_init(&bar_in[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // the bulk copies go out first: they do not depend on the per-channel parameters staged below
-    auto issue_stage = [&](int it) {  // thread 0 only
-        const int s = it % STAGES;
-        float *dst = s_stage + (size_t)s * 2 * SEG;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slot was written through the generic proxy (Y0 / Y1)
-        mbar_expect_tx(&bar_full[s], 2u * seg_bytes);
-        bulk_load(dst, u_src + it * a.u_ds, seg_bytes, &bar_full[s]);
-        bulk_load(dst + SEG, dl_src + it * a.delta_ds, seg_bytes, &bar_full[s]);
-    };
-    if (threadIdx.x == 0) {
         const float *Bg = reinterpret_cast<const float *>(a.B) + b * a.B_bs + g * a.B_gs + seg0;
         const float *Cg = reinterpret_cast<const float *>(a.C) + b * a.C_bs + g * a.C_gs + seg0;
         mbar_expect_tx(bar_bc, 2u * seg_bytes);
@@ -99,155 +93,168 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
         for (int s = 0; s < STAGES - 1; ++s)
             if (s < n_iter) issue_stage(s);
     }
-
     const unsigned epoch = *reinterpret_cast<volatile unsigned *>(a.ws_header + 2) % 0xfffffffeu + 1u;
-    for (int i = threadIdx.x; i < 3 * n_iter; i += NT) {
-        const int which = i / n_iter, cc = i - which * n_iter;
+    if (threadIdx.x < 3 * n_iter) {
+        const int which = threadIdx.x / n_iter, cc = threadIdx.x - which * n_iter;
         const int d = d0 + cc;
         float v;
         if (which == 0) v = __ldg(a.A + d * a.A_ds);
         else if (which == 1) v = a.D ? __ldg(a.D + d) : 0.0f;
         else v = (a.delta_bias ? __ldg(a.delta_bias + d) : 0.0f) * kLog2e;
-        s_par[which * kPipeMaxChannels + cc] = v;
+        s_par[which * STAGES + cc] = v;
     }
     __syncthreads();
 
-    float2 Bl[4], Cv[4];  // ln2 * B (the scan runs on dt in the log2 domain) and C of this thread's positions
-    mbar_wait(bar_bc, 0);
-    lds8(s_bc + threadIdx.x * ITEMS, Bl);
-    lds8(s_bc + SEG + threadIdx.x * ITEMS, Cv);
-    __syncthreads();  // B / C are in registers: the last stage is free for data now
-    if (threadIdx.x == 0 && STAGES - 1 < n_iter) issue_stage(STAGES - 1);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        Bl[j] = mul2(Bl[j], f2(kLn2));
-        if (TAIL) {  // positions past the end: keep the arithmetic finite
-            if (2 * j >= nvalid) { Bl[j].x = 0.0f; Cv[j].x = 0.0f; }
-            if (2 * j + 1 >= nvalid) { Bl[j].y = 0.0f; Cv[j].y = 0.0f; }
-        }
-    }
-
-    const int n_groups16 = (a.n_chunks + 15) >> 4;
     const long long seq0 = (long long)b * a.dim + d0;  // (batch, channel) row of the tile's first channel
-    CarryLook look;
-    look.ptr = nullptr;
-    look.e = make_uint4(0u, 0u, 0u, 0u);
-    Aff exc_prev = {1.0f, 0.0f};  // warp-exclusive prefix of this thread, channel j - 1
-
-    for (int j = 0; j <= n_iter; ++j) {
-        Aff exc_cur = {1.0f, 0.0f};
-        if (j < n_iter) {
-            // ---- P1(j) ----
-            const int s = j % STAGES;
-            const float Av = s_par[j];
-            const float Dv = s_par[kPipeMaxChannels + j];
-            const float bias2 = s_par[2 * kPipeMaxChannels + j];
-            float *su = s_stage + (size_t)s * 2 * SEG + threadIdx.x * ITEMS;
-            mbar_wait(&bar_full[s], (unsigned)((j / STAGES) & 1));
-            float2 uv[4], dl[4], Y0[4], Y1[4];
-            lds8(su, uv);
-            lds8(su + SEG, dl);
-            float p = 1.0f, q = 0.0f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (TAIL) {
-                    if (2 * k >= nvalid) { uv[k].x = 0.0f; dl[k].x = 0.0f; }
-                    if (2 * k + 1 >= nvalid) { uv[k].y = 0.0f; dl[k].y = 0.0f; }
-                }
-                float2 dt2 = fma2(dl[k], f2(kLog2e), f2(bias2));
-                if (SP) {
-                    float2 e, sp;
-                    dt2 = softplus2_pair(dt2, e, sp);
-                }
-                const float2 da = mul2(dt2, f2(Av));
-                float2 av = make_float2(ex2_approx(da.x), ex2_approx(da.y));
-                const float2 bx = mul2(mul2(dt2, Bl[k]), uv[k]);
-                if (TAIL) {  // identity map past the end
-                    if (2 * k >= nvalid) av.x = 1.0f;
-                    if (2 * k + 1 >= nvalid) av.y = 1.0f;
-                }
-                float2 P, Q;
-                q = fmaf(av.x, q, bx.x);
-                p *= av.x;
-                P.x = p;
-                Q.x = q;
-                q = fmaf(av.y, q, bx.y);
-                p *= av.y;
-                P.y = p;
-                Q.y = q;
-                Y0[k] = fma2(Cv[k], Q, mul2(uv[k], f2(Dv)));
-                Y1[k] = mul2(Cv[k], P);
-            }
-            stg8(su, Y0);
-            stg8(su + SEG, Y1);
-            const Aff inc = warp_scan_up_fast<32>(Aff{p, q});
-            exc_cur = shift_up1(inc, lane);
-            if (lane == 31) s_tot[(j & (SLOTS - 1)) * WPR + warp] = make_float2(inc.p, inc.q);
-            __syncwarp();
-            if (lane == 31) mbar_arrive(&bar_tot[j & (SLOTS - 1)]);
+    if (exchange) {
+        // ================= exchange warp =================
+        mbar_wait(bar_bc, 0);
+        __syncthreads();  // the compute warps hold B / C in registers: the last stage is free for data now
+        if (lane == 0 && STAGES - 1 < n_iter) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_stage(STAGES - 1);
         }
-        if (leader) {
-            if (j < n_iter) {
-                // ---- La(j): chunk aggregate of channel j -> global; refill the ring slot everyone is done with ----
-                mbar_wait(&bar_tot[j & (SLOTS - 1)], (unsigned)((j / SLOTS) & 1));
-                if (lane == 0 && j >= 2 && j + STAGES - 2 < n_iter) issue_stage(j + STAGES - 2);  // slot of channel j - 2
-                const float2 t = (lane < WPR) ? s_tot[(j & (SLOTS - 1)) * WPR + lane] : make_float2(1.0f, 0.0f);
-                const Aff cum = warp_scan_up_fast<WPR>(Aff{t.x, t.y});
-                if (lane == WPR - 1) publish_entry(a.ws_entries + (seq0 + j) * a.n_chunks + chunk, epoch, cum.p, cum.q);
-            }
-            if (j >= 1) {
-                // ---- Lb(j - 1): state entering the chunk (look-back), then the state entering each warp ----
-                const int c = j - 1;
-                const long long seq = seq0 + c;
-                const CarryEntry *l2_row = a.ws_entries2 + seq * n_groups16;
-                const float2 t = (lane < WPR) ? s_tot[(c & (SLOTS - 1)) * WPR + lane] : make_float2(1.0f, 0.0f);
-                const Aff cum = warp_scan_up_fast<WPR>(Aff{t.x, t.y});
-                const Aff before = shift_up1(cum, lane);
-                const Aff total = {__shfl_sync(0xffffffffu, cum.p, WPR - 1), __shfl_sync(0xffffffffu, cum.q, WPR - 1)};
-                bool ok;
-                Aff grp = {1.0f, 0.0f};
-                Aff acc = look_reduce(look, epoch, lane, ok, grp);
-                acc = look_finish(look, acc, ok, l2_row, chunk, epoch, lane, grp);
-                if (lane == 0) {
-                    if ((chunk & 15) == 15) {
-                        const Aff g16 = compose(grp, total);
-                        publish_entry(a.ws_entries2 + seq * n_groups16 + (chunk >> 4), epoch, g16.p, g16.q);
-                    }
-                    reinterpret_cast<float2 *>(a.x)[seq * a.n_chunks + chunk] =
-                        make_float2(total.p * acc.p, fmaf(total.p, acc.q, total.q));
+        const int n_groups16 = (a.n_chunks + 15) >> 4;
+        CarryLook look[STAGES];
+        Aff cum[STAGES];
+        // per channel: publish the chunk aggregate as soon as it exists and start its look-back; finish the look-back of the
+        // channel before (its loads have been in flight for one P1 sweep of the compute warps)
+        auto finish = [&](int j, const CarryLook &lk, const Aff &cm) {
+            const long long seq = seq0 + j;
+            CarryEntry *l2_row = a.ws_entries2 + seq * n_groups16;
+            const Aff before = shift_up1(cm, lane);
+            const Aff total = {__shfl_sync(0xffffffffu, cm.p, WPR - 1), __shfl_sync(0xffffffffu, cm.q, WPR - 1)};
+            bool ok;
+            Aff grp = {1.0f, 0.0f};
+            CarryLook l = lk;
+            Aff acc = look_reduce(l, epoch, lane, ok, grp);
+            acc = look_finish(l, acc, ok, l2_row, chunk, epoch, lane, grp);
+            if (lane == 0) {
+                if ((chunk & 15) == 15) {
+                    const Aff g16 = compose(grp, total);
+                    publish_entry(l2_row + (chunk >> 4), epoch, g16.p, g16.q);
                 }
-                if (lane < WPR) s_in[(c & (SLOTS - 1)) * WPR + lane] = fmaf(before.p, acc.q, before.q);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_in[c & (SLOTS - 1)]);
+                reinterpret_cast<float2 *>(a.x)[seq * a.n_chunks + chunk] = make_float2(total.p * acc.p, fmaf(total.p, acc.q, total.q));
             }
+            if (lane < WPR) s_in[j * WPR + lane] = fmaf(before.p, acc.q, before.q);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_in[j]);
+        };
+#pragma unroll
+        for (int j = 0; j < STAGES; ++j) {
             if (j < n_iter) {
                 const long long seq = seq0 + j;
-                look = look_issue(a.ws_entries + seq * a.n_chunks, a.ws_entries2 + seq * n_groups16, chunk, lane);
+                CarryEntry *l1_row = a.ws_entries + seq * a.n_chunks;
+                mbar_wait(&bar_tot[j], 0);
+                const float2 t = (lane < WPR) ? s_tot[j * WPR + lane] : make_float2(1.0f, 0.0f);
+                cum[j] = warp_scan_up_fast<WPR>(Aff{t.x, t.y});
+                if (lane == WPR - 1) publish_entry(l1_row + chunk, epoch, cum[j].p, cum[j].q);
+                look[j] = look_issue(l1_row, a.ws_entries2 + seq * n_groups16, chunk, lane);
+                if (j >= 1) finish(j - 1, look[j - 1], cum[j - 1]);
             }
         }
-        if (j >= 1) {
-            // ---- P2(j - 1) ----
-            const int c = j - 1;
-            mbar_wait(&bar_in[c & (SLOTS - 1)], (unsigned)((c / SLOTS) & 1));
-            const float h_in = fmaf(exc_prev.p, s_in[(c & (SLOTS - 1)) * WPR + warp], exc_prev.q);
-            const float *sy = s_stage + (size_t)(c % STAGES) * 2 * SEG + threadIdx.x * ITEMS;
-            float2 Y0[4], Y1[4], y[4];
-            lds8(sy, Y0);
-            lds8(sy + SEG, Y1);
+        // the last channel (n_iter is uniform over the CTA; the loop above is unrolled, so index by constant)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) y[k] = fma2(Y1[k], f2(h_in), Y0[k]);
-            float *o = out_ptr + (long long)c * a.out_ds;
-            if (!TAIL || nvalid == ITEMS) {
-                stg8(o, y);
-            } else {
+        for (int j = 0; j < STAGES; ++j)
+            if (j == n_iter - 1) finish(j, look[j], cum[j]);
+    } else {
+        // ================= compute warps =================
+        const int pos = seg0 + threadIdx.x * ITEMS;
+        int nvalid = ITEMS;
+        if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
+        float *out_ptr = reinterpret_cast<float *>(a.out) + b * a.out_bs + (long long)d0 * a.out_ds + pos;
+
+        float2 Bl[4], Cv[4];  // ln2 * B (the scan runs on dt in the log2 domain) and C of this thread's positions
+        mbar_wait(bar_bc, 0);
+        lds8(s_bc + threadIdx.x * ITEMS, Bl);
+        lds8(s_bc + SEG + threadIdx.x * ITEMS, Cv);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            Bl[k] = mul2(Bl[k], f2(kLn2));
+            if (TAIL) {  // positions past the end: keep the arithmetic finite
+                if (2 * k >= nvalid) { Bl[k].x = 0.0f; Cv[k].x = 0.0f; }
+                if (2 * k + 1 >= nvalid) { Bl[k].y = 0.0f; Cv[k].y = 0.0f; }
+            }
+        }
+
+        Aff exc[STAGES];  // warp-exclusive prefix of this thread, per channel
+#pragma unroll
+        for (int j = 0; j < STAGES; ++j) {
+            if (j < n_iter) {
+                // ---- P1(j) ----
+                const float Av = s_par[j];
+                const float Dv = s_par[STAGES + j];
+                const float bias2 = s_par[2 * STAGES + j];
+                float *su = s_stage + (size_t)j * 2 * SEG + threadIdx.x * ITEMS;
+                mbar_wait(&bar_full[j], 0);
+                float2 uv[4], dl[4], Y0[4], Y1[4];
+                lds8(su, uv);
+                lds8(su + SEG, dl);
+                float p = 1.0f, q = 0.0f;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (2 * k < nvalid) o[2 * k] = y[k].x;
-                    if (2 * k + 1 < nvalid) o[2 * k + 1] = y[k].y;
+                    if (TAIL) {
+                        if (2 * k >= nvalid) { uv[k].x = 0.0f; dl[k].x = 0.0f; }
+                        if (2 * k + 1 >= nvalid) { uv[k].y = 0.0f; dl[k].y = 0.0f; }
+                    }
+                    float2 dt2 = fma2(dl[k], f2(kLog2e), f2(bias2));
+                    if (SP) {
+                        float2 e, sp;
+                        dt2 = softplus2_pair(dt2, e, sp);
+                    }
+                    const float2 da = mul2(dt2, f2(Av));
+                    float2 av = make_float2(ex2_approx(da.x), ex2_approx(da.y));
+                    const float2 bx = mul2(mul2(dt2, Bl[k]), uv[k]);
+                    if (TAIL) {  // identity map past the end
+                        if (2 * k >= nvalid) av.x = 1.0f;
+                        if (2 * k + 1 >= nvalid) av.y = 1.0f;
+                    }
+                    float2 P, Q;
+                    q = fmaf(av.x, q, bx.x);
+                    p *= av.x;
+                    P.x = p;
+                    Q.x = q;
+                    q = fmaf(av.y, q, bx.y);
+                    p *= av.y;
+                    P.y = p;
+                    Q.y = q;
+                    Y0[k] = fma2(Cv[k], Q, mul2(uv[k], f2(Dv)));
+                    Y1[k] = mul2(Cv[k], P);
+                }
+                stg8(su, Y0);
+                stg8(su + SEG, Y1);
+                const Aff inc = warp_scan_up_fast<32>(Aff{p, q});
+                exc[j] = shift_up1(inc, lane);
+                if (lane == 31) s_tot[j * WPR + warp] = make_float2(inc.p, inc.q);
+                __syncwarp();
+                if (lane == 31) mbar_arrive(&bar_tot[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < STAGES; ++j) {
+            if (j < n_iter) {
+                // ---- P2(j) ----
+                mbar_wait(&bar_in[j], 0);
+                const float h_in = fmaf(exc[j].p, s_in[j * WPR + warp], exc[j].q);
+                const float *sy = s_stage + (size_t)j * 2 * SEG + threadIdx.x * ITEMS;
+                float2 Y0[4], Y1[4], y[4];
+                lds8(sy, Y0);
+                lds8(sy + SEG, Y1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) y[k] = fma2(Y1[k], f2(h_in), Y0[k]);
+                float *o = out_ptr + (long long)j * a.out_ds;
+                if (!TAIL || nvalid == ITEMS) {
+                    stg8(o, y);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (2 * k < nvalid) o[2 * k] = y[k].x;
+                        if (2 * k + 1 < nvalid) o[2 * k + 1] = y[k].y;
+                    }
                 }
             }
         }
-        exc_prev = exc_cur;
     }
 
     __syncthreads();
@@ -263,7 +270,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
 }
 
 template <bool SP>
-__global__ void __launch_bounds__(256, 3) scan_fwd_pipe_kernel(const __grid_constant__ ScanArgs a) {
+__global__ void __launch_bounds__(kPipeThreads, 3) scan_fwd_pipe_kernel(const __grid_constant__ ScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_fwd_pipe[];
     const int chunk = blockIdx.x / a.n_rowgroups;  // chunk-major: a tile only waits on tiles dispatched before it
     const int rg = blockIdx.x - chunk * a.n_rowgroups;
@@ -282,12 +289,13 @@ static int launch_fwd_pipe(const ScanArgs &a, int grid, cudaStream_t stream) {
             return rc;
         configured = true;
     }
-    scan_fwd_pipe_kernel<SP><<<grid, 256, smem, stream>>>(a);
+    scan_fwd_pipe_kernel<SP><<<grid, kPipeThreads, smem, stream>>>(a);
     return check_cuda(cudaGetLastError(), "scan_fwd_pipe launch");
 }
 
-// n_chunks > 1 only (then a row segment is the whole 2048-position chunk, one row per CTA)
+// n_chunks > 1 and at most kPipeStages channels per tile (scan_host.cu plans it so)
 int scan_fwd_pipe_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream) {
+    if (a.chan_per_tile > kPipeStages) return fail("scan_fwd_pipe: %d channels per tile (max %d)", a.chan_per_tile, kPipeStages);
     return a.softplus ? launch_fwd_pipe<true>(a, pl.grid, stream) : launch_fwd_pipe<false>(a, pl.grid, stream);
 }
 

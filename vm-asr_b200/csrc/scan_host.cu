@@ -50,7 +50,7 @@ static int validate(const vmasr_scan_params *p, bool bwd) {
     return 0;
 }
 
-static ScanPlan make_plan(const vmasr_scan_params *p, int n_chunks, int &chan_per_tile, int &n_ctiles) {
+static ScanPlan make_plan(const vmasr_scan_params *p, int n_chunks, bool bwd, int &chan_per_tile, int &n_ctiles) {
     ScanPlan pl;
     pl.items = 8;
     pl.threads = 256;
@@ -70,11 +70,12 @@ static ScanPlan make_plan(const vmasr_scan_params *p, int n_chunks, int &chan_pe
     if (want > max_ctiles) want = max_ctiles;
     chan_per_tile = (int)((cpg + want - 1) / want);
     {
-        // A tile walks its channels serially and every channel waits for the carry of the chunk before it, which the
-        // neighbouring CTA publishes at the same point of ITS walk: long walks skew the CTAs of a row against each
-        // other (measured: 4 channels per tile beats both 1 and 16 on every multi-chunk shape of the configs).
-        static const int cap_multi = [] { const char *e = getenv("VMASR_SCAN_CPT"); return e ? atoi(e) : 4; }();
-        if (cap_multi > 0 && n_chunks > 1 && chan_per_tile > cap_multi) chan_per_tile = cap_multi;
+        // Sequences of more than one chunk: the pipelined kernels keep the whole tile resident in shared memory
+        // (scan_fwd_pipe.cu / scan_bwd_pipe.cu), at most 4 channels.  VMASR_SCAN_CPT = 1..4 is a tuning knob.
+        static const int cap_multi = [] { const char *e = getenv("VMASR_SCAN_CPT"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : v > 4 ? 4 : v; }();
+        static const int cap_multi_fwd = [] { const char *e = getenv("VMASR_SCAN_CPT_FWD"); const int v = e ? atoi(e) : 3; return v < 1 ? 1 : v > 4 ? 4 : v; }();
+        const int cap = bwd ? cap_multi : (cap_multi < cap_multi_fwd ? cap_multi : cap_multi_fwd);  // measured: 3 (forward), 4 (backward)
+        if (n_chunks > 1 && chan_per_tile > cap) chan_per_tile = cap;
     }
     chan_per_tile = ((chan_per_tile + pl.rows - 1) / pl.rows) * pl.rows;
     n_ctiles = (cpg + chan_per_tile - 1) / chan_per_tile;
@@ -128,7 +129,7 @@ static int run(const vmasr_scan_params *p, bool bwd) {
     if (!guard.ok) return fail("selective_scan: cannot select CUDA device %d", p->device);
     const int n_chunks = (p->seqlen + VMASR_SCAN_CHUNK - 1) / VMASR_SCAN_CHUNK;
     int chan_per_tile = 1, n_ctiles = 1;
-    ScanPlan pl = make_plan(p, n_chunks, chan_per_tile, n_ctiles);
+    ScanPlan pl = make_plan(p, n_chunks, bwd, chan_per_tile, n_ctiles);
     ScanArgs a = make_args(p, n_chunks, chan_per_tile, n_ctiles);
     const size_t es = dtype_size(p->io_dtype);
     const long long vec_elems = 16 / (long long)es;
