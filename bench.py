@@ -13,7 +13,7 @@ the reference test's distributions.  Metric: algorithmic scan bytes (SURVEY.md 8
 * ``e2e``    : the same step through the public operator API (``selective_scan_cuda_core``-style ``fwd``/``bwd``),
                every call's inputs copied from pinned host memory and its outputs copied back, inside the timed
                region.
-* ``roofline``: the dominant kernel (backward, 256-thread row variant) timed launch by launch with CUDA events.
+* ``roofline``: the dominant kernel (backward, multi-chunk variant scan_bwd_pipe_kernel) timed launch by launch with CUDA events.
 * ``cpu_baseline`` / ``--impl reference``: the oracle's torch restatement of the reference's pure-PyTorch path
                (``selective_scan_ref`` + autograd-equivalent closed form) on the host cores, on a bounded sample.
 * N > 1 (torchrun): every rank runs the step on its own batch shard (weak scaling, no data-path collective);
@@ -202,11 +202,11 @@ class DeviceStep:
 
 
 def time_dominant_kernel(ds: DeviceStep, steps: int):
-    """CUDA events around every launch of the dominant kernel (selective-scan backward, 256-thread row variant:
-    every call with seqlen > 1024) on the launching stream.  The whole step is enqueued behind a device-side
+    """CUDA events around every launch of the dominant kernel (selective-scan backward, multi-chunk variant
+    scan_bwd_pipe_kernel: every call with seqlen > 2048) on the launching stream.  The whole step is enqueued behind a device-side
     delay without any host synchronisation in between, so the event pairs bracket kernel time and not the host's
     launch latency.  Returns (avg_ms, avg_algorithmic_bytes, launches per step)."""
-    idx = {i for i, (c, _, _) in enumerate(ds.calls) if c.L > 1024}
+    idx = {i for i, (c, _, _) in enumerate(ds.calls) if c.L > 2048}
     total_ms, total_bytes, n = 0.0, 0, 0
     B = ds.wl.batch
     for _ in range(steps):
@@ -472,7 +472,7 @@ def main():
             "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic,
-                         "kernel": "scan_bwd_tma_kernel<256,softplus> (csrc/scan_bwd_tma.cu), every backward call with seqlen > 1024", "launches_per_step": k_per_step,
+                         "kernel": "scan_bwd_pipe_kernel<softplus> (csrc/scan_bwd_pipe.cu), every backward call with seqlen > 2048 (18 of the 34 calls, 85 % of the backward bytes)", "launches_per_step": k_per_step,
                          "avg_launch_ms": round(k_ms, 5), "avg_algorithmic_bytes_per_launch": int(k_bytes),
                          "peak_source": peak_src},
             "cpu_baseline": cpu_base,

@@ -269,3 +269,35 @@ def test_torch_reference_chain_small():
                                       db.view(-1).cuda(), True)
     y = cross.CrossMerge.apply(ys.view(Bsz, 4, C, H, W))
     assert rel_err(y, ref.numpy()) < 2e-4  # einsums run in tf32-free fp32 on the GPU; summation order differs
+
+
+def test_ss2d_core_chain_forward_backward():
+    """vm_asr_b200.ss2d.ss2d_core (forward_corev2's chain on the library's operators) against the float64 torch oracle,
+    outputs and gradients of the map and of every parameter; multi-chunk map (L = 4608)."""
+    from vm_asr_b200 import ss2d
+    torch.manual_seed(2)
+    Bsz, C, H, W, N, R = 2, 8, 72, 64, 1, 2
+    names = ("x", "xw", "dw", "db", "A_logs", "Ds")
+    vals = (torch.randn(Bsz, C, H, W), torch.randn(4, R + 2 * N, C) * 0.3, torch.randn(4, C, R) * 0.3, torch.rand(4, C) * 0.5,
+            torch.log(torch.rand(4 * C, N) + 0.5), torch.ones(4 * C))
+    dy = torch.randn(Bsz, C, H * W)
+    ref_in = [v.double().requires_grad_() for v in vals]
+    ref = ss2d_ref.ss2d_core(*ref_in, dtype=torch.float64)
+    ref.backward(dy.double())
+    got_in = [v.cuda().requires_grad_() for v in vals]
+    got = ss2d.ss2d_core(*got_in)
+    got.backward(dy.cuda())
+    assert rel_err(got, ref.detach().numpy()) < 2e-4
+    for n, g, r in zip(names, got_in, ref_in):
+        assert rel_err(g.grad, r.grad.numpy()) < 5e-4, n
+
+
+def test_ring_variant_subprocess():
+    """The persistent ring variant of the multi-chunk forward kernel (scan_fwd_ring.cu, selected by VMASR_SCAN_FWD=ring)
+    passes the same config-shape parity checks; run in a subprocess because the variant is latched at first use."""
+    import os, subprocess, sys
+    env = dict(os.environ, VMASR_SCAN_FWD="ring", VMASR_SCAN_CPT_FWD="4")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.abspath(__file__), "-m", "gpu", "-k",
+                        "config_shapes_full_size or golden_vectors or ragged_shapes or cuda_graph_replay"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

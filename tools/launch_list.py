@@ -50,9 +50,8 @@ with open(out, "w") as f:
     for name, (n, t, by) in sorted(per.items(), key=lambda kv: -kv[1][1]):
         f.write(f"# {name},{n},{t:.1f},{t / max(t_ours, 1e-9):.3f},{t / n:.2f},{by / n:.0f}\n")
     f.write(f"# all launches profiled: {len(launches)}, total {t_all:.1f} us; ours: {len(ours)}, total {t_ours:.1f} us\n")
-# dominant kernel = the backward kernel launches of sequences longer than 1024 (256-thread rows: grid tiles of 2048 positions)
-dom = [e for _, e in ours if "scan_bwd_tma_kernel<256" in e["kernel"].replace(" ", "") or
-       ("scan_bwd_tma_kernel" in e["kernel"] and "256" in e["kernel"].split("<")[-1].split(",")[0])]
+# dominant kernel = the multi-chunk backward kernel (every backward call with seqlen > 2048)
+dom = [e for _, e in ours if "scan_bwd_pipe_kernel" in e["kernel"]]
 if dom:
     tr = sum(e.get("dram__bytes_read.sum", 0.0) + e.get("dram__bytes_write.sum", 0.0) for e in dom) / len(dom)
     json.dump({"traffic_bytes_per_launch": round(tr), "launches_averaged": len(dom),

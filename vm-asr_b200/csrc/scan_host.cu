@@ -12,6 +12,7 @@ int scan_fwd_tma_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t st
 int scan_bwd_tma_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
 int scan_fwd_pipe_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
 int scan_bwd_pipe_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
+int scan_fwd_ring_dispatch(const ScanArgs &a, const ScanPlan &pl, int device, cudaStream_t stream);
 constexpr int kMaxTileChannelsHost = 64;  // scan_fwd_tma.cu stages this many channels' parameters per tile
 
 static size_t dtype_size(int dt) { return dt == VMASR_F32 ? 4 : 2; }
@@ -158,6 +159,8 @@ static int run(const vmasr_scan_params *p, bool bwd) {
     static const bool fwd_nopipe = [] { const char *e = getenv("VMASR_SCAN_FWD"); return e && e[0] == 't'; }();
     if (fast && !fwd_generic) {
         // more than one chunk: the software-pipelined kernel (no CTA-wide barrier around the carry exchange)
+        static const bool fwd_ring = [] { const char *e = getenv("VMASR_SCAN_FWD"); return e && e[0] == 'r'; }();
+        if (n_chunks > 1 && fwd_ring && a.chan_per_group % a.chan_per_tile == 0) return scan_fwd_ring_dispatch(a, pl, p->device, stream);
         if (n_chunks > 1 && !fwd_nopipe) return scan_fwd_pipe_dispatch(a, pl, stream);
         return scan_fwd_tma_dispatch(a, pl, stream);
     }
