@@ -31,6 +31,35 @@ __device__ __forceinline__ void stg8(float *p, const float2 (&v)[4]) {
     reinterpret_cast<float4 *>(p)[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
 }
 
+// ---- bank-conflict-free variants ---------------------------------------------------------------------------------
+// A thread owns 32 contiguous bytes of a shared-memory row; a plain 128-bit access at a 32-byte thread stride makes lanes
+// t and t + 4 of every quarter-warp hit the same banks (2-way conflict: ncu counted 44 % of all shared wavefronts as
+// conflicts).  With sel = (thread >> 2) & 1, lanes with sel = 1 touch their SECOND 16-byte half first: every quarter-warp
+// then covers all 32 banks once.
+//   lds8_sw : data laid out linearly (written by TMA): swizzled access order + a register swap, result in logical order;
+//   *_priv  : data only this thread writes and reads back: logical half h lives at physical half h ^ sel, no swap.
+__device__ __forceinline__ void lds8_sw(const float *p, int sel, float2 (&v)[4]) {
+    const float4 a = *reinterpret_cast<const float4 *>(p + 4 * sel);
+    const float4 b = *reinterpret_cast<const float4 *>(p + 4 * (1 - sel));
+    const float4 lo = sel ? b : a, hi = sel ? a : b;
+    v[0] = make_float2(lo.x, lo.y);
+    v[1] = make_float2(lo.z, lo.w);
+    v[2] = make_float2(hi.x, hi.y);
+    v[3] = make_float2(hi.z, hi.w);
+}
+__device__ __forceinline__ void lds8_priv(const float *p, int sel, float2 (&v)[4]) {
+    const float4 lo = *reinterpret_cast<const float4 *>(p + 4 * sel);
+    const float4 hi = *reinterpret_cast<const float4 *>(p + 4 * (1 - sel));
+    v[0] = make_float2(lo.x, lo.y);
+    v[1] = make_float2(lo.z, lo.w);
+    v[2] = make_float2(hi.x, hi.y);
+    v[3] = make_float2(hi.z, hi.w);
+}
+__device__ __forceinline__ void sts8_priv(float *p, int sel, const float2 (&v)[4]) {
+    *reinterpret_cast<float4 *>(p + 4 * sel) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    *reinterpret_cast<float4 *>(p + 4 * (1 - sel)) = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+}
+
 // softplus of a position pair in the log2 domain.  x2 = (delta + bias) * log2(e); returns dt2 = softplus * log2(e).
 // lg2(1 + e) from the MUFU above e = 1/32, the alternating series below it (1 + e would round the small e away);
 // identity above the reference's threshold of 20 (selective_scan_fwd_kernel.cuh:117), tested on x2.

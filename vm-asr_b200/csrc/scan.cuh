@@ -33,6 +33,7 @@ struct ScanArgs {
     int n_ctiles;         // ceil(chan_per_group / chan_per_tile)
     int n_rowgroups;      // batch * ngroups * n_ctiles
     int softplus;
+    int debug_nowait;     // timing experiment only (VMASR_DEBUG_NOWAIT=1): do not wait for neighbours' aggregates -> WRONG results
     long long u_bs, u_ds, delta_bs, delta_ds, A_ds, A_ns, B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;
     long long out_bs, out_ds, dout_bs, dout_ds, du_bs, du_ds, ddelta_bs, ddelta_ds;
 };

@@ -120,21 +120,17 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
         }
         const int n_groups16 = (a.n_chunks + 15) >> 4;
         const int jrev = a.n_chunks - 1 - chunk;  // position of this chunk in the adjoint's scan order
-        CarryLook look[STAGES];
-        Aff cum_f[STAGES], cum_r[STAGES];
-        float h_chunk[STAGES];
         // per channel: publish the chunk's adjoint aggregate as soon as it exists and start its look-back; finish the
-        // look-back of the channel before (its loads have been in flight for one P1 sweep of the compute warps)
-        auto finish = [&](int j, const CarryLook &lk, const Aff &cf, const Aff &cr, float hc) {
+        // look-back of the channel before (its loads have been in flight for one P1 of the compute warps)
+        auto finish = [&](int j, CarryLook &l, const Aff &cf, const Aff &cr, float hc) {
             CarryEntry *l2_row = a.ws_entries2 + (seq0 + j) * n_groups16;
             const Aff before_f = shift_up1(cf, lane);
             const Aff before_r = shift_down1(cr, lane);
             const Aff total_r = {__shfl_sync(0xffffffffu, cr.p, 0), __shfl_sync(0xffffffffu, cr.q, 0)};
             bool ok;
             Aff grp = {1.0f, 0.0f};
-            CarryLook l = lk;
             Aff acc = look_reduce(l, epoch, lane, ok, grp);
-            acc = look_finish(l, acc, ok, l2_row, jrev, epoch, lane, grp);
+            if (!a.debug_nowait) acc = look_finish(l, acc, ok, l2_row, jrev, epoch, lane, grp);
             if (lane == 0 && (jrev & 15) == 15) {
                 const Aff g16 = compose(grp, total_r);
                 publish_entry(l2_row + (jrev >> 4), epoch, g16.p, g16.q);
@@ -144,30 +140,34 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_in[j]);
         };
+        CarryLook p_look;
+        p_look.ptr = nullptr;
+        p_look.e = make_uint4(0u, 0u, 0u, 0u);
+        Aff p_cf = {1.0f, 0.0f}, p_cr = {1.0f, 0.0f};
+        float p_h = 0.0f;
+#pragma unroll 1
+        for (int j = 0; j < n_iter; ++j) {
+            const long long seq = seq0 + j;
+            CarryEntry *l1_row = a.ws_entries + seq * a.n_chunks;
+            const float h_chunk = (chunk > 0) ? __ldg(a.x + (seq * a.n_chunks + (chunk - 1)) * 2 + 1) : 0.0f;
+            mbar_wait(&bar_tot[j], 0);
+            float4 t = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+            if (lane < WPR) t = s_tot[j * WPR + lane];
+            Aff cum_f = {t.x, t.y}, cum_r = {t.x, t.z};
 #pragma unroll
-        for (int j = 0; j < STAGES; ++j) {
-            if (j < n_iter) {
-                const long long seq = seq0 + j;
-                CarryEntry *l1_row = a.ws_entries + seq * a.n_chunks;
-                h_chunk[j] = (chunk > 0) ? __ldg(a.x + (seq * a.n_chunks + (chunk - 1)) * 2 + 1) : 0.0f;
-                mbar_wait(&bar_tot[j], 0);
-                float4 t = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
-                if (lane < WPR) t = s_tot[j * WPR + lane];
-                cum_f[j] = Aff{t.x, t.y};
-                cum_r[j] = Aff{t.x, t.z};
-#pragma unroll
-                for (int off = 1; off < WPR; off <<= 1) {
-                    scan_step_down(cum_r[j].p, cum_r[j].q, off);
-                    scan_step_up(cum_f[j].p, cum_f[j].q, off);
-                }
-                if (lane == 0) publish_entry(l1_row + jrev, epoch, cum_r[j].p, cum_r[j].q);
-                look[j] = look_issue(l1_row, a.ws_entries2 + seq * n_groups16, jrev, lane);
-                if (j >= 1) finish(j - 1, look[j - 1], cum_f[j - 1], cum_r[j - 1], h_chunk[j - 1]);
+            for (int off = 1; off < WPR; off <<= 1) {
+                scan_step_down(cum_r.p, cum_r.q, off);
+                scan_step_up(cum_f.p, cum_f.q, off);
             }
+            if (lane == 0) publish_entry(l1_row + jrev, epoch, cum_r.p, cum_r.q);
+            const CarryLook look = look_issue(l1_row, a.ws_entries2 + seq * n_groups16, jrev, lane);
+            if (j >= 1) finish(j - 1, p_look, p_cf, p_cr, p_h);
+            p_look = look;
+            p_cf = cum_f;
+            p_cr = cum_r;
+            p_h = h_chunk;
         }
-#pragma unroll
-        for (int j = 0; j < STAGES; ++j)
-            if (j == n_iter - 1) finish(j, look[j], cum_f[j], cum_r[j], h_chunk[j]);
+        finish(n_iter - 1, p_look, p_cf, p_cr, p_h);
         __syncthreads();  // every compute warp is done: the channel sums are complete
         if (lane < 3 * n_iter) {
             const int c = lane / 3, which = lane - 3 * c;
@@ -180,6 +180,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
     } else {
         // ================= compute warps =================
         const int pos = seg0 + threadIdx.x * ITEMS;
+        const int sel = (threadIdx.x >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
         int nvalid = ITEMS;
         if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
         float *du_ptr = reinterpret_cast<float *>(a.du) + b * a.du_bs + (long long)d0 * a.du_ds + pos;
@@ -188,7 +189,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
         float2 Bv[4], dBacc[4], dCacc[4];
         float *sC = s_c + threadIdx.x * ITEMS;  // this thread's C values (only this thread touches them)
         mbar_wait(bar_bc, 0);
-        lds8(s_b + threadIdx.x * ITEMS, Bv);
+        lds8_sw(s_b + threadIdx.x * ITEMS, sel, Bv);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             dBacc[k] = f2(0.0f);
@@ -196,7 +197,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
         }
         if (TAIL) {  // positions past the end contribute nothing and stay finite
             float2 Cv[4];
-            lds8(sC, Cv);
+            lds8_sw(sC, sel, Cv);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (2 * k >= nvalid) { Bv[k].x = 0.0f; Cv[k].x = 0.0f; }
@@ -206,20 +207,25 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
         }
         __syncthreads();
 
-        Aff excf[STAGES], excr[STAGES];
+        Aff excf[STAGES], excr[STAGES];  // registers: only constant indices below
 #pragma unroll
-        for (int j = 0; j < STAGES; ++j) {
-            if (j < n_iter) {
+        for (int i = 0; i < STAGES; ++i) {
+            excf[i] = Aff{1.0f, 0.0f};
+            excr[i] = Aff{1.0f, 0.0f};
+        }
+#pragma unroll 1
+        for (int j = 0; j < n_iter; ++j) {
+            {
                 // ---- P1(j) ----
                 const float Av = s_par[j];
                 const float bias2 = s_par[2 * STAGES + j];
                 float *su = s_stage + (size_t)j * 3 * SEG + threadIdx.x * ITEMS;
                 mbar_wait(&bar_full[j], 0);
                 float2 uv[4], dl[4], dy[4], Cv[4], dts[4];
-                lds8(su, uv);
-                lds8(su + SEG, dl);
-                lds8(su + 2 * SEG, dy);
-                lds8(sC, Cv);
+                lds8_sw(su, sel, uv);
+                lds8_sw(su + SEG, sel, dl);
+                lds8_sw(su + 2 * SEG, sel, dy);
+                lds8_sw(sC, sel, Cv);
                 if (TAIL) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -251,7 +257,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                     p *= av.y;
                     qr = fmaf(p, cdy.y, qr);
                 }
-                stg8(su + SEG, dts);
+                sts8_priv(su + SEG, sel, dts);
                 // two independent warp scans, interleaved level by level (each level is shuffle-latency bound)
                 Aff inc_f = {p, q}, inc_r = {p, qr};
 #pragma unroll
@@ -259,32 +265,44 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                     scan_step_up(inc_f.p, inc_f.q, off);
                     scan_step_down(inc_r.p, inc_r.q, off);
                 }
-                excf[j] = shift_up1(inc_f, lane);
-                excr[j] = shift_down1(inc_r, lane);
+                const Aff exf = shift_up1(inc_f, lane), exr = shift_down1(inc_r, lane);
+#pragma unroll
+                for (int i = 0; i < STAGES; ++i)
+                    if (i == j) {
+                        excf[i] = exf;
+                        excr[i] = exr;
+                    }
                 const float qr0 = __shfl_sync(0xffffffffu, inc_r.q, 0);
                 if (lane == 31) s_tot[j * WPR + warp] = make_float4(inc_f.p, inc_f.q, qr0, 0.0f);
                 __syncwarp();
                 if (lane == 31) mbar_arrive(&bar_tot[j]);
             }
         }
-#pragma unroll
-        for (int j = 0; j < STAGES; ++j) {
-            if (j < n_iter) {
+#pragma unroll 1
+        for (int j = 0; j < n_iter; ++j) {
+            {
                 // ---- P2(j) ----
+                Aff exf = excf[0], exr = excr[0];
+#pragma unroll
+                for (int i = 1; i < STAGES; ++i)
+                    if (i == j) {
+                        exf = excf[i];
+                        exr = excr[i];
+                    }
                 const float Av = s_par[j];
                 const float Dv = s_par[STAGES + j];
                 mbar_wait(&bar_in[j], 0);
                 const float2 in = s_in[j * WPR + warp];
                 const float *su = s_stage + (size_t)j * 3 * SEG + threadIdx.x * ITEMS;
                 float2 uv[4], dts[4], dy[4], Cv[4];
-                lds8(su, uv);
-                lds8(su + SEG, dts);
-                lds8(su + 2 * SEG, dy);
-                lds8(sC, Cv);
+                lds8_sw(su, sel, uv);
+                lds8_priv(su + SEG, sel, dts);
+                lds8_sw(su + 2 * SEG, sel, dy);
+                lds8_sw(sC, sel, Cv);
                 float2 av[4], bu[4], dtn[4], hs[4], gl[4];
                 // forward states of this thread's positions
                 {
-                    float h = fmaf(excf[j].p, in.x, excf[j].q);
+                    float h = fmaf(exf.p, in.x, exf.q);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const float2 da = mul2(dts[k], f2(Av));
@@ -300,7 +318,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                 }
                 // adjoint walk, right to left
                 {
-                    float G = fmaf(excr[j].p, in.y, excr[j].q);
+                    float G = fmaf(exr.p, in.y, exr.q);
 #pragma unroll
                     for (int k = 3; k >= 0; --k) {
                         const float2 cdy = mul2(Cv[k], dy[k]);

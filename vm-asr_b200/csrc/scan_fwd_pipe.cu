@@ -115,20 +115,17 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
             issue_stage(STAGES - 1);
         }
         const int n_groups16 = (a.n_chunks + 15) >> 4;
-        CarryLook look[STAGES];
-        Aff cum[STAGES];
         // per channel: publish the chunk aggregate as soon as it exists and start its look-back; finish the look-back of the
-        // channel before (its loads have been in flight for one P1 sweep of the compute warps)
-        auto finish = [&](int j, const CarryLook &lk, const Aff &cm) {
+        // channel before (its loads have been in flight for one P1 of the compute warps)
+        auto finish = [&](int j, CarryLook &l, const Aff &cm) {
             const long long seq = seq0 + j;
             CarryEntry *l2_row = a.ws_entries2 + seq * n_groups16;
             const Aff before = shift_up1(cm, lane);
             const Aff total = {__shfl_sync(0xffffffffu, cm.p, WPR - 1), __shfl_sync(0xffffffffu, cm.q, WPR - 1)};
             bool ok;
             Aff grp = {1.0f, 0.0f};
-            CarryLook l = lk;
             Aff acc = look_reduce(l, epoch, lane, ok, grp);
-            acc = look_finish(l, acc, ok, l2_row, chunk, epoch, lane, grp);
+            if (!a.debug_nowait) acc = look_finish(l, acc, ok, l2_row, chunk, epoch, lane, grp);
             if (lane == 0) {
                 if ((chunk & 15) == 15) {
                     const Aff g16 = compose(grp, total);
@@ -140,34 +137,36 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_in[j]);
         };
-#pragma unroll
-        for (int j = 0; j < STAGES; ++j) {
-            if (j < n_iter) {
-                const long long seq = seq0 + j;
-                CarryEntry *l1_row = a.ws_entries + seq * a.n_chunks;
-                mbar_wait(&bar_tot[j], 0);
-                const float2 t = (lane < WPR) ? s_tot[j * WPR + lane] : make_float2(1.0f, 0.0f);
-                cum[j] = warp_scan_up_fast<WPR>(Aff{t.x, t.y});
-                if (lane == WPR - 1) publish_entry(l1_row + chunk, epoch, cum[j].p, cum[j].q);
-                look[j] = look_issue(l1_row, a.ws_entries2 + seq * n_groups16, chunk, lane);
-                if (j >= 1) finish(j - 1, look[j - 1], cum[j - 1]);
-            }
+        CarryLook p_look;
+        p_look.ptr = nullptr;
+        p_look.e = make_uint4(0u, 0u, 0u, 0u);
+        Aff p_cum = {1.0f, 0.0f};
+#pragma unroll 1
+        for (int j = 0; j < n_iter; ++j) {
+            const long long seq = seq0 + j;
+            CarryEntry *l1_row = a.ws_entries + seq * a.n_chunks;
+            mbar_wait(&bar_tot[j], 0);
+            const float2 t = (lane < WPR) ? s_tot[j * WPR + lane] : make_float2(1.0f, 0.0f);
+            const Aff cum = warp_scan_up_fast<WPR>(Aff{t.x, t.y});
+            if (lane == WPR - 1) publish_entry(l1_row + chunk, epoch, cum.p, cum.q);
+            const CarryLook look = look_issue(l1_row, a.ws_entries2 + seq * n_groups16, chunk, lane);
+            if (j >= 1) finish(j - 1, p_look, p_cum);
+            p_look = look;
+            p_cum = cum;
         }
-        // the last channel (n_iter is uniform over the CTA; the loop above is unrolled, so index by constant)
-#pragma unroll
-        for (int j = 0; j < STAGES; ++j)
-            if (j == n_iter - 1) finish(j, look[j], cum[j]);
+        finish(n_iter - 1, p_look, p_cum);
     } else {
         // ================= compute warps =================
         const int pos = seg0 + threadIdx.x * ITEMS;
+        const int sel = (threadIdx.x >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
         int nvalid = ITEMS;
         if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
         float *out_ptr = reinterpret_cast<float *>(a.out) + b * a.out_bs + (long long)d0 * a.out_ds + pos;
 
         float2 Bl[4], Cv[4];  // ln2 * B (the scan runs on dt in the log2 domain) and C of this thread's positions
         mbar_wait(bar_bc, 0);
-        lds8(s_bc + threadIdx.x * ITEMS, Bl);
-        lds8(s_bc + SEG + threadIdx.x * ITEMS, Cv);
+        lds8_sw(s_bc + threadIdx.x * ITEMS, sel, Bl);
+        lds8_sw(s_bc + SEG + threadIdx.x * ITEMS, sel, Cv);
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -178,10 +177,12 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
             }
         }
 
-        Aff exc[STAGES];  // warp-exclusive prefix of this thread, per channel
+        Aff exc[STAGES];  // warp-exclusive prefix of this thread, per channel (registers: only constant indices below)
 #pragma unroll
-        for (int j = 0; j < STAGES; ++j) {
-            if (j < n_iter) {
+        for (int i = 0; i < STAGES; ++i) exc[i] = Aff{1.0f, 0.0f};
+#pragma unroll 1
+        for (int j = 0; j < n_iter; ++j) {
+            {
                 // ---- P1(j) ----
                 const float Av = s_par[j];
                 const float Dv = s_par[STAGES + j];
@@ -189,8 +190,8 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
                 float *su = s_stage + (size_t)j * 2 * SEG + threadIdx.x * ITEMS;
                 mbar_wait(&bar_full[j], 0);
                 float2 uv[4], dl[4], Y0[4], Y1[4];
-                lds8(su, uv);
-                lds8(su + SEG, dl);
+                lds8_sw(su, sel, uv);
+                lds8_sw(su + SEG, sel, dl);
                 float p = 1.0f, q = 0.0f;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -222,25 +223,32 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
                     Y0[k] = fma2(Cv[k], Q, mul2(uv[k], f2(Dv)));
                     Y1[k] = mul2(Cv[k], P);
                 }
-                stg8(su, Y0);
-                stg8(su + SEG, Y1);
+                sts8_priv(su, sel, Y0);
+                sts8_priv(su + SEG, sel, Y1);
                 const Aff inc = warp_scan_up_fast<32>(Aff{p, q});
-                exc[j] = shift_up1(inc, lane);
+                const Aff ex = shift_up1(inc, lane);
+#pragma unroll
+                for (int i = 0; i < STAGES; ++i)
+                    if (i == j) exc[i] = ex;
                 if (lane == 31) s_tot[j * WPR + warp] = make_float2(inc.p, inc.q);
                 __syncwarp();
                 if (lane == 31) mbar_arrive(&bar_tot[j]);
             }
         }
-#pragma unroll
-        for (int j = 0; j < STAGES; ++j) {
-            if (j < n_iter) {
+#pragma unroll 1
+        for (int j = 0; j < n_iter; ++j) {
+            {
                 // ---- P2(j) ----
+                Aff ex = exc[0];
+#pragma unroll
+                for (int i = 1; i < STAGES; ++i)
+                    if (i == j) ex = exc[i];
                 mbar_wait(&bar_in[j], 0);
-                const float h_in = fmaf(exc[j].p, s_in[j * WPR + warp], exc[j].q);
+                const float h_in = fmaf(ex.p, s_in[j * WPR + warp], ex.q);
                 const float *sy = s_stage + (size_t)j * 2 * SEG + threadIdx.x * ITEMS;
                 float2 Y0[4], Y1[4], y[4];
-                lds8(sy, Y0);
-                lds8(sy + SEG, Y1);
+                lds8_priv(sy, sel, Y0);
+                lds8_priv(sy + SEG, sel, Y1);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) y[k] = fma2(Y1[k], f2(h_in), Y0[k]);
                 float *o = out_ptr + (long long)j * a.out_ds;

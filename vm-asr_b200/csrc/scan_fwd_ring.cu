@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(kRingThreads, 3) scan_fwd_ring_kernel(const __
         // ================= compute warps =================
         ItemCursor cc;
         cc.init(a);
+        const int sel = (threadIdx.x >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
         float2 Bl[4], Cv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -223,8 +224,8 @@ __global__ void __launch_bounds__(kRingThreads, 3) scan_fwd_ring_kernel(const __
                         bias2 = (a.delta_bias ? __ldg(a.delta_bias + d) : 0.0f) * kLog2e;
                     }
                     mbar_wait(&bar_full[s], (unsigned)((k >> 2) & 1));
-                    lds8(su, Bl);
-                    lds8(su + SEG, Cv);
+                    lds8_sw(su, sel, Bl);
+                    lds8_sw(su + SEG, sel, Cv);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         Bl[i] = mul2(Bl[i], f2(kLn2));
@@ -248,8 +249,8 @@ __global__ void __launch_bounds__(kRingThreads, 3) scan_fwd_ring_kernel(const __
                     }
                     mbar_wait(&bar_full[s], (unsigned)((k >> 2) & 1));
                     float2 uv[4], dl[4], Y0[4], Y1[4];
-                    lds8(su, uv);
-                    lds8(su + SEG, dl);
+                    lds8_sw(su, sel, uv);
+                    lds8_sw(su + SEG, sel, dl);
                     float p = 1.0f, q = 0.0f;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -281,8 +282,8 @@ __global__ void __launch_bounds__(kRingThreads, 3) scan_fwd_ring_kernel(const __
                         Y0[i] = fma2(Cv[i], Q, mul2(uv[i], f2(Dc)));
                         Y1[i] = mul2(Cv[i], P);
                     }
-                    stg8(su, Y0);
-                    stg8(su + SEG, Y1);
+                    sts8_priv(su, sel, Y0);
+                    sts8_priv(su + SEG, sel, Y1);
                     const Aff inc = warp_scan_up_fast<32>(Aff{p, q});
                     exc[0] = shift_up1(inc, lane);
                     nv[0] = nvalid;
@@ -298,8 +299,8 @@ __global__ void __launch_bounds__(kRingThreads, 3) scan_fwd_ring_kernel(const __
                 const float h_in = fmaf(exc[LAG].p, s_in[sp * WPR + warp], exc[LAG].q);
                 const float *sy = s_stage + (size_t)sp * 2 * SEG + threadIdx.x * ITEMS;
                 float2 Y0[4], Y1[4], y[4];
-                lds8(sy, Y0);
-                lds8(sy + SEG, Y1);
+                lds8_priv(sy, sel, Y0);
+                lds8_priv(sy + SEG, sel, Y1);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) y[i] = fma2(Y1[i], f2(h_in), Y0[i]);
                 float *o = outp[LAG];

@@ -112,6 +112,8 @@ static ScanArgs make_args(const vmasr_scan_params *p, int n_chunks, int chan_per
     a.n_ctiles = n_ctiles;
     a.n_rowgroups = p->batch * p->ngroups * n_ctiles;
     a.softplus = p->delta_softplus;
+    static const int nowait = [] { const char *e = getenv("VMASR_DEBUG_NOWAIT"); return e ? atoi(e) : 0; }();
+    a.debug_nowait = nowait;
     a.u_bs = p->u_batch_stride; a.u_ds = p->u_d_stride;
     a.delta_bs = p->delta_batch_stride; a.delta_ds = p->delta_d_stride;
     a.A_ds = p->A_d_stride; a.A_ns = p->A_dstate_stride;
