@@ -46,6 +46,7 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
     const int warp_in_row = t_in_row >> 5;
     const int warp_slot = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int sel = (t_in_row >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
     const int L = a.seqlen;
     const int seg0 = chunk * SEG;
     const int pos = seg0 + t_in_row * ITEMS;
@@ -111,7 +112,7 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
 
     float2 Bv[4], dBacc[4], dCacc[4];
     mbar_wait(bar_bc, 0);
-    lds8(s_bc + t_in_row * ITEMS, Bv);
+    lds8_sw(s_bc + t_in_row * ITEMS, sel, Bv);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         dBacc[j] = f2(0.0f);
@@ -161,10 +162,10 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
         float2 dtn[4], av[4], bx[4], cdy[4];
         {
             float2 uv[4], dl[4], dy[4], Cv[4], sig[4];
-            lds8(su, uv);
-            lds8(su + SEG, dl);
-            lds8(su + 2 * SEG, dy);
-            lds8(s_bc + SEG + t_in_row * ITEMS, Cv);
+            lds8_sw(su, sel, uv);
+            lds8_sw(su + SEG, sel, dl);
+            lds8_sw(su + 2 * SEG, sel, dy);
+            lds8_sw(s_bc + SEG + t_in_row * ITEMS, sel, Cv);
             if (TAIL) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -195,7 +196,7 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
                 bx[j] = mul2(dtn[j], mul2(Bv[j], uv[j]));
                 cdy[j] = mul2(Cv[j], dy[j]);
             }
-            stg8(su + SEG, sig);
+            sts8_priv(su + SEG, sel, sig);
         }
         // local aggregates of both recurrences in one left-to-right walk:
         //   forward   s -> p s + q;      adjoint (entering from the right)  G -> p G + qr,  qr = sum_i (prod_{j<=i} a_j) C_i dout_i
@@ -290,9 +291,9 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
         }
         // gradients, position pairs
         float2 du[4], ddl[4], uv[4], dy[4], sig[4];
-        lds8(su, uv);
-        lds8(su + 2 * SEG, dy);
-        lds8(su + SEG, sig);
+        lds8_sw(su, sel, uv);
+        lds8_sw(su + 2 * SEG, sel, dy);
+        lds8_priv(su + SEG, sel, sig);
         float2 sA = f2(0.0f), sD = f2(0.0f), sB = f2(0.0f);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {

@@ -48,6 +48,7 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
     const int warp_in_row = t_in_row >> 5;
     const int warp_slot = threadIdx.x >> 5;  // row * WPR + warp_in_row
     const int lane = threadIdx.x & 31;
+    const int sel = (t_in_row >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
     const int L = a.seqlen;
     const int seg0 = chunk * SEG;                       // first position of the tile
     const int pos = seg0 + t_in_row * ITEMS;
@@ -110,8 +111,8 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
 
     float2 Bl[4], Cv[4];  // ln2 * B (the scan runs on dt in the log2 domain) and C of this thread's positions
     mbar_wait(bar_bc, 0);
-    lds8(s_bc + t_in_row * ITEMS, Bl);
-    lds8(s_bc + SEG + t_in_row * ITEMS, Cv);
+    lds8_sw(s_bc + t_in_row * ITEMS, sel, Bl);
+    lds8_sw(s_bc + SEG + t_in_row * ITEMS, sel, Cv);
     __syncthreads();  // B / C are in registers: the last stage is free for data now
     if (t_in_row == 0 && STAGES - 1 < n_iter) issue_stage(STAGES - 1);
 #pragma unroll
@@ -140,8 +141,8 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
         {
             const float *su = my_stage + (size_t)s * ROWS * 2 * SEG + t_in_row * ITEMS;
             float2 dl[4];
-            lds8(su, uv);
-            lds8(su + SEG, dl);
+            lds8_sw(su, sel, uv);
+            lds8_sw(su + SEG, sel, dl);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float2 dt2 = fma2(dl[j], f2(kLog2e), f2(bias2));
