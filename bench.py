@@ -354,7 +354,7 @@ def main():
         steps = max(1, min(args.steps, 5))
         gbs, ms, cores = run_cpu_reference(wl, steps, warm, args.cpu_sample_len)
         print(json.dumps({
-            "impl": "reference", "metric": "ss2d_scan_fwd_bwd_GBps", "value": round(gbs, 4), "unit": "GB/s", "n_gpus": 0,
+            "impl": "reference", "metric": "ss2d_scan_fwd_bwd_GBps", "value": round(gbs, 4), "unit": "GB/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl.yaml} SS2D selective-scan fwd+bwd (34 calls), batch {wl.batch}", "sample": sample_desc},

@@ -36,11 +36,12 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                                                    const unsigned epoch) {
     constexpr int NC = 256, ITEMS = 8, WPR = 8, SEG = NC * ITEMS, STAGES = kBPipeStages;
 
-    // shared memory carve-up (header 2048 bytes; [1016, 1024) is the tile ticket of the kernel wrapper)
+    // shared memory carve-up (header 2048 bytes)
     unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(smem);  // [STAGES] TMA completion
     unsigned long long *bar_bc = bar_full + STAGES;                               // B / C segment
     unsigned long long *bar_tot = bar_bc + 1;                                     // [STAGES] 8 arrivals
     unsigned long long *bar_in = bar_tot + STAGES;                                // [STAGES] 1 arrival
+    unsigned long long *bar_done = bar_in + STAGES;                                  // 8 arrivals: a compute warp has finished its sweeps
     float4 *s_tot = reinterpret_cast<float4 *>(smem + 128);                       // [STAGES][8] warp totals {p, q fwd, q adjoint, -}
     float2 *s_in = reinterpret_cast<float2 *>(smem + 640);                        // [STAGES][8] {h, g} entering each warp
     float *s_red = reinterpret_cast<float *>(smem + 896);                         // [STAGES][4] channel sums dA, dD, dbias
@@ -86,6 +87,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
             mbar_init(&bar_tot[i], WPR);
             mbar_init(&bar_in[i], 1);
         }
+        mbar_init(bar_done, WPR);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const float *Bg = reinterpret_cast<const float *>(a.B) + b * a.B_bs + g * a.B_gs + seg0;
         const float *Cg = reinterpret_cast<const float *>(a.C) + b * a.C_bs + g * a.C_gs + seg0;
@@ -112,7 +114,6 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
     const long long seq0 = (long long)b * a.dim + d0;
     if (exchange) {
         // ================= exchange warp =================
-        mbar_wait(bar_bc, 0);
         __syncthreads();  // the compute warps hold B in registers: the last stage is free for data now
         if (lane == 0 && STAGES - 1 < n_iter) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -168,7 +169,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
             p_h = h_chunk;
         }
         finish(n_iter - 1, p_look, p_cf, p_cr, p_h);
-        __syncthreads();  // every compute warp is done: the channel sums are complete
+        mbar_wait(bar_done, 0);  // every compute warp is done: the channel sums are complete
         if (lane < 3 * n_iter) {
             const int c = lane / 3, which = lane - 3 * c;
             const float v = s_red[c * 4 + which];
@@ -176,6 +177,17 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
             if (which == 0) atomicAdd(a.dA + d * a.A_ds, v);
             else if (which == 1) { if (a.dD) atomicAdd(a.dD + d, v); }
             else { if (a.ddelta_bias) atomicAdd(a.ddelta_bias + d, v); }
+        }
+        // last CTA out recycles the carry workspace for the next launch on this stream (only this warp wrote entries)
+        if (lane == 0) {
+            __threadfence();
+            const unsigned prev = atomicAdd(a.ws_header + 1, 1u);
+            if (prev == gridDim.x - 1) {
+                a.ws_header[0] = 0u;
+                a.ws_header[1] = 0u;
+                a.ws_header[2] = a.ws_header[2] + 1u;
+                __threadfence();
+            }
         }
     } else {
         // ================= compute warps =================
@@ -205,7 +217,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
             }
             stg8(sC, Cv);
         }
-        __syncthreads();
+        __syncthreads();  // (also keeps the register allocation of the sweeps below in check: without it ptxas spills 3x more)
 
         Aff excf[STAGES], excr[STAGES];  // registers: only constant indices below
 #pragma unroll
@@ -372,7 +384,8 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                 if ((lane & 7) == 0 && lane < 24) atomicAdd(s_red + j * 4 + (lane >> 3), r);
             }
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_done);  // this warp's shared-memory atomics are done (release)
 
         // dB / dC of this tile's positions, summed over the tile's channels
         float *dBg = a.dB + ((long long)b * a.ngroups + g) * (long long)L;
@@ -390,16 +403,15 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
             }
         }
     }
-    retire_tile(a);
 }
 
 template <bool SP>
 __global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const __grid_constant__ ScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_bwd_pipe[];
-    unsigned tile, epoch;
-    claim_tile(a, reinterpret_cast<unsigned *>(smem_bwd_pipe + 1016), tile, epoch);
-    const int chunk = a.n_chunks - 1 - (int)(tile / a.n_rowgroups);  // adjoint: high chunks first
-    const int rg = tile % a.n_rowgroups;
+    // adjoint: high chunks first; block order = scan order, so a tile only waits on tiles dispatched before it
+    const unsigned epoch = *reinterpret_cast<volatile unsigned *>(a.ws_header + 2) % 0xfffffffeu + 1u;
+    const int chunk = a.n_chunks - 1 - (int)(blockIdx.x / a.n_rowgroups);
+    const int rg = blockIdx.x % a.n_rowgroups;
     const bool tail = (chunk + 1) * 2048 > a.seqlen;
     if (tail) scan_bwd_pipe_body<true, SP>(a, smem_bwd_pipe, chunk, rg, epoch);
     else scan_bwd_pipe_body<false, SP>(a, smem_bwd_pipe, chunk, rg, epoch);

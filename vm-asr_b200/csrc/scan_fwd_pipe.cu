@@ -42,6 +42,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
     unsigned long long *bar_bc = bar_full + STAGES;                               // B / C segment
     unsigned long long *bar_tot = bar_bc + 1;                                     // [STAGES] 8 arrivals: warp totals written
     unsigned long long *bar_in = bar_tot + STAGES;                                // [STAGES] 1 arrival: entering states written
+    unsigned long long *bar_free = bar_in + STAGES;                               // 8 arrivals: B / C are in registers, their slot is free
     float2 *s_tot = reinterpret_cast<float2 *>(smem + 256);                       // [STAGES][8] warp totals (p, q)
     float *s_in = reinterpret_cast<float *>(smem + 512);                          // [STAGES][8] state entering each warp
     float *s_par = reinterpret_cast<float *>(smem + 1024);                        // [3][STAGES]
@@ -83,6 +84,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
             mbar_init(&bar_tot[i], WPR);
             mbar_init(&bar_in[i], 1);
         }
+        mbar_init(bar_free, WPR);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const float *Bg = reinterpret_cast<const float *>(a.B) + b * a.B_bs + g * a.B_gs + seg0;
         const float *Cg = reinterpret_cast<const float *>(a.C) + b * a.C_bs + g * a.C_gs + seg0;
@@ -108,11 +110,12 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
     const long long seq0 = (long long)b * a.dim + d0;  // (batch, channel) row of the tile's first channel
     if (exchange) {
         // ================= exchange warp =================
-        mbar_wait(bar_bc, 0);
-        __syncthreads();  // the compute warps hold B / C in registers: the last stage is free for data now
-        if (lane == 0 && STAGES - 1 < n_iter) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue_stage(STAGES - 1);
+        if (STAGES - 1 < n_iter) {
+            mbar_wait(bar_free, 0);  // the compute warps hold B / C in registers: the last stage is free for data now
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_stage(STAGES - 1);
+            }
         }
         const int n_groups16 = (a.n_chunks + 15) >> 4;
         // per channel: publish the chunk aggregate as soon as it exists and start its look-back; finish the look-back of the
@@ -155,6 +158,16 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
             p_cum = cum;
         }
         finish(n_iter - 1, p_look, p_cum);
+        // last CTA out recycles the carry workspace for the next launch on this stream (only this warp wrote entries)
+        if (lane == 0) {
+            __threadfence();
+            const unsigned prev = atomicAdd(a.ws_header + 1, 1u);
+            if (prev == gridDim.x - 1) {
+                a.ws_header[1] = 0u;
+                a.ws_header[2] = a.ws_header[2] + 1u;
+                __threadfence();
+            }
+        }
     } else {
         // ================= compute warps =================
         const int pos = seg0 + threadIdx.x * ITEMS;
@@ -167,7 +180,8 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
         mbar_wait(bar_bc, 0);
         lds8_sw(s_bc + threadIdx.x * ITEMS, sel, Bl);
         lds8_sw(s_bc + SEG + threadIdx.x * ITEMS, sel, Cv);
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             Bl[k] = mul2(Bl[k], f2(kLn2));
@@ -265,16 +279,6 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
         }
     }
 
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned prev = atomicAdd(a.ws_header + 1, 1u);
-        if (prev == gridDim.x - 1) {
-            a.ws_header[1] = 0u;
-            a.ws_header[2] = a.ws_header[2] + 1u;
-            __threadfence();
-        }
-    }
 }
 
 template <bool SP>
