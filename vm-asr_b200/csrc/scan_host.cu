@@ -74,8 +74,8 @@ static ScanPlan make_plan(const vmasr_scan_params *p, int n_chunks, bool bwd, in
         // Sequences of more than one chunk: the pipelined kernels keep the whole tile resident in shared memory
         // (scan_fwd_pipe.cu / scan_bwd_pipe.cu), at most 4 channels.  VMASR_SCAN_CPT = 1..4 is a tuning knob.
         static const int cap_multi = [] { const char *e = getenv("VMASR_SCAN_CPT"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : v > 4 ? 4 : v; }();
-        static const int cap_multi_fwd = [] { const char *e = getenv("VMASR_SCAN_CPT_FWD"); const int v = e ? atoi(e) : 3; return v < 1 ? 1 : v > 4 ? 4 : v; }();
-        const int cap = bwd ? cap_multi : (cap_multi < cap_multi_fwd ? cap_multi : cap_multi_fwd);  // measured: 3 (forward), 4 (backward)
+        static const int cap_multi_fwd = [] { const char *e = getenv("VMASR_SCAN_CPT_FWD"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : v > 4 ? 4 : v; }();
+        const int cap = bwd ? cap_multi : (cap_multi < cap_multi_fwd ? cap_multi : cap_multi_fwd);  // measured best: 4 for both
         if (n_chunks > 1 && chan_per_tile > cap) chan_per_tile = cap;
     }
     chan_per_tile = ((chan_per_tile + pl.rows - 1) / pl.rows) * pl.rows;
