@@ -257,35 +257,49 @@ class HostStep:
         self.copy_in, self.copy_out = torch.cuda.Stream(), torch.cuda.Stream()
 
     def step(self):
+        """Copies and kernels are ordered so that PCIe runs in both directions at once: forward inputs go up in call
+        order and every forward output goes down as soon as its call is done; `dout` goes up in reverse call order
+        behind them and every backward call's gradients go down as soon as they exist.  Consecutive steps overlap
+        the same way (the next step's uploads do not wait for this step's downloads)."""
         main = torch.cuda.current_stream()
-        dev_in, saved = [], []
+        n = len(self.host_in)
+        dev_in, saved = [None] * n, [None] * n
+        ready_fwd, ready_bwd = [None] * n, [None] * n
         with torch.cuda.stream(self.copy_in):
-            for inp in self.host_in:
-                dev_in.append({k: v.to(self.device, non_blocking=True) for k, v in inp.items()})
-                for v in dev_in[-1].values():
+            for i, inp in enumerate(self.host_in):
+                dev_in[i] = {k: v.to(self.device, non_blocking=True) for k, v in inp.items() if k != "dout"}
+                for v in dev_in[i].values():
                     v.record_stream(main)
-                ev = torch.cuda.Event()
-                ev.record()
-                dev_in[-1]["_ready"] = ev
-        pending = []
-        for i, d in enumerate(dev_in):
-            main.wait_event(d["_ready"])
-            out, x = self.scan.fwd(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], d["bias"], True, 1)
-            saved.append(x)
-            pending.append((i, {"out": out}))
-        for i in reversed(range(len(dev_in))):
-            d = dev_in[i]
-            du, ddelta, dA, dB, dC, dD, dbias = self.scan.bwd(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], d["bias"],
-                                                             d["dout"], saved[i], True, 1)
-            pending.append((i, dict(du=du, ddelta=ddelta, dA=dA, dB=dB, dC=dC, dD=dD, dbias=dbias)))
-        done = torch.cuda.Event()
-        done.record(main)
-        with torch.cuda.stream(self.copy_out):
-            self.copy_out.wait_event(done)
-            for i, outs in pending:
+                ready_fwd[i] = torch.cuda.Event()
+                ready_fwd[i].record()
+            for i in reversed(range(n)):
+                dout = self.host_in[i]["dout"].to(self.device, non_blocking=True)
+                dout.record_stream(main)
+                dev_in[i]["dout"] = dout
+                ready_bwd[i] = torch.cuda.Event()
+                ready_bwd[i].record()
+
+        def download(i, outs):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self.copy_out):
+                self.copy_out.wait_event(ev)
                 for k, v in outs.items():
                     v.record_stream(self.copy_out)
                     self.host_out[i][k].copy_(v, non_blocking=True)
+
+        for i in range(n):
+            d = dev_in[i]
+            main.wait_event(ready_fwd[i])
+            out, x = self.scan.fwd(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], d["bias"], True, 1)
+            saved[i] = x
+            download(i, {"out": out})
+        for i in reversed(range(n)):
+            d = dev_in[i]
+            main.wait_event(ready_bwd[i])
+            du, ddelta, dA, dB, dC, dD, dbias = self.scan.bwd(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], d["bias"],
+                                                             d["dout"], saved[i], True, 1)
+            download(i, dict(du=du, ddelta=ddelta, dA=dA, dB=dB, dC=dC, dD=dD, dbias=dbias))
         main.wait_stream(self.copy_out)
 
 

@@ -62,7 +62,8 @@ static ScanPlan make_plan(const vmasr_scan_params *p, int n_chunks, bool bwd, in
     // enough tiles to fill the machine a few times over, otherwise as many channels per tile as possible
     // (B/C stay in registers across a tile's channels and dB/dC need fewer atomics)
     const long long base_tiles = (long long)p->batch * p->ngroups * n_chunks;
-    const long long target = 2LL * sm_count(p->device);
+    static const int tiles_per_sm = [] { const char *e = getenv("VMASR_SCAN_TILES_PER_SM"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+    const long long target = (long long)tiles_per_sm * sm_count(p->device);
     const int max_ctiles = (cpg + pl.rows - 1) / pl.rows;
     long long want = (target + base_tiles - 1) / base_tiles;
     if (want < 1) want = 1;
