@@ -128,6 +128,9 @@ def test_reference_parametrisation(itype, seqlen, has_delta_bias, delta_softplus
     (2, 12, 4100, 4),     # ragged tail, three channels per group
     (1, 20, 6150, 2),     # length not a multiple of 4: scalar IO with look-back
     (3, 40, 300, 4),      # 10 channels per group, several rows per CTA with an idle row
+    (2, 20, 8196, 4),     # five channels per group: tiles of 4 + 1 channels, ragged last chunk (multi-chunk fast path)
+    (1, 8, 40964, 4),     # 21 chunks: level-2 look-back entries, ragged last chunk, two channels per group
+    (1, 28, 4104, 4),     # seven channels per group: tiles of 4 + 3 (both backward variants in one launch order)
 ])
 def test_ragged_shapes(Bsz, Dm, L, G):
     cpu, gpu = make_inputs(Bsz, Dm, L, G, 1, torch.float32)

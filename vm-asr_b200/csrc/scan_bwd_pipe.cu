@@ -40,7 +40,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
     unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(smem);  // [STAGES] TMA completion
     unsigned long long *bar_bc = bar_full + STAGES;                               // B / C segment
     unsigned long long *bar_tot = bar_bc + 1;                                     // [STAGES] 8 arrivals
-    unsigned long long *bar_in = bar_tot + STAGES;                                // [STAGES] 1 arrival
+    unsigned long long *bar_in = bar_tot + STAGES;                                // [STAGES] 8 arrivals (exchange-warp lanes)
     unsigned long long *bar_done = bar_in + STAGES;                                  // 8 arrivals: a compute warp has finished its sweeps
     float4 *s_tot = reinterpret_cast<float4 *>(smem + 128);                       // [STAGES][8] warp totals {p, q fwd, q adjoint, -}
     float2 *s_in = reinterpret_cast<float2 *>(smem + 640);                        // [STAGES][8] {h, g} entering each warp
@@ -85,7 +85,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
 #pragma unroll
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&bar_tot[i], WPR);
-            mbar_init(&bar_in[i], 1);
+            mbar_init(&bar_in[i], WPR);
         }
         mbar_init(bar_done, WPR);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -136,10 +136,10 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                 const Aff g16 = compose(grp, total_r);
                 publish_entry(l2_row + (jrev >> 4), epoch, g16.p, g16.q);
             }
-            if (lane < WPR)
+            if (lane < WPR) {  // every writer releases its own store
                 s_in[j * WPR + lane] = make_float2(fmaf(before_f.p, hc, before_f.q), fmaf(before_r.p, acc.q, before_r.q));
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_in[j]);
+                mbar_arrive(&bar_in[j]);
+            }
         };
         CarryLook p_look;
         p_look.ptr = nullptr;

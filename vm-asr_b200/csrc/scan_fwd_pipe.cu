@@ -41,7 +41,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
     unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(smem);  // [STAGES] TMA completion
     unsigned long long *bar_bc = bar_full + STAGES;                               // B / C segment
     unsigned long long *bar_tot = bar_bc + 1;                                     // [STAGES] 8 arrivals: warp totals written
-    unsigned long long *bar_in = bar_tot + STAGES;                                // [STAGES] 1 arrival: entering states written
+    unsigned long long *bar_in = bar_tot + STAGES;                                // [STAGES] 8 arrivals (exchange-warp lanes): entering states written
     unsigned long long *bar_free = bar_in + STAGES;                               // 8 arrivals: B / C are in registers, their slot is free
     float2 *s_tot = reinterpret_cast<float2 *>(smem + 256);                       // [STAGES][8] warp totals (p, q)
     float *s_in = reinterpret_cast<float *>(smem + 512);                          // [STAGES][8] state entering each warp
@@ -82,7 +82,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
 #pragma unroll
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&bar_tot[i], WPR);
-            mbar_init(&bar_in[i], 1);
+            mbar_init(&bar_in[i], WPR);
         }
         mbar_init(bar_free, WPR);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -136,9 +136,10 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
                 }
                 reinterpret_cast<float2 *>(a.x)[seq * a.n_chunks + chunk] = make_float2(total.p * acc.p, fmaf(total.p, acc.q, total.q));
             }
-            if (lane < WPR) s_in[j * WPR + lane] = fmaf(before.p, acc.q, before.q);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_in[j]);
+            if (lane < WPR) {  // every writer releases its own store
+                s_in[j * WPR + lane] = fmaf(before.p, acc.q, before.q);
+                mbar_arrive(&bar_in[j]);
+            }
         };
         CarryLook p_look;
         p_look.ptr = nullptr;

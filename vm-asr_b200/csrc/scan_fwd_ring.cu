@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kRingThreads, 3) scan_fwd_ring_kernel(const __
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(smem);  // [STAGES] TMA completion
     unsigned long long *bar_tot = bar_full + STAGES;                              // [STAGES] 8 arrivals
-    unsigned long long *bar_in = bar_tot + STAGES;                                // [STAGES] 1 arrival
+    unsigned long long *bar_in = bar_tot + STAGES;                                // [STAGES] 8 arrivals (exchange-warp lanes)
     float2 *s_tot = reinterpret_cast<float2 *>(smem + 256);                       // [STAGES][8] warp totals (p, q)
     float *s_in = reinterpret_cast<float *>(smem + 512);                          // [STAGES][8] state entering each warp
     float *s_stage = reinterpret_cast<float *>(smem + 2048);                      // [STAGES][2][SEG]
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kRingThreads, 3) scan_fwd_ring_kernel(const __
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_tot[i], WPR);
-            mbar_init(&bar_in[i], 1);
+            mbar_init(&bar_in[i], WPR);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -146,9 +146,10 @@ __global__ void __launch_bounds__(kRingThreads, 3) scan_fwd_ring_kernel(const __
                 }
                 reinterpret_cast<float2 *>(a.x)[p_seq * a.n_chunks + p_chunk] = make_float2(total.p * acc.p, fmaf(total.p, acc.q, total.q));
             }
-            if (lane < WPR) s_in[p_slot * WPR + lane] = fmaf(before.p, acc.q, before.q);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_in[p_slot]);
+            if (lane < WPR) {  // every writer releases its own store
+                s_in[p_slot * WPR + lane] = fmaf(before.p, acc.q, before.q);
+                mbar_arrive(&bar_in[p_slot]);
+            }
             pending = false;
         };
         for (int k = 0; k < K; ++k) {
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(kRingThreads, 3) scan_fwd_ring_kernel(const __
             if (k >= 1) issue_next();  // every compute warp is past P2(k - 1 - LAG): its slot takes item k + AHEAD
             if (cc.r == 0) {
                 if (pending) finish();
-                if (lane == 0) mbar_arrive(&bar_in[s]);  // nobody waits for it; keeps the slot's phase in step with k
+                if (lane < WPR) mbar_arrive(&bar_in[s]);  // nobody waits for it; keeps the slot's phase in step with k
             } else {
                 const long long seq = (long long)cc.b * a.dim + cc.d0 + cc.r - 1;
                 CarryEntry *l1_row = a.ws_entries + seq * a.n_chunks;

@@ -92,6 +92,7 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
         const int s = it % STAGES;
         unsigned long long *bar = my_bars + s * ROWS;
         float *dst = my_stage + (size_t)s * ROWS * 2 * SEG;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of the slot are ordered before the refill
         mbar_expect_tx(bar, 2u * seg_bytes);
         bulk_load(dst, u_src + it * u_step, seg_bytes, bar);
         bulk_load(dst + SEG, dl_src + it * dl_step, seg_bytes, bar);
