@@ -1,6 +1,7 @@
 // Error plumbing and small utilities of the C ABI (include/vmasr_b200.h).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -20,6 +21,11 @@ int fail(const char *fmt, ...) {
 int check_cuda(cudaError_t e, const char *what) {
     if (e == cudaSuccess) return 0;
     return fail("%s: %s", what, cudaGetErrorString(e));
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char *e = getenv("VMASR_PDL"); return e ? atoi(e) != 0 : false; }();
+    return on;
 }
 
 int sm_count(int device) {

@@ -408,6 +408,8 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
 template <bool SP, int STAGES>
 __global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const __grid_constant__ ScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_bwd_pipe[];
+    pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
     // adjoint: high chunks first; block order = scan order, so a tile only waits on tiles dispatched before it
     const unsigned epoch = *reinterpret_cast<volatile unsigned *>(a.ws_header + 2) % 0xfffffffeu + 1u;
     const int chunk = a.n_chunks - 1 - (int)(blockIdx.x / a.n_rowgroups);
@@ -427,8 +429,7 @@ static int launch_bwd_pipe(const ScanArgs &a, int grid, cudaStream_t stream) {
             return rc;
         configured = true;
     }
-    scan_bwd_pipe_kernel<SP, STAGES><<<grid, kBPipeThreads, smem, stream>>>(a);
-    return check_cuda(cudaGetLastError(), "scan_bwd_pipe launch");
+    return launch_pdl(scan_bwd_pipe_kernel<SP, STAGES>, grid, kBPipeThreads, smem, stream, "scan_bwd_pipe launch", a);
 }
 
 // n_chunks > 1 and at most kBPipeStages channels per tile (scan_host.cu plans it so)

@@ -385,6 +385,8 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
 template <int TPR, bool SP>
 __global__ void __launch_bounds__(256, 2) scan_bwd_tma_kernel(const __grid_constant__ ScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_bwd_tma[];
+    pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
     constexpr int SEG = TPR * 8;
     unsigned tile, epoch;
     claim_tile(a, reinterpret_cast<unsigned *>(smem_bwd_tma + 384), tile, epoch);
@@ -410,8 +412,7 @@ static int launch_tma(const ScanArgs &a, int grid, cudaStream_t stream) {
             return rc;
         configured = true;
     }
-    scan_bwd_tma_kernel<TPR, SP><<<grid, 256, smem, stream>>>(a);
-    return check_cuda(cudaGetLastError(), "scan_bwd_tma launch");
+    return launch_pdl(scan_bwd_tma_kernel<TPR, SP>, grid, 256, smem, stream, "scan_bwd_tma launch", a);
 }
 
 template <bool SP>

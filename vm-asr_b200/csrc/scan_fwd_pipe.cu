@@ -285,6 +285,8 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
 template <bool SP>
 __global__ void __launch_bounds__(kPipeThreads, 3) scan_fwd_pipe_kernel(const __grid_constant__ ScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_fwd_pipe[];
+    pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
     const int chunk = blockIdx.x / a.n_rowgroups;  // chunk-major: a tile only waits on tiles dispatched before it
     const int rg = blockIdx.x - chunk * a.n_rowgroups;
     const bool tail = (chunk + 1) * 2048 > a.seqlen;
@@ -302,8 +304,7 @@ static int launch_fwd_pipe(const ScanArgs &a, int grid, cudaStream_t stream) {
             return rc;
         configured = true;
     }
-    scan_fwd_pipe_kernel<SP><<<grid, kPipeThreads, smem, stream>>>(a);
-    return check_cuda(cudaGetLastError(), "scan_fwd_pipe launch");
+    return launch_pdl(scan_fwd_pipe_kernel<SP>, grid, kPipeThreads, smem, stream, "scan_fwd_pipe launch", a);
 }
 
 // n_chunks > 1 and at most kPipeStages channels per tile (scan_host.cu plans it so)

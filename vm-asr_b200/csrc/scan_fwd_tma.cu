@@ -264,6 +264,8 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
 template <int TPR, bool SP, int STAGES>
 __global__ void __launch_bounds__(256, 3) scan_fwd_tma_kernel(const __grid_constant__ ScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_fwd_tma[];
+    pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
+    pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
     constexpr int SEG = TPR * 8;
     const int chunk = blockIdx.x / a.n_rowgroups;
     const int rg = blockIdx.x - chunk * a.n_rowgroups;
@@ -284,8 +286,7 @@ static int launch_tma(const ScanArgs &a, int grid, cudaStream_t stream) {
             return rc;
         configured = true;
     }
-    scan_fwd_tma_kernel<TPR, SP, STAGES><<<grid, 256, smem, stream>>>(a);
-    return check_cuda(cudaGetLastError(), "scan_fwd_tma launch");
+    return launch_pdl(scan_fwd_tma_kernel<TPR, SP, STAGES>, grid, 256, smem, stream, "scan_fwd_tma launch", a);
 }
 
 template <bool SP, int STAGES>
