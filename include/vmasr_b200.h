@@ -103,6 +103,12 @@ typedef struct vmasr_scan_params {
 } vmasr_scan_params;
 
 VMASR_API uint64_t vmasr_scan_workspace_bytes(int batch, int dim, int seqlen, int dstate);
+/* Host-side planning only (no device access, no launch): validates `p` exactly as vmasr_scan_fwd / vmasr_scan_bwd would
+ * (same return codes and messages, mirroring the TORCH_CHECKs of selective_scan.cpp:165-215, 262-317) and reports how the
+ * call would be run: out[0] = grid size (tiles), out[1] = kernel family (0 generic, 1 single-chunk fast path, 2 multi-chunk
+ * fast path, 3 persistent ring), out[2] = channels per tile, out[3] = channel tiles per B/C group, out[4] = chunks per
+ * sequence, out[5] = threads per row segment.  Pointers in `p` are only tested for null and 16-byte alignment. */
+VMASR_API int vmasr_scan_plan(const vmasr_scan_params *p, int backward, int32_t *out);
 VMASR_API int vmasr_scan_fwd(const vmasr_scan_params *p);
 VMASR_API int vmasr_scan_bwd(const vmasr_scan_params *p);
 

@@ -46,6 +46,7 @@ EXPORTS = {
     "vmasr_abi_version": (ctypes.c_int, []),
     "vmasr_last_error": (ctypes.c_char_p, []),
     "vmasr_scan_workspace_bytes": (_u64, [ctypes.c_int] * 4),
+    "vmasr_scan_plan": (ctypes.c_int, [ctypes.POINTER(ScanParams), ctypes.c_int, ctypes.POINTER(ctypes.c_int32)]),
     "vmasr_scan_fwd": (ctypes.c_int, [ctypes.POINTER(ScanParams)]),
     "vmasr_scan_bwd": (ctypes.c_int, [ctypes.POINTER(ScanParams)]),
     "vmasr_cross_scan": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),

@@ -74,14 +74,14 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 64) s_red[threadIdx.x] = 0.0f;
-    for (int i = threadIdx.x; i < 3 * n_chan; i += NT) {
-        const int which = i / n_chan, cc = i - which * n_chan;
+    // the parameter loads start first, but nothing waits for them until the bulk copies below are on their way
+    float par_v = 0.0f;
+    if ((int)threadIdx.x < 3 * n_chan) {  // 3 * n_chan <= 192 < NT
+        const int which = threadIdx.x / n_chan, cc = threadIdx.x - which * n_chan;
         const int d = d0 + cc;
-        float v;
-        if (which == 0) v = __ldg(a.A + d * a.A_ds);
-        else if (which == 1) v = a.D ? __ldg(a.D + d) : 0.0f;
-        else v = (a.delta_bias ? __ldg(a.delta_bias + d) : 0.0f) * kLog2e;
-        s_par[which * kBwdMaxTileChannels + cc] = v;
+        if (which == 0) par_v = __ldg(a.A + d * a.A_ds);
+        else if (which == 1) par_v = a.D ? __ldg(a.D + d) : 0.0f;
+        else par_v = (a.delta_bias ? __ldg(a.delta_bias + d) : 0.0f) * kLog2e;
     }
     __syncthreads();
 
@@ -109,6 +109,11 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
         for (int s = 0; s < STAGES; ++s)
             if (s < n_iter) issue_stage(s);
     }
+    if ((int)threadIdx.x < 3 * n_chan) {
+        const int which = threadIdx.x / n_chan, cc = threadIdx.x - which * n_chan;
+        s_par[which * kBwdMaxTileChannels + cc] = par_v;
+    }
+    __syncthreads();
 
     float2 Bv[4], dBacc[4], dCacc[4];
     mbar_wait(bar_bc, 0);

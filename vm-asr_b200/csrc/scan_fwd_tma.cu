@@ -75,14 +75,14 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
     }
     if (a.n_chunks > 1) epoch = *reinterpret_cast<volatile unsigned *>(a.ws_header + 2) % 0xfffffffeu + 1u;
     // per-channel parameters of the tile
-    for (int i = threadIdx.x; i < 3 * n_chan; i += NT) {
-        const int which = i / n_chan, cc = i - which * n_chan;
+    // the parameter loads start first, but nothing waits for them until the bulk copies below are on their way
+    float par_v = 0.0f;
+    if ((int)threadIdx.x < 3 * n_chan) {  // 3 * n_chan <= 192 < NT
+        const int which = threadIdx.x / n_chan, cc = threadIdx.x - which * n_chan;
         const int d = d0 + cc;
-        float v;
-        if (which == 0) v = __ldg(a.A + d * a.A_ds);
-        else if (which == 1) v = a.D ? __ldg(a.D + d) : 0.0f;
-        else v = (a.delta_bias ? __ldg(a.delta_bias + d) : 0.0f) * kLog2e;
-        s_par[which * kMaxTileChannels + cc] = v;
+        if (which == 0) par_v = __ldg(a.A + d * a.A_ds);
+        else if (which == 1) par_v = a.D ? __ldg(a.D + d) : 0.0f;
+        else par_v = (a.delta_bias ? __ldg(a.delta_bias + d) : 0.0f) * kLog2e;
     }
     __syncthreads();
 
@@ -109,6 +109,11 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
         for (int s = 0; s < STAGES - 1; ++s)
             if (s < n_iter) issue_stage(s);
     }
+    if ((int)threadIdx.x < 3 * n_chan) {
+        const int which = threadIdx.x / n_chan, cc = threadIdx.x - which * n_chan;
+        s_par[which * kMaxTileChannels + cc] = par_v;
+    }
+    __syncthreads();
 
     float2 Bl[4], Cv[4];  // ln2 * B (the scan runs on dt in the log2 domain) and C of this thread's positions
     mbar_wait(bar_bc, 0);

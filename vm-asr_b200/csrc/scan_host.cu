@@ -127,14 +127,15 @@ static ScanArgs make_args(const vmasr_scan_params *p, int n_chunks, int chan_per
     return a;
 }
 
-static int run(const vmasr_scan_params *p, bool bwd) {
+enum ScanVariant { kGeneric = 0, kSingleChunk = 1, kMultiChunk = 2, kRing = 3 };
+
+// Everything the launch needs, decided on the host without touching the device (also behind vmasr_scan_plan).
+static int decide(const vmasr_scan_params *p, bool bwd, ScanPlan &pl, ScanArgs &a, int &variant) {
     if (int rc = validate(p, bwd)) return rc;
-    DeviceGuard guard(p->device);
-    if (!guard.ok) return fail("selective_scan: cannot select CUDA device %d", p->device);
     const int n_chunks = (p->seqlen + VMASR_SCAN_CHUNK - 1) / VMASR_SCAN_CHUNK;
     int chan_per_tile = 1, n_ctiles = 1;
-    ScanPlan pl = make_plan(p, n_chunks, bwd, chan_per_tile, n_ctiles);
-    ScanArgs a = make_args(p, n_chunks, chan_per_tile, n_ctiles);
+    pl = make_plan(p, n_chunks, bwd, chan_per_tile, n_ctiles);
+    a = make_args(p, n_chunks, chan_per_tile, n_ctiles);
     const size_t es = dtype_size(p->io_dtype);
     const long long vec_elems = 16 / (long long)es;
     auto mult = [&](long long s) { return s % vec_elems == 0; };
@@ -145,28 +146,35 @@ static int run(const vmasr_scan_params *p, bool bwd) {
                  aligned16(p->dC) && mult(p->dout_batch_stride) && mult(p->dout_d_stride) && mult(p->du_batch_stride) &&
                  mult(p->du_d_stride) && mult(p->ddelta_batch_stride) && mult(p->ddelta_d_stride) && (p->seqlen % 4 == 0);
     }
-    cudaStream_t stream = static_cast<cudaStream_t>(p->stream);
-    // fast path: fp32, d_state 1, 16-byte aligned rows -> TMA-staged packed-fp32x2 kernels
-    // (VMASR_SCAN_FWD=generic / VMASR_SCAN_BWD=generic force the generic ones)
-    static const bool fwd_generic = [] { const char *e = getenv("VMASR_SCAN_FWD"); return e && e[0] == 'g'; }();
-    static const bool bwd_generic = [] { const char *e = getenv("VMASR_SCAN_BWD"); return e && e[0] == 'g'; }();
+    // fast path: fp32, d_state 1, 16-byte aligned rows -> TMA-staged packed-fp32x2 kernels; more than one chunk: the
+    // kernels with the exchange warp (scan_*_pipe.cu).  VMASR_SCAN_FWD / VMASR_SCAN_BWD = generic | tma | ring
+    static const char fwd_force = [] { const char *e = getenv("VMASR_SCAN_FWD"); return e ? e[0] : '\0'; }();
+    static const char bwd_force = [] { const char *e = getenv("VMASR_SCAN_BWD"); return e ? e[0] : '\0'; }();
+    const char force = bwd ? bwd_force : fwd_force;
     const bool fast = p->io_dtype == VMASR_F32 && p->dstate == 1 && pl.vec && a.chan_per_tile <= kMaxTileChannelsHost;
+    if (!fast || force == 'g') variant = kGeneric;
+    else if (n_chunks > 1 && !bwd && force == 'r' && a.chan_per_group % a.chan_per_tile == 0) variant = kRing;
+    else if (n_chunks > 1 && force != 't') variant = kMultiChunk;
+    else variant = kSingleChunk;
+    return 0;
+}
+
+static int run(const vmasr_scan_params *p, bool bwd) {
+    ScanPlan pl;
+    ScanArgs a;
+    int variant = kGeneric;
+    if (int rc = decide(p, bwd, pl, a, variant)) return rc;
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail("selective_scan: cannot select CUDA device %d", p->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(p->stream);
     if (bwd) {
-        static const bool bwd_nopipe = [] { const char *e = getenv("VMASR_SCAN_BWD"); return e && e[0] == 't'; }();
-        if (fast && !bwd_generic) {
-            if (n_chunks > 1 && !bwd_nopipe) return scan_bwd_pipe_dispatch(a, pl, stream);
-            return scan_bwd_tma_dispatch(a, pl, stream);
-        }
+        if (variant == kMultiChunk) return scan_bwd_pipe_dispatch(a, pl, stream);
+        if (variant == kSingleChunk) return scan_bwd_tma_dispatch(a, pl, stream);
         return scan_bwd_dispatch(a, pl, p->io_dtype, stream);
     }
-    static const bool fwd_nopipe = [] { const char *e = getenv("VMASR_SCAN_FWD"); return e && e[0] == 't'; }();
-    if (fast && !fwd_generic) {
-        // more than one chunk: the software-pipelined kernel (no CTA-wide barrier around the carry exchange)
-        static const bool fwd_ring = [] { const char *e = getenv("VMASR_SCAN_FWD"); return e && e[0] == 'r'; }();
-        if (n_chunks > 1 && fwd_ring && a.chan_per_group % a.chan_per_tile == 0) return scan_fwd_ring_dispatch(a, pl, p->device, stream);
-        if (n_chunks > 1 && !fwd_nopipe) return scan_fwd_pipe_dispatch(a, pl, stream);
-        return scan_fwd_tma_dispatch(a, pl, stream);
-    }
+    if (variant == kRing) return scan_fwd_ring_dispatch(a, pl, p->device, stream);
+    if (variant == kMultiChunk) return scan_fwd_pipe_dispatch(a, pl, stream);
+    if (variant == kSingleChunk) return scan_fwd_tma_dispatch(a, pl, stream);
     return scan_fwd_dispatch(a, pl, p->io_dtype, stream);
 }
 
@@ -180,6 +188,21 @@ extern "C" uint64_t vmasr_scan_workspace_bytes(int batch, int dim, int seqlen, i
     const uint64_t cap = (uint64_t)batch * dim * dstate * (n_chunks + n_groups);
     const uint64_t bytes = 64 + 16 * cap;
     return (bytes + 255) / 256 * 256;
+}
+
+extern "C" int vmasr_scan_plan(const vmasr_scan_params *p, int backward, int32_t *out) {
+    if (!out) return vmasr::fail("vmasr_scan_plan: null output");
+    vmasr::ScanPlan pl;
+    vmasr::ScanArgs a;
+    int variant = 0;
+    if (int rc = vmasr::decide(p, backward != 0, pl, a, variant)) return rc;
+    out[0] = pl.grid;
+    out[1] = variant;
+    out[2] = a.chan_per_tile;
+    out[3] = a.n_ctiles;
+    out[4] = a.n_chunks;
+    out[5] = pl.tpr;
+    return 0;
 }
 
 extern "C" int vmasr_scan_fwd(const vmasr_scan_params *p) { return vmasr::run(p, false); }
