@@ -300,7 +300,8 @@ class HostStep:
             du, ddelta, dA, dB, dC, dD, dbias = self.scan.bwd(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], d["bias"],
                                                              d["dout"], saved[i], True, 1)
             download(i, dict(du=du, ddelta=ddelta, dA=dA, dB=dB, dC=dC, dD=dD, dbias=dbias))
-        main.wait_stream(self.copy_out)
+        # no join here: the next step's uploads and kernels may start while this step's last gradients are still on
+        # their way down (stream order keeps the pinned output buffers consistent); the timed loop ends with a device sync
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -344,7 +345,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vm_asr_48k_MPD")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-sample-len", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -17,6 +17,8 @@ import ctypes
 
 import torch
 
+import contextlib
+
 from . import _lib
 from ._lib import ScanParams
 
@@ -59,6 +61,15 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_NO_SWITCH = contextlib.nullcontext()
+
+
+def _device_of(t):
+    """Device guard only when the tensor does not live on the current device (the common case costs nothing)."""
+    idx = t.device.index
+    return _NO_SWITCH if idx is None or idx == torch.cuda.current_device() else torch.cuda.device(t.device)
+
+
 def _fill_common(p: ScanParams, u, delta, A, B, C, D, delta_bias, dims, delta_softplus):
     batch, dim, seqlen, dstate, ngroups = dims
     p.u, p.delta, p.A, p.B, p.C = u.data_ptr(), delta.data_ptr(), A.data_ptr(), B.data_ptr(), C.data_ptr()
@@ -82,12 +93,12 @@ def _fill_common(p: ScanParams, u, delta, A, B, C, D, delta_bias, dims, delta_so
     return n_chunks
 
 
-def fwd_out(u, delta, A, B, C, D, delta_bias, delta_softplus, out, x):
+def fwd_out(u, delta, A, B, C, D, delta_bias, delta_softplus, out, x, _dims=None):
     """Launch the forward into caller-provided ``out`` (like delta) and ``x`` (batch, dim, n_chunks, 2*dstate)
     float32.  No allocation: usable under CUDA-graph capture (the stream's carry workspace must already exist,
     i.e. one eager call first)."""
     lib = _lib.load_library()
-    dims = _validate(u, delta, A, B, C, D, delta_bias)
+    dims = _dims if _dims is not None else _validate(u, delta, A, B, C, D, delta_bias)
     batch, dim, seqlen, dstate, _ = dims
     n_chunks = (seqlen + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
     _check(out.dtype == u.dtype and tuple(out.shape) == (batch, dim, seqlen) and (out.stride(-1) == 1 or seqlen == 1),
@@ -95,7 +106,7 @@ def fwd_out(u, delta, A, B, C, D, delta_bias, delta_softplus, out, x):
     _check(x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (batch, dim, n_chunks, 2 * dstate),
            "selective_scan: x has the wrong shape")
     p = ScanParams()
-    with torch.cuda.device(u.device):
+    with _device_of(u):
         _fill_common(p, u, delta, A, B, C, D, delta_bias, dims, delta_softplus)
         p.out, p.x = out.data_ptr(), x.data_ptr()
         p.out_batch_stride, p.out_d_stride = out.stride(0), out.stride(1)
@@ -110,15 +121,15 @@ def fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=
     n_chunks = (seqlen + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
     out = torch.empty_like(delta)
     x = torch.empty((batch, dim, n_chunks, 2 * dstate), dtype=torch.float32, device=u.device)
-    fwd_out(u, delta, A, B, C, D, delta_bias, delta_softplus, out, x)
+    fwd_out(u, delta, A, B, C, D, delta_bias, delta_softplus, out, x, _dims=dims)
     return [out, x]
 
 
-def bwd_out(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, du, ddelta, dA, dB, dC, dD, ddelta_bias):
+def bwd_out(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, du, ddelta, dA, dB, dC, dD, ddelta_bias, _dims=None):
     """Launch the backward into caller-provided buffers.  ``dA, dB, dC, dD, ddelta_bias`` are float32 and are
     ACCUMULATED INTO (zero them first); ``dB, dC`` are (batch, n_groups, dstate, seqlen) contiguous."""
     lib = _lib.load_library()
-    dims = _validate(u, delta, A, B, C, D, delta_bias)
+    dims = _dims if _dims is not None else _validate(u, delta, A, B, C, D, delta_bias)
     batch, dim, seqlen, dstate, ngroups = dims
     _check(dout.dtype == u.dtype, "selective_scan: dout must have the dtype of u")
     _lib.require_cuda(dout, "dout")
@@ -135,7 +146,7 @@ def bwd_out(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, du, ddelt
                f"selective_scan: {name} must be contiguous float32 (batch, n_groups, dstate, seqlen)")
     _check(dA.dtype == torch.float32 and dA.stride() == A.stride(), "selective_scan: dA must look like A")
     p = ScanParams()
-    with torch.cuda.device(u.device):
+    with _device_of(u):
         _fill_common(p, u, delta, A, B, C, D, delta_bias, dims, delta_softplus)
         p.dout, p.x = dout.data_ptr(), _ptr(x)
         p.du, p.ddelta, p.dA, p.dB, p.dC = du.data_ptr(), ddelta.data_ptr(), dA.data_ptr(), dB.data_ptr(), dC.data_ptr()
@@ -152,12 +163,19 @@ def bwd(u, delta, A, B, C, D, delta_bias, dout, x=None, delta_softplus=False, nr
     batch, dim, seqlen, dstate, ngroups = dims
     du = torch.empty_like(u)
     ddelta = torch.empty_like(delta)
-    dA = torch.zeros_like(A)
-    dB = torch.zeros((batch, ngroups, dstate, seqlen), dtype=torch.float32, device=u.device)
-    dC = torch.zeros((batch, ngroups, dstate, seqlen), dtype=torch.float32, device=u.device)
-    dD = torch.zeros_like(D) if D is not None else None
-    dbias = torch.zeros_like(delta_bias) if delta_bias is not None else None
-    bwd_out(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, du, ddelta, dA, dB, dC, dD, dbias)
+    # the five accumulated gradients (selective_scan.cpp:319-327 allocates five zero tensors) share ONE zero-filled
+    # buffer: one memset launch per call instead of five; dB / dC first so that they stay 16-byte aligned
+    n_bc = batch * ngroups * dstate * seqlen
+    n_bc_pad = (n_bc + 3) // 4 * 4
+    n_a = dim * dstate
+    flat = torch.zeros(2 * n_bc_pad + n_a + 2 * dim, dtype=torch.float32, device=u.device)
+    dB = flat[:n_bc].view(batch, ngroups, dstate, seqlen)
+    dC = flat[n_bc_pad:n_bc_pad + n_bc].view(batch, ngroups, dstate, seqlen)
+    off = 2 * n_bc_pad
+    dA = flat[off:off + n_a].view(dim, dstate) if A.is_contiguous() else torch.zeros_like(A)
+    dD = flat[off + n_a:off + n_a + dim] if D is not None else None
+    dbias = flat[off + n_a + dim:off + n_a + 2 * dim] if delta_bias is not None else None
+    bwd_out(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, du, ddelta, dA, dB, dC, dD, dbias, _dims=dims)
     return [du, ddelta, dA, dB.to(B.dtype), dC.to(C.dtype), dD, dbias]
 
 
