@@ -83,3 +83,24 @@ def test_argument_checks_mirror_reference():
         scan.fwd(u.double(), u.double(), torch.zeros(4, 1), torch.zeros(1, 1, 1, 8).double(), torch.zeros(1, 1, 1, 8).double())
     with pytest.raises(RuntimeError, match="A must be float32"):
         scan.fwd(u, u, torch.zeros(4, 1).half(), torch.zeros(1, 1, 1, 8), torch.zeros(1, 1, 1, 8))
+
+
+def test_header_is_valid_c_and_the_library_links_from_c(tmp_path):
+    """include/vmasr_b200.h compiles as C99 (-Wall -Wextra -pedantic) and a plain C program links the shared library and
+    gets plans, sizes and error text back without a GPU (tests/c/abi_smoke.c)."""
+    import shutil
+    import subprocess
+    import vm_asr_b200
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    vm_asr_b200.load_library()
+    libdir = os.path.dirname(vm_asr_b200.library_path())
+    exe = str(tmp_path / "abi_smoke")
+    build = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                            os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-L", libdir, "-lvmasr_b200",
+                            "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert "family 2" in run.stdout
