@@ -29,6 +29,17 @@ struct DeviceGuard {
 
 int sm_count(int device);
 
+// One-time-per-DEVICE flag for function attributes (cudaFuncSetAttribute is per device context: a process that drives
+// several GPUs must set the dynamic shared-memory limit on each of them).
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool &operator()() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+        return done[dev];
+    }
+};
+
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
 // The scan kernels of a model run back to back on one stream.  Launched with the programmatic-stream-serialization
 // attribute, the CTAs of kernel N + 1 are scheduled while the last wave of kernel N drains; they park on

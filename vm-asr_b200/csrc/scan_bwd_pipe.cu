@@ -422,12 +422,12 @@ __global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const _
 template <bool SP, int STAGES>
 static int launch_bwd_pipe(const ScanArgs &a, int grid, cudaStream_t stream) {
     const size_t smem = 2048 + sizeof(float) * (2048 + (size_t)STAGES * 3 * 2048);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;  // the attribute is per function and per device
+    if (!configured()) {
         if (int rc = check_cuda(cudaFuncSetAttribute(scan_bwd_pipe_kernel<SP, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "scan_bwd_pipe smem attribute"))
             return rc;
-        configured = true;
+        configured() = true;
     }
     return launch_pdl(scan_bwd_pipe_kernel<SP, STAGES>, grid, kBPipeThreads, smem, stream, "scan_bwd_pipe launch", a);
 }

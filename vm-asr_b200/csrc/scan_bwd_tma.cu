@@ -410,12 +410,12 @@ static size_t scan_bwd_tma_smem(int tpr) {
 template <int TPR, bool SP>
 static int launch_tma(const ScanArgs &a, int grid, cudaStream_t stream) {
     const size_t smem = scan_bwd_tma_smem(TPR);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;  // the attribute is per function and per device
+    if (!configured()) {
         if (int rc = check_cuda(cudaFuncSetAttribute(scan_bwd_tma_kernel<TPR, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "scan_bwd_tma smem attribute"))
             return rc;
-        configured = true;
+        configured() = true;
     }
     return launch_pdl(scan_bwd_tma_kernel<TPR, SP>, grid, 256, smem, stream, "scan_bwd_tma launch", a);
 }

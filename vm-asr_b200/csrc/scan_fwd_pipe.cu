@@ -297,12 +297,12 @@ __global__ void __launch_bounds__(kPipeThreads, 3) scan_fwd_pipe_kernel(const __
 template <bool SP>
 static int launch_fwd_pipe(const ScanArgs &a, int grid, cudaStream_t stream) {
     const size_t smem = 2048 + sizeof(float) * ((size_t)kPipeStages * 2 * 2048);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;  // the attribute is per function and per device
+    if (!configured()) {
         if (int rc = check_cuda(cudaFuncSetAttribute(scan_fwd_pipe_kernel<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "scan_fwd_pipe smem attribute"))
             return rc;
-        configured = true;
+        configured() = true;
     }
     return launch_pdl(scan_fwd_pipe_kernel<SP>, grid, kPipeThreads, smem, stream, "scan_fwd_pipe launch", a);
 }

@@ -334,7 +334,8 @@ __global__ void __launch_bounds__(kRingThreads, 3) scan_fwd_ring_kernel(const __
 template <bool SP, int LAG>
 static int launch_fwd_ring(const ScanArgs &a, int n_tiles, int device, cudaStream_t stream) {
     const size_t smem = 2048 + sizeof(float) * ((size_t)kRingStages * 2 * 2048);
-    static int slots = 0;  // resident CTAs on the device (every CTA of the grid must be resident: they wait on each other)
+    static int slots_of[64] = {};  // resident CTAs per device (every CTA of the grid must be resident: they wait on each other)
+    int &slots = slots_of[device >= 0 && device < 64 ? device : 0];
     if (slots == 0) {
         if (int rc = check_cuda(cudaFuncSetAttribute(scan_fwd_ring_kernel<SP, LAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "scan_fwd_ring smem attribute"))

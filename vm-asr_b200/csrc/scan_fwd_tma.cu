@@ -284,12 +284,12 @@ static size_t scan_fwd_tma_smem(int stages) { return 2048 + sizeof(float) * ((si
 template <int TPR, bool SP, int STAGES>
 static int launch_tma(const ScanArgs &a, int grid, cudaStream_t stream) {
     const size_t smem = scan_fwd_tma_smem(STAGES);
-    static bool configured = false;  // attribute is per function; setting it repeatedly is harmless
-    if (!configured) {
+    static PerDeviceOnce configured;  // the attribute is per function and per device
+    if (!configured()) {
         if (int rc = check_cuda(cudaFuncSetAttribute(scan_fwd_tma_kernel<TPR, SP, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "scan_fwd_tma smem attribute"))
             return rc;
-        configured = true;
+        configured() = true;
     }
     return launch_pdl(scan_fwd_tma_kernel<TPR, SP, STAGES>, grid, 256, smem, stream, "scan_fwd_tma launch", a);
 }
