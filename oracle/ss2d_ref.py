@@ -202,6 +202,37 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, dtyp
     return cross_merge(ys.reshape(Bsz, K, C, H, W))
 
 
+def ss2d_core_storage_order(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, dtype=torch.float32):
+    """The SS2D core computed the way the planned fused kernel will, as a check of that plan's
+    algebra: no `xs` / `ys` copies.  Directions 0/2 work on the map in row-major STORAGE order, directions 1/3 on one
+    transposed copy (column-major storage order); `delta`, `B`, `C` come from un-replicated einsums over the storage order;
+    the time-reversed directions (2, 3) read every positional tensor of their group back to front and write their outputs
+    back to front; outputs are summed per storage order (y0 + y2, y1 + y3) and the column-major plane is transposed back once.
+    Must equal `ss2d_core` (the reference's chain, vmamba.py:1472-1497) up to summation order of the einsums."""
+    Bsz, C, H, W = x.shape
+    K, _, R = dt_projs_weight.shape
+    N = A_logs.shape[1]
+    L = H * W
+    src = [x.reshape(Bsz, C, L), x.transpose(2, 3).reshape(Bsz, C, L)]   # row-major map, column-major map (one copy)
+    As = -torch.exp(A_logs.float()).reshape(K, C, N)
+    Dk = Ds.float().reshape(K, C)
+    bias = dt_projs_bias.float().reshape(K, C)
+    planes = [None, None]
+    for k in range(K):
+        s = src[k & 1]                                                     # storage order of this direction's pair
+        x_dbl = torch.einsum("bdl,cd->bcl", s, x_proj_weight[k])           # (B, R + 2N, L), storage order
+        dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=1)
+        dts = torch.einsum("brl,dr->bdl", dts, dt_projs_weight[k])         # (B, C, L), storage order
+        rev = k >= 2
+        tf = (lambda t: t.flip(-1)) if rev else (lambda t: t)              # reversed directions: back to front
+        out = selective_scan(tf(s).float(), tf(dts).float(), As[k], tf(Bs).unsqueeze(1).float().contiguous(),
+                             tf(Cs).unsqueeze(1).float().contiguous(), Dk[k], bias[k], True, dtype=dtype)
+        out = tf(out)                                                      # written back to front: storage order again
+        planes[k & 1] = out if planes[k & 1] is None else planes[k & 1] + out   # y0 + y2, y1 + y3
+    y_cm = planes[1].reshape(Bsz, C, W, H).transpose(2, 3).reshape(Bsz, C, L)
+    return planes[0] + y_cm
+
+
 def scan_algorithmic_bytes(Bsz, Dm, L, G, N, itemsize=4):
     """bytes the scan must move, forward and backward."""
     fwd = itemsize * (3 * Bsz * Dm * L + 2 * Bsz * G * N * L)

@@ -133,3 +133,18 @@ def test_ss2d_core_chain_shapes():
     y = ss2d_ref.ss2d_core(x, torch.randn(4, R + 2 * N, C), torch.randn(4, C, R), torch.rand(4, C),
                            torch.zeros(4 * C, N), torch.ones(4 * C))
     assert y.shape == (B, C, H * W) and torch.isfinite(y).all()
+
+
+def test_fused_core_plan_is_algebraically_the_reference_chain():
+    """The storage-order formulation the fused SS2D kernel is planned on (no xs / ys copies, reversed
+    directions read back to front, two output planes merged by one transpose-add) equals the reference's chain
+    (ss2d_core, pinned above) -- non-square map, float64 accumulation."""
+    torch.manual_seed(7)
+    Bsz, C, H, W, N, R = 2, 6, 9, 14, 1, 2
+    x = torch.randn(Bsz, C, H, W, dtype=torch.float64)
+    xw, dw, db = torch.randn(4, R + 2 * N, C, dtype=torch.float64) * 0.3, torch.randn(4, C, R, dtype=torch.float64) * 0.3, torch.rand(4, C) * 0.5
+    A_logs, Ds = torch.log(torch.rand(4 * C, N) + 0.5), torch.randn(4 * C)
+    ref = ss2d_ref.ss2d_core(x, xw, dw, db, A_logs, Ds, dtype=torch.float64)
+    got = ss2d_ref.ss2d_core_storage_order(x, xw, dw, db, A_logs, Ds, dtype=torch.float64)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() < 1e-5 * ref.abs().max().item()   # the scan inputs pass through float32 on both sides
