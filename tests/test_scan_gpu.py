@@ -131,6 +131,7 @@ def test_reference_parametrisation(itype, seqlen, has_delta_bias, delta_softplus
     (2, 20, 8196, 4),     # five channels per group: tiles of 4 + 1 channels, ragged last chunk (multi-chunk fast path)
     (1, 8, 40964, 4),     # 21 chunks: level-2 look-back entries, ragged last chunk, two channels per group
     (1, 28, 4104, 4),     # seven channels per group: tiles of 4 + 3 (both backward variants in one launch order)
+    (1, 4, 614400, 2),    # 300 chunks: more than the 272 one look-back round covers (second round of level-2 entries)
 ])
 def test_ragged_shapes(Bsz, Dm, L, G):
     cpu, gpu = make_inputs(Bsz, Dm, L, G, 1, torch.float32)
