@@ -11,7 +11,7 @@ CPU restatement, in plain torch, of the reference's SS2D hot path:
                                            written out as the closed-form adjoint recurrence.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this
-module.  The shipped operators in ``vm-asr_b200/`` never do: they call the CUDA library or raise.
+module.  The shipped operators in ``vm_asr_b200/`` never do: they call the CUDA library or raise.
 
 Parity of this restatement is PINNED: ``tests/test_oracle_golden.py`` checks every function here against
 fixtures under ``tests/golden/`` that ``oracle/make_golden.py`` produced by importing and running the

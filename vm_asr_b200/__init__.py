@@ -1,7 +1,5 @@
-"""Import alias: the package lives in ``vm-asr_b200/`` (not a Python identifier), so this stub package
-extends its search path to that directory.  ``import vm_asr_b200.scan`` loads ``vm-asr_b200/scan.py``."""
-import os as _os
+"""vm_asr_b200 -- the SS2D + STFT hot path of VM-ASR on B200 (sm_100a).
 
-__path__.append(_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "vm-asr_b200"))
-
-from ._lib import library_path, load_library  # noqa: E402,F401
+Python operator surface (the reference is Python) over the C ABI of ``include/vmasr_b200.h``; the CUDA library is
+``vm_asr_b200/lib/libvmasr_b200.so``, built from ``vm_asr_b200/csrc``.  No CPU path, no fallback."""
+from ._lib import library_path, load_library  # noqa: F401

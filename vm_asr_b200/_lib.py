@@ -2,7 +2,7 @@
 
 There is no fallback: if the CUDA library has not been built, or a tensor is not on a CUDA device, the
 operators raise.  Build with ``python -c "import __graft_entry__ as g; g.build()"`` or
-``make -C vm-asr_b200/csrc``.
+``make -C vm_asr_b200/csrc``.
 """
 from __future__ import annotations
 
@@ -69,7 +69,7 @@ def load_library():
             if _lib is None:
                 if not os.path.exists(_LIB_PATH):
                     raise RuntimeError(
-                        f"vmasr_b200: CUDA library not built ({_LIB_PATH} missing). Run `make -C vm-asr_b200/csrc` "
+                        f"vmasr_b200: CUDA library not built ({_LIB_PATH} missing). Run `make -C vm_asr_b200/csrc` "
                         "(needs nvcc, sm_100a). There is no CPU or PyTorch fallback for these operators.")
                 lib = ctypes.CDLL(_LIB_PATH)
                 for name, (res, args) in EXPORTS.items():
