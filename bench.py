@@ -135,9 +135,10 @@ class DeviceStep:
     """All buffers of one step on the device (distinct per call: ~5.4 GB touched per step >> 126 MB L2) and the
     CUDA graph that replays it."""
 
-    def __init__(self, wl, device):
+    def __init__(self, wl, device, pairing="grouped"):
         from vm_asr_b200 import scan
-        self.scan, self.wl, self.device = scan, wl, device
+        self.scan, self.wl, self.device, self.pairing = scan, wl, device, pairing
+        self.side = None
         gen = torch.Generator(device=device).manual_seed(1234)
         self.calls = []
         acc_floats = 0
@@ -174,12 +175,53 @@ class DeviceStep:
         self.scan.bwd_out(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], inp["dout"], b["x"],
                           True, b["du"], b["ddelta"], b["dA"], b["dB"], b["dC"], b["dD"], b["dbias"])
 
+    # The generator's two streams (magnitude, phase) issue the same-shape SS2D call independently between their interaction
+    # points (model/model.py:1124-1127, 1167-1176): calls 2j and 2j + 1 of the workload are such a pair.
+    def fwd_pair(self, i):
+        args, outs = [], []
+        for k in (i, i + 1):
+            c, inp, b = self.calls[k]
+            args.append((inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], True))
+            outs.append((b["out"], b["x"]))
+        self.scan.fwd_grouped(args, outs)
+
+    def bwd_pair(self, i):
+        args, outs = [], []
+        for k in (i, i + 1):
+            c, inp, b = self.calls[k]
+            args.append((inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], inp["dout"], b["x"], True))
+            outs.append((b["du"], b["ddelta"], b["dA"], b["dB"], b["dC"], b["dD"], b["dbias"]))
+        self.scan.bwd_grouped(args, outs)
+
+    def _two_streams(self, fn, i):
+        """call i on the current stream, call i + 1 on a side stream, joined afterwards (a fork / join inside the graph)"""
+        main = torch.cuda.current_stream()
+        if self.side is None:
+            self.side = torch.cuda.Stream()
+        self.side.wait_stream(main)
+        fn(i)
+        with torch.cuda.stream(self.side):
+            fn(i + 1)
+        main.wait_stream(self.side)
+
     def run_eager(self):
         self.arena.zero_()
-        for i in range(len(self.calls)):
-            self.fwd_call(i)
-        for i in reversed(range(len(self.calls))):
-            self.bwd_call(i)
+        n = len(self.calls)
+        if self.pairing == "grouped":
+            for i in range(0, n, 2):
+                self.fwd_pair(i)
+            for i in reversed(range(0, n, 2)):
+                self.bwd_pair(i)
+        elif self.pairing == "streams":
+            for i in range(0, n, 2):
+                self._two_streams(self.fwd_call, i)
+            for i in reversed(range(0, n, 2)):
+                self._two_streams(self.bwd_call, i)
+        else:
+            for i in range(n):
+                self.fwd_call(i)
+            for i in reversed(range(n)):
+                self.bwd_call(i)
 
     def capture(self):
         self.run_eager()  # creates this stream's carry workspace before capture
@@ -198,15 +240,19 @@ class DeviceStep:
     def step(self):
         self.graph.replay()
 
-    gpu_launches_per_step = property(lambda self: 2 * len(self.calls))
+    gpu_launches_per_step = property(lambda self: len(self.calls) if self.pairing == "grouped" else 2 * len(self.calls))
 
 
 def time_dominant_kernel(ds: DeviceStep, steps: int):
     """CUDA events around every launch of the dominant kernel (selective-scan backward, multi-chunk variant
     scan_bwd_pipe_kernel: every call with seqlen > 2048) on the launching stream.  The whole step is enqueued behind a device-side
     delay without any host synchronisation in between, so the event pairs bracket kernel time and not the host's
-    launch latency.  Returns (avg_ms, avg_algorithmic_bytes, launches per step)."""
-    idx = {i for i, (c, _, _) in enumerate(ds.calls) if c.L > 2048}
+    launch latency.  With grouped pairing one launch covers the two calls of a pair.  Returns (avg_ms, avg_algorithmic_bytes,
+    launches per step)."""
+    grouped = ds.pairing == "grouped"
+    stride = 2 if grouped else 1
+    n_calls = len(ds.calls)
+    idx = {i for i in range(0, n_calls, stride) if ds.calls[i][0].L > 2048}
     total_ms, total_bytes, n = 0.0, 0, 0
     B = ds.wl.batch
     for _ in range(steps):
@@ -214,22 +260,22 @@ def time_dominant_kernel(ds: DeviceStep, steps: int):
         torch.cuda.synchronize()
         torch.cuda._sleep(20_000_000)  # ~10 ms of device-side delay: the host gets ahead of the GPU
         ds.arena.zero_()
-        for i in range(len(ds.calls)):
-            ds.fwd_call(i)
-        for i in reversed(range(len(ds.calls))):
+        for i in range(0, n_calls, stride):
+            ds.fwd_pair(i) if grouped else ds.fwd_call(i)
+        for i in reversed(range(0, n_calls, stride)):
             if i in idx:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                ds.bwd_call(i)
+                ds.bwd_pair(i) if grouped else ds.bwd_call(i)
                 e1.record()
                 pairs.append((i, e0, e1))
             else:
-                ds.bwd_call(i)
+                ds.bwd_pair(i) if grouped else ds.bwd_call(i)
         torch.cuda.synchronize()
         for i, e0, e1 in pairs:
             c = ds.calls[i][0]
             total_ms += e0.elapsed_time(e1)
-            total_bytes += 4 * (5 * B * c.D * c.L + 4 * B * 4 * c.L)
+            total_bytes += stride * 4 * (5 * B * c.D * c.L + 4 * B * 4 * c.L)
             n += 1
     return total_ms / n, total_bytes / n, n // steps
 
@@ -350,6 +396,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly (profiling aid)")
+    ap.add_argument("--pairing", default="grouped", choices=["grouped", "streams", "none"],
+                    help="how the two generator streams' same-shape calls are issued: one grouped launch per pair (default), "
+                         "two CUDA streams, or one call after the other")
     args = ap.parse_args()
 
     from vm_asr_b200 import workload as W
@@ -393,7 +442,7 @@ def main():
         cpu_base = {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample_desc,
                     "ms_per_sample_step": round(ms, 1)}
 
-    ds = DeviceStep(wl, device)
+    ds = DeviceStep(wl, device, args.pairing)
     if args.no_graph:
         ds.step = ds.run_eager
         ds.run_eager()
@@ -477,7 +526,7 @@ def main():
                             f"batch {wl.batch} per GPU, d_state 1, 4 groups",
                 "algorithmic_bytes_per_step": step_bytes, "scan_elements_per_step": wl.scan_elements(),
                 "l2": "inputs larger than L2: every call has its own buffers, ~5.4 GB touched per step vs 126 MB L2",
-                "launch": "eager launches" if args.no_graph else "one CUDA graph per step", "parallelism": f"dp{world}" if world > 1 else "single",
+                "launch": "eager launches" if args.no_graph else "one CUDA graph per step", "pairing": args.pairing, "parallelism": f"dp{world}" if world > 1 else "single",
                 "collective": "NCCL all-reduce of a 3.01M-float gradient buffer per step" if world > 1 else "none",
             },
             "frac_of_hbm_peak": round(value / world / peak, 4), "hbm_peak_gbs": peak, "hbm_peak_source": peak_src,

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define VMASR_ABI_VERSION 1
+#define VMASR_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define VMASR_API __attribute__((visibility("default")))
@@ -98,9 +98,22 @@ typedef struct vmasr_scan_params {
     int32_t io_dtype;       /* enum vmasr_dtype */
     int32_t delta_softplus; /* softplus(delta + delta_bias), identity above 20 (fwd_kernel.cuh:117) */
     int32_t device;         /* CUDA device ordinal the pointers live on */
-    int32_t reserved;
+    int32_t flags;          /* VMASR_SCAN_* bits below; 0 = the reference's semantics */
     void *stream; /* cudaStream_t */
 } vmasr_scan_params;
+
+/* flags (fast path only: float32, d_state 1, seqlen a multiple of 4, 16-byte aligned rows and strides; otherwise the call
+ * fails).  They exist for the fused SS2D core, whose directions 2 and 3 are directions 0 and 1 run back to front
+ * (model/vmamba.py:33, 54-55), and whose four outputs are summed (vmamba.py:55-60).
+ *   VMASR_SCAN_REVERSE    : time runs against memory order: position l of the recurrence is element seqlen-1-l of u, delta,
+ *                           B, C, out (dout, du, ddelta, dB, dC).  Every tensor keeps its memory layout; x (chunk states) is
+ *                           indexed in time order.
+ *   VMASR_SCAN_ACCUMULATE : `out` (forward) and `du` (backward) are ADDED INTO with 128-bit reductions instead of stored;
+ *                           the caller zero-fills them. */
+#define VMASR_SCAN_REVERSE 1
+#define VMASR_SCAN_ACCUMULATE 2
+/* most problems one grouped launch takes */
+#define VMASR_SCAN_MAX_GROUP 8
 
 VMASR_API uint64_t vmasr_scan_workspace_bytes(int batch, int dim, int seqlen, int dstate);
 /* Host-side planning only (no device access, no launch): validates `p` exactly as vmasr_scan_fwd / vmasr_scan_bwd would
@@ -111,6 +124,12 @@ VMASR_API uint64_t vmasr_scan_workspace_bytes(int batch, int dim, int seqlen, in
 VMASR_API int vmasr_scan_plan(const vmasr_scan_params *p, int backward, int32_t *out);
 VMASR_API int vmasr_scan_fwd(const vmasr_scan_params *p);
 VMASR_API int vmasr_scan_bwd(const vmasr_scan_params *p);
+/* n <= VMASR_SCAN_MAX_GROUP independent calls as ONE grid (same device and stream, one carry workspace EACH).  The two
+ * streams of the generator issue the same-shape SS2D call independently (model/model.py:1167-1176, 1124-1127): launched
+ * together they fill the machine where one call alone is a 0.6 - 1.7 wave launch.  Problems that need different kernel
+ * families are launched family by family; results are identical to n separate calls. */
+VMASR_API int vmasr_scan_fwd_grouped(int n, const vmasr_scan_params *p);
+VMASR_API int vmasr_scan_bwd_grouped(int n, const vmasr_scan_params *p);
 
 /* ------------------------------------------------------------------------------------------------
  * 4-direction cross scan / merge.  Replace CrossScan / CrossMerge (model/vmamba.py:27-73) and the Triton
@@ -125,6 +144,64 @@ VMASR_API int vmasr_cross_scan(const void *x, void *xs, int B, int C, int H, int
 VMASR_API int vmasr_cross_merge(const void *ys, void *y, int B, int C, int H, int W, int dtype, int device, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused SS2D core: CrossScan -> selective scan -> CrossMerge of SS2D.forward_corev2 (model/vmamba.py:1472-1497; the Triton
+ * kernels model/csm_triton.py:7-154 and the scan extension in between) WITHOUT the four-fold copies `xs` (B, 4, C, L) and
+ * `ys` (B, 4, C, L).  The four directions are four scan problems of ONE grid (see vmasr_scan_fwd_grouped):
+ *   k = 0: the map read row-major;            k = 2: the same memory, time reversed (VMASR_SCAN_REVERSE);
+ *   k = 1: the TRANSPOSED map read row-major; k = 3: the same memory, time reversed.
+ * Everything positional of direction k (delta_k, B_k, C_k and their gradients) is laid out in the MEMORY order of its
+ * pair -- row-major (l = h*W + w) for k = 0, 2, column-major (l = w*H + h) for k = 1, 3 -- and NOT flipped for k = 2, 3:
+ * that is what the projections give when they are applied to the map and to its transpose instead of to `xs`
+ * (einsum(x, x_proj_weight[k]) commutes with the permutation of positions).  Outputs of a pair are added into one
+ * zero-filled plane with 128-bit reductions (exact and order-independent: 0 + a + b), and
+ *   y = (y0 + y2) + transpose(y1 + y3)     -- the association of vmamba.py:55-60.
+ * float32, d_state 1, H % 4 == 0 and W % 4 == 0 (every map of the configs); otherwise the call fails and the caller chains
+ * vmasr_cross_scan / vmasr_scan_* / vmasr_cross_merge.
+ *
+ *   x        (B, C, H, W)            xT   (B, C, W, H) = vmasr_map_transpose(x)
+ *   delta[k] (B, C, L) with strides  B[k], C[k] (B, L) with a batch stride (unit stride along L)
+ *   A, D, delta_bias (4*C,) direction-major (As / Ds / dt_projs_bias.view(-1) of vmamba.py:1481-1485)
+ *   y        (B, C, H, W) out        planes  2 x (B, C, L) scratch (forward) / the two gradient planes (backward)
+ *   states   (4, B, C, n_chunks, 2) chunk states per direction: written by fwd, read by bwd
+ *   backward: dy (B, C, H, W) in, dyT (B, C, W, H) scratch; ddelta[k] like delta[k]; dB, dC (4, B, L), dA, dD, ddelta_bias
+ *   (4*C,) ACCUMULATED INTO (caller zero-fills); planes[0] = d x through directions 0, 2 (row-major), planes[1] = d xT
+ *   through directions 1, 3; dx (optional) = planes[0] + transpose(planes[1]).
+ *   workspace: vmasr_ss2d_workspace_bytes(), zero-filled once, one per concurrently running call (as for the scan).
+ * vmasr_ss2d_core_fwd / _bwd take n = 1 or 2 parameter blocks: the generator's two streams run the same-shape core
+ * independently (model/model.py:1124-1127) and share one grid.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vmasr_ss2d_params {
+    const float *x, *xT;
+    const float *delta[4];
+    int64_t delta_batch_stride[4], delta_d_stride[4];
+    const float *B[4], *C[4];
+    int64_t B_batch_stride[4], C_batch_stride[4];
+    const float *A, *D, *delta_bias; /* D, delta_bias nullable */
+    float *y;
+    float *planes;
+    float *states;
+    /* backward */
+    const float *dy;
+    float *dyT;
+    float *dx; /* nullable */
+    float *ddelta[4];
+    int64_t ddelta_batch_stride[4], ddelta_d_stride[4];
+    float *dA, *dB, *dC, *dD, *ddelta_bias;
+    void *workspace;
+    uint64_t workspace_bytes;
+    int32_t batch, channels, H, W;
+    int32_t delta_softplus, device;
+    void *stream;
+} vmasr_ss2d_params;
+
+VMASR_API uint64_t vmasr_ss2d_workspace_bytes(int batch, int channels, int H, int W);
+VMASR_API int vmasr_ss2d_core_fwd(int n, const vmasr_ss2d_params *p);
+VMASR_API int vmasr_ss2d_core_bwd(int n, const vmasr_ss2d_params *p);
+/* x (planes, H, W) -> xT (planes, W, H); y = p_rm + transpose(p_cm).  float32, H % 4 == 0, W % 4 == 0, 16-byte aligned. */
+VMASR_API int vmasr_map_transpose(const float *x, float *xT, int64_t planes, int H, int W, int device, void *stream);
+VMASR_API int vmasr_map_merge2(const float *p_rm, const float *p_cm, float *y, int64_t planes, int H, int W, int device, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Magnitude/phase STFT and inverse.  Replace wav2spectro / spectro2wav (utils/stft.py:22-68, 71-115),
  * i.e. torch.stft / torch.istft(normalized=True, center=True, reflect pad, periodic Hann of win_length
  * zero-padded to n_fft, onesided) fused with log2(|X|+1e-8)/angle and exp2/polar.  float32 only.
@@ -132,7 +209,7 @@ VMASR_API int vmasr_cross_merge(const void *ys, void *y, int B, int C, int H, in
  *   mag, phase : (B, n_fft/2+1, n_frames) contiguous, n_frames = 1 + T/hop
  *   istft output length = hop*(n_frames-1)
  *   istft_bwd : d wave -> d mag, d phase (the generator loss flows through spectro2wav, model/model.py:1223)
- * n_fft must be a power of two in [64, 4096]; win_length <= n_fft.
+ * n_fft must be a power of two in [64, 2048]; win_length <= n_fft.
  * ---------------------------------------------------------------------------------------------- */
 VMASR_API int vmasr_stft_fwd(const float *wave, float *mag, float *phase, int B, int T, int n_fft, int hop,
                    int win_length, int device, void *stream);

@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in _declared_symbols():
         assert hasattr(raw, name), name
         assert name in _lib.EXPORTS, f"{name} missing from the ctypes binding table"
-    assert lib.vmasr_abi_version() == 1
+    assert lib.vmasr_abi_version() == _lib.ABI_VERSION
 
 
 def test_workspace_sizing():

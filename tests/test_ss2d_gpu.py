@@ -1,0 +1,250 @@
+"""GPU parity of the FUSED SS2D core (vmasr_ss2d_core_fwd / _bwd, vm_asr_b200.ss2d) -- SURVEY.md 8 row a9:
+CrossScan -> selective scan -> CrossMerge of SS2D.forward_corev2 (model/vmamba.py:1472-1497) without the xs / ys copies.
+
+Checked against (i) the oracle chain cross_scan -> C float64 scan -> cross_merge on every config map, outputs and all
+gradients; (ii) the float64 torch oracle of the whole core (projections included) through autograd; (iii) the unfused chain
+of this library's own operators; and, bit for bit, (iv) the merge association (y0 + y2) + transpose(y1 + y3) of
+vmamba.py:55-60 and (v) the two map kernels."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_ref, ss2d_ref
+
+pytestmark = pytest.mark.gpu
+
+REL_FP32 = 1e-4
+
+
+def rel_err(got, ref):
+    got = got.detach().double().cpu().numpy() if torch.is_tensor(got) else np.asarray(got, dtype=np.float64)
+    ref = ref.detach().double().cpu().numpy() if torch.is_tensor(ref) else np.asarray(ref, dtype=np.float64)
+    return np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30)
+
+
+def elem_rel_err(got, ref, floor_rms=0.1):
+    got = got.detach().double().cpu().numpy() if torch.is_tensor(got) else np.asarray(got, dtype=np.float64)
+    ref = ref.detach().double().cpu().numpy() if torch.is_tensor(ref) else np.asarray(ref, dtype=np.float64)
+    floor = floor_rms * max(float(np.sqrt(np.mean(ref * ref))), 1e-30)
+    return float((np.abs(got - ref) / np.maximum(np.abs(ref), floor)).max())
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 64, 64), (2, 7, 128, 36), (1, 3, 16, 16), (10, 300, 8, 12), (2, 2, 1024, 512)])
+def test_map_transpose_and_merge2_bit_exact(shape):
+    from vm_asr_b200 import ss2d
+    torch.manual_seed(0)
+    x = torch.randn(*shape, device="cuda")
+    xT = ss2d.map_transpose(x)
+    assert torch.equal(xT, x.transpose(-1, -2).contiguous())
+    H, W = shape[-2:]
+    q = torch.randn_like(xT)
+    y = ss2d.map_merge2(x.flatten(-2), q.flatten(-2), H, W)
+    assert torch.equal(y, (x + q.transpose(-1, -2)).flatten(-2))
+
+
+def _time_to_memory_order(t):
+    """(B, 4, C, L) per-direction tensors in TIME order (the reference's layout) -> the (rm, cm) pairs (B, 2, C, L) in
+    memory order the fused core takes: directions 2 / 3 un-flipped."""
+    rm = torch.stack([t[:, 0], t[:, 2].flip(-1)], dim=1).contiguous()
+    cm = torch.stack([t[:, 1], t[:, 3].flip(-1)], dim=1).contiguous()
+    return rm, cm
+
+
+def _memory_to_time_order(rm, cm):
+    return torch.stack([rm[:, 0], cm[:, 0], rm[:, 1].flip(-1), cm[:, 1].flip(-1)], dim=1)
+
+
+def _scan_inputs(Bsz, C, H, W, seed=0):
+    torch.manual_seed(seed)
+    L = H * W
+    x = torch.randn(Bsz, C, H, W)
+    dts = 0.5 * torch.rand(Bsz, 4, C, L)
+    Bs, Cs = torch.randn(Bsz, 4, 1, L), torch.randn(Bsz, 4, 1, L)
+    As = -0.5 * torch.rand(4 * C, 1)
+    Ds, bias = torch.randn(4 * C), 0.5 * torch.rand(4 * C)
+    dy = torch.randn(Bsz, C, L)
+    return x, dts, Bs, Cs, As, Ds, bias, dy
+
+
+def _run_fused(x, dts, Bs, Cs, As, Ds, bias, dy=None):
+    from vm_asr_b200 import ss2d
+    dev = "cuda"
+    xg = x.to(dev).requires_grad_(dy is not None)
+    xT = ss2d.MapTranspose.apply(xg)
+    leaves = []
+    for t in (dts, Bs, Cs):
+        rm, cm = _time_to_memory_order(t)
+        leaves += [rm.to(dev).requires_grad_(dy is not None), cm.to(dev).requires_grad_(dy is not None)]
+    dts_rm, dts_cm, Bs_rm, Bs_cm, Cs_rm, Cs_cm = leaves
+    par = [t.to(dev).requires_grad_(dy is not None) for t in (As, Ds, bias)]
+    y = ss2d._SS2DScan.apply(True, 1, xg, xT, dts_rm, dts_cm, Bs_rm, Bs_cm, Cs_rm, Cs_cm, *par)
+    if dy is None:
+        return y
+    y.backward(dy.to(dev))
+    torch.cuda.synchronize()
+    g = lambda a, b: _memory_to_time_order(a.grad, b.grad)
+    return y, dict(dx=xg.grad, ddelta=g(dts_rm, dts_cm), dB=g(Bs_rm, Bs_cm), dC=g(Cs_rm, Cs_cm), dA=par[0].grad, dD=par[1].grad,
+                   dbias=par[2].grad)
+
+
+def _run_oracle(x, dts, Bs, Cs, As, Ds, bias, dy):
+    Bsz, C, H, W = x.shape
+    L = H * W
+    u = ss2d_ref.cross_scan(x).reshape(Bsz, 4 * C, L).numpy()
+    delta = dts.reshape(Bsz, 4 * C, L).numpy()
+    out, _, _ = c_ref.scan_fwd(u, delta, As.numpy(), Bs.numpy(), Cs.numpy(), Ds.numpy(), bias.numpy(), True)
+    y = ss2d_ref.cross_merge(torch.from_numpy(out).reshape(Bsz, 4, C, H, W))
+    dys = ss2d_ref.cross_merge_bwd(dy, H, W).reshape(Bsz, 4 * C, L).numpy()
+    du, ddelta, dA, dB, dC, dD, dbias = c_ref.scan_bwd(u, delta, As.numpy(), Bs.numpy(), Cs.numpy(), Ds.numpy(), bias.numpy(), True, dys)
+    dx = ss2d_ref.cross_scan_bwd(torch.from_numpy(du).reshape(Bsz, 4, C, L), H, W).reshape(Bsz, C, H, W)
+    return y, dict(dx=dx, ddelta=ddelta.reshape(Bsz, 4, C, L), dB=dB, dC=dC, dA=dA, dD=dD, dbias=dbias)
+
+
+# every SS2D map of the BASELINE.json configs at its full size, plus small / ragged-chunk / non-square ones
+CONFIG_MAPS = [
+    (4, 2, 512, 512), (4, 16, 256, 256), (4, 32, 128, 128), (4, 64, 64, 64), (4, 128, 32, 32), (4, 256, 16, 16),
+    (8, 2, 1024, 512), (8, 16, 512, 256), (8, 32, 256, 128), (8, 64, 128, 64), (8, 128, 64, 32), (8, 256, 32, 16),
+    (8, 32, 256, 256), (8, 64, 128, 128), (8, 128, 64, 64), (8, 256, 32, 32), (8, 512, 16, 16), (8, 2, 512, 512),
+]
+SMALL_MAPS = [(2, 3, 8, 12), (1, 5, 36, 60), (2, 6, 44, 52), (1, 4, 100, 84), (2, 1, 64, 40)]
+
+
+@pytest.mark.parametrize("Bsz,C,H,W", SMALL_MAPS + CONFIG_MAPS)
+def test_fused_core_against_oracle_chain(Bsz, C, H, W):
+    """Outputs and every gradient of the fused core vs cross_scan -> float64 C scan -> cross_merge (and their adjoints)."""
+    inp = _scan_inputs(Bsz, C, H, W)
+    y, grads = _run_fused(*inp)
+    y_ref, g_ref = _run_oracle(*inp)
+    assert rel_err(y, y_ref) < REL_FP32
+    assert elem_rel_err(y, y_ref) < REL_FP32
+    for name in ("dx", "ddelta", "dB", "dC", "dA", "dD", "dbias"):
+        assert rel_err(grads[name], g_ref[name]) < REL_FP32, f"{name}: {rel_err(grads[name], g_ref[name])}"
+    assert elem_rel_err(grads["dx"], g_ref["dx"]) < REL_FP32
+    assert elem_rel_err(grads["ddelta"], g_ref["ddelta"]) < REL_FP32
+
+
+@pytest.mark.parametrize("Bsz,C,H,W", [(2, 4, 16, 16), (2, 8, 64, 48), (1, 4, 128, 96)])
+def test_merge_association_is_the_references(Bsz, C, H, W):
+    """y of the fused core == (y0 + y2) + transpose(y1 + y3) BIT FOR BIT (model/vmamba.py:55-60), the four direction
+    outputs taken from the same kernels launched one by one without accumulation."""
+    from vm_asr_b200 import scan, ss2d
+    x, dts, Bs, Cs, As, Ds, bias, _ = _scan_inputs(Bsz, C, H, W, seed=4)
+    L = H * W
+    y = _run_fused(x, dts, Bs, Cs, As, Ds, bias)
+    xg = x.cuda()
+    xT = ss2d.map_transpose(xg)
+    (dts_rm, dts_cm), (Bs_rm, Bs_cm), (Cs_rm, Cs_cm) = (_time_to_memory_order(t) for t in (dts, Bs, Cs))
+    outs = []
+    for k in range(4):
+        u = (xT if k & 1 else xg).view(Bsz, C, L)
+        pick = lambda rm, cm: (cm if k & 1 else rm)[:, k // 2].cuda().contiguous()
+        out = torch.empty(Bsz, C, L, device="cuda")
+        xs = torch.empty(Bsz, C, (L + 2047) // 2048, 2, device="cuda")
+        sl = slice(k * C, (k + 1) * C)
+        scan.fwd_out(u, pick(dts_rm, dts_cm), As[sl].cuda(), pick(Bs_rm, Bs_cm).unsqueeze(1), pick(Cs_rm, Cs_cm).unsqueeze(1),
+                     Ds[sl].cuda(), bias[sl].cuda(), True, out, xs, flags=scan.SCAN_REVERSE if k >= 2 else 0)
+        outs.append(out)
+    rowp = outs[0] + outs[2]
+    colp = (outs[1] + outs[3]).view(Bsz, C, W, H).transpose(2, 3).reshape(Bsz, C, L)
+    assert torch.equal(y, rowp + colp)
+
+
+def _core_params(C, R, N=1, seed=2):
+    torch.manual_seed(seed)
+    return (torch.randn(4, R + 2 * N, C) * 0.3, torch.randn(4, C, R) * 0.3, torch.rand(4, C) * 0.5,
+            torch.log(torch.rand(4 * C, N) + 0.5), torch.ones(4 * C))
+
+
+@pytest.mark.parametrize("Bsz,C,H,W,R", [(2, 8, 72, 64, 2), (2, 4, 16, 16, 1), (1, 16, 32, 48, 1), (1, 6, 128, 60, 3)])
+def test_ss2d_core_fused_forward_backward(Bsz, C, H, W, R):
+    """vm_asr_b200.ss2d.ss2d_core (projections in memory order + fused kernels) against the float64 torch oracle of
+    forward_corev2, outputs and gradients of the map and of every parameter."""
+    from vm_asr_b200 import ss2d
+    names = ("x", "xw", "dw", "db", "A_logs", "Ds")
+    vals = (torch.randn(Bsz, C, H, W, generator=torch.Generator().manual_seed(5)),) + _core_params(C, R)
+    dy = torch.randn(Bsz, C, H * W, generator=torch.Generator().manual_seed(6))
+    ref_in = [v.double().requires_grad_() for v in vals]
+    ref = ss2d_ref.ss2d_core(*ref_in, dtype=torch.float64)
+    ref.backward(dy.double())
+    got_in = [v.cuda().requires_grad_() for v in vals]
+    got = ss2d.ss2d_core(*got_in, fused=True)
+    got.backward(dy.cuda())
+    chain_in = [v.cuda().requires_grad_() for v in vals]
+    chain = ss2d.ss2d_core_chain(*chain_in)
+    chain.backward(dy.cuda())
+    assert rel_err(got, ref) < 2e-4  # the einsums run in fp32 on the GPU; summation order differs
+    assert rel_err(got, chain) < 2e-5
+    for n, g, c, r in zip(names, got_in, chain_in, ref_in):
+        assert rel_err(g.grad, r.grad) < 5e-4, n
+        assert rel_err(g.grad, c.grad) < 1e-4, n
+
+
+def test_x_proj_bias():
+    """x_proj_bias (vmamba.py:1474-1475) in both paths."""
+    from vm_asr_b200 import ss2d
+    Bsz, C, H, W, R = 2, 4, 24, 20, 2
+    x = torch.randn(Bsz, C, H, W, generator=torch.Generator().manual_seed(7)).cuda()
+    xw, dw, db, A_logs, Ds = (t.cuda() for t in _core_params(C, R))
+    xb = (0.2 * torch.randn(4, R + 2, generator=torch.Generator().manual_seed(8))).cuda()
+    a = ss2d.ss2d_core(x, xw, dw, db, A_logs, Ds, x_proj_bias=xb, fused=True)
+    b = ss2d.ss2d_core_chain(x, xw, dw, db, A_logs, Ds, x_proj_bias=xb)
+    c = ss2d.ss2d_core_chain(x, xw, dw, db, A_logs, Ds)
+    assert rel_err(a, b) < 2e-5 and rel_err(b, c) > 1e-3
+
+
+def test_pair_equals_two_single_calls():
+    """ss2d_core_pair (the generator's two streams in one grid) is bit-identical to two single calls."""
+    from vm_asr_b200 import ss2d
+    outs = {}
+    for mode in ("single", "pair"):
+        maps, prms = [], []
+        for s in (11, 12):
+            x = torch.randn(2, 8, 64, 80, generator=torch.Generator().manual_seed(s)).cuda().requires_grad_()
+            prm = [t.cuda().requires_grad_() for t in _core_params(8, 1, seed=s)]
+            maps.append(x)
+            prms.append(prm)
+        if mode == "single":
+            ys = [ss2d.ss2d_core(x, *p, fused=True) for x, p in zip(maps, prms)]
+        else:
+            ys = ss2d.ss2d_core_pair(maps[0], prms[0], maps[1], prms[1])
+        (ys[0].sum() + (ys[1] * ys[1]).sum()).backward()
+        outs[mode] = (ys, maps, prms)
+    for a, b in zip(outs["single"][0], outs["pair"][0]):
+        assert torch.equal(a, b)
+    for a, b in zip(outs["single"][1], outs["pair"][1]):
+        assert rel_err(b.grad, a.grad) < 1e-6
+
+
+def test_fused_core_allocates_no_fourfold_copies():
+    """xs and ys (4 map-sizes each) are never allocated: the fused call's peak extra memory stays below 4 map-sizes
+    (y + 2 planes + chunk states), while the chain needs more than 8."""
+    from vm_asr_b200 import ss2d
+    Bsz, C, H, W = 4, 16, 256, 256
+    x, dts, Bs, Cs, As, Ds, bias, _ = _scan_inputs(Bsz, C, H, W)
+    map_bytes = Bsz * C * H * W * 4
+    xg = x.cuda()
+    xT = ss2d.map_transpose(xg)
+    args = []
+    for t in (dts, Bs, Cs):
+        rm, cm = _time_to_memory_order(t)
+        args += [rm.cuda(), cm.cuda()]
+    par = [t.cuda() for t in (As, Ds, bias)]
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    with torch.no_grad():
+        y = ss2d._SS2DScan.apply(True, 1, xg, xT, *args, *par)
+    torch.cuda.synchronize()
+    peak = torch.cuda.max_memory_allocated() - base
+    assert peak < 3.6 * map_bytes, peak / map_bytes
+    assert y.shape == (Bsz, C, H * W)
+
+
+def test_fused_core_rejects_unsupported_maps():
+    from vm_asr_b200 import ss2d
+    x = torch.randn(1, 2, 6, 10, device="cuda")
+    prm = [t.cuda() for t in _core_params(2, 1)]
+    with pytest.raises(RuntimeError):
+        ss2d.ss2d_core(x, *prm, fused=True)
+    y = ss2d.ss2d_core(x, *prm)  # falls back to the chain of this library's operators
+    assert y.shape == (1, 2, 60)

@@ -18,6 +18,9 @@ _lib = None
 _lock = threading.Lock()
 
 VMASR_F32, VMASR_F16, VMASR_BF16 = 0, 1, 2
+SCAN_REVERSE, SCAN_ACCUMULATE = 1, 2
+SCAN_MAX_GROUP = 8
+ABI_VERSION = 2
 SCAN_CHUNK = 2048
 DTYPE_CODE = {torch.float32: VMASR_F32, torch.float16: VMASR_F16, torch.bfloat16: VMASR_BF16}
 
@@ -37,9 +40,28 @@ class ScanParams(ctypes.Structure):
             "B_batch_stride", "B_group_stride", "B_dstate_stride", "C_batch_stride", "C_group_stride", "C_dstate_stride",
             "out_batch_stride", "out_d_stride", "dout_batch_stride", "dout_d_stride", "du_batch_stride", "du_d_stride",
             "ddelta_batch_stride", "ddelta_d_stride")]
-        + [(n, _i32) for n in ("io_dtype", "delta_softplus", "device", "reserved")]
+        + [(n, _i32) for n in ("io_dtype", "delta_softplus", "device", "flags")]
         + [("stream", _vp)]
     )
+
+
+class SS2DParams(ctypes.Structure):
+    """Mirror of ``vmasr_ss2d_params`` (include/vmasr_b200.h)."""
+
+    _fields_ = [
+        ("x", _vp), ("xT", _vp),
+        ("delta", _vp * 4), ("delta_batch_stride", _i64 * 4), ("delta_d_stride", _i64 * 4),
+        ("B", _vp * 4), ("C", _vp * 4), ("B_batch_stride", _i64 * 4), ("C_batch_stride", _i64 * 4),
+        ("A", _vp), ("D", _vp), ("delta_bias", _vp),
+        ("y", _vp), ("planes", _vp), ("states", _vp),
+        ("dy", _vp), ("dyT", _vp), ("dx", _vp),
+        ("ddelta", _vp * 4), ("ddelta_batch_stride", _i64 * 4), ("ddelta_d_stride", _i64 * 4),
+        ("dA", _vp), ("dB", _vp), ("dC", _vp), ("dD", _vp), ("ddelta_bias", _vp),
+        ("workspace", _vp), ("workspace_bytes", _u64),
+        ("batch", _i32), ("channels", _i32), ("H", _i32), ("W", _i32),
+        ("delta_softplus", _i32), ("device", _i32),
+        ("stream", _vp),
+    ]
 
 
 EXPORTS = {
@@ -49,6 +71,13 @@ EXPORTS = {
     "vmasr_scan_plan": (ctypes.c_int, [ctypes.POINTER(ScanParams), ctypes.c_int, ctypes.POINTER(ctypes.c_int32)]),
     "vmasr_scan_fwd": (ctypes.c_int, [ctypes.POINTER(ScanParams)]),
     "vmasr_scan_bwd": (ctypes.c_int, [ctypes.POINTER(ScanParams)]),
+    "vmasr_scan_fwd_grouped": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ScanParams)]),
+    "vmasr_scan_bwd_grouped": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ScanParams)]),
+    "vmasr_ss2d_workspace_bytes": (_u64, [ctypes.c_int] * 4),
+    "vmasr_ss2d_core_fwd": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(SS2DParams)]),
+    "vmasr_ss2d_core_bwd": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(SS2DParams)]),
+    "vmasr_map_transpose": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+    "vmasr_map_merge2": (ctypes.c_int, [_vp, _vp, _vp, _i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "vmasr_cross_scan": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
     "vmasr_cross_merge": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
     "vmasr_stft_fwd": (ctypes.c_int, [_vp, _vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
@@ -92,21 +121,39 @@ def require_cuda(t: torch.Tensor, name: str):
 
 
 def current_stream_ptr(device: torch.device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
 
 
-# ---- carry workspace of the scan: one per (device, stream), zero-filled once, recycled by the kernels ----
+# ---- carry workspace of the scan ------------------------------------------------------------------------------------
+# One per (device, stream, "is this stream being captured into a CUDA graph"): zero-filled once, recycled by the kernels
+# (epoch tags), so two scans that run one after the other on a stream share it and nothing is cleared between launches.
+#   * a buffer that has been handed out is NEVER freed: when a larger one is needed the old one is retired, not released,
+#     because its address may be baked into a captured graph;
+#   * calls made while the stream is capturing get a workspace of their own (allocated inside the capture, i.e. from the
+#     graph's pool; its zero-fill is a node of the graph), so replaying the graph -- on whatever stream -- never shares a
+#     workspace with eager calls;
+#   * scans that may run CONCURRENTLY (two streams, two graphs replayed side by side) must not share one: give each its own
+#     stream, or capture each graph after `reset_capture_workspaces()`.
 _workspaces = {}
+_retired = []
 
 
 def scan_workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(device).cuda_stream)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, torch._C._cuda_getCurrentRawStream(idx), torch.cuda.is_current_stream_capturing())
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         size = max(int(nbytes), 1 << 20)
         if ws is not None:
             size = max(size, 2 * ws.numel())
+            _retired.append(ws)
         ws = torch.zeros(size, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+def reset_capture_workspaces():
+    """Forget (not free) the workspaces handed to captured calls: the next capture allocates its own."""
+    for key in [k for k in _workspaces if k[2]]:
+        _retired.append(_workspaces.pop(key))

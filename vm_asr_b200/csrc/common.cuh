@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/vmasr_b200.h"
 
@@ -39,6 +40,18 @@ struct PerDeviceOnce {
         return done[dev];
     }
 };
+
+// ---- tuning knobs --------------------------------------------------------------------------------------------------
+// The product library reads no environment variables.  A build with -DVMASR_TUNING (make TUNING=1) turns the knobs of
+// DESIGN.md 5.1 back on for measurement sessions.
+inline const char *tuning_env(const char *name) {
+#ifdef VMASR_TUNING
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
 // The scan kernels of a model run back to back on one stream.  Launched with the programmatic-stream-serialization

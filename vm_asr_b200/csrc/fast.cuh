@@ -31,6 +31,67 @@ __device__ __forceinline__ void stg8(float *p, const float2 (&v)[4]) {
     reinterpret_cast<float4 *>(p)[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
 }
 
+// 128-bit reductions into global memory (SASS RED.E.ADD.F32x4 on sm_100a): the fused SS2D core adds the outputs of two scan
+// directions that share a memory order into one zero-filled plane, which keeps the sum exact and order-independent
+// (0 + a + b == a + b whichever comes first).
+__device__ __forceinline__ void red4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red8(float *p, const float2 (&v)[4]) {
+    red4(p, v[0].x, v[0].y, v[1].x, v[1].y);
+    red4(p + 4, v[2].x, v[2].y, v[3].x, v[3].y);
+}
+
+// ---- time order inside a thread ----------------------------------------------------------------------------------------
+// A thread owns 8 consecutive MEMORY positions (4 pairs).  With REV the scan runs over the row back to front: the thread that
+// is t-th in time owns the t-th segment from the END of the tile and walks its pairs 3..0, .y before .x.  Everything
+// element-wise stays in memory order (packed pairs as loaded); only the serial recurrences use these helpers.
+template <bool REV> __device__ __forceinline__ constexpr int pair_at(int kk) { return REV ? 3 - kk : kk; }
+// forward recurrence over one pair: (p, q) <- running affine map, P / Q = its value after each position
+template <bool REV>
+__device__ __forceinline__ void walk_pair(const float2 av, const float2 bx, float &p, float &q, float2 &P, float2 &Q) {
+    if (!REV) {
+        q = fmaf(av.x, q, bx.x); p *= av.x; P.x = p; Q.x = q;
+        q = fmaf(av.y, q, bx.y); p *= av.y; P.y = p; Q.y = q;
+    } else {
+        q = fmaf(av.y, q, bx.y); p *= av.y; P.y = p; Q.y = q;
+        q = fmaf(av.x, q, bx.x); p *= av.x; P.x = p; Q.x = q;
+    }
+}
+// state walk: h <- a h + bx, the state after each position
+template <bool REV>
+__device__ __forceinline__ void walk_state(const float2 av, const float2 bx, float &h, float2 &hs) {
+    if (!REV) {
+        h = fmaf(av.x, h, bx.x); hs.x = h;
+        h = fmaf(av.y, h, bx.y); hs.y = h;
+    } else {
+        h = fmaf(av.y, h, bx.y); hs.y = h;
+        h = fmaf(av.x, h, bx.x); hs.x = h;
+    }
+}
+// forward + adjoint aggregates in one walk in time order: q as above, qr = sum_i (prod_{m <= i} a_m) c_i
+template <bool REV>
+__device__ __forceinline__ void walk_pair2(const float2 av, const float2 bx, const float2 cdy, float &p, float &q, float &qr) {
+    if (!REV) {
+        q = fmaf(av.x, q, bx.x); p *= av.x; qr = fmaf(p, cdy.x, qr);
+        q = fmaf(av.y, q, bx.y); p *= av.y; qr = fmaf(p, cdy.y, qr);
+    } else {
+        q = fmaf(av.y, q, bx.y); p *= av.y; qr = fmaf(p, cdy.y, qr);
+        q = fmaf(av.x, q, bx.x); p *= av.x; qr = fmaf(p, cdy.x, qr);
+    }
+}
+// adjoint walk over one pair, AGAINST time order: g_l = c_l + G, G <- a_l g_l
+template <bool REV>
+__device__ __forceinline__ void walk_adjoint(const float2 av, const float2 cdy, float &G, float2 &gl) {
+    if (!REV) {
+        gl.y = cdy.y + G; G = av.y * gl.y;
+        gl.x = cdy.x + G; G = av.x * gl.x;
+    } else {
+        gl.x = cdy.x + G; G = av.x * gl.x;
+        gl.y = cdy.y + G; G = av.y * gl.y;
+    }
+}
+
 // ---- bank-conflict-free variants ---------------------------------------------------------------------------------
 // A thread owns 32 contiguous bytes of a shared-memory row; a plain 128-bit access at a 32-byte thread stride makes lanes
 // t and t + 4 of every quarter-warp hit the same banks (2-way conflict: ncu counted 44 % of all shared wavefronts as

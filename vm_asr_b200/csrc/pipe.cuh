@@ -91,17 +91,27 @@ __device__ __forceinline__ Aff look_reduce(const CarryLook &c, unsigned tag, int
     return Aff{__shfl_sync(0xffffffffu, v.p, 0), __shfl_sync(0xffffffffu, v.q, 0)};
 }
 
+// Forward progress.  A tile waits only for entries of tiles that precede it in block-index order (chunk-major launch
+// order), and the hardware hands out the blocks of a 1-D grid in ascending index order, so every tile a resident tile waits
+// for is resident or finished (the same assumption CUB's decoupled look-back scan makes).  Should that ever not hold (a
+// tool that serialises or reorders blocks), the wait is BOUNDED: after a few seconds of polling the kernel traps, which surfaces as
+// a launch failure on the stream instead of a hang.
+__device__ __forceinline__ uint4 wait_entry(const CarryEntry *p, uint4 e, unsigned tag) {
+    unsigned spins = 0;
+    while (e.y != tag || e.w != tag) {
+        __nanosleep(32);
+        e = load_entry(p);
+        if (++spins > (1u << 22)) __trap();
+    }
+    return e;
+}
+
 // Slow path, after the chunk's own aggregate is published: wait for the entries that were not there yet, reduce
 // again; then (sequences of more than 272 chunks) the remaining level-2 entries, 32 per round, nearest first.
 __device__ __forceinline__ Aff look_finish(CarryLook &c, Aff acc, bool ok, const CarryEntry *l2_row, int j, unsigned tag, int lane,
                                            Aff &ingroup) {
     if (!ok) {
-        if (c.ptr) {
-            while (c.e.y != tag || c.e.w != tag) {
-                __nanosleep(32);
-                c.e = load_entry(c.ptr);
-            }
-        }
+        if (c.ptr) c.e = wait_entry(c.ptr, c.e, tag);
         __syncwarp();
         bool again;
         acc = look_reduce(c, tag, lane, again, ingroup);
@@ -112,11 +122,7 @@ __device__ __forceinline__ Aff look_finish(CarryLook &c, Aff acc, bool ok, const
         const int i = base + lane;
         if (i < gi) {
             const CarryEntry *p = l2_row + (gi - 1 - i);
-            uint4 e = load_entry(p);
-            while (e.y != tag || e.w != tag) {
-                __nanosleep(32);
-                e = load_entry(p);
-            }
+            const uint4 e = wait_entry(p, load_entry(p), tag);
             w = Aff{__uint_as_float(e.x), __uint_as_float(e.z)};
         }
         __syncwarp();

@@ -33,7 +33,10 @@ struct ScanArgs {
     int n_ctiles;         // ceil(chan_per_group / chan_per_tile)
     int n_rowgroups;      // batch * ngroups * n_ctiles
     int softplus;
-    int debug_nowait;     // timing experiment only (VMASR_DEBUG_NOWAIT=1): do not wait for neighbours' aggregates -> WRONG results
+    int rev;              // fast kernels only: the scan runs over the row back to front (time index l <-> seqlen - 1 - l); every positional
+                          // tensor (u, delta, B, C, out, dout, du, ddelta, dB, dC) keeps its memory order.  Directions 2 and 3 of SS2D.
+    int accum;            // fast kernels only: `out` (forward) / `du` (backward) are added into (128-bit red.global.add) instead of stored
+    int debug_nowait;     // VMASR_TUNING builds only, timing experiment: do not wait for neighbours' aggregates -> WRONG results
     long long u_bs, u_ds, delta_bs, delta_ds, A_ds, A_ns, B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;
     long long out_bs, out_ds, dout_bs, dout_ds, du_bs, du_ds, ddelta_bs, ddelta_ds;
 };
@@ -118,7 +121,7 @@ __device__ __forceinline__ void retire_tile(const ScanArgs &a) {
         if (threadIdx.x == 0) {
             __threadfence();
             const unsigned prev = atomicAdd(a.ws_header + 1, 1u);
-            if (prev == gridDim.x - 1) {
+            if (prev == (unsigned)(a.n_chunks * a.n_rowgroups) - 1u) {
                 a.ws_header[0] = 0u;
                 a.ws_header[1] = 0u;
                 a.ws_header[2] = a.ws_header[2] + 1u;
@@ -126,6 +129,23 @@ __device__ __forceinline__ void retire_tile(const ScanArgs &a) {
             }
         }
     }
+}
+
+// One launch over up to kMaxGroup independent scan problems (same kernel variant): tiles of problem i are the block indices
+// [tile_end[i - 1], tile_end[i]).  Each problem has its own carry workspace.  Used for the two streams of the generator, which
+// issue same-shape calls independently (model/model.py:1167-1176), and for the four directions of the fused SS2D core.
+constexpr int kMaxGroup = 8;
+struct GroupArgs {
+    ScanArgs a[kMaxGroup];
+    int tile_end[kMaxGroup];
+    int n;
+};
+// problem of this CTA and its tile index inside the problem
+__device__ __forceinline__ int group_problem(const GroupArgs &ga, int &tile) {
+    int prob = 0, start = 0;
+    while (prob + 1 < ga.n && (int)blockIdx.x >= ga.tile_end[prob]) start = ga.tile_end[prob++];
+    tile = (int)blockIdx.x - start;
+    return prob;
 }
 
 // host side (scan_host.cu)

@@ -31,7 +31,8 @@ namespace vmasr {
 constexpr int kBPipeStages = 4;        // most channels per tile = resident stages (u + delta + dout, 24 KB per channel); 3 and 4 are built
 constexpr int kBPipeThreads = 288;     // 8 compute warps + the exchange warp
 
-template <bool TAIL, bool SP, int STAGES>
+// `chunk` is the chunk's index in TIME order (the forward scan's order); with REV it sits at the mirrored place in memory.
+template <bool TAIL, bool SP, int STAGES, bool REV>
 __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned char *smem, const int chunk, const int rg,
                                                    const unsigned epoch) {
     constexpr int NC = 256, ITEMS = 8, WPR = 8, SEG = NC * ITEMS;
@@ -59,7 +60,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
     const int lane = threadIdx.x & 31;
     const bool exchange = warp == WPR;
     const int L = a.seqlen;
-    const int seg0 = chunk * SEG;
+    const int seg0 = (REV ? a.n_chunks - 1 - chunk : chunk) * SEG;  // first MEMORY position of the tile
     const int seg_len = min(SEG, L - seg0);
     const unsigned seg_bytes = (unsigned)seg_len * 4u;
 
@@ -182,7 +183,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
         if (lane == 0) {
             __threadfence();
             const unsigned prev = atomicAdd(a.ws_header + 1, 1u);
-            if (prev == gridDim.x - 1) {
+            if (prev == (unsigned)(a.n_chunks * a.n_rowgroups) - 1u) {
                 a.ws_header[0] = 0u;
                 a.ws_header[1] = 0u;
                 a.ws_header[2] = a.ws_header[2] + 1u;
@@ -191,17 +192,19 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
         }
     } else {
         // ================= compute warps =================
-        const int pos = seg0 + threadIdx.x * ITEMS;
-        const int sel = (threadIdx.x >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
+        const int tseg = REV ? NC - 1 - (int)threadIdx.x : (int)threadIdx.x;  // this thread's 8-position segment of the tile (memory order)
+        const int pos = seg0 + tseg * ITEMS;
+        const int sel = (tseg >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
+        const bool accum = a.accum != 0;
         int nvalid = ITEMS;
         if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
         float *du_ptr = reinterpret_cast<float *>(a.du) + b * a.du_bs + (long long)d0 * a.du_ds + pos;
         float *dd_ptr = reinterpret_cast<float *>(a.ddelta) + b * a.ddelta_bs + (long long)d0 * a.ddelta_ds + pos;
 
         float2 Bv[4], dBacc[4], dCacc[4];
-        float *sC = s_c + threadIdx.x * ITEMS;  // this thread's C values (only this thread touches them)
+        float *sC = s_c + tseg * ITEMS;  // this thread's C values (only this thread touches them)
         mbar_wait(bar_bc, 0);
-        lds8_sw(s_b + threadIdx.x * ITEMS, sel, Bv);
+        lds8_sw(s_b + tseg * ITEMS, sel, Bv);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             dBacc[k] = f2(0.0f);
@@ -231,7 +234,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                 // ---- P1(j) ----
                 const float Av = s_par[j];
                 const float bias2 = s_par[2 * 4 + j];
-                float *su = s_stage + (size_t)j * 3 * SEG + threadIdx.x * ITEMS;
+                float *su = s_stage + (size_t)j * 3 * SEG + tseg * ITEMS;
                 mbar_wait(&bar_full[j], 0);
                 float2 uv[4], dl[4], dy[4], Cv[4], dts[4];
                 lds8_sw(su, sel, uv);
@@ -249,7 +252,8 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                 }
                 float p = 1.0f, q = 0.0f, qr = 0.0f;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int k = pair_at<REV>(kk);  // pairs in time order
                     float2 dt2 = fma2(dl[k], f2(kLog2e), f2(bias2));
                     if (SP) {
                         float2 e, sp;
@@ -260,14 +264,9 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                     const float2 av = make_float2(ex2_approx(da.x), ex2_approx(da.y));
                     const float2 bx = mul2(mul2(dt2, f2(kLn2)), mul2(Bv[k], uv[k]));
                     const float2 cdy = mul2(Cv[k], dy[k]);
-                    // local aggregates of both recurrences in one left-to-right walk:
-                    //   forward  s -> p s + q;   adjoint (entering from the right)  G -> p G + qr,  qr = sum_i (prod_{m<=i} a_m) C_i dout_i
-                    q = fmaf(av.x, q, bx.x);
-                    p *= av.x;
-                    qr = fmaf(p, cdy.x, qr);
-                    q = fmaf(av.y, q, bx.y);
-                    p *= av.y;
-                    qr = fmaf(p, cdy.y, qr);
+                    // local aggregates of both recurrences in one walk in time order:
+                    //   forward  s -> p s + q;   adjoint (entering from the future)  G -> p G + qr,  qr = sum_i (prod_{m<=i} a_m) C_i dout_i
+                    walk_pair2<REV>(av, bx, cdy, p, q, qr);
                 }
                 sts8_priv(su + SEG, sel, dts);
                 // two independent warp scans, interleaved level by level (each level is shuffle-latency bound)
@@ -305,7 +304,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                 const float Dv = s_par[4 + j];
                 mbar_wait(&bar_in[j], 0);
                 const float2 in = s_in[j * WPR + warp];
-                const float *su = s_stage + (size_t)j * 3 * SEG + threadIdx.x * ITEMS;
+                const float *su = s_stage + (size_t)j * 3 * SEG + tseg * ITEMS;
                 float2 uv[4], dts[4], dy[4], Cv[4];
                 lds8_sw(su, sel, uv);
                 lds8_priv(su + SEG, sel, dts);
@@ -316,28 +315,24 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                 {
                     float h = fmaf(exf.p, in.x, exf.q);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int k = pair_at<REV>(kk);  // time order
                         const float2 da = mul2(dts[k], f2(Av));
                         av[k] = make_float2(ex2_approx(da.x), ex2_approx(da.y));
                         dtn[k] = mul2(dts[k], f2(kLn2));
                         bu[k] = mul2(Bv[k], uv[k]);
                         const float2 bx = mul2(dtn[k], bu[k]);
-                        h = fmaf(av[k].x, h, bx.x);
-                        hs[k].x = h;
-                        h = fmaf(av[k].y, h, bx.y);
-                        hs[k].y = h;
+                        walk_state<REV>(av[k], bx, h, hs[k]);
                     }
                 }
-                // adjoint walk, right to left
+                // adjoint walk, against time order
                 {
                     float G = fmaf(exr.p, in.y, exr.q);
 #pragma unroll
-                    for (int k = 3; k >= 0; --k) {
+                    for (int kk = 3; kk >= 0; --kk) {
+                        const int k = pair_at<REV>(kk);
                         const float2 cdy = mul2(Cv[k], dy[k]);
-                        gl[k].y = cdy.y + G;
-                        G = av[k].y * gl[k].y;
-                        gl[k].x = cdy.x + G;
-                        G = av[k].x * gl[k].x;
+                        walk_adjoint<REV>(av[k], cdy, G, gl[k]);
                     }
                 }
                 // gradients, position pairs
@@ -351,8 +346,17 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                     const float2 gc = mul2(gl[k], carried);
                     const float2 ddt = fma2(gl[k], bu[k], mul2(gc, f2(Av)));
                     if (SP) {
-                        // sigmoid(delta + bias) = 1 - exp(-softplus) = 1 - 2^(-dt2); exactly 1 above the reference's threshold
+                        // sigmoid(delta + bias) = 1 - exp(-softplus) = 1 - 2^(-dt2); exactly 1 above the reference's threshold.
+                        // Below softplus = 1/16 the subtraction would cancel (the Mamba-style dt range 1e-3 .. 1e-1 lives there):
+                        // 1 - exp(-s) = s (1 - s/2 + s^2/6 - s^3/24), next term s^4/120 < 1.3e-7 relative.
+                        const float2 sn = dtn[k];  // softplus, natural units
+                        float2 ser = fma2(sn, f2(-1.0f / 24.0f), f2(1.0f / 6.0f));
+                        ser = fma2(sn, ser, f2(-0.5f));
+                        ser = fma2(sn, ser, f2(1.0f));
+                        ser = mul2(sn, ser);
                         float2 sig = make_float2(1.0f - ex2_approx(-dts[k].x), 1.0f - ex2_approx(-dts[k].y));
+                        if (sn.x < 0.0625f) sig.x = ser.x;
+                        if (sn.y < 0.0625f) sig.y = ser.y;
                         if (dts[k].x > kSoftplusThr2) sig.x = 1.0f;
                         if (dts[k].y > kSoftplusThr2) sig.y = 1.0f;
                         ddl[k] = mul2(ddt, sig);
@@ -369,13 +373,20 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                     float *o_du = du_ptr + (long long)j * a.du_ds;
                     float *o_dd = dd_ptr + (long long)j * a.ddelta_ds;
                     if (!TAIL || nvalid == ITEMS) {
-                        stg8(o_du, du);
+                        if (accum) red8(o_du, du);
+                        else stg8(o_du, du);
                         stg8(o_dd, ddl);
                     } else {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            if (2 * k < nvalid) { o_du[2 * k] = du[k].x; o_dd[2 * k] = ddl[k].x; }
-                            if (2 * k + 1 < nvalid) { o_du[2 * k + 1] = du[k].y; o_dd[2 * k + 1] = ddl[k].y; }
+                            if (2 * k < nvalid) {
+                                if (accum) atomicAdd(o_du + 2 * k, du[k].x); else o_du[2 * k] = du[k].x;
+                                o_dd[2 * k] = ddl[k].x;
+                            }
+                            if (2 * k + 1 < nvalid) {
+                                if (accum) atomicAdd(o_du + 2 * k + 1, du[k].y); else o_du[2 * k + 1] = du[k].y;
+                                o_dd[2 * k + 1] = ddl[k].y;
+                            }
                         }
                     }
                 }
@@ -391,10 +402,8 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
         float *dBg = a.dB + ((long long)b * a.ngroups + g) * (long long)L;
         float *dCg = a.dC + ((long long)b * a.ngroups + g) * (long long)L;
         if (!TAIL || nvalid == ITEMS) {
-            atomicAdd(reinterpret_cast<float4 *>(dBg + pos), make_float4(dBacc[0].x, dBacc[0].y, dBacc[1].x, dBacc[1].y));
-            atomicAdd(reinterpret_cast<float4 *>(dBg + pos + 4), make_float4(dBacc[2].x, dBacc[2].y, dBacc[3].x, dBacc[3].y));
-            atomicAdd(reinterpret_cast<float4 *>(dCg + pos), make_float4(dCacc[0].x, dCacc[0].y, dCacc[1].x, dCacc[1].y));
-            atomicAdd(reinterpret_cast<float4 *>(dCg + pos + 4), make_float4(dCacc[2].x, dCacc[2].y, dCacc[3].x, dCacc[3].y));
+            red8(dBg + pos, dBacc);
+            red8(dCg + pos, dCacc);
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -406,21 +415,29 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
 }
 
 template <bool SP, int STAGES>
-__global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const __grid_constant__ ScanArgs a) {
+__global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const __grid_constant__ GroupArgs ga) {
     extern __shared__ __align__(128) unsigned char smem_bwd_pipe[];
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
     pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
-    // adjoint: high chunks first; block order = scan order, so a tile only waits on tiles dispatched before it
+    int tile;
+    const ScanArgs &a = ga.a[group_problem(ga, tile)];
+    // adjoint: late chunks first; block order = the adjoint's scan order, so a tile only waits on tiles dispatched before it
     const unsigned epoch = *reinterpret_cast<volatile unsigned *>(a.ws_header + 2) % 0xfffffffeu + 1u;
-    const int chunk = a.n_chunks - 1 - (int)(blockIdx.x / a.n_rowgroups);
-    const int rg = blockIdx.x % a.n_rowgroups;
-    const bool tail = (chunk + 1) * 2048 > a.seqlen;
-    if (tail) scan_bwd_pipe_body<true, SP, STAGES>(a, smem_bwd_pipe, chunk, rg, epoch);
-    else scan_bwd_pipe_body<false, SP, STAGES>(a, smem_bwd_pipe, chunk, rg, epoch);
+    const int chunk = a.n_chunks - 1 - tile / a.n_rowgroups;
+    const int rg = tile % a.n_rowgroups;
+    const int mchunk = a.rev ? a.n_chunks - 1 - chunk : chunk;
+    const bool tail = (mchunk + 1) * 2048 > a.seqlen;
+    if (a.rev) {
+        if (tail) scan_bwd_pipe_body<true, SP, STAGES, true>(a, smem_bwd_pipe, chunk, rg, epoch);
+        else scan_bwd_pipe_body<false, SP, STAGES, true>(a, smem_bwd_pipe, chunk, rg, epoch);
+    } else {
+        if (tail) scan_bwd_pipe_body<true, SP, STAGES, false>(a, smem_bwd_pipe, chunk, rg, epoch);
+        else scan_bwd_pipe_body<false, SP, STAGES, false>(a, smem_bwd_pipe, chunk, rg, epoch);
+    }
 }
 
 template <bool SP, int STAGES>
-static int launch_bwd_pipe(const ScanArgs &a, int grid, cudaStream_t stream) {
+static int launch_bwd_pipe(const GroupArgs &ga, int grid, cudaStream_t stream) {
     const size_t smem = 2048 + sizeof(float) * (2048 + (size_t)STAGES * 3 * 2048);
     static PerDeviceOnce configured;  // the attribute is per function and per device
     if (!configured()) {
@@ -429,15 +446,17 @@ static int launch_bwd_pipe(const ScanArgs &a, int grid, cudaStream_t stream) {
             return rc;
         configured() = true;
     }
-    return launch_pdl(scan_bwd_pipe_kernel<SP, STAGES>, grid, kBPipeThreads, smem, stream, "scan_bwd_pipe launch", a);
+    return launch_pdl(scan_bwd_pipe_kernel<SP, STAGES>, grid, kBPipeThreads, smem, stream, "scan_bwd_pipe launch", ga);
 }
 
-// n_chunks > 1 and at most kBPipeStages channels per tile (scan_host.cu plans it so)
-int scan_bwd_pipe_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream) {
-    if (a.chan_per_tile > kBPipeStages) return fail("scan_bwd_pipe: %d channels per tile (max %d)", a.chan_per_tile, kBPipeStages);
-    if (a.chan_per_tile <= 3)  // smaller tile (groups of 2 channels): 82 KB of shared memory, fewer live registers (measured +11 %)
-        return a.softplus ? launch_bwd_pipe<true, 3>(a, pl.grid, stream) : launch_bwd_pipe<false, 3>(a, pl.grid, stream);
-    return a.softplus ? launch_bwd_pipe<true, 4>(a, pl.grid, stream) : launch_bwd_pipe<false, 4>(a, pl.grid, stream);
+// every problem: n_chunks > 1, at most kBPipeStages channels per tile, same softplus flag and the same side of the
+// 3-channel boundary (scan_host.cu groups them so)
+int scan_bwd_pipe_dispatch(const GroupArgs &ga, int grid, cudaStream_t stream) {
+    for (int i = 0; i < ga.n; ++i)
+        if (ga.a[i].chan_per_tile > kBPipeStages) return fail("scan_bwd_pipe: %d channels per tile (max %d)", ga.a[i].chan_per_tile, kBPipeStages);
+    if (ga.a[0].chan_per_tile <= 3)  // smaller tile (groups of 2 channels): 82 KB of shared memory, fewer live registers (measured +11 %)
+        return ga.a[0].softplus ? launch_bwd_pipe<true, 3>(ga, grid, stream) : launch_bwd_pipe<false, 3>(ga, grid, stream);
+    return ga.a[0].softplus ? launch_bwd_pipe<true, 4>(ga, grid, stream) : launch_bwd_pipe<false, 4>(ga, grid, stream);
 }
 
 }  // namespace vmasr

@@ -18,7 +18,8 @@ namespace vmasr {
 constexpr int kBwdStages = 3;
 constexpr int kBwdMaxTileChannels = 64;
 
-template <int TPR, bool TAIL, bool SP>
+// REV (time runs against memory order) is supported for single-chunk sequences, which is all the host sends here.
+template <int TPR, bool TAIL, bool SP, bool REV>
 __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned char *smem, const int chunk, const int rg,
                                                   const unsigned epoch) {
     constexpr int NT = 256, ITEMS = 8, STAGES = kBwdStages;
@@ -46,10 +47,12 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
     const int warp_in_row = t_in_row >> 5;
     const int warp_slot = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int sel = (t_in_row >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
+    const int tseg = REV ? TPR - 1 - t_in_row : t_in_row;  // this thread's 8-position segment of the row segment (memory order)
+    const int sel = (tseg >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
     const int L = a.seqlen;
     const int seg0 = chunk * SEG;
-    const int pos = seg0 + t_in_row * ITEMS;
+    const int pos = seg0 + tseg * ITEMS;
+    const bool accum = a.accum != 0;
     const int seg_len = min(SEG, L - seg0);
     const unsigned seg_bytes = (unsigned)seg_len * 4u;
     int nvalid = ITEMS;
@@ -117,7 +120,7 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
 
     float2 Bv[4], dBacc[4], dCacc[4];
     mbar_wait(bar_bc, 0);
-    lds8_sw(s_bc + t_in_row * ITEMS, sel, Bv);
+    lds8_sw(s_bc + tseg * ITEMS, sel, Bv);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         dBacc[j] = f2(0.0f);
@@ -163,14 +166,14 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
         mbar_wait(my_bars + s * ROWS, (unsigned)((it / STAGES) & 1));
         // The stage stays valid for the whole iteration (it is refilled one iteration later), so u and dout are read
         // again where they are needed instead of being held in registers, and sigmoid is parked in delta's slot.
-        float *su = my_stage + (size_t)s * ROWS * 3 * SEG + t_in_row * ITEMS;
+        float *su = my_stage + (size_t)s * ROWS * 3 * SEG + tseg * ITEMS;
         float2 dtn[4], av[4], bx[4], cdy[4];
         {
             float2 uv[4], dl[4], dy[4], Cv[4], sig[4];
             lds8_sw(su, sel, uv);
             lds8_sw(su + SEG, sel, dl);
             lds8_sw(su + 2 * SEG, sel, dy);
-            lds8_sw(s_bc + SEG + t_in_row * ITEMS, sel, Cv);
+            lds8_sw(s_bc + SEG + tseg * ITEMS, sel, Cv);
             if (TAIL) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -203,17 +206,13 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
             }
             sts8_priv(su + SEG, sel, sig);
         }
-        // local aggregates of both recurrences in one left-to-right walk:
-        //   forward   s -> p s + q;      adjoint (entering from the right)  G -> p G + qr,  qr = sum_i (prod_{j<=i} a_j) C_i dout_i
+        // local aggregates of both recurrences in one walk in time order:
+        //   forward   s -> p s + q;      adjoint (entering from the future)  G -> p G + qr,  qr = sum_i (prod_{j<=i} a_j) C_i dout_i
         float p = 1.0f, q = 0.0f, qr = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            q = fmaf(av[j].x, q, bx[j].x);
-            p *= av[j].x;
-            qr = fmaf(p, cdy[j].x, qr);
-            q = fmaf(av[j].y, q, bx[j].y);
-            p *= av[j].y;
-            qr = fmaf(p, cdy[j].y, qr);
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = pair_at<REV>(jj);
+            walk_pair2<REV>(av[j], bx[j], cdy[j], p, q, qr);
         }
         const Aff inc_f = warp_scan_up_fast<32>(Aff{p, q});
         const Aff inc_r = warp_scan_down_fast<32>(Aff{p, qr});
@@ -275,23 +274,19 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
         {
             float h = fmaf(exc_f.p, h_warp, exc_f.q);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                h = fmaf(av[j].x, h, bx[j].x);
-                hs[j].x = h;
-                h = fmaf(av[j].y, h, bx[j].y);
-                hs[j].y = h;
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = pair_at<REV>(jj);
+                walk_state<REV>(av[j], bx[j], h, hs[j]);
             }
         }
-        // adjoint walk, right to left
+        // adjoint walk, against time order
         float2 gl[4];
         {
             float G = fmaf(exc_r.p, g_warp, exc_r.q);
 #pragma unroll
-            for (int j = 3; j >= 0; --j) {
-                gl[j].y = cdy[j].y + G;
-                G = av[j].y * gl[j].y;
-                gl[j].x = cdy[j].x + G;
-                G = av[j].x * gl[j].x;
+            for (int jj = 3; jj >= 0; --jj) {
+                const int j = pair_at<REV>(jj);
+                walk_adjoint<REV>(av[j], cdy[j], G, gl[j]);
             }
         }
         // gradients, position pairs
@@ -318,13 +313,20 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
             float *o_du = du_ptr + it * du_step;
             float *o_dd = dd_ptr + it * dd_step;
             if (!TAIL || nvalid == ITEMS) {
-                stg8(o_du, du);
+                if (accum) red8(o_du, du);
+                else stg8(o_du, du);
                 stg8(o_dd, ddl);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if (2 * j < nvalid) { o_du[2 * j] = du[j].x; o_dd[2 * j] = ddl[j].x; }
-                    if (2 * j + 1 < nvalid) { o_du[2 * j + 1] = du[j].y; o_dd[2 * j + 1] = ddl[j].y; }
+                    if (2 * j < nvalid) {
+                        if (accum) atomicAdd(o_du + 2 * j, du[j].x); else o_du[2 * j] = du[j].x;
+                        o_dd[2 * j] = ddl[j].x;
+                    }
+                    if (2 * j + 1 < nvalid) {
+                        if (accum) atomicAdd(o_du + 2 * j + 1, du[j].y); else o_du[2 * j + 1] = du[j].y;
+                        o_dd[2 * j + 1] = ddl[j].y;
+                    }
                 }
             }
         }
@@ -372,10 +374,8 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
     }
     if (row == 0) {
         if (!TAIL || nvalid == ITEMS) {
-            atomicAdd(reinterpret_cast<float4 *>(dBg + pos), make_float4(dBacc[0].x, dBacc[0].y, dBacc[1].x, dBacc[1].y));
-            atomicAdd(reinterpret_cast<float4 *>(dBg + pos + 4), make_float4(dBacc[2].x, dBacc[2].y, dBacc[3].x, dBacc[3].y));
-            atomicAdd(reinterpret_cast<float4 *>(dCg + pos), make_float4(dCacc[0].x, dCacc[0].y, dCacc[1].x, dCacc[1].y));
-            atomicAdd(reinterpret_cast<float4 *>(dCg + pos + 4), make_float4(dCacc[2].x, dCacc[2].y, dCacc[3].x, dCacc[3].y));
+            red8(dBg + pos, dBacc);
+            red8(dCg + pos, dCacc);
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -388,18 +388,25 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
 }
 
 template <int TPR, bool SP>
-__global__ void __launch_bounds__(256, 2) scan_bwd_tma_kernel(const __grid_constant__ ScanArgs a) {
+__global__ void __launch_bounds__(256, 2) scan_bwd_tma_kernel(const __grid_constant__ GroupArgs ga) {
     extern __shared__ __align__(128) unsigned char smem_bwd_tma[];
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
     pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
     constexpr int SEG = TPR * 8;
-    unsigned tile, epoch;
-    claim_tile(a, reinterpret_cast<unsigned *>(smem_bwd_tma + 384), tile, epoch);
-    const int chunk = a.n_chunks - 1 - (int)(tile / a.n_rowgroups);  // adjoint: high chunks first
+    int gtile;
+    const ScanArgs &a = ga.a[group_problem(ga, gtile)];
+    unsigned tile = (unsigned)gtile, epoch = 0;
+    if (a.n_chunks > 1) claim_tile(a, reinterpret_cast<unsigned *>(smem_bwd_tma + 384), tile, epoch);  // VMASR_TUNING builds only
+    const int chunk = a.n_chunks - 1 - (int)(tile / a.n_rowgroups);  // adjoint: late chunks first
     const int rg = tile % a.n_rowgroups;
     const bool tail = (chunk + 1) * SEG > a.seqlen;
-    if (tail) scan_bwd_tma_body<TPR, true, SP>(a, smem_bwd_tma, chunk, rg, epoch);
-    else scan_bwd_tma_body<TPR, false, SP>(a, smem_bwd_tma, chunk, rg, epoch);
+    if (a.rev) {  // single chunk only (host-checked)
+        if (tail) scan_bwd_tma_body<TPR, true, SP, true>(a, smem_bwd_tma, chunk, rg, epoch);
+        else scan_bwd_tma_body<TPR, false, SP, true>(a, smem_bwd_tma, chunk, rg, epoch);
+    } else {
+        if (tail) scan_bwd_tma_body<TPR, true, SP, false>(a, smem_bwd_tma, chunk, rg, epoch);
+        else scan_bwd_tma_body<TPR, false, SP, false>(a, smem_bwd_tma, chunk, rg, epoch);
+    }
 }
 
 static size_t scan_bwd_tma_smem(int tpr) {
@@ -408,7 +415,7 @@ static size_t scan_bwd_tma_smem(int tpr) {
 }
 
 template <int TPR, bool SP>
-static int launch_tma(const ScanArgs &a, int grid, cudaStream_t stream) {
+static int launch_tma(const GroupArgs &ga, int grid, cudaStream_t stream) {
     const size_t smem = scan_bwd_tma_smem(TPR);
     static PerDeviceOnce configured;  // the attribute is per function and per device
     if (!configured()) {
@@ -417,21 +424,26 @@ static int launch_tma(const ScanArgs &a, int grid, cudaStream_t stream) {
             return rc;
         configured() = true;
     }
-    return launch_pdl(scan_bwd_tma_kernel<TPR, SP>, grid, 256, smem, stream, "scan_bwd_tma launch", a);
+    return launch_pdl(scan_bwd_tma_kernel<TPR, SP>, grid, 256, smem, stream, "scan_bwd_tma launch", ga);
 }
 
 template <bool SP>
-static int dispatch_tpr(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream) {
-    switch (pl.tpr) {
-        case 32: return launch_tma<32, SP>(a, pl.grid, stream);
-        case 64: return launch_tma<64, SP>(a, pl.grid, stream);
-        case 128: return launch_tma<128, SP>(a, pl.grid, stream);
-        default: return launch_tma<256, SP>(a, pl.grid, stream);
+static int dispatch_tpr(const GroupArgs &ga, int tpr, int grid, cudaStream_t stream) {
+    switch (tpr) {
+        case 32: return launch_tma<32, SP>(ga, grid, stream);
+        case 64: return launch_tma<64, SP>(ga, grid, stream);
+        case 128: return launch_tma<128, SP>(ga, grid, stream);
+        default: return launch_tma<256, SP>(ga, grid, stream);
     }
 }
 
-int scan_bwd_tma_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream) {
-    return a.softplus ? dispatch_tpr<true>(a, pl, stream) : dispatch_tpr<false>(a, pl, stream);
+// every problem of the group: same threads-per-row and softplus flag (scan_host.cu groups them so)
+int scan_bwd_tma_dispatch(const GroupArgs &ga, int tpr, int grid, cudaStream_t stream) {
+    for (int i = 0; i < ga.n; ++i) {
+        if (ga.a[i].rev && ga.a[i].n_chunks > 1) return fail("scan_bwd_tma: reversed scans of more than one chunk go to the multi-chunk kernel");
+        if (ga.n > 1 && ga.a[i].n_chunks > 1) return fail("scan_bwd_tma: grouped launches take single-chunk problems only");
+    }
+    return ga.a[0].softplus ? dispatch_tpr<true>(ga, tpr, grid, stream) : dispatch_tpr<false>(ga, tpr, grid, stream);
 }
 
 }  // namespace vmasr

@@ -33,7 +33,8 @@ namespace vmasr {
 constexpr int kPipeStages = 4;        // channels per tile = resident stages (u + delta, 16 KB per channel)
 constexpr int kPipeThreads = 288;     // 8 compute warps + the exchange warp
 
-template <bool TAIL, bool SP>
+// `chunk` is the chunk's index in TIME order; with REV (time runs against memory order) it sits at the mirrored place in memory.
+template <bool TAIL, bool SP, bool REV>
 __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned char *smem, const int chunk, const int rg) {
     constexpr int NC = 256, ITEMS = 8, WPR = 8, SEG = NC * ITEMS, STAGES = kPipeStages;
 
@@ -58,7 +59,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
     const int lane = threadIdx.x & 31;
     const bool exchange = warp == WPR;  // the ninth warp
     const int L = a.seqlen;
-    const int seg0 = chunk * SEG;
+    const int seg0 = (REV ? a.n_chunks - 1 - chunk : chunk) * SEG;  // first MEMORY position of the tile
     const int seg_len = min(SEG, L - seg0);  // multiple of 4
     const unsigned seg_bytes = (unsigned)seg_len * 4u;
 
@@ -163,7 +164,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
         if (lane == 0) {
             __threadfence();
             const unsigned prev = atomicAdd(a.ws_header + 1, 1u);
-            if (prev == gridDim.x - 1) {
+            if (prev == (unsigned)(a.n_chunks * a.n_rowgroups) - 1u) {
                 a.ws_header[1] = 0u;
                 a.ws_header[2] = a.ws_header[2] + 1u;
                 __threadfence();
@@ -171,16 +172,18 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
         }
     } else {
         // ================= compute warps =================
-        const int pos = seg0 + threadIdx.x * ITEMS;
-        const int sel = (threadIdx.x >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
+        const int tseg = REV ? NC - 1 - (int)threadIdx.x : (int)threadIdx.x;  // this thread's 8-position segment of the tile (memory order)
+        const int pos = seg0 + tseg * ITEMS;
+        const int sel = (tseg >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
         int nvalid = ITEMS;
         if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
         float *out_ptr = reinterpret_cast<float *>(a.out) + b * a.out_bs + (long long)d0 * a.out_ds + pos;
+        const bool accum = a.accum != 0;
 
         float2 Bl[4], Cv[4];  // ln2 * B (the scan runs on dt in the log2 domain) and C of this thread's positions
         mbar_wait(bar_bc, 0);
-        lds8_sw(s_bc + threadIdx.x * ITEMS, sel, Bl);
-        lds8_sw(s_bc + SEG + threadIdx.x * ITEMS, sel, Cv);
+        lds8_sw(s_bc + tseg * ITEMS, sel, Bl);
+        lds8_sw(s_bc + SEG + tseg * ITEMS, sel, Cv);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free);
 #pragma unroll
@@ -202,14 +205,15 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
                 const float Av = s_par[j];
                 const float Dv = s_par[STAGES + j];
                 const float bias2 = s_par[2 * STAGES + j];
-                float *su = s_stage + (size_t)j * 2 * SEG + threadIdx.x * ITEMS;
+                float *su = s_stage + (size_t)j * 2 * SEG + tseg * ITEMS;
                 mbar_wait(&bar_full[j], 0);
                 float2 uv[4], dl[4], Y0[4], Y1[4];
                 lds8_sw(su, sel, uv);
                 lds8_sw(su + SEG, sel, dl);
                 float p = 1.0f, q = 0.0f;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int k = pair_at<REV>(kk);  // pairs in time order
                     if (TAIL) {
                         if (2 * k >= nvalid) { uv[k].x = 0.0f; dl[k].x = 0.0f; }
                         if (2 * k + 1 >= nvalid) { uv[k].y = 0.0f; dl[k].y = 0.0f; }
@@ -227,14 +231,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
                         if (2 * k + 1 >= nvalid) av.y = 1.0f;
                     }
                     float2 P, Q;
-                    q = fmaf(av.x, q, bx.x);
-                    p *= av.x;
-                    P.x = p;
-                    Q.x = q;
-                    q = fmaf(av.y, q, bx.y);
-                    p *= av.y;
-                    P.y = p;
-                    Q.y = q;
+                    walk_pair<REV>(av, bx, p, q, P, Q);
                     Y0[k] = fma2(Cv[k], Q, mul2(uv[k], f2(Dv)));
                     Y1[k] = mul2(Cv[k], P);
                 }
@@ -260,7 +257,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
                     if (i == j) ex = exc[i];
                 mbar_wait(&bar_in[j], 0);
                 const float h_in = fmaf(ex.p, s_in[j * WPR + warp], ex.q);
-                const float *sy = s_stage + (size_t)j * 2 * SEG + threadIdx.x * ITEMS;
+                const float *sy = s_stage + (size_t)j * 2 * SEG + tseg * ITEMS;
                 float2 Y0[4], Y1[4], y[4];
                 lds8_priv(sy, sel, Y0);
                 lds8_priv(sy + SEG, sel, Y1);
@@ -268,12 +265,18 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
                 for (int k = 0; k < 4; ++k) y[k] = fma2(Y1[k], f2(h_in), Y0[k]);
                 float *o = out_ptr + (long long)j * a.out_ds;
                 if (!TAIL || nvalid == ITEMS) {
-                    stg8(o, y);
+                    if (accum) red8(o, y);
+                    else stg8(o, y);
                 } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (2 * k < nvalid) o[2 * k] = y[k].x;
-                        if (2 * k + 1 < nvalid) o[2 * k + 1] = y[k].y;
+                        if (accum) {
+                            if (2 * k < nvalid) atomicAdd(o + 2 * k, y[k].x);
+                            if (2 * k + 1 < nvalid) atomicAdd(o + 2 * k + 1, y[k].y);
+                        } else {
+                            if (2 * k < nvalid) o[2 * k] = y[k].x;
+                            if (2 * k + 1 < nvalid) o[2 * k + 1] = y[k].y;
+                        }
                     }
                 }
             }
@@ -283,19 +286,27 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
 }
 
 template <bool SP>
-__global__ void __launch_bounds__(kPipeThreads, 3) scan_fwd_pipe_kernel(const __grid_constant__ ScanArgs a) {
+__global__ void __launch_bounds__(kPipeThreads, 3) scan_fwd_pipe_kernel(const __grid_constant__ GroupArgs ga) {
     extern __shared__ __align__(128) unsigned char smem_fwd_pipe[];
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
     pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
-    const int chunk = blockIdx.x / a.n_rowgroups;  // chunk-major: a tile only waits on tiles dispatched before it
-    const int rg = blockIdx.x - chunk * a.n_rowgroups;
-    const bool tail = (chunk + 1) * 2048 > a.seqlen;
-    if (tail) scan_fwd_pipe_body<true, SP>(a, smem_fwd_pipe, chunk, rg);
-    else scan_fwd_pipe_body<false, SP>(a, smem_fwd_pipe, chunk, rg);
+    int tile;
+    const ScanArgs &a = ga.a[group_problem(ga, tile)];
+    const int chunk = tile / a.n_rowgroups;  // chunk-major in TIME order: a tile only waits on tiles dispatched before it
+    const int rg = tile - chunk * a.n_rowgroups;
+    const int mchunk = a.rev ? a.n_chunks - 1 - chunk : chunk;
+    const bool tail = (mchunk + 1) * 2048 > a.seqlen;
+    if (a.rev) {
+        if (tail) scan_fwd_pipe_body<true, SP, true>(a, smem_fwd_pipe, chunk, rg);
+        else scan_fwd_pipe_body<false, SP, true>(a, smem_fwd_pipe, chunk, rg);
+    } else {
+        if (tail) scan_fwd_pipe_body<true, SP, false>(a, smem_fwd_pipe, chunk, rg);
+        else scan_fwd_pipe_body<false, SP, false>(a, smem_fwd_pipe, chunk, rg);
+    }
 }
 
 template <bool SP>
-static int launch_fwd_pipe(const ScanArgs &a, int grid, cudaStream_t stream) {
+static int launch_fwd_pipe(const GroupArgs &ga, int grid, cudaStream_t stream) {
     const size_t smem = 2048 + sizeof(float) * ((size_t)kPipeStages * 2 * 2048);
     static PerDeviceOnce configured;  // the attribute is per function and per device
     if (!configured()) {
@@ -304,13 +315,14 @@ static int launch_fwd_pipe(const ScanArgs &a, int grid, cudaStream_t stream) {
             return rc;
         configured() = true;
     }
-    return launch_pdl(scan_fwd_pipe_kernel<SP>, grid, kPipeThreads, smem, stream, "scan_fwd_pipe launch", a);
+    return launch_pdl(scan_fwd_pipe_kernel<SP>, grid, kPipeThreads, smem, stream, "scan_fwd_pipe launch", ga);
 }
 
-// n_chunks > 1 and at most kPipeStages channels per tile (scan_host.cu plans it so)
-int scan_fwd_pipe_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream) {
-    if (a.chan_per_tile > kPipeStages) return fail("scan_fwd_pipe: %d channels per tile (max %d)", a.chan_per_tile, kPipeStages);
-    return a.softplus ? launch_fwd_pipe<true>(a, pl.grid, stream) : launch_fwd_pipe<false>(a, pl.grid, stream);
+// every problem: n_chunks > 1, at most kPipeStages channels per tile, same softplus flag (scan_host.cu groups them so)
+int scan_fwd_pipe_dispatch(const GroupArgs &ga, int grid, cudaStream_t stream) {
+    for (int i = 0; i < ga.n; ++i)
+        if (ga.a[i].chan_per_tile > kPipeStages) return fail("scan_fwd_pipe: %d channels per tile (max %d)", ga.a[i].chan_per_tile, kPipeStages);
+    return ga.a[0].softplus ? launch_fwd_pipe<true>(ga, grid, stream) : launch_fwd_pipe<false>(ga, grid, stream);
 }
 
 }  // namespace vmasr

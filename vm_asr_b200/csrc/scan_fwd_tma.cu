@@ -14,15 +14,14 @@
 //   * full tiles carry no bounds checks; tiles are taken in blockIdx order (chunk-major), so a tile only ever waits
 //     on carries of tiles that were dispatched before it.
 // Outputs go straight from registers to HBM with 128-bit stores.
-#include <cstdlib>
-
 #include "fast.cuh"
 
 namespace vmasr {
 
 constexpr int kMaxTileChannels = 64;
 
-template <int TPR, bool TAIL, bool SP, int STAGES>
+// REV (time runs against memory order) is supported for single-chunk sequences, which is all the host sends here.
+template <int TPR, bool TAIL, bool SP, int STAGES, bool REV>
 __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned char *smem, const int chunk, const int rg) {
     constexpr int NT = 256, ITEMS = 8;
     constexpr int ROWS = NT / TPR;
@@ -48,10 +47,12 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
     const int warp_in_row = t_in_row >> 5;
     const int warp_slot = threadIdx.x >> 5;  // row * WPR + warp_in_row
     const int lane = threadIdx.x & 31;
-    const int sel = (t_in_row >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
+    const int tseg = REV ? TPR - 1 - t_in_row : t_in_row;  // this thread's 8-position segment of the row segment (memory order)
+    const int sel = (tseg >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
     const int L = a.seqlen;
     const int seg0 = chunk * SEG;                       // first position of the tile
-    const int pos = seg0 + t_in_row * ITEMS;
+    const int pos = seg0 + tseg * ITEMS;
+    const bool accum = a.accum != 0;
     const int seg_len = min(SEG, L - seg0);             // valid positions in this tile (multiple of 4)
     const unsigned seg_bytes = (unsigned)seg_len * 4u;
     int nvalid = ITEMS;
@@ -117,8 +118,8 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
 
     float2 Bl[4], Cv[4];  // ln2 * B (the scan runs on dt in the log2 domain) and C of this thread's positions
     mbar_wait(bar_bc, 0);
-    lds8_sw(s_bc + t_in_row * ITEMS, sel, Bl);
-    lds8_sw(s_bc + SEG + t_in_row * ITEMS, sel, Cv);
+    lds8_sw(s_bc + tseg * ITEMS, sel, Bl);
+    lds8_sw(s_bc + SEG + tseg * ITEMS, sel, Cv);
     __syncthreads();  // B / C are in registers: the last stage is free for data now
     if (t_in_row == 0 && STAGES - 1 < n_iter) issue_stage(STAGES - 1);
 #pragma unroll
@@ -145,7 +146,7 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
         mbar_wait(my_bars + s * ROWS, (unsigned)((it / STAGES) & 1));
         float2 uv[4], av[4], bx[4];
         {
-            const float *su = my_stage + (size_t)s * ROWS * 2 * SEG + t_in_row * ITEMS;
+            const float *su = my_stage + (size_t)s * ROWS * 2 * SEG + tseg * ITEMS;
             float2 dl[4];
             lds8_sw(su, sel, uv);
             lds8_sw(su + SEG, sel, dl);
@@ -170,11 +171,10 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
         }
         Aff loc = {1.0f, 0.0f};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            loc.q = fmaf(av[j].x, loc.q, bx[j].x);
-            loc.p *= av[j].x;
-            loc.q = fmaf(av[j].y, loc.q, bx[j].y);
-            loc.p *= av[j].y;
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = pair_at<REV>(jj);  // pairs in time order
+            float2 P, Q;
+            walk_pair<REV>(av[j], bx[j], loc.p, loc.q, P, Q);
         }
         const Aff inc = warp_scan_up_fast<32>(loc);
         const Aff exc = shift_up1(inc, lane);
@@ -233,22 +233,26 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
         float h = fmaf(exc.p, h_warp, exc.q);
         float2 y[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = pair_at<REV>(jj);
             float2 hh;
-            h = fmaf(av[j].x, h, bx[j].x);
-            hh.x = h;
-            h = fmaf(av[j].y, h, bx[j].y);
-            hh.y = h;
+            walk_state<REV>(av[j], bx[j], h, hh);
             y[j] = fma2(Cv[j], hh, mul2(uv[j], f2(Dv)));
         }
         float *o = out_ptr + it * out_step;
         if (!TAIL || nvalid == ITEMS) {
-            stg8(o, y);
+            if (accum) red8(o, y);
+            else stg8(o, y);
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (2 * j < nvalid) o[2 * j] = y[j].x;
-                if (2 * j + 1 < nvalid) o[2 * j + 1] = y[j].y;
+                if (accum) {
+                    if (2 * j < nvalid) atomicAdd(o + 2 * j, y[j].x);
+                    if (2 * j + 1 < nvalid) atomicAdd(o + 2 * j + 1, y[j].y);
+                } else {
+                    if (2 * j < nvalid) o[2 * j] = y[j].x;
+                    if (2 * j + 1 < nvalid) o[2 * j + 1] = y[j].y;
+                }
             }
         }
     }
@@ -257,7 +261,7 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
         if (threadIdx.x == 0) {
             __threadfence();
             const unsigned prev = atomicAdd(a.ws_header + 1, 1u);
-            if (prev == gridDim.x - 1) {
+            if (prev == (unsigned)(a.n_chunks * a.n_rowgroups) - 1u) {
                 a.ws_header[1] = 0u;
                 a.ws_header[2] = a.ws_header[2] + 1u;
                 __threadfence();
@@ -267,22 +271,29 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
 }
 
 template <int TPR, bool SP, int STAGES>
-__global__ void __launch_bounds__(256, 3) scan_fwd_tma_kernel(const __grid_constant__ ScanArgs a) {
+__global__ void __launch_bounds__(256, 3) scan_fwd_tma_kernel(const __grid_constant__ GroupArgs ga) {
     extern __shared__ __align__(128) unsigned char smem_fwd_tma[];
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
     pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
     constexpr int SEG = TPR * 8;
-    const int chunk = blockIdx.x / a.n_rowgroups;
-    const int rg = blockIdx.x - chunk * a.n_rowgroups;
+    int tile;
+    const ScanArgs &a = ga.a[group_problem(ga, tile)];
+    const int chunk = tile / a.n_rowgroups;
+    const int rg = tile - chunk * a.n_rowgroups;
     const bool tail = (chunk + 1) * SEG > a.seqlen;
-    if (tail) scan_fwd_tma_body<TPR, true, SP, STAGES>(a, smem_fwd_tma, chunk, rg);
-    else scan_fwd_tma_body<TPR, false, SP, STAGES>(a, smem_fwd_tma, chunk, rg);
+    if (a.rev) {  // single chunk only (host-checked)
+        if (tail) scan_fwd_tma_body<TPR, true, SP, STAGES, true>(a, smem_fwd_tma, chunk, rg);
+        else scan_fwd_tma_body<TPR, false, SP, STAGES, true>(a, smem_fwd_tma, chunk, rg);
+    } else {
+        if (tail) scan_fwd_tma_body<TPR, true, SP, STAGES, false>(a, smem_fwd_tma, chunk, rg);
+        else scan_fwd_tma_body<TPR, false, SP, STAGES, false>(a, smem_fwd_tma, chunk, rg);
+    }
 }
 
 static size_t scan_fwd_tma_smem(int stages) { return 2048 + sizeof(float) * ((size_t)stages * 2 * 2048); }
 
 template <int TPR, bool SP, int STAGES>
-static int launch_tma(const ScanArgs &a, int grid, cudaStream_t stream) {
+static int launch_tma(const GroupArgs &ga, int grid, cudaStream_t stream) {
     const size_t smem = scan_fwd_tma_smem(STAGES);
     static PerDeviceOnce configured;  // the attribute is per function and per device
     if (!configured()) {
@@ -291,32 +302,25 @@ static int launch_tma(const ScanArgs &a, int grid, cudaStream_t stream) {
             return rc;
         configured() = true;
     }
-    return launch_pdl(scan_fwd_tma_kernel<TPR, SP, STAGES>, grid, 256, smem, stream, "scan_fwd_tma launch", a);
+    return launch_pdl(scan_fwd_tma_kernel<TPR, SP, STAGES>, grid, 256, smem, stream, "scan_fwd_tma launch", ga);
 }
 
 template <bool SP, int STAGES>
-static int dispatch_tpr(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream) {
-    switch (pl.tpr) {
-        case 32: return launch_tma<32, SP, STAGES>(a, pl.grid, stream);
-        case 64: return launch_tma<64, SP, STAGES>(a, pl.grid, stream);
-        case 128: return launch_tma<128, SP, STAGES>(a, pl.grid, stream);
-        default: return launch_tma<256, SP, STAGES>(a, pl.grid, stream);
+static int dispatch_tpr(const GroupArgs &ga, int tpr, int grid, cudaStream_t stream) {
+    switch (tpr) {
+        case 32: return launch_tma<32, SP, STAGES>(ga, grid, stream);
+        case 64: return launch_tma<64, SP, STAGES>(ga, grid, stream);
+        case 128: return launch_tma<128, SP, STAGES>(ga, grid, stream);
+        default: return launch_tma<256, SP, STAGES>(ga, grid, stream);
     }
 }
 
-template <bool SP>
-static int dispatch_stages(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream) {
-    // depth of the TMA ring: bytes in flight per CTA = STAGES x 16 KB (tuning knob: VMASR_FWD_STAGES = 2 | 3 | 4)
-    static const int stages = [] { const char *e = getenv("VMASR_FWD_STAGES"); return e ? atoi(e) : 4; }();
-    switch (stages) {
-        case 2: return dispatch_tpr<SP, 2>(a, pl, stream);
-        case 3: return dispatch_tpr<SP, 3>(a, pl, stream);
-        default: return dispatch_tpr<SP, 4>(a, pl, stream);
-    }
-}
-
-int scan_fwd_tma_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream) {
-    return a.softplus ? dispatch_stages<true>(a, pl, stream) : dispatch_stages<false>(a, pl, stream);
+// every problem of the group: same threads-per-row and softplus flag (scan_host.cu groups them so); TMA ring of 4 stages
+// (bytes in flight per CTA = 4 x 16 KB; 2 and 3 were measured slower)
+int scan_fwd_tma_dispatch(const GroupArgs &ga, int tpr, int grid, cudaStream_t stream) {
+    for (int i = 0; i < ga.n; ++i)
+        if (ga.a[i].rev && ga.a[i].n_chunks > 1) return fail("scan_fwd_tma: reversed scans of more than one chunk go to the multi-chunk kernel");
+    return ga.a[0].softplus ? dispatch_tpr<true, 4>(ga, tpr, grid, stream) : dispatch_tpr<false, 4>(ga, tpr, grid, stream);
 }
 
 }  // namespace vmasr

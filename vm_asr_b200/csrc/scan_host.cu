@@ -1,19 +1,18 @@
 // Host side of the selective scan: argument checks (mirroring the TORCH_CHECKs of
-// kernels/selective_scan/csrc/selective_scan/cus/selective_scan.cpp:165-215, 262-317), tile planning, launch.
-#include <cstdlib>
-
+// kernels/selective_scan/csrc/selective_scan/cus/selective_scan.cpp:165-215, 262-317), tile planning, launch of one
+// call or of a GROUP of independent calls as one grid.
 #include "scan.cuh"
 
 namespace vmasr {
 
 int scan_fwd_dispatch(const ScanArgs &a, const ScanPlan &pl, int io_dtype, cudaStream_t stream);
 int scan_bwd_dispatch(const ScanArgs &a, const ScanPlan &pl, int io_dtype, cudaStream_t stream);
-int scan_fwd_tma_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
-int scan_bwd_tma_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
-int scan_fwd_pipe_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
-int scan_bwd_pipe_dispatch(const ScanArgs &a, const ScanPlan &pl, cudaStream_t stream);
-int scan_fwd_ring_dispatch(const ScanArgs &a, const ScanPlan &pl, int device, cudaStream_t stream);
-constexpr int kMaxTileChannelsHost = 64;  // scan_fwd_tma.cu stages this many channels' parameters per tile
+int scan_fwd_tma_dispatch(const GroupArgs &ga, int tpr, int grid, cudaStream_t stream);
+int scan_bwd_tma_dispatch(const GroupArgs &ga, int tpr, int grid, cudaStream_t stream);
+int scan_fwd_pipe_dispatch(const GroupArgs &ga, int grid, cudaStream_t stream);
+int scan_bwd_pipe_dispatch(const GroupArgs &ga, int grid, cudaStream_t stream);
+constexpr int kMaxTileChannelsHost = 64;  // the single-chunk kernels stage this many channels' parameters per tile
+constexpr int kMultiChunkTileChannels = 4;  // the multi-chunk kernels keep the whole tile resident in shared memory
 
 static size_t dtype_size(int dt) { return dt == VMASR_F32 ? 4 : 2; }
 
@@ -28,6 +27,7 @@ static int validate(const vmasr_scan_params *p, bool bwd) {
                     p->dim, p->seqlen, p->dstate, p->ngroups);
     if (p->dim % p->ngroups != 0) return fail("dims should be dividable by n_groups");
     if (p->dstate > 256) return fail("selective_scan only supports state dimension <= 256");
+    if (p->flags & ~(VMASR_SCAN_REVERSE | VMASR_SCAN_ACCUMULATE)) return fail("selective_scan: unknown flag bits 0x%x", p->flags);
     if (!p->u || !p->delta || !p->A || !p->B || !p->C) return fail("selective_scan: u, delta, A, B, C must be non-null");
     if (!bwd && (!p->out || !p->x)) return fail("selective_scan_fwd: out and x must be non-null");
     if (bwd) {
@@ -51,7 +51,46 @@ static int validate(const vmasr_scan_params *p, bool bwd) {
     return 0;
 }
 
-static ScanPlan make_plan(const vmasr_scan_params *p, int n_chunks, bool bwd, int &chan_per_tile, int &n_ctiles) {
+// Channels per tile.  `peers` = problems launched in the same grid (their tiles fill the machine together).
+//   multi-chunk sequences: the resident-tile kernels take at most 4 channels (measured best: 4);
+//   single-chunk sequences: a tile walks its channels through a TMA ring, ROWS at a time, so the tile count is free.  Pick
+//   the channel count that minimises  waves x (start-up + iterations per row segment), waves = ceil(tiles / resident slots):
+//   a launch of 0.6 or 1.15 waves costs as much as one of 1.0 or 2.0 (profiles/r1_summary.md 4a).
+static int plan_channels(const vmasr_scan_params *p, int n_chunks, bool bwd, int rows, int peers) {
+    const int cpg = p->dim / p->ngroups;
+    if (n_chunks > 1) {
+        int cap = kMultiChunkTileChannels;
+        if (const char *e = tuning_env(bwd ? "VMASR_SCAN_CPT" : "VMASR_SCAN_CPT_FWD")) cap = atoi(e) < 1 ? 1 : atoi(e) > 4 ? 4 : atoi(e);
+        return cpg < cap ? cpg : cap;
+    }
+    const long long base_tiles = (long long)p->batch * p->ngroups * (peers < 1 ? 1 : peers);
+    const long long slots = (long long)sm_count(p->device) * (bwd ? 2 : 3);  // resident CTAs: __launch_bounds__(256, 2 | 3)
+    const char *legacy = tuning_env("VMASR_PLAN_LEGACY");
+    if (legacy && atoi(legacy)) {  // round-1 rule: at least two tiles per SM, otherwise as many channels per tile as possible
+        long long want = (2ll * sm_count(p->device) + base_tiles - 1) / base_tiles;
+        const long long max_ctiles = (cpg + rows - 1) / rows, min_ctiles = (cpg + kMaxTileChannelsHost - 1) / kMaxTileChannelsHost;
+        want = want < min_ctiles ? min_ctiles : want > max_ctiles ? max_ctiles : want;
+        const int c = (int)((cpg + want - 1) / want);
+        return ((c + rows - 1) / rows) * rows;
+    }
+    constexpr double kStartup = 3.0;  // tile start-up (TMA round trip, B / C, parameters) in units of one ring iteration
+    int best = rows;
+    double best_cost = 1e30;
+    for (int c = rows; c <= kMaxTileChannelsHost; c += rows) {
+        const long long ctiles = (cpg + c - 1) / c;
+        const long long tiles = base_tiles * ctiles;
+        const long long waves = (tiles + slots - 1) / slots;
+        const double cost = (double)waves * (kStartup + (double)(c / rows));
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best = c;
+        }
+        if (c >= cpg) break;
+    }
+    return best;
+}
+
+static ScanPlan make_plan(const vmasr_scan_params *p, int n_chunks, bool bwd, int peers, int &chan_per_tile, int &n_ctiles) {
     ScanPlan pl;
     pl.items = 8;
     pl.threads = 256;
@@ -59,29 +98,10 @@ static ScanPlan make_plan(const vmasr_scan_params *p, int n_chunks, bool bwd, in
     pl.tpr = L <= 256 ? 32 : L <= 512 ? 64 : L <= 1024 ? 128 : 256;
     pl.rows = pl.threads / pl.tpr;
     const int cpg = p->dim / p->ngroups;
-    // enough tiles to fill the machine a few times over, otherwise as many channels per tile as possible
-    // (B/C stay in registers across a tile's channels and dB/dC need fewer atomics)
-    const long long base_tiles = (long long)p->batch * p->ngroups * n_chunks;
-    static const int tiles_per_sm = [] { const char *e = getenv("VMASR_SCAN_TILES_PER_SM"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
-    const long long target = (long long)tiles_per_sm * sm_count(p->device);
-    const int max_ctiles = (cpg + pl.rows - 1) / pl.rows;
-    long long want = (target + base_tiles - 1) / base_tiles;
-    if (want < 1) want = 1;
-    const long long min_ctiles = (cpg + kMaxTileChannelsHost - 1) / kMaxTileChannelsHost;
-    if (want < min_ctiles) want = min_ctiles;
-    if (want > max_ctiles) want = max_ctiles;
-    chan_per_tile = (int)((cpg + want - 1) / want);
-    {
-        // Sequences of more than one chunk: the pipelined kernels keep the whole tile resident in shared memory
-        // (scan_fwd_pipe.cu / scan_bwd_pipe.cu), at most 4 channels.  VMASR_SCAN_CPT = 1..4 is a tuning knob.
-        static const int cap_multi = [] { const char *e = getenv("VMASR_SCAN_CPT"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : v > 4 ? 4 : v; }();
-        static const int cap_multi_fwd = [] { const char *e = getenv("VMASR_SCAN_CPT_FWD"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : v > 4 ? 4 : v; }();
-        const int cap = bwd ? cap_multi : (cap_multi < cap_multi_fwd ? cap_multi : cap_multi_fwd);  // measured best: 4 for both
-        if (n_chunks > 1 && chan_per_tile > cap) chan_per_tile = cap;
-    }
+    chan_per_tile = plan_channels(p, n_chunks, bwd, pl.rows, peers);
     chan_per_tile = ((chan_per_tile + pl.rows - 1) / pl.rows) * pl.rows;
     n_ctiles = (cpg + chan_per_tile - 1) / chan_per_tile;
-    pl.grid = (int)(base_tiles * n_ctiles);
+    pl.grid = (int)((long long)p->batch * p->ngroups * n_chunks * n_ctiles);
 
     const size_t es = dtype_size(p->io_dtype);
     const long long vec_elems = 16 / (long long)es;
@@ -113,8 +133,10 @@ static ScanArgs make_args(const vmasr_scan_params *p, int n_chunks, int chan_per
     a.n_ctiles = n_ctiles;
     a.n_rowgroups = p->batch * p->ngroups * n_ctiles;
     a.softplus = p->delta_softplus;
-    static const int nowait = [] { const char *e = getenv("VMASR_DEBUG_NOWAIT"); return e ? atoi(e) : 0; }();
-    a.debug_nowait = nowait;
+    a.rev = (p->flags & VMASR_SCAN_REVERSE) ? 1 : 0;
+    a.accum = (p->flags & VMASR_SCAN_ACCUMULATE) ? 1 : 0;
+    const char *nowait = tuning_env("VMASR_DEBUG_NOWAIT");
+    a.debug_nowait = nowait ? atoi(nowait) : 0;
     a.u_bs = p->u_batch_stride; a.u_ds = p->u_d_stride;
     a.delta_bs = p->delta_batch_stride; a.delta_ds = p->delta_d_stride;
     a.A_ds = p->A_d_stride; a.A_ns = p->A_dstate_stride;
@@ -127,14 +149,14 @@ static ScanArgs make_args(const vmasr_scan_params *p, int n_chunks, int chan_per
     return a;
 }
 
-enum ScanVariant { kGeneric = 0, kSingleChunk = 1, kMultiChunk = 2, kRing = 3 };
+enum ScanVariant { kGeneric = 0, kSingleChunk = 1, kMultiChunk = 2 };
 
 // Everything the launch needs, decided on the host without touching the device (also behind vmasr_scan_plan).
-static int decide(const vmasr_scan_params *p, bool bwd, ScanPlan &pl, ScanArgs &a, int &variant) {
+static int decide(const vmasr_scan_params *p, bool bwd, int peers, ScanPlan &pl, ScanArgs &a, int &variant) {
     if (int rc = validate(p, bwd)) return rc;
     const int n_chunks = (p->seqlen + VMASR_SCAN_CHUNK - 1) / VMASR_SCAN_CHUNK;
     int chan_per_tile = 1, n_ctiles = 1;
-    pl = make_plan(p, n_chunks, bwd, chan_per_tile, n_ctiles);
+    pl = make_plan(p, n_chunks, bwd, peers, chan_per_tile, n_ctiles);
     a = make_args(p, n_chunks, chan_per_tile, n_ctiles);
     const size_t es = dtype_size(p->io_dtype);
     const long long vec_elems = 16 / (long long)es;
@@ -147,35 +169,73 @@ static int decide(const vmasr_scan_params *p, bool bwd, ScanPlan &pl, ScanArgs &
                  mult(p->du_d_stride) && mult(p->ddelta_batch_stride) && mult(p->ddelta_d_stride) && (p->seqlen % 4 == 0);
     }
     // fast path: fp32, d_state 1, 16-byte aligned rows -> TMA-staged packed-fp32x2 kernels; more than one chunk: the
-    // kernels with the exchange warp (scan_*_pipe.cu).  VMASR_SCAN_FWD / VMASR_SCAN_BWD = generic | tma | ring
-    static const char fwd_force = [] { const char *e = getenv("VMASR_SCAN_FWD"); return e ? e[0] : '\0'; }();
-    static const char bwd_force = [] { const char *e = getenv("VMASR_SCAN_BWD"); return e ? e[0] : '\0'; }();
-    const char force = bwd ? bwd_force : fwd_force;
+    // kernels with the exchange warp (scan_*_pipe.cu).  VMASR_TUNING builds: VMASR_SCAN_FWD / VMASR_SCAN_BWD = generic | tma
+    const char *force_env = tuning_env(bwd ? "VMASR_SCAN_BWD" : "VMASR_SCAN_FWD");
+    const char force = force_env ? force_env[0] : '\0';
     const bool fast = p->io_dtype == VMASR_F32 && p->dstate == 1 && pl.vec && a.chan_per_tile <= kMaxTileChannelsHost;
     if (!fast || force == 'g') variant = kGeneric;
-    else if (n_chunks > 1 && !bwd && force == 'r' && a.chan_per_group % a.chan_per_tile == 0) variant = kRing;
-    else if (n_chunks > 1 && force != 't') variant = kMultiChunk;
+    else if (n_chunks > 1 && !(force == 't' && p->flags == 0)) variant = kMultiChunk;
     else variant = kSingleChunk;
+    if (variant == kGeneric && p->flags != 0)
+        return fail("selective_scan: VMASR_SCAN_REVERSE / VMASR_SCAN_ACCUMULATE need the fast path (float32, d_state 1, seqlen a multiple of 4, "
+                    "16-byte aligned rows and strides)");
     return 0;
 }
 
-static int run(const vmasr_scan_params *p, bool bwd) {
-    ScanPlan pl;
-    ScanArgs a;
-    int variant = kGeneric;
-    if (int rc = decide(p, bwd, pl, a, variant)) return rc;
-    DeviceGuard guard(p->device);
-    if (!guard.ok) return fail("selective_scan: cannot select CUDA device %d", p->device);
-    cudaStream_t stream = static_cast<cudaStream_t>(p->stream);
-    if (bwd) {
-        if (variant == kMultiChunk) return scan_bwd_pipe_dispatch(a, pl, stream);
-        if (variant == kSingleChunk) return scan_bwd_tma_dispatch(a, pl, stream);
-        return scan_bwd_dispatch(a, pl, p->io_dtype, stream);
+// kernel family + the template parameters the problems of one launch must share
+static long long launch_key(int variant, const ScanArgs &a, const ScanPlan &pl, bool bwd) {
+    long long k = variant * 1000 + (a.softplus ? 500 : 0);
+    if (variant == kSingleChunk) k += pl.tpr;
+    if (variant == kMultiChunk && bwd) k += (a.chan_per_tile <= 3) ? 1 : 2;
+    return k;
+}
+
+int scan_run_group(int n, const vmasr_scan_params *ps, bool bwd) {
+    if (n <= 0) return fail("selective_scan: empty group");
+    if (n > kMaxGroup) return fail("selective_scan: at most %d problems per grouped launch (got %d)", kMaxGroup, n);
+    if (!ps) return fail("selective_scan: null params");
+    ScanPlan pl[kMaxGroup];
+    ScanArgs a[kMaxGroup];
+    int variant[kMaxGroup];
+    long long key[kMaxGroup];
+    for (int i = 0; i < n; ++i) {
+        if (ps[i].device != ps[0].device || ps[i].stream != ps[0].stream)
+            return fail("selective_scan: the problems of a grouped launch must share device and stream");
+        if (int rc = decide(&ps[i], bwd, n, pl[i], a[i], variant[i])) return rc;
+        key[i] = launch_key(variant[i], a[i], pl[i], bwd);
+        for (int j = 0; j < i; ++j)
+            if (a[i].ws_header && a[i].ws_header == a[j].ws_header)
+                return fail("selective_scan: problems %d and %d of a grouped launch share a carry workspace", j, i);
     }
-    if (variant == kRing) return scan_fwd_ring_dispatch(a, pl, p->device, stream);
-    if (variant == kMultiChunk) return scan_fwd_pipe_dispatch(a, pl, stream);
-    if (variant == kSingleChunk) return scan_fwd_tma_dispatch(a, pl, stream);
-    return scan_fwd_dispatch(a, pl, p->io_dtype, stream);
+    DeviceGuard guard(ps[0].device);
+    if (!guard.ok) return fail("selective_scan: cannot select CUDA device %d", ps[0].device);
+    cudaStream_t stream = static_cast<cudaStream_t>(ps[0].stream);
+    bool done[kMaxGroup] = {};
+    for (int i = 0; i < n; ++i) {
+        if (done[i]) continue;
+        if (variant[i] == kGeneric) {  // generic kernels (half precision, d_state > 1, unaligned views): one launch each
+            done[i] = true;
+            const int rc = bwd ? scan_bwd_dispatch(a[i], pl[i], ps[i].io_dtype, stream) : scan_fwd_dispatch(a[i], pl[i], ps[i].io_dtype, stream);
+            if (rc) return rc;
+            continue;
+        }
+        GroupArgs ga{};
+        int grid = 0;
+        for (int j = i; j < n; ++j) {
+            if (done[j] || key[j] != key[i]) continue;
+            done[j] = true;
+            ga.a[ga.n] = a[j];
+            grid += pl[j].grid;
+            ga.tile_end[ga.n] = grid;
+            ++ga.n;
+        }
+        for (int j = ga.n; j < kMaxGroup; ++j) ga.tile_end[j] = grid;
+        int rc;
+        if (variant[i] == kMultiChunk) rc = bwd ? scan_bwd_pipe_dispatch(ga, grid, stream) : scan_fwd_pipe_dispatch(ga, grid, stream);
+        else rc = bwd ? scan_bwd_tma_dispatch(ga, pl[i].tpr, grid, stream) : scan_fwd_tma_dispatch(ga, pl[i].tpr, grid, stream);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 }  // namespace vmasr
@@ -184,7 +244,7 @@ extern "C" uint64_t vmasr_scan_workspace_bytes(int batch, int dim, int seqlen, i
     if (batch <= 0 || dim <= 0 || seqlen <= 0 || dstate <= 0) return 0;
     const uint64_t n_chunks = ((uint64_t)seqlen + VMASR_SCAN_CHUNK - 1) / VMASR_SCAN_CHUNK;
     if (n_chunks <= 1) return 0;
-    const uint64_t n_groups = (n_chunks + 15) / 16;  // level-2 entries of the persistent kernels' look-back
+    const uint64_t n_groups = (n_chunks + 15) / 16;  // level-2 entries of the look-back
     const uint64_t cap = (uint64_t)batch * dim * dstate * (n_chunks + n_groups);
     const uint64_t bytes = 64 + 16 * cap;
     return (bytes + 255) / 256 * 256;
@@ -195,7 +255,7 @@ extern "C" int vmasr_scan_plan(const vmasr_scan_params *p, int backward, int32_t
     vmasr::ScanPlan pl;
     vmasr::ScanArgs a;
     int variant = 0;
-    if (int rc = vmasr::decide(p, backward != 0, pl, a, variant)) return rc;
+    if (int rc = vmasr::decide(p, backward != 0, 1, pl, a, variant)) return rc;
     out[0] = pl.grid;
     out[1] = variant;
     out[2] = a.chan_per_tile;
@@ -205,5 +265,7 @@ extern "C" int vmasr_scan_plan(const vmasr_scan_params *p, int backward, int32_t
     return 0;
 }
 
-extern "C" int vmasr_scan_fwd(const vmasr_scan_params *p) { return vmasr::run(p, false); }
-extern "C" int vmasr_scan_bwd(const vmasr_scan_params *p) { return vmasr::run(p, true); }
+extern "C" int vmasr_scan_fwd(const vmasr_scan_params *p) { return vmasr::scan_run_group(1, p, false); }
+extern "C" int vmasr_scan_bwd(const vmasr_scan_params *p) { return vmasr::scan_run_group(1, p, true); }
+extern "C" int vmasr_scan_fwd_grouped(int n, const vmasr_scan_params *p) { return vmasr::scan_run_group(n, p, false); }
+extern "C" int vmasr_scan_bwd_grouped(int n, const vmasr_scan_params *p) { return vmasr::scan_run_group(n, p, true); }

@@ -10,17 +10,24 @@ Mirrors, name for name:
 
 Argument checks raise ``RuntimeError`` for the same conditions the reference's TORCH_CHECKs do
 (selective_scan.cpp:165-215).  No CPU path, no fallback.
+
+Beyond the reference surface: ``fwd_grouped`` / ``bwd_grouped`` launch several independent calls as one grid
+(``vmasr_scan_fwd_grouped``), and ``flags`` (``SCAN_REVERSE``, ``SCAN_ACCUMULATE``) select the time-reversed /
+accumulating variants the fused SS2D core is built from (``vm_asr_b200.ss2d``).
+
+Host cost.  A call site (same shapes, strides, dtypes, device) is validated ONCE; its filled-in parameter block is cached
+per thread and later calls only refresh pointers, stream and workspace (the reference's pybind entry re-checks every call).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
+import threading
 
 import torch
 
-import contextlib
-
 from . import _lib
-from ._lib import ScanParams
+from ._lib import SCAN_ACCUMULATE, SCAN_REVERSE, ScanParams  # noqa: F401
 
 
 def _check(cond: bool, msg: str):
@@ -70,11 +77,36 @@ def _device_of(t):
     return _NO_SWITCH if idx is None or idx == torch.cuda.current_device() else torch.cuda.device(t.device)
 
 
-def _fill_common(p: ScanParams, u, delta, A, B, C, D, delta_bias, dims, delta_softplus):
+# ---- call sites: validated once, parameter block cached per thread -------------------------------------------------
+class _Site:
+    __slots__ = ("p", "dims", "n_chunks", "ws_bytes", "dev")
+
+
+_tls = threading.local()
+_SITE_CAP = 4096
+
+
+def _sig(t):
+    return None if t is None else (t.shape, t.stride(), t.dtype, t.device)
+
+
+def _site(u, delta, A, B, C, D, delta_bias, delta_softplus, flags) -> _Site:
+    cache = getattr(_tls, "sites", None)
+    if cache is None:
+        cache = _tls.sites = {}
+    key = (_sig(u), _sig(delta), _sig(A), _sig(B), _sig(C), _sig(D), _sig(delta_bias), bool(delta_softplus), flags)
+    s = cache.get(key)
+    if s is not None:
+        return s
+    dims = _validate(u, delta, A, B, C, D, delta_bias)
     batch, dim, seqlen, dstate, ngroups = dims
-    p.u, p.delta, p.A, p.B, p.C = u.data_ptr(), delta.data_ptr(), A.data_ptr(), B.data_ptr(), C.data_ptr()
-    p.D, p.delta_bias = _ptr(D), _ptr(delta_bias)
-    p.batch, p.dim, p.seqlen, p.dstate, p.ngroups = batch, dim, seqlen, dstate, ngroups
+    s = _Site()
+    s.dims = dims
+    s.n_chunks = (seqlen + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
+    s.dev = u.device.index if u.device.index is not None else torch.cuda.current_device()
+    s.ws_bytes = int(_lib.load_library().vmasr_scan_workspace_bytes(batch, dim, seqlen, dstate)) if s.n_chunks > 1 else 0
+    p = s.p = ScanParams()
+    p.batch, p.dim, p.seqlen, p.dstate, p.ngroups = dims
     p.u_batch_stride, p.u_d_stride = u.stride(0), u.stride(1)
     p.delta_batch_stride, p.delta_d_stride = delta.stride(0), delta.stride(1)
     p.A_d_stride, p.A_dstate_stride = A.stride(0), A.stride(1)
@@ -82,101 +114,218 @@ def _fill_common(p: ScanParams, u, delta, A, B, C, D, delta_bias, dims, delta_so
     p.C_batch_stride, p.C_group_stride, p.C_dstate_stride = C.stride(0), C.stride(1), C.stride(2)
     p.io_dtype = _lib.DTYPE_CODE[u.dtype]
     p.delta_softplus = 1 if delta_softplus else 0
-    p.device = u.device.index if u.device.index is not None else torch.cuda.current_device()
-    p.stream = _lib.current_stream_ptr(u.device)
-    n_chunks = (seqlen + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
-    if n_chunks > 1:
-        lib = _lib.load_library()
-        need = lib.vmasr_scan_workspace_bytes(batch, dim, seqlen, dstate)
-        ws = _lib.scan_workspace(u.device, need)
+    p.device = s.dev
+    p.flags = int(flags)
+    if len(cache) >= _SITE_CAP:
+        cache.clear()
+    cache[key] = s
+    return s
+
+
+def _fill_inputs(s: _Site, u, delta, A, B, C, D, delta_bias, workspace=None):
+    p = s.p
+    p.u, p.delta, p.A, p.B, p.C = u.data_ptr(), delta.data_ptr(), A.data_ptr(), B.data_ptr(), C.data_ptr()
+    p.D = None if D is None else D.data_ptr()
+    p.delta_bias = None if delta_bias is None else delta_bias.data_ptr()
+    p.stream = torch._C._cuda_getCurrentRawStream(s.dev)
+    if s.n_chunks > 1:
+        ws = workspace if workspace is not None else _lib.scan_workspace(u.device, s.ws_bytes)
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
-    return n_chunks
+    return p
 
 
-def fwd_out(u, delta, A, B, C, D, delta_bias, delta_softplus, out, x, _dims=None):
-    """Launch the forward into caller-provided ``out`` (like delta) and ``x`` (batch, dim, n_chunks, 2*dstate)
-    float32.  No allocation: usable under CUDA-graph capture (the stream's carry workspace must already exist,
-    i.e. one eager call first)."""
-    lib = _lib.load_library()
-    dims = _dims if _dims is not None else _validate(u, delta, A, B, C, D, delta_bias)
-    batch, dim, seqlen, dstate, _ = dims
-    n_chunks = (seqlen + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
-    _check(out.dtype == u.dtype and tuple(out.shape) == (batch, dim, seqlen) and (out.stride(-1) == 1 or seqlen == 1),
+def _fill_fwd(s: _Site, out, x):
+    batch, dim, seqlen, dstate, _ = s.dims
+    _check(out.dtype == _DTYPE_OF[s.p.io_dtype] and tuple(out.shape) == (batch, dim, seqlen) and (out.stride(-1) == 1 or seqlen == 1),
            "selective_scan: out must look like delta")
-    _check(x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (batch, dim, n_chunks, 2 * dstate),
+    _check(x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (batch, dim, s.n_chunks, 2 * dstate),
            "selective_scan: x has the wrong shape")
-    p = ScanParams()
+    p = s.p
+    p.out, p.x = out.data_ptr(), x.data_ptr()
+    p.out_batch_stride, p.out_d_stride = out.stride(0), out.stride(1)
+
+
+def _fill_bwd(s: _Site, A, dout, x, du, ddelta, dA, dB, dC, dD, ddelta_bias):
+    batch, dim, seqlen, dstate, ngroups = s.dims
+    _check(dout.dtype == _DTYPE_OF[s.p.io_dtype], "selective_scan: dout must have the dtype of u")
+    _lib.require_cuda(dout, "dout")
+    _check(tuple(dout.shape) == (batch, dim, seqlen), "selective_scan: dout has the wrong shape")
+    _check(dout.stride(-1) == 1 or dout.size(-1) == 1, "selective_scan: dout must have unit stride along seqlen")
+    if s.n_chunks > 1:
+        _check(x is not None, "selective_scan: x is required when seqlen > 2048")
+    if x is not None:
+        _check(x.dtype == torch.float32 and x.is_cuda and x.is_contiguous(), "selective_scan: x must be contiguous float32 CUDA")
+        _check(tuple(x.shape) == (batch, dim, s.n_chunks, 2 * dstate), "selective_scan: x has the wrong shape")
+    for name, t in (("dB", dB), ("dC", dC)):
+        _check(t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (batch, ngroups, dstate, seqlen),
+               f"selective_scan: {name} must be contiguous float32 (batch, n_groups, dstate, seqlen)")
+    _check(dA.dtype == torch.float32 and dA.stride() == A.stride(), "selective_scan: dA must look like A")
+    p = s.p
+    p.dout, p.x = dout.data_ptr(), _ptr(x)
+    p.du, p.ddelta, p.dA, p.dB, p.dC = du.data_ptr(), ddelta.data_ptr(), dA.data_ptr(), dB.data_ptr(), dC.data_ptr()
+    p.dD, p.ddelta_bias = _ptr(dD), _ptr(ddelta_bias)
+    p.dout_batch_stride, p.dout_d_stride = dout.stride(0), dout.stride(1)
+    p.du_batch_stride, p.du_d_stride = du.stride(0), du.stride(1)
+    p.ddelta_batch_stride, p.ddelta_d_stride = ddelta.stride(0), ddelta.stride(1)
+
+
+_DTYPE_OF = {v: k for k, v in _lib.DTYPE_CODE.items()}
+
+
+def fwd_out(u, delta, A, B, C, D, delta_bias, delta_softplus, out, x, flags=0, workspace=None):
+    """Launch the forward into caller-provided ``out`` (like delta) and ``x`` (batch, dim, n_chunks, 2*dstate)
+    float32.  No allocation when the stream's carry workspace exists already (or ``workspace`` is given)."""
+    _fwd_launch(_site(u, delta, A, B, C, D, delta_bias, delta_softplus, flags), u, delta, A, B, C, D, delta_bias, out, x, workspace)
+
+
+def _fwd_launch(s, u, delta, A, B, C, D, delta_bias, out, x, workspace=None):
+    lib = _lib.load_library()
     with _device_of(u):
-        _fill_common(p, u, delta, A, B, C, D, delta_bias, dims, delta_softplus)
-        p.out, p.x = out.data_ptr(), x.data_ptr()
-        p.out_batch_stride, p.out_d_stride = out.stride(0), out.stride(1)
-        _lib.check(lib.vmasr_scan_fwd(ctypes.byref(p)))
+        _fill_inputs(s, u, delta, A, B, C, D, delta_bias, workspace)
+        _fill_fwd(s, out, x)
+        _lib.check(lib.vmasr_scan_fwd(ctypes.byref(s.p)))
 
 
 def fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1):
     """``selective_scan_cuda_core.fwd``: returns ``[out, x]``.  ``nrows`` is accepted and ignored, like the
     reference's core kernel does (selective_scan.cpp:163)."""
-    dims = _validate(u, delta, A, B, C, D, delta_bias)
-    batch, dim, seqlen, dstate, _ = dims
-    n_chunks = (seqlen + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
+    s = _site(u, delta, A, B, C, D, delta_bias, delta_softplus, 0)
+    batch, dim, seqlen, dstate, _ = s.dims
     out = torch.empty_like(delta)
-    x = torch.empty((batch, dim, n_chunks, 2 * dstate), dtype=torch.float32, device=u.device)
-    fwd_out(u, delta, A, B, C, D, delta_bias, delta_softplus, out, x, _dims=dims)
+    x = torch.empty((batch, dim, s.n_chunks, 2 * dstate), dtype=torch.float32, device=u.device)
+    _fwd_launch(s, u, delta, A, B, C, D, delta_bias, out, x)
     return [out, x]
 
 
-def bwd_out(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, du, ddelta, dA, dB, dC, dD, ddelta_bias, _dims=None):
+def bwd_out(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, du, ddelta, dA, dB, dC, dD, ddelta_bias, flags=0,
+            workspace=None):
     """Launch the backward into caller-provided buffers.  ``dA, dB, dC, dD, ddelta_bias`` are float32 and are
     ACCUMULATED INTO (zero them first); ``dB, dC`` are (batch, n_groups, dstate, seqlen) contiguous."""
+    _bwd_launch(_site(u, delta, A, B, C, D, delta_bias, delta_softplus, flags), u, delta, A, B, C, D, delta_bias, dout, x, du, ddelta,
+                dA, dB, dC, dD, ddelta_bias, workspace)
+
+
+def _bwd_launch(s, u, delta, A, B, C, D, delta_bias, dout, x, du, ddelta, dA, dB, dC, dD, ddelta_bias, workspace=None):
     lib = _lib.load_library()
-    dims = _dims if _dims is not None else _validate(u, delta, A, B, C, D, delta_bias)
-    batch, dim, seqlen, dstate, ngroups = dims
-    _check(dout.dtype == u.dtype, "selective_scan: dout must have the dtype of u")
-    _lib.require_cuda(dout, "dout")
-    _check(tuple(dout.shape) == (batch, dim, seqlen), "selective_scan: dout has the wrong shape")
-    _check(dout.stride(-1) == 1 or dout.size(-1) == 1, "selective_scan: dout must have unit stride along seqlen")
-    n_chunks = (seqlen + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
-    if n_chunks > 1:
-        _check(x is not None, "selective_scan: x is required when seqlen > 2048")
-    if x is not None:
-        _check(x.dtype == torch.float32 and x.is_cuda and x.is_contiguous(), "selective_scan: x must be contiguous float32 CUDA")
-        _check(tuple(x.shape) == (batch, dim, n_chunks, 2 * dstate), "selective_scan: x has the wrong shape")
-    for name, t in (("dB", dB), ("dC", dC)):
-        _check(t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (batch, ngroups, dstate, seqlen),
-               f"selective_scan: {name} must be contiguous float32 (batch, n_groups, dstate, seqlen)")
-    _check(dA.dtype == torch.float32 and dA.stride() == A.stride(), "selective_scan: dA must look like A")
-    p = ScanParams()
     with _device_of(u):
-        _fill_common(p, u, delta, A, B, C, D, delta_bias, dims, delta_softplus)
-        p.dout, p.x = dout.data_ptr(), _ptr(x)
-        p.du, p.ddelta, p.dA, p.dB, p.dC = du.data_ptr(), ddelta.data_ptr(), dA.data_ptr(), dB.data_ptr(), dC.data_ptr()
-        p.dD, p.ddelta_bias = _ptr(dD), _ptr(ddelta_bias)
-        p.dout_batch_stride, p.dout_d_stride = dout.stride(0), dout.stride(1)
-        p.du_batch_stride, p.du_d_stride = du.stride(0), du.stride(1)
-        p.ddelta_batch_stride, p.ddelta_d_stride = ddelta.stride(0), ddelta.stride(1)
-        _lib.check(lib.vmasr_scan_bwd(ctypes.byref(p)))
+        _fill_inputs(s, u, delta, A, B, C, D, delta_bias, workspace)
+        _fill_bwd(s, A, dout, x, du, ddelta, dA, dB, dC, dD, ddelta_bias)
+        _lib.check(lib.vmasr_scan_bwd(ctypes.byref(s.p)))
+
+
+def _grad_buffers(u, A, D, delta_bias, dims):
+    """The five accumulated gradients (selective_scan.cpp:319-327 allocates five zero tensors): dB and dC share one
+    zero-filled buffer, the three small parameter gradients another, so that a parameter's ``.grad`` never keeps the
+    large buffer alive; two memsets per call instead of five."""
+    batch, dim, seqlen, dstate, ngroups = dims
+    n_bc = batch * ngroups * dstate * seqlen
+    n_bc_pad = (n_bc + 3) // 4 * 4
+    big = torch.zeros(2 * n_bc_pad, dtype=torch.float32, device=u.device)
+    dB = big[:n_bc].view(batch, ngroups, dstate, seqlen)
+    dC = big[n_bc_pad:n_bc_pad + n_bc].view(batch, ngroups, dstate, seqlen)
+    n_a = dim * dstate
+    a_dense = A.is_contiguous()
+    small = torch.zeros((n_a if a_dense else 0) + 2 * dim, dtype=torch.float32, device=u.device)
+    if a_dense:
+        dA = small[:n_a].view(dim, dstate)
+        off = n_a
+    else:
+        dA = torch.empty_strided(A.size(), A.stride(), dtype=torch.float32, device=u.device).zero_()
+        off = 0
+    dD = small[off:off + dim] if D is not None else None
+    dbias = small[off + dim:off + 2 * dim] if delta_bias is not None else None
+    return dA, dB, dC, dD, dbias
 
 
 def bwd(u, delta, A, B, C, D, delta_bias, dout, x=None, delta_softplus=False, nrows=1):
     """``selective_scan_cuda_core.bwd``: returns ``[du, ddelta, dA, dB, dC, dD, ddelta_bias]``."""
-    dims = _validate(u, delta, A, B, C, D, delta_bias)
-    batch, dim, seqlen, dstate, ngroups = dims
+    s = _site(u, delta, A, B, C, D, delta_bias, delta_softplus, 0)
     du = torch.empty_like(u)
     ddelta = torch.empty_like(delta)
-    # the five accumulated gradients (selective_scan.cpp:319-327 allocates five zero tensors) share ONE zero-filled
-    # buffer: one memset launch per call instead of five; dB / dC first so that they stay 16-byte aligned
-    n_bc = batch * ngroups * dstate * seqlen
-    n_bc_pad = (n_bc + 3) // 4 * 4
-    n_a = dim * dstate
-    flat = torch.zeros(2 * n_bc_pad + n_a + 2 * dim, dtype=torch.float32, device=u.device)
-    dB = flat[:n_bc].view(batch, ngroups, dstate, seqlen)
-    dC = flat[n_bc_pad:n_bc_pad + n_bc].view(batch, ngroups, dstate, seqlen)
-    off = 2 * n_bc_pad
-    dA = flat[off:off + n_a].view(dim, dstate) if A.is_contiguous() else torch.zeros_like(A)
-    dD = flat[off + n_a:off + n_a + dim] if D is not None else None
-    dbias = flat[off + n_a + dim:off + n_a + 2 * dim] if delta_bias is not None else None
-    bwd_out(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, du, ddelta, dA, dB, dC, dD, dbias, _dims=dims)
+    dA, dB, dC, dD, dbias = _grad_buffers(u, A, D, delta_bias, s.dims)
+    _bwd_launch(s, u, delta, A, B, C, D, delta_bias, dout, x, du, ddelta, dA, dB, dC, dD, dbias)
     return [du, ddelta, dA, dB.to(B.dtype), dC.to(C.dtype), dD, dbias]
+
+
+# ---- grouped launches -------------------------------------------------------------------------------------------------
+def _group_workspaces(sites, device):
+    """One buffer from the stream's workspace, cut into 256-byte aligned regions (one per problem)."""
+    total = sum(s.ws_bytes for s in sites)
+    if total == 0:
+        return [None] * len(sites)
+    ws = _lib.scan_workspace(device, total)
+    out, off = [], 0
+    for s in sites:
+        out.append(ws[off:off + s.ws_bytes] if s.ws_bytes else None)
+        off += s.ws_bytes
+    return out
+
+
+def fwd_grouped(calls, outs=None):
+    """``calls``: list of ``(u, delta, A, B, C, D, delta_bias, delta_softplus[, flags])`` tuples, at most
+    ``SCAN_MAX_GROUP`` of them, all on one device.  One launch per kernel family (normally one).  Returns a list of
+    ``[out, x]``; ``outs`` may give pre-allocated ``(out, x)`` pairs."""
+    _check(0 < len(calls) <= _lib.SCAN_MAX_GROUP, f"fwd_grouped: 1..{_lib.SCAN_MAX_GROUP} calls")
+    sites, args = [], []
+    for c in calls:
+        u, delta, A, B, C, D, bias, sp = c[:8]
+        flags = c[8] if len(c) > 8 else 0
+        # a site's parameter block is reused between calls: equal call sites inside one group need their own copy
+        s = _site(u, delta, A, B, C, D, bias, sp, flags)
+        sites.append(s)
+        args.append((u, delta, A, B, C, D, bias))
+    device = calls[0][0].device
+    wss = _group_workspaces(sites, device)
+    results = []
+    n = len(calls)
+    arr = (ScanParams * n)()
+    size = ctypes.sizeof(ScanParams)
+    with _device_of(calls[0][0]):
+        for i, (s, a) in enumerate(zip(sites, args)):
+            batch, dim, seqlen, dstate, _ = s.dims
+            if outs is not None:
+                out, x = outs[i]
+            else:
+                out = torch.empty_like(a[1])
+                x = torch.empty((batch, dim, s.n_chunks, 2 * dstate), dtype=torch.float32, device=device)
+            _fill_inputs(s, *a, workspace=wss[i])
+            _fill_fwd(s, out, x)
+            ctypes.memmove(ctypes.addressof(arr[i]), ctypes.addressof(s.p), size)
+            results.append([out, x])
+        _lib.check(_lib.load_library().vmasr_scan_fwd_grouped(n, arr))
+    return results
+
+
+def bwd_grouped(calls, outs=None):
+    """``calls``: list of ``(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus[, flags])``; returns a list of
+    ``[du, ddelta, dA, dB, dC, dD, ddelta_bias]`` (dB / dC float32).  ``outs`` may give pre-allocated 7-tuples (the five
+    accumulated ones zero-filled by the caller)."""
+    _check(0 < len(calls) <= _lib.SCAN_MAX_GROUP, f"bwd_grouped: 1..{_lib.SCAN_MAX_GROUP} calls")
+    device = calls[0][0].device
+    sites = []
+    for c in calls:
+        u, delta, A, B, C, D, bias, dout, x, sp = c[:10]
+        flags = c[10] if len(c) > 10 else 0
+        sites.append(_site(u, delta, A, B, C, D, bias, sp, flags))
+    wss = _group_workspaces(sites, device)
+    n = len(calls)
+    arr = (ScanParams * n)()
+    size = ctypes.sizeof(ScanParams)
+    results = []
+    with _device_of(calls[0][0]):
+        for i, (s, c) in enumerate(zip(sites, calls)):
+            u, delta, A, B, C, D, bias, dout, x, sp = c[:10]
+            if outs is not None:
+                du, ddelta, dA, dB, dC, dD, dbias = outs[i]
+            else:
+                du, ddelta = torch.empty_like(u), torch.empty_like(delta)
+                dA, dB, dC, dD, dbias = _grad_buffers(u, A, D, bias, s.dims)
+            _fill_inputs(s, u, delta, A, B, C, D, bias, workspace=wss[i])
+            _fill_bwd(s, A, dout, x, du, ddelta, dA, dB, dC, dD, dbias)
+            ctypes.memmove(ctypes.addressof(arr[i]), ctypes.addressof(s.p), size)
+            results.append([du, ddelta, dA, dB, dC, dD, dbias])
+        _lib.check(_lib.load_library().vmasr_scan_bwd_grouped(n, arr))
+    return results
 
 
 class SelectiveScanCore(torch.autograd.Function):

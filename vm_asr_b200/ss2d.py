@@ -1,32 +1,273 @@
-"""The SS2D core of a VSS block, ``SS2D.forward_corev2`` (model/vmamba.py:1472-1497), on this library's operators:
+"""The SS2D core of a VSS block, ``SS2D.forward_corev2`` (model/vmamba.py:1472-1497):
 
     xs = CrossScan(x) -> x_dbl = einsum(xs, x_proj_weight) -> dts = einsum(dts, dt_projs_weight)
        -> ys = SelectiveScanCore(xs, dts, -exp(A_logs), Bs, Cs, Ds, dt_projs_bias, delta_softplus=True) -> y = CrossMerge(ys)
 
-The two small einsums stay on PyTorch/cuBLAS (they are not on the named path); the scan inputs are cast to fp32 as the
-reference does with ``force_fp32`` (vmamba.py:1487-1491).  This is a CHAIN of the library's kernels, differentiable end
-to end through their autograd functions; a single kernel that reads the map through the four index maps and writes the
-merged map (no ``xs`` / ``ys`` copies) is the next row of SURVEY.md 8(f), not this function."""
+``ss2d_core`` runs it FUSED (``vmasr_ss2d_core_fwd`` / ``_bwd``): the four-fold copies ``xs`` and ``ys`` are never made.
+
+* The projections commute with the permutation of positions, so they are applied to the map itself (directions 0, 2) and to
+  its transpose (directions 1, 3) instead of to ``xs``: ``delta_k``, ``B_k``, ``C_k`` come out in the MEMORY order of
+  their pair (row-major / column-major), not flipped, at a quarter of the einsum work on the input side.
+* The scan kernels read ``x`` / ``x^T`` in place; directions 2, 3 run time-reversed over the same memory; the outputs of a
+  pair are added into one zero-filled plane; ``y = (y0 + y2) + transpose(y1 + y3)`` (the association of vmamba.py:55-60).
+* The two small einsums stay on PyTorch/cuBLAS (they are not on the named path), as do autograd's sums.
+
+``ss2d_core_chain`` is the unfused chain of the library's three operators (what round 1 shipped); it remains the path for
+maps the fused kernels do not take (H or W not a multiple of 4) and the reference point of the fused path's tests.
+``ss2d_core_pair`` runs the cores of the generator's two streams (same shapes, independent: model/model.py:1124-1127) as
+one grid.
+"""
 from __future__ import annotations
+
+import ctypes  # noqa: F401
 
 import torch
 
+from . import _lib
 from .cross import CrossMerge, CrossScan
 from .scan import SelectiveScanCore
 
+from ._lib import SS2DParams
+
+
+def _dev(t):
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def map_transpose(x: torch.Tensor) -> torch.Tensor:
+    """(..., H, W) float32 contiguous -> (..., W, H), one tiled pass (``vmasr_map_transpose``)."""
+    lib = _lib.load_library()
+    _lib.require_cuda(x, "x")
+    if x.dtype != torch.float32:
+        raise RuntimeError("map_transpose: float32 only")
+    x = x.contiguous()
+    *lead, H, W = x.shape
+    out = x.new_empty(*lead, W, H)
+    planes = x.numel() // (H * W)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.vmasr_map_transpose(x.data_ptr(), out.data_ptr(), planes, H, W, _dev(x), _lib.current_stream_ptr(x.device)))
+    return out
+
+
+def map_merge2(p_rm: torch.Tensor, p_cm: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """p_rm (..., H*W) + transpose(p_cm (..., W*H)) -> (..., H*W): the outer addition of CrossMerge (vmamba.py:57-60)."""
+    lib = _lib.load_library()
+    p_rm, p_cm = p_rm.contiguous(), p_cm.contiguous()
+    out = torch.empty_like(p_rm)
+    planes = p_rm.numel() // (H * W)
+    with torch.cuda.device(p_rm.device):
+        _lib.check(lib.vmasr_map_merge2(p_rm.data_ptr(), p_cm.data_ptr(), out.data_ptr(), planes, H, W, _dev(p_rm),
+                                        _lib.current_stream_ptr(p_rm.device)))
+    return out
+
+
+class MapTranspose(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return map_transpose(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return map_transpose(g)
+
+
+_PER_MAP = 11  # tensors per map of _SS2DScan
+
+
+def _fill(p: SS2DParams, x, xT, dts_rm, dts_cm, Bs_rm, Bs_cm, Cs_rm, Cs_cm, As, Ds, bias, softplus):
+    Bsz, C, H, W = x.shape
+    p.x, p.xT = x.data_ptr(), xT.data_ptr()
+    for k in range(4):
+        pair, j = (dts_rm, Bs_rm, Cs_rm) if k % 2 == 0 else (dts_cm, Bs_cm, Cs_cm), k // 2
+        d, b, c = pair[0][:, j], pair[1][:, j], pair[2][:, j]
+        p.delta[k], p.delta_batch_stride[k], p.delta_d_stride[k] = d.data_ptr(), d.stride(0), d.stride(1)
+        p.B[k], p.B_batch_stride[k] = b.data_ptr(), b.stride(0)
+        p.C[k], p.C_batch_stride[k] = c.data_ptr(), c.stride(0)
+    p.A, p.D, p.delta_bias = As.data_ptr(), Ds.data_ptr(), bias.data_ptr()
+    p.batch, p.channels, p.H, p.W = Bsz, C, H, W
+    p.delta_softplus = 1 if softplus else 0
+    p.device = _dev(x)
+    p.stream = _lib.current_stream_ptr(x.device)
+
+
+def _check_map(x, xT, dts_rm, dts_cm, Bs_rm, Bs_cm, Cs_rm, Cs_cm, As, Ds, bias):
+    Bsz, C, H, W = x.shape
+    L = H * W
+    ok = x.is_contiguous() and xT.is_contiguous() and tuple(xT.shape) == (Bsz, C, W, H)
+    for t in (dts_rm, dts_cm):
+        ok = ok and tuple(t.shape) == (Bsz, 2, C, L) and t.stride(-1) == 1
+    for t in (Bs_rm, Bs_cm, Cs_rm, Cs_cm):
+        ok = ok and tuple(t.shape) == (Bsz, 2, 1, L) and t.stride(-1) == 1
+    ok = ok and tuple(As.shape) == (4 * C, 1) and As.is_contiguous() and Ds.numel() == 4 * C and bias.numel() == 4 * C
+    for t in (x, xT, dts_rm, dts_cm, Bs_rm, Bs_cm, Cs_rm, Cs_cm, As, Ds, bias):
+        ok = ok and t.is_cuda and t.dtype == torch.float32
+    if not ok:
+        raise RuntimeError("ss2d_core: fused core expects float32 CUDA tensors x (B,C,H,W), xT (B,C,W,H), dts (B,2,C,L), "
+                           "Bs / Cs (B,2,1,L) with unit stride along L, As (4C,1), Ds / delta_bias (4C)")
+
+
+class _SS2DScan(torch.autograd.Function):
+    """CrossScan -> selective scan -> CrossMerge of ``n_maps`` maps in one grid.  Per map, in order:
+    x (B,C,H,W), xT (B,C,W,H), dts_rm, dts_cm (B,2,C,L), Bs_rm, Bs_cm, Cs_rm, Cs_cm (B,2,1,L), As (4C,1), Ds (4C), delta_bias (4C);
+    index 0 / 1 of a ``_rm`` tensor is direction 0 / 2, of a ``_cm`` tensor direction 1 / 3.  Returns y (B,C,L) per map."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, softplus, n_maps, *tensors):
+        lib = _lib.load_library()
+        arr = (SS2DParams * n_maps)()
+        keep, ys = [], []
+        dev = tensors[0].device
+        wbytes = [int(lib.vmasr_ss2d_workspace_bytes(*tensors[m * _PER_MAP].shape)) for m in range(n_maps)]
+        ws = _lib.scan_workspace(dev, sum(wbytes)) if sum(wbytes) else None
+        off = 0
+        for m in range(n_maps):
+            t = tensors[m * _PER_MAP:(m + 1) * _PER_MAP]
+            _check_map(*t)
+            x = t[0]
+            Bsz, C, H, W = x.shape
+            L = H * W
+            n_chunks = (L + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
+            y = torch.empty((Bsz, C, L), dtype=torch.float32, device=dev)
+            planes = torch.empty((2, Bsz, C, L), dtype=torch.float32, device=dev)
+            states = torch.empty((4, Bsz, C, n_chunks, 2), dtype=torch.float32, device=dev)
+            p = arr[m]
+            _fill(p, *t, softplus)
+            p.y, p.planes, p.states = y.data_ptr(), planes.data_ptr(), states.data_ptr()
+            if wbytes[m]:
+                p.workspace, p.workspace_bytes = ws.data_ptr() + off, wbytes[m]
+                off += wbytes[m]
+            keep.append((planes, states))
+            ys.append(y)
+        with torch.cuda.device(dev):
+            _lib.check(lib.vmasr_ss2d_core_fwd(n_maps, arr))
+        ctx.softplus, ctx.n_maps = softplus, n_maps
+        ctx.save_for_backward(*tensors, *[k[1] for k in keep])
+        return tuple(ys) if n_maps > 1 else ys[0]
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, *dys):
+        lib = _lib.load_library()
+        n_maps = ctx.n_maps
+        saved = ctx.saved_tensors
+        tensors, states_all = saved[:n_maps * _PER_MAP], saved[n_maps * _PER_MAP:]
+        arr = (SS2DParams * n_maps)()
+        dev = tensors[0].device
+        wbytes = [int(lib.vmasr_ss2d_workspace_bytes(*tensors[m * _PER_MAP].shape)) for m in range(n_maps)]
+        ws = _lib.scan_workspace(dev, sum(wbytes)) if sum(wbytes) else None
+        off = 0
+        grads, keep = [], []
+        for m in range(n_maps):
+            t = tensors[m * _PER_MAP:(m + 1) * _PER_MAP]
+            x = t[0]
+            Bsz, C, H, W = x.shape
+            L = H * W
+            dy = dys[m].to(torch.float32).contiguous()
+            planes = torch.empty((2, Bsz, C, L), dtype=torch.float32, device=dev)
+            dyT = torch.empty((Bsz, C, L), dtype=torch.float32, device=dev)
+            ddts = torch.empty((2, Bsz, 2, C, L), dtype=torch.float32, device=dev)   # [rm | cm]
+            dBC = torch.zeros((2, 4, Bsz, L), dtype=torch.float32, device=dev)       # [dB | dC], direction-major
+            small = torch.zeros((3, 4 * C), dtype=torch.float32, device=dev)         # dA, dD, ddelta_bias
+            p = arr[m]
+            _fill(p, *t, ctx.softplus)
+            p.planes, p.states = planes.data_ptr(), states_all[m].data_ptr()
+            p.dy, p.dyT, p.dx = dy.data_ptr(), dyT.data_ptr(), None
+            for k in range(4):
+                d = ddts[k % 2][:, k // 2]
+                p.ddelta[k], p.ddelta_batch_stride[k], p.ddelta_d_stride[k] = d.data_ptr(), d.stride(0), d.stride(1)
+            p.dA, p.dD, p.ddelta_bias = small[0].data_ptr(), small[1].data_ptr(), small[2].data_ptr()
+            p.dB, p.dC = dBC[0].data_ptr(), dBC[1].data_ptr()
+            if wbytes[m]:
+                p.workspace, p.workspace_bytes = ws.data_ptr() + off, wbytes[m]
+                off += wbytes[m]
+            keep.append((dy, dyT))
+            # (4, B, L) direction-major -> the (B, 2, 1, L) layout of the forward inputs: k = 2 j + parity
+            dB4, dC4 = dBC[0].view(2, 2, Bsz, L), dBC[1].view(2, 2, Bsz, L)
+            pair = lambda g, par: g[:, par].permute(1, 0, 2).unsqueeze(2)
+            grads += [planes[0].view(Bsz, C, H, W), planes[1].view(Bsz, C, W, H), ddts[0], ddts[1],
+                      pair(dB4, 0), pair(dB4, 1), pair(dC4, 0), pair(dC4, 1),
+                      small[0].view(4 * C, 1), small[1].view_as(t[9]), small[2].view_as(t[10])]
+        with torch.cuda.device(dev):
+            _lib.check(lib.vmasr_ss2d_core_bwd(n_maps, arr))
+        return (None, None, *grads)
+
+
+def _projections(x, xT, x_proj_weight, x_proj_bias, dt_projs_weight, R, N):
+    """x_dbl and dts of vmamba.py:1473-1477 in memory order: the row-major pair from the map, the column-major pair from
+    its transpose.  Returns dts (B,2,C,L), Bs, Cs (B,2,N,L) per pair; Bs / Cs are VIEWS of x_dbl (no contiguous copies)."""
+    Bsz, C, H, W = x.shape
+    L = H * W
+    out = []
+    for par, src in ((0, x.view(Bsz, C, L)), (1, xT.view(Bsz, C, L))):
+        x_dbl = torch.einsum("bdl,kcd->bkcl", src, x_proj_weight[par::2])
+        if x_proj_bias is not None:
+            x_dbl = x_dbl + x_proj_bias[par::2].view(1, 2, -1, 1)
+        dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+        dts = torch.einsum("bkrl,kdr->bkdl", dts, dt_projs_weight[par::2])
+        out.append((dts, Bs, Cs))
+    return out
+
+
+def _fusable(x, N):
+    return x.is_cuda and x.dim() == 4 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0 and N == 1
+
+
+def _prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias):
+    K, _, R = dt_projs_weight.shape
+    N = A_logs.shape[1]
+    x32 = x.to(torch.float32).contiguous()
+    xT = MapTranspose.apply(x32)
+    (dts_rm, Bs_rm, Cs_rm), (dts_cm, Bs_cm, Cs_cm) = _projections(x32, xT, x_proj_weight, x_proj_bias, dt_projs_weight, R, N)
+    f = lambda t: t.to(torch.float32)   # force_fp32 (vmamba.py:1487-1491); a no-op outside autocast
+    As = -torch.exp(A_logs.to(torch.float))                           # vmamba.py:1481
+    return (x32, xT, f(dts_rm).contiguous(), f(dts_cm).contiguous(), f(Bs_rm), f(Bs_cm), f(Cs_rm), f(Cs_cm), As.contiguous(),
+            Ds.to(torch.float).contiguous(), dt_projs_bias.reshape(-1).to(torch.float).contiguous())
+
 
 def ss2d_core(x: torch.Tensor, x_proj_weight: torch.Tensor, dt_projs_weight: torch.Tensor, dt_projs_bias: torch.Tensor,
-              A_logs: torch.Tensor, Ds: torch.Tensor, delta_softplus: bool = True, force_fp32: bool = True) -> torch.Tensor:
-    """x (B, C, H, W) -> y (B, C, H*W).  Parameter layouts as in ``SS2D.__initv2__`` (vmamba.py:772-850):
-    x_proj_weight (K=4, R + 2N, C), dt_projs_weight (K, C, R), dt_projs_bias (K, C), A_logs (K*C, N), Ds (K*C)."""
+              A_logs: torch.Tensor, Ds: torch.Tensor, delta_softplus: bool = True, force_fp32: bool = True,
+              x_proj_bias: torch.Tensor | None = None, fused: bool | None = None) -> torch.Tensor:
+    """x (B, C, H, W) -> y (B, C, H*W), float32.  Parameter layouts as in ``SS2D.__initv2__`` (vmamba.py:772-850):
+    x_proj_weight (K=4, R + 2N, C), dt_projs_weight (K, C, R), dt_projs_bias (K, C), A_logs (K*C, N), Ds (K*C),
+    x_proj_bias (K, R + 2N) or None (vmamba.py:1474-1475).  ``fused=None`` picks the fused core whenever it applies."""
     if x.dim() != 4:
         raise RuntimeError("ss2d_core: expected (B, C, H, W)")
+    N = A_logs.shape[1]
+    if fused is None:
+        fused = _fusable(x, N)
+    if not fused:
+        return ss2d_core_chain(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, delta_softplus, force_fp32, x_proj_bias)
+    if not _fusable(x, N):
+        raise RuntimeError("ss2d_core: the fused core needs a CUDA map with H, W multiples of 4 and d_state 1")
+    return _SS2DScan.apply(delta_softplus, 1, *_prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias))
+
+
+def ss2d_core_pair(x_a, params_a, x_b, params_b, delta_softplus: bool = True):
+    """The cores of the generator's two streams as one grid.  ``params_*`` = (x_proj_weight, dt_projs_weight, dt_projs_bias,
+    A_logs, Ds[, x_proj_bias]).  Returns (y_a, y_b)."""
+    args = []
+    for x, prm in ((x_a, params_a), (x_b, params_b)):
+        if not _fusable(x, prm[3].shape[1]):
+            raise RuntimeError("ss2d_core_pair: the fused core needs CUDA maps with H, W multiples of 4 and d_state 1")
+        bias = prm[5] if len(prm) > 5 else None
+        args += list(_prepare(x, prm[0], prm[1], prm[2], prm[3], prm[4], bias))
+    return _SS2DScan.apply(delta_softplus, 2, *args)
+
+
+def ss2d_core_chain(x: torch.Tensor, x_proj_weight: torch.Tensor, dt_projs_weight: torch.Tensor, dt_projs_bias: torch.Tensor,
+                    A_logs: torch.Tensor, Ds: torch.Tensor, delta_softplus: bool = True, force_fp32: bool = True,
+                    x_proj_bias: torch.Tensor | None = None) -> torch.Tensor:
+    """The same core as a chain of the three operators, statement for statement vmamba.py:1472-1497 (materialises ``xs``
+    and ``ys``)."""
     Bsz, C, H, W = x.shape
     K, _, R = dt_projs_weight.shape
     N = A_logs.shape[1]
     L = H * W
     xs = CrossScan.apply(x)                                           # vmamba.py:1472
     x_dbl = torch.einsum("bkdl,kcd->bkcl", xs, x_proj_weight)         # :1473
+    if x_proj_bias is not None:
+        x_dbl = x_dbl + x_proj_bias.view(1, K, -1, 1)                 # :1474-1475
     dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                # :1476
     dts = torch.einsum("bkrl,kdr->bkdl", dts, dt_projs_weight)        # :1477
     xs = xs.view(Bsz, -1, L)
