@@ -108,10 +108,13 @@ typedef struct vmasr_scan_params {
  *   VMASR_SCAN_REVERSE    : time runs against memory order: position l of the recurrence is element seqlen-1-l of u, delta,
  *                           B, C, out (dout, du, ddelta, dB, dC).  Every tensor keeps its memory layout; x (chunk states) is
  *                           indexed in time order.
- *   VMASR_SCAN_ACCUMULATE : `out` (forward) and `du` (backward) are ADDED INTO with 128-bit reductions instead of stored;
- *                           the caller zero-fills them. */
+ *   VMASR_SCAN_ACCUMULATE : `out` (forward) and `du` (backward) are ADDED INTO with 128-bit reductions (red.global.add)
+ *                           instead of stored: any number of calls may add into one buffer concurrently.
+ *   VMASR_SCAN_ADD        : the same sum as a plain load / add / store: cheaper, but the call must be the ONLY writer of the
+ *                           buffer while it runs (stream order after whatever wrote it before).  Exclusive with ACCUMULATE. */
 #define VMASR_SCAN_REVERSE 1
 #define VMASR_SCAN_ACCUMULATE 2
+#define VMASR_SCAN_ADD 4
 /* most problems one grouped launch takes */
 #define VMASR_SCAN_MAX_GROUP 8
 
@@ -152,8 +155,8 @@ VMASR_API int vmasr_cross_merge(const void *ys, void *y, int B, int C, int H, in
  * Everything positional of direction k (delta_k, B_k, C_k and their gradients) is laid out in the MEMORY order of its
  * pair -- row-major (l = h*W + w) for k = 0, 2, column-major (l = w*H + h) for k = 1, 3 -- and NOT flipped for k = 2, 3:
  * that is what the projections give when they are applied to the map and to its transpose instead of to `xs`
- * (einsum(x, x_proj_weight[k]) commutes with the permutation of positions).  Outputs of a pair are added into one
- * zero-filled plane with 128-bit reductions (exact and order-independent: 0 + a + b), and
+ * (einsum(x, x_proj_weight[k]) commutes with the permutation of positions).  The outputs of a pair meet in one plane
+ * (directions 0, 1 store, directions 2, 3 run in a second grid and add to what is there: one rounding of y_k + y_{k+2}), and
  *   y = (y0 + y2) + transpose(y1 + y3)     -- the association of vmamba.py:55-60.
  * float32, d_state 1, H % 4 == 0 and W % 4 == 0 (every map of the configs); otherwise the call fails and the caller chains
  * vmasr_cross_scan / vmasr_scan_* / vmasr_cross_merge.

@@ -8,7 +8,7 @@ import sys
 from collections import OrderedDict, defaultdict
 
 raw, out, traffic_path = sys.argv[1:4]
-OURS = ("scan_", "cross_", "stft", "ss2d_")
+OURS = ("scan_", "cross_", "stft", "ss2d_", "map_")
 rows = []
 with open(raw, newline="") as f:
     lines = [l for l in f if not l.startswith("==")]

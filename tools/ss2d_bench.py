@@ -35,13 +35,17 @@ def main():
     ap.add_argument("--workload", default="vm_asr_48k_MPD")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--pair", action="store_true", help="fused: the two streams' cores in one grid (ss2d pair)")
+    ap.add_argument("--only", default="", help="comma-separated d_inner values to run (default: every shape)")
     args = ap.parse_args()
     wl = W.WORKLOADS[args.workload]
     peak, _ = load_peaks()
     dev = torch.device("cuda")
     gen = torch.Generator(device=dev).manual_seed(0)
     B = wl.batch
+    only = {int(v) for v in args.only.split(",") if v}
     for call, count in W.distinct_shapes(wl):
+        if only and call.d_inner not in only:
+            continue
         C, H, Wd, L = call.d_inner, call.H, call.W, call.L
         D = 4 * C
         fused_fwd = 4 * (B * C * L + B * D * L + 2 * B * 4 * L + B * C * L)

@@ -13,7 +13,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libvmasr_b200.so")
+# VMASR_B200_LIBRARY: developer switch to load another build of the same library (e.g. `make TUNING=1 OUT=../lib_tuning`)
+_LIB_PATH = os.environ.get("VMASR_B200_LIBRARY") or os.path.join(_HERE, "lib", "libvmasr_b200.so")
 _lib = None
 _lock = threading.Lock()
 
@@ -133,15 +134,19 @@ def current_stream_ptr(device: torch.device) -> int:
 #   * calls made while the stream is capturing get a workspace of their own (allocated inside the capture, i.e. from the
 #     graph's pool; its zero-fill is a node of the graph), so replaying the graph -- on whatever stream -- never shares a
 #     workspace with eager calls;
+#   * a buffer is cut into regions (one per problem of a grouped launch) in one way only: the kernels keep a header at the
+#     start of every region, so each layout has a buffer of its own;
 #   * scans that may run CONCURRENTLY (two streams, two graphs replayed side by side) must not share one: give each its own
 #     stream, or capture each graph after `reset_capture_workspaces()`.
 _workspaces = {}
 _retired = []
 
 
-def scan_workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+def scan_workspace(device: torch.device, nbytes: int, layout=None) -> torch.Tensor:
+    """``layout``: how the caller cuts the buffer into regions (grouped launches, the fused SS2D core).  Every region starts
+    with its own header, so a buffer must only ever be cut ONE way: each layout gets a buffer of its own."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    key = (idx, torch._C._cuda_getCurrentRawStream(idx), torch.cuda.is_current_stream_capturing())
+    key = (idx, torch._C._cuda_getCurrentRawStream(idx), torch.cuda.is_current_stream_capturing(), layout)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         size = max(int(nbytes), 1 << 20)

@@ -26,6 +26,14 @@ __device__ __forceinline__ void lds8(const float *p, float2 (&v)[4]) {
     v[2] = make_float2(hi.x, hi.y);
     v[3] = make_float2(hi.z, hi.w);
 }
+__device__ __forceinline__ void ldg8(const float *p, float2 (&v)[4]) {
+    const float4 lo = reinterpret_cast<const float4 *>(p)[0];
+    const float4 hi = reinterpret_cast<const float4 *>(p)[1];
+    v[0] = make_float2(lo.x, lo.y);
+    v[1] = make_float2(lo.z, lo.w);
+    v[2] = make_float2(hi.x, hi.y);
+    v[3] = make_float2(hi.z, hi.w);
+}
 __device__ __forceinline__ void stg8(float *p, const float2 (&v)[4]) {
     reinterpret_cast<float4 *>(p)[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
     reinterpret_cast<float4 *>(p)[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);

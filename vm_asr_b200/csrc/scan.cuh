@@ -35,7 +35,8 @@ struct ScanArgs {
     int softplus;
     int rev;              // fast kernels only: the scan runs over the row back to front (time index l <-> seqlen - 1 - l); every positional
                           // tensor (u, delta, B, C, out, dout, du, ddelta, dB, dC) keeps its memory order.  Directions 2 and 3 of SS2D.
-    int accum;            // fast kernels only: `out` (forward) / `du` (backward) are added into (128-bit red.global.add) instead of stored
+    int accum;            // fast kernels only: `out` (forward) / `du` (backward) are added into instead of stored:
+                          // 1 = 128-bit red.global.add (concurrent writers), 2 = load / add / store (this launch is the only writer)
     int debug_nowait;     // VMASR_TUNING builds only, timing experiment: do not wait for neighbours' aggregates -> WRONG results
     long long u_bs, u_ds, delta_bs, delta_ds, A_ds, A_ns, B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;
     long long out_bs, out_ds, dout_bs, dout_ds, du_bs, du_ds, ddelta_bs, ddelta_ds;

@@ -195,7 +195,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
         const int tseg = REV ? NC - 1 - (int)threadIdx.x : (int)threadIdx.x;  // this thread's 8-position segment of the tile (memory order)
         const int pos = seg0 + tseg * ITEMS;
         const int sel = (tseg >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
-        const bool accum = a.accum != 0;
+        const bool accum = a.accum == 1, addm = a.accum == 2;  // red.add / load-add-store (scan.cuh)
         int nvalid = ITEMS;
         if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
         float *du_ptr = reinterpret_cast<float *>(a.du) + b * a.du_bs + (long long)d0 * a.du_ds + pos;
@@ -302,6 +302,8 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                     }
                 const float Av = s_par[j];
                 const float Dv = s_par[4 + j];
+                float *o_du = du_ptr + (long long)j * a.du_ds;
+                float *o_dd = dd_ptr + (long long)j * a.ddelta_ds;
                 mbar_wait(&bar_in[j], 0);
                 const float2 in = s_in[j * WPR + warp];
                 const float *su = s_stage + (size_t)j * 3 * SEG + tseg * ITEMS;
@@ -370,21 +372,28 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                     sB = add2(sB, ddl[k]);
                 }
                 {
-                    float *o_du = du_ptr + (long long)j * a.du_ds;
-                    float *o_dd = dd_ptr + (long long)j * a.ddelta_ds;
                     if (!TAIL || nvalid == ITEMS) {
-                        if (accum) red8(o_du, du);
-                        else stg8(o_du, du);
+                        if (accum) {
+                            red8(o_du, du);
+                        } else {
+                            if (addm) {  // (the load sits behind the gradient arithmetic above; registers are too scarce here to issue it earlier)
+                                float2 old[4];
+                                ldg8(o_du, old);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) du[k] = add2(old[k], du[k]);
+                            }
+                            stg8(o_du, du);
+                        }
                         stg8(o_dd, ddl);
                     } else {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             if (2 * k < nvalid) {
-                                if (accum) atomicAdd(o_du + 2 * k, du[k].x); else o_du[2 * k] = du[k].x;
+                                if (accum || addm) atomicAdd(o_du + 2 * k, du[k].x); else o_du[2 * k] = du[k].x;
                                 o_dd[2 * k] = ddl[k].x;
                             }
                             if (2 * k + 1 < nvalid) {
-                                if (accum) atomicAdd(o_du + 2 * k + 1, du[k].y); else o_du[2 * k + 1] = du[k].y;
+                                if (accum || addm) atomicAdd(o_du + 2 * k + 1, du[k].y); else o_du[2 * k + 1] = du[k].y;
                                 o_dd[2 * k + 1] = ddl[k].y;
                             }
                         }

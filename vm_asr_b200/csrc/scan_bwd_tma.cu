@@ -52,7 +52,7 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
     const int L = a.seqlen;
     const int seg0 = chunk * SEG;
     const int pos = seg0 + tseg * ITEMS;
-    const bool accum = a.accum != 0;
+    const bool accum = a.accum == 1, addm = a.accum == 2;  // red.add / load-add-store (scan.cuh)
     const int seg_len = min(SEG, L - seg0);
     const unsigned seg_bytes = (unsigned)seg_len * 4u;
     int nvalid = ITEMS;
@@ -313,18 +313,27 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
             float *o_du = du_ptr + it * du_step;
             float *o_dd = dd_ptr + it * dd_step;
             if (!TAIL || nvalid == ITEMS) {
-                if (accum) red8(o_du, du);
-                else stg8(o_du, du);
+                if (accum) {
+                    red8(o_du, du);
+                } else {
+                    if (addm) {
+                        float2 old[4];
+                        ldg8(o_du, old);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) du[j] = add2(old[j], du[j]);
+                    }
+                    stg8(o_du, du);
+                }
                 stg8(o_dd, ddl);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (2 * j < nvalid) {
-                        if (accum) atomicAdd(o_du + 2 * j, du[j].x); else o_du[2 * j] = du[j].x;
+                        if (accum || addm) atomicAdd(o_du + 2 * j, du[j].x); else o_du[2 * j] = du[j].x;
                         o_dd[2 * j] = ddl[j].x;
                     }
                     if (2 * j + 1 < nvalid) {
-                        if (accum) atomicAdd(o_du + 2 * j + 1, du[j].y); else o_du[2 * j + 1] = du[j].y;
+                        if (accum || addm) atomicAdd(o_du + 2 * j + 1, du[j].y); else o_du[2 * j + 1] = du[j].y;
                         o_dd[2 * j + 1] = ddl[j].y;
                     }
                 }

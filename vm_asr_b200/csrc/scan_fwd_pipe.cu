@@ -178,7 +178,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
         int nvalid = ITEMS;
         if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
         float *out_ptr = reinterpret_cast<float *>(a.out) + b * a.out_bs + (long long)d0 * a.out_ds + pos;
-        const bool accum = a.accum != 0;
+        const bool accum = a.accum == 1, addm = a.accum == 2;  // red.add / load-add-store (scan.cuh)
 
         float2 Bl[4], Cv[4];  // ln2 * B (the scan runs on dt in the log2 domain) and C of this thread's positions
         mbar_wait(bar_bc, 0);
@@ -255,6 +255,9 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
 #pragma unroll
                 for (int i = 1; i < STAGES; ++i)
                     if (i == j) ex = exc[i];
+                float *o = out_ptr + (long long)j * a.out_ds;
+                float2 old[4];
+                if (addm && (!TAIL || nvalid == ITEMS)) ldg8(o, old);  // in flight while this warp waits for its entering state
                 mbar_wait(&bar_in[j], 0);
                 const float h_in = fmaf(ex.p, s_in[j * WPR + warp], ex.q);
                 const float *sy = s_stage + (size_t)j * 2 * SEG + tseg * ITEMS;
@@ -263,14 +266,20 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
                 lds8_priv(sy + SEG, sel, Y1);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) y[k] = fma2(Y1[k], f2(h_in), Y0[k]);
-                float *o = out_ptr + (long long)j * a.out_ds;
                 if (!TAIL || nvalid == ITEMS) {
-                    if (accum) red8(o, y);
-                    else stg8(o, y);
+                    if (accum) {
+                        red8(o, y);
+                    } else {
+                        if (addm) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) y[k] = add2(old[k], y[k]);
+                        }
+                        stg8(o, y);
+                    }
                 } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (accum) {
+                        if (accum || addm) {
                             if (2 * k < nvalid) atomicAdd(o + 2 * k, y[k].x);
                             if (2 * k + 1 < nvalid) atomicAdd(o + 2 * k + 1, y[k].y);
                         } else {

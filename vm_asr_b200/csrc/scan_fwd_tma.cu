@@ -52,7 +52,7 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
     const int L = a.seqlen;
     const int seg0 = chunk * SEG;                       // first position of the tile
     const int pos = seg0 + tseg * ITEMS;
-    const bool accum = a.accum != 0;
+    const bool accum = a.accum == 1, addm = a.accum == 2;  // red.add / load-add-store (scan.cuh)
     const int seg_len = min(SEG, L - seg0);             // valid positions in this tile (multiple of 4)
     const unsigned seg_bytes = (unsigned)seg_len * 4u;
     int nvalid = ITEMS;
@@ -241,12 +241,21 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
         }
         float *o = out_ptr + it * out_step;
         if (!TAIL || nvalid == ITEMS) {
-            if (accum) red8(o, y);
-            else stg8(o, y);
+            if (accum) {
+                red8(o, y);
+            } else {
+                if (addm) {
+                    float2 old[4];
+                    ldg8(o, old);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) y[j] = add2(old[j], y[j]);
+                }
+                stg8(o, y);
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (accum) {
+                if (accum || addm) {
                     if (2 * j < nvalid) atomicAdd(o + 2 * j, y[j].x);
                     if (2 * j + 1 < nvalid) atomicAdd(o + 2 * j + 1, y[j].y);
                 } else {

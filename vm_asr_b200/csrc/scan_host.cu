@@ -27,7 +27,8 @@ static int validate(const vmasr_scan_params *p, bool bwd) {
                     p->dim, p->seqlen, p->dstate, p->ngroups);
     if (p->dim % p->ngroups != 0) return fail("dims should be dividable by n_groups");
     if (p->dstate > 256) return fail("selective_scan only supports state dimension <= 256");
-    if (p->flags & ~(VMASR_SCAN_REVERSE | VMASR_SCAN_ACCUMULATE)) return fail("selective_scan: unknown flag bits 0x%x", p->flags);
+    if (p->flags & ~(VMASR_SCAN_REVERSE | VMASR_SCAN_ACCUMULATE | VMASR_SCAN_ADD)) return fail("selective_scan: unknown flag bits 0x%x", p->flags);
+    if ((p->flags & VMASR_SCAN_ACCUMULATE) && (p->flags & VMASR_SCAN_ADD)) return fail("selective_scan: VMASR_SCAN_ACCUMULATE and VMASR_SCAN_ADD exclude each other");
     if (!p->u || !p->delta || !p->A || !p->B || !p->C) return fail("selective_scan: u, delta, A, B, C must be non-null");
     if (!bwd && (!p->out || !p->x)) return fail("selective_scan_fwd: out and x must be non-null");
     if (bwd) {
@@ -134,7 +135,7 @@ static ScanArgs make_args(const vmasr_scan_params *p, int n_chunks, int chan_per
     a.n_rowgroups = p->batch * p->ngroups * n_ctiles;
     a.softplus = p->delta_softplus;
     a.rev = (p->flags & VMASR_SCAN_REVERSE) ? 1 : 0;
-    a.accum = (p->flags & VMASR_SCAN_ACCUMULATE) ? 1 : 0;
+    a.accum = (p->flags & VMASR_SCAN_ACCUMULATE) ? 1 : (p->flags & VMASR_SCAN_ADD) ? 2 : 0;
     const char *nowait = tuning_env("VMASR_DEBUG_NOWAIT");
     a.debug_nowait = nowait ? atoi(nowait) : 0;
     a.u_bs = p->u_batch_stride; a.u_ds = p->u_d_stride;
@@ -177,7 +178,7 @@ static int decide(const vmasr_scan_params *p, bool bwd, int peers, ScanPlan &pl,
     else if (n_chunks > 1 && !(force == 't' && p->flags == 0)) variant = kMultiChunk;
     else variant = kSingleChunk;
     if (variant == kGeneric && p->flags != 0)
-        return fail("selective_scan: VMASR_SCAN_REVERSE / VMASR_SCAN_ACCUMULATE need the fast path (float32, d_state 1, seqlen a multiple of 4, "
+        return fail("selective_scan: VMASR_SCAN_REVERSE / _ACCUMULATE / _ADD need the fast path (float32, d_state 1, seqlen a multiple of 4, "
                     "16-byte aligned rows and strides)");
     return 0;
 }

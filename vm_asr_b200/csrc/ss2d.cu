@@ -1,6 +1,8 @@
 // Fused SS2D core (include/vmasr_b200.h): the four directions of SS2D.forward_corev2 (model/vmamba.py:1472-1497) as four
 // problems of one grouped scan launch, reading the map (and its transpose) in place and adding their outputs into two
 // planes; no (B, 4, C, L) copy is ever made.  This file only assembles the scan problems; the kernels are the scan kernels.
+#include <cstdlib>
+
 #include "scan.cuh"
 
 namespace vmasr {
@@ -31,8 +33,19 @@ static uint64_t dir_ws_bytes(const vmasr_ss2d_params *p) {
     return vmasr_scan_workspace_bytes(p->batch, p->channels, p->H * p->W, 1);
 }
 
+// How the two directions of a pair meet in their plane:
+//   two passes (default): directions 0, 1 of every map in one grid with plain stores, then directions 2, 3 in a second grid
+//                that adds to what the first left (VMASR_SCAN_ADD: load / add / store, one writer per element) -- no
+//                zero-fill, no atomics;
+//   one pass:    all four directions in one grid, each adding into a zero-filled plane with red.global.add.
+// Either way a plane holds exactly y_k + y_{k+2}, one rounding, so the results are bit-identical.
+static bool ss2d_one_pass() {
+    const char *e = tuning_env("VMASR_SS2D_ONE_PASS");
+    return e && atoi(e) != 0;
+}
+
 // scan problem of direction k of map problem p
-static vmasr_scan_params direction(const vmasr_ss2d_params *p, int k, bool bwd) {
+static vmasr_scan_params direction(const vmasr_ss2d_params *p, int k, bool bwd, bool one_pass) {
     const long long C = p->channels, L = (long long)p->H * p->W, Bz = p->batch;
     const long long n_chunks = (L + VMASR_SCAN_CHUNK - 1) / VMASR_SCAN_CHUNK;
     vmasr_scan_params s{};
@@ -89,7 +102,7 @@ static vmasr_scan_params direction(const vmasr_ss2d_params *p, int k, bool bwd) 
     s.io_dtype = VMASR_F32;
     s.delta_softplus = p->delta_softplus;
     s.device = p->device;
-    s.flags = VMASR_SCAN_ACCUMULATE | (k >= 2 ? VMASR_SCAN_REVERSE : 0);
+    s.flags = one_pass ? (VMASR_SCAN_ACCUMULATE | (k >= 2 ? VMASR_SCAN_REVERSE : 0)) : (k >= 2 ? (VMASR_SCAN_REVERSE | VMASR_SCAN_ADD) : 0);
     s.stream = p->stream;
     return s;
 }
@@ -98,7 +111,8 @@ static int ss2d_run(int n, const vmasr_ss2d_params *ps, bool bwd) {
     const char *who = bwd ? "ss2d_core_bwd" : "ss2d_core_fwd";
     if (n < 1 || n > kMaxGroup / 4) return fail("%s: 1 or %d maps per call (got %d)", who, kMaxGroup / 4, n);
     if (!ps) return fail("%s: null params", who);
-    vmasr_scan_params sp[kMaxGroup];
+    const bool one_pass = ss2d_one_pass();
+    vmasr_scan_params sp[kMaxGroup];  // [first pass: directions 0, 1 of every map | second pass: directions 2, 3]
     for (int i = 0; i < n; ++i) {
         const vmasr_ss2d_params *p = &ps[i];
         if (int rc = ss2d_check(p, bwd, who)) return rc;
@@ -106,7 +120,7 @@ static int ss2d_run(int n, const vmasr_ss2d_params *ps, bool bwd) {
         const uint64_t need = 4 * dir_ws_bytes(p);
         if (need && (!p->workspace || p->workspace_bytes < need))
             return fail("%s: workspace too small (%llu < %llu bytes)", who, (unsigned long long)p->workspace_bytes, (unsigned long long)need);
-        for (int k = 0; k < 4; ++k) sp[4 * i + k] = direction(p, k, bwd);
+        for (int k = 0; k < 4; ++k) sp[(k >> 1) * 2 * n + 2 * i + (k & 1)] = direction(p, k, bwd, one_pass);
     }
     DeviceGuard guard(ps[0].device);
     if (!guard.ok) return fail("%s: cannot select CUDA device %d", who, ps[0].device);
@@ -114,11 +128,18 @@ static int ss2d_run(int n, const vmasr_ss2d_params *ps, bool bwd) {
     for (int i = 0; i < n; ++i) {
         const vmasr_ss2d_params *p = &ps[i];
         const long long planes = (long long)p->batch * p->channels, L = (long long)p->H * p->W;
+        (void)L;
         if (bwd)
             if (int rc = map_transpose_launch(p->dy, p->dyT, planes, p->H, p->W, stream)) return rc;
-        if (int rc = check_cuda(cudaMemsetAsync(p->planes, 0, sizeof(float) * 2 * planes * L, stream), "ss2d planes memset")) return rc;
+        if (one_pass)
+            if (int rc = check_cuda(cudaMemsetAsync(p->planes, 0, sizeof(float) * 2 * planes * L, stream), "ss2d planes memset")) return rc;
     }
-    if (int rc = scan_run_group(4 * n, sp, bwd)) return rc;
+    if (one_pass) {
+        if (int rc = scan_run_group(4 * n, sp, bwd)) return rc;
+    } else {
+        if (int rc = scan_run_group(2 * n, sp, bwd)) return rc;
+        if (int rc = scan_run_group(2 * n, sp + 2 * n, bwd)) return rc;
+    }
     for (int i = 0; i < n; ++i) {
         const vmasr_ss2d_params *p = &ps[i];
         const long long planes = (long long)p->batch * p->channels, L = (long long)p->H * p->W;

@@ -253,7 +253,7 @@ def _group_workspaces(sites, device):
     total = sum(s.ws_bytes for s in sites)
     if total == 0:
         return [None] * len(sites)
-    ws = _lib.scan_workspace(device, total)
+    ws = _lib.scan_workspace(device, total, layout=tuple(s.ws_bytes for s in sites))
     out, off = [], 0
     for s in sites:
         out.append(ws[off:off + s.ws_bytes] if s.ws_bytes else None)

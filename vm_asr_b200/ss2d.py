@@ -119,7 +119,7 @@ class _SS2DScan(torch.autograd.Function):
         keep, ys = [], []
         dev = tensors[0].device
         wbytes = [int(lib.vmasr_ss2d_workspace_bytes(*tensors[m * _PER_MAP].shape)) for m in range(n_maps)]
-        ws = _lib.scan_workspace(dev, sum(wbytes)) if sum(wbytes) else None
+        ws = _lib.scan_workspace(dev, sum(wbytes), layout=("ss2d",) + tuple(wbytes)) if sum(wbytes) else None
         off = 0
         for m in range(n_maps):
             t = tensors[m * _PER_MAP:(m + 1) * _PER_MAP]
@@ -155,7 +155,7 @@ class _SS2DScan(torch.autograd.Function):
         arr = (SS2DParams * n_maps)()
         dev = tensors[0].device
         wbytes = [int(lib.vmasr_ss2d_workspace_bytes(*tensors[m * _PER_MAP].shape)) for m in range(n_maps)]
-        ws = _lib.scan_workspace(dev, sum(wbytes)) if sum(wbytes) else None
+        ws = _lib.scan_workspace(dev, sum(wbytes), layout=("ss2d",) + tuple(wbytes)) if sum(wbytes) else None
         off = 0
         grads, keep = [], []
         for m in range(n_maps):
