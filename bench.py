@@ -1,24 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- headline measurement of the SS2D hot path on B200.
-
-One STEP = the selective-scan work of one VM-ASR training step of ``configs/vm_asr_48k_MPD.yaml`` (BASELINE.json
-configs[1]): the 34 SS2D selective-scan forwards in forward order, then the 34 backwards in reverse order, at the
-config's batch (4 clips, fp32 scan IO as the model forces, d_state 1, 4 B/C groups), on synthetic inputs with
-the reference test's distributions.  Metric: algorithmic scan bytes per second, whole job.
+"""bench.py -- measurement of the SS2D + STFT hot path on B200 (BASELINE.json metric, configs[1] by default).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
-* ``value``  : inputs resident in HBM; the step is captured once in a CUDA graph (68 kernel launches + one memset
-               that zeroes the gradient accumulators) and replayed; timed with CUDA events, max over ranks.
-* ``e2e``    : the same step through the public operator API (``selective_scan_cuda_core``-style ``fwd``/``bwd``),
-               every call's inputs copied from pinned host memory and its outputs copied back, inside the timed
-               region.
-* ``roofline``: the dominant kernel (backward, multi-chunk variant scan_bwd_pipe_kernel) timed launch by launch with CUDA events.
-* ``cpu_baseline`` / ``--impl reference``: the oracle's torch restatement of the reference's pure-PyTorch path
-               (``selective_scan_ref`` + autograd-equivalent closed form) on the host cores, on a bounded sample.
-* N > 1 (torchrun): every rank runs the step on its own batch shard (weak scaling, no data-path collective);
-               the 3.01 M-parameter generator gradient buffer that carries the scan parameters' gradients is
-               all-reduced over NCCL each step, as data-parallel training would.
+One JSON line.  What each key is:
+
+* ``value`` (GB/s, headline, continuity with round 1): one STEP = the selective-scan work of one VM-ASR training step of the
+  workload -- its 34 SS2D selective-scan forwards in forward order, then the 34 backwards in reverse order, at the config's
+  batch, fp32 scan IO, d_state 1, 4 B/C groups, synthetic inputs with the reference test's distributions.  Inputs resident
+  in HBM, every call on its own buffers (5.4 GB touched per step >> 126 MB L2), the step captured in one CUDA graph, CUDA
+  events, max over ranks.  The two generator streams' same-shape calls go out as ONE grouped launch per pair
+  (``vmasr_scan_fwd_grouped``; --pairing streams | none for the alternatives).  value = algorithmic scan bytes
+  / time.  N > 1: every rank runs the step on its own batch shard, no collective (the path shards by clip).
+* ``roofline``: the dominant kernel (scan_bwd_pipe_kernel: every backward launch with seqlen > 2048), CUDA events around
+  each launch, algorithmic bytes of the launch / time against the measured HBM copy peak.
+* ``ss2d_core``: the same 34 calls as FUSED SS2D cores (CrossScan -> scan -> CrossMerge in ``vmasr_ss2d_core_fwd/bwd``, no
+  xs / ys copies) against the chain of the three operators, both under autograd in one CUDA graph: fused algorithmic GB/s
+  (SURVEY.md 8d fused formula) and "effective" GB/s (the chain's algorithmic bytes over the fused time).
+* ``train`` / ``infer``: the step harness (vm_asr_b200/harness.py: STFT -> 34 fused cores with glue -> iSTFT -> L1 loss ->
+  backward -> bucketed, overlapped NCCL all-reduce of the real gradients + an MPD-sized 164 MB payload -> fused AdamW),
+  launched eagerly: audio-seconds per second (SURVEY.md 8d "Throughput metric"), exposed communication time.
+* ``e2e``: the headline metric END TO END through the public operator API: one harness training step per step with the
+  waveforms in pinned HOST memory -- upload, STFT, 34 fused cores fwd + bwd, iSTFT, loss read back to the host -- the step's
+  algorithmic scan bytes / wall time (device-synchronised), max over ranks.
+* ``eager``: the ``value`` step launched call by call from Python (no graph): host cost per call.
+* ``stft``: wav2spectro / spectro2wav (+ backward) kernel times next to the torch.stft / torch.istft chains.
+* ``cpu_baseline`` and ``--impl reference``: the oracle's C restatement of the reference's scan forward + backward on the host
+  cores (one clip of every distinct SS2D shape of the workload at FULL sequence length per step, threaded over B/C groups).
 Nothing here reads /root/reference.
 """
 from __future__ import annotations
@@ -36,8 +44,6 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
-
-GEN_PARAMS = 3_010_000  # generator parameters (README.md:8), the data-parallel gradient payload
 
 
 def load_peaks():
@@ -112,7 +118,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-# workload buffers
+# the scan step (headline)
 # ---------------------------------------------------------------------------------------------------------
 def make_call_inputs(call, batch, device, gen, pinned=False):
     """Reference test distributions (test_selective_scan.py:593-654)."""
@@ -129,6 +135,35 @@ def make_call_inputs(call, batch, device, gen, pinned=False):
         u=rnd(batch, D, L), delta=rnd(batch, D, L, kind="u").mul_(0.5), A=rnd(D, N, kind="u").mul_(-0.5),
         B=rnd(batch, G, N, L), C=rnd(batch, G, N, L), D=rnd(D), bias=rnd(D, kind="u").mul_(0.5), dout=rnd(batch, D, L),
     )
+
+
+def graph_of(fn):
+    """Run ``fn`` eagerly twice on a side stream (allocates this stream's workspaces), then capture it."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+        fn()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    return graph
+
+
+def time_graph(graph, steps, warmup):
+    for _ in range(max(warmup, 3)):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
 
 
 class DeviceStep:
@@ -224,18 +259,7 @@ class DeviceStep:
                 self.bwd_call(i)
 
     def capture(self):
-        self.run_eager()  # creates this stream's carry workspace before capture
-        torch.cuda.synchronize()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            self.run_eager()
-            torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=side):
-                self.run_eager()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
+        self.graph = graph_of(self.run_eager)
 
     def step(self):
         self.graph.replay()
@@ -280,107 +304,206 @@ def time_dominant_kernel(ds: DeviceStep, steps: int):
     return total_ms / n, total_bytes / n, n // steps
 
 
-class HostStep:
-    """The step through the public API with HOST buffers: pinned inputs -> device, fwd/bwd, outputs -> pinned host."""
-
-    def __init__(self, wl, device):
-        from vm_asr_b200 import scan
-        self.scan, self.wl, self.device = scan, wl, device
-        gen = torch.Generator().manual_seed(99)
-        self.host_in, self.host_out = [], []
-        self.h2d = self.d2h = 0
-        for c in wl.calls:
-            inp = make_call_inputs(c, wl.batch, "cpu", gen, pinned=True)
-            self.host_in.append(inp)
-            outs = {}
-            for name, shape in (("out", (wl.batch, c.D, c.L)), ("du", (wl.batch, c.D, c.L)), ("ddelta", (wl.batch, c.D, c.L)),
-                                ("dB", (wl.batch, 4, 1, c.L)), ("dC", (wl.batch, 4, 1, c.L)), ("dA", (c.D, 1)), ("dD", (c.D,)),
-                                ("dbias", (c.D,))):
-                outs[name] = torch.empty(shape, dtype=torch.float32, pin_memory=True)
-                self.d2h += outs[name].numel() * 4
-            self.host_out.append(outs)
-            self.h2d += sum(t.numel() * 4 for t in inp.values())
-        self.copy_in, self.copy_out = torch.cuda.Stream(), torch.cuda.Stream()
-
-    def step(self):
-        """Copies and kernels are ordered so that PCIe runs in both directions at once: forward inputs go up in call
-        order and every forward output goes down as soon as its call is done; `dout` goes up in reverse call order
-        behind them and every backward call's gradients go down as soon as they exist.  Consecutive steps overlap
-        the same way (the next step's uploads do not wait for this step's downloads)."""
-        main = torch.cuda.current_stream()
-        n = len(self.host_in)
-        dev_in, saved = [None] * n, [None] * n
-        ready_fwd, ready_bwd = [None] * n, [None] * n
-        with torch.cuda.stream(self.copy_in):
-            for i, inp in enumerate(self.host_in):
-                dev_in[i] = {k: v.to(self.device, non_blocking=True) for k, v in inp.items() if k != "dout"}
-                for v in dev_in[i].values():
-                    v.record_stream(main)
-                ready_fwd[i] = torch.cuda.Event()
-                ready_fwd[i].record()
-            for i in reversed(range(n)):
-                dout = self.host_in[i]["dout"].to(self.device, non_blocking=True)
-                dout.record_stream(main)
-                dev_in[i]["dout"] = dout
-                ready_bwd[i] = torch.cuda.Event()
-                ready_bwd[i].record()
-
-        def download(i, outs):
-            ev = torch.cuda.Event()
-            ev.record(main)
-            with torch.cuda.stream(self.copy_out):
-                self.copy_out.wait_event(ev)
-                for k, v in outs.items():
-                    v.record_stream(self.copy_out)
-                    self.host_out[i][k].copy_(v, non_blocking=True)
-
-        for i in range(n):
-            d = dev_in[i]
-            main.wait_event(ready_fwd[i])
-            out, x = self.scan.fwd(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], d["bias"], True, 1)
-            saved[i] = x
-            download(i, {"out": out})
-        for i in reversed(range(n)):
-            d = dev_in[i]
-            main.wait_event(ready_bwd[i])
-            du, ddelta, dA, dB, dC, dD, dbias = self.scan.bwd(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], d["bias"],
-                                                             d["dout"], saved[i], True, 1)
-            download(i, dict(du=du, ddelta=ddelta, dA=dA, dB=dB, dC=dC, dD=dD, dbias=dbias))
-        # no join here: the next step's uploads and kernels may start while this step's last gradients are still on
-        # their way down (stream order keeps the pinned output buffers consistent); the timed loop ends with a device sync
-
-
-# ---------------------------------------------------------------------------------------------------------
-# CPU reference arm (the oracle's torch restatement of the reference's pure-PyTorch path)
-# ---------------------------------------------------------------------------------------------------------
-def cpu_sample_step(wl, sample_len):
-    """fwd+bwd over the workload's distinct shapes truncated to their first `sample_len` positions; returns the
-    algorithmic bytes processed."""
-    from oracle import ss2d_ref
-    from vm_asr_b200 import workload as W
-    gen = torch.Generator().manual_seed(5)
-    total = 0
-    for call, _count in W.distinct_shapes(wl):
-        L = min(call.L, sample_len)
-        sub = W.SS2DCall(call.d_inner, 1, L)
-        inp = make_call_inputs(sub, wl.batch, "cpu", gen)
-        ss2d_ref.selective_scan(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], True)
-        ss2d_ref.selective_scan_bwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], True,
-                                    inp["dout"], dtype=torch.float32)
-        total += 4 * (8 * wl.batch * call.D * L + 6 * wl.batch * 4 * L)
-    return total
-
-
-def run_cpu_reference(wl, steps, warmup, sample_len):
-    torch.set_num_threads(os.cpu_count() or 1)
-    for _ in range(warmup):
-        cpu_sample_step(wl, sample_len)
+def time_eager(ds: DeviceStep, steps: int):
+    """The step launched call by call from Python, wall clock with a device sync at both ends: host-bound when the host
+    cost per call exceeds the kernel time."""
+    ds.run_eager()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    nbytes = 0
     for _ in range(steps):
-        nbytes += cpu_sample_step(wl, sample_len)
-    dt = time.perf_counter() - t0
-    return nbytes / dt / 1e9, dt / steps * 1e3, torch.get_num_threads()
+        ds.run_eager()
+    t_host = (time.perf_counter() - t0) / steps   # host enqueue time (the device may lag behind)
+    torch.cuda.synchronize()
+    t_all = (time.perf_counter() - t0) / steps
+    launches = ds.gpu_launches_per_step
+    return {"ms_per_step": round(t_all * 1e3, 3), "host_ms_per_step": round(t_host * 1e3, 3),
+            "host_us_per_launch": round(t_host * 1e6 / launches, 2), "launches_per_step": launches,
+            "note": "Python -> ctypes -> C ABI -> cudaLaunchKernelEx per launch (grouped: one launch per pair of calls); "
+                    "the reference's pybind entry costs ~9 us per call (round-1 measurement on the same box)"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused SS2D core vs the chain of the three operators (both under autograd, one CUDA graph each)
+# ---------------------------------------------------------------------------------------------------------
+class CoreStep:
+    def __init__(self, wl, device):
+        from vm_asr_b200 import cross, scan, ss2d
+        self.cross, self.scan, self.ss2d, self.wl = cross, scan, ss2d, wl
+        gen = torch.Generator(device=device).manual_seed(77)
+        B = wl.batch
+        r = lambda *s: torch.randn(*s, device=device, generator=gen)
+        u = lambda *s: torch.rand(*s, device=device, generator=gen)
+        self.sets = []
+        for c in wl.calls:
+            C, H, W, L = c.d_inner, c.H, c.W, c.L
+            self.sets.append(dict(call=c, x=r(B, C, H, W), dts_rm=0.5 * u(B, 2, C, L), dts_cm=0.5 * u(B, 2, C, L),
+                                  Bs_rm=r(B, 2, 1, L), Bs_cm=r(B, 2, 1, L), Cs_rm=r(B, 2, 1, L), Cs_cm=r(B, 2, 1, L),
+                                  As=-0.5 * u(4 * C, 1), Ds=r(4 * C), bias=0.5 * u(4 * C), dy=r(B, C, L)))
+        self.names = ("x", "dts_rm", "dts_cm", "Bs_rm", "Bs_cm", "Cs_rm", "Cs_cm", "As", "Ds", "bias")
+
+    def bytes(self):
+        B = self.wl.batch
+        fused = chain = 0
+        for c in self.wl.calls:
+            CL, DL, GL = B * c.d_inner * c.L, B * c.D * c.L, B * 4 * c.L
+            fused += 4 * (CL + DL + 2 * GL + CL) + 4 * (2 * CL + DL + 2 * GL) + 4 * (CL + DL + 2 * GL)   # SURVEY.md 8d
+            chain += 4 * (10 * CL + 3 * DL + 2 * GL) + 4 * (10 * CL + 5 * DL + 4 * GL)
+        return fused, chain
+
+    def fused_step(self):
+        ss2d = self.ss2d
+        n = len(self.sets)
+        pending = []
+        for i in range(0, n, 2):   # forward, the two streams' cores of a pair in one grid
+            ts = []
+            for d in (self.sets[i], self.sets[i + 1]):
+                t = [d[k].requires_grad_(True) for k in self.names]
+                xT = ss2d.MapTranspose.apply(t[0])
+                ts += [t[0], xT] + t[1:]
+            ys = ss2d._SS2DScan.apply(True, 2, *ts)
+            pending.append((ys, ts, (self.sets[i]["dy"], self.sets[i + 1]["dy"])))
+        for ys, ts, dys in reversed(pending):
+            leaves = [t for t in ts if t.is_leaf]
+            torch.autograd.grad(ys, leaves, dys)
+
+    def chain_step(self):
+        cross, scan = self.cross, self.scan
+        B = self.wl.batch
+        pending = []
+        for d in self.sets:
+            c = d["call"]
+            C, H, W, L = c.d_inner, c.H, c.W, c.L
+            x = d["x"].requires_grad_(True)
+            if "dts4" not in d:   # time-order tensors of the chain (values do not matter for timing)
+                d["dts4"] = torch.cat([d["dts_rm"], d["dts_cm"]], dim=1).view(B, 4 * C, L).contiguous()
+                d["Bs4"] = torch.cat([d["Bs_rm"], d["Bs_cm"]], dim=1).contiguous()
+                d["Cs4"] = torch.cat([d["Cs_rm"], d["Cs_cm"]], dim=1).contiguous()
+            ts = [x] + [d[k].requires_grad_(True) for k in ("dts4", "As", "Bs4", "Cs4", "Ds", "bias")]
+            xs = cross.CrossScan.apply(x)
+            ys = scan.SelectiveScanCore.apply(xs.view(B, 4 * C, L), ts[1], ts[2], ts[3], ts[4], ts[5], ts[6], True)
+            y = cross.CrossMerge.apply(ys.view(B, 4, C, H, W))
+            pending.append((y, ts, d["dy"]))
+        for y, ts, dy in reversed(pending):
+            torch.autograd.grad(y, ts, dy)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C restatement of the reference scan (forward + backward), threaded over B/C groups
+# ---------------------------------------------------------------------------------------------------------
+CPU_SAMPLE = ("one clip (batch index 0) of each of the workload's 6 distinct SS2D selective-scan shapes at FULL sequence length, "
+              "forward + backward, oracle/scan_ref.c (float64 accumulation, plain C), one thread per B/C group slice")
+
+
+class CpuStep:
+    def __init__(self, wl):
+        import numpy as np
+        from oracle import c_ref
+        from vm_asr_b200 import workload as W
+        self.c_ref, self.np = c_ref, np
+        c_ref.lib()
+        rng = np.random.default_rng(5)
+        self.jobs, self.bytes = [], 0
+        for call, _count in W.distinct_shapes(wl):
+            D, L, G = call.D, call.L, 4
+            cpg = D // G
+            f = lambda *s: rng.standard_normal(s, dtype=np.float32)
+            un = lambda *s: rng.random(s, dtype=np.float32)
+            u, delta, dout = f(1, D, L), 0.5 * un(1, D, L), f(1, D, L)
+            A, Dv, bias = -0.5 * un(D, 1), f(D), 0.5 * un(D)
+            Bm, Cm = f(1, G, 1, L), f(1, G, 1, L)
+            for g in range(G):
+                sl = slice(g * cpg, (g + 1) * cpg)
+                self.jobs.append((u[:, sl], delta[:, sl], A[sl], Bm[:, g:g + 1], Cm[:, g:g + 1], Dv[sl], bias[sl], dout[:, sl]))
+            self.bytes += 4 * (8 * D * L + 6 * G * L)
+        self.threads = os.cpu_count() or 1
+
+    def _job(self, j):
+        u, delta, A, Bm, Cm, Dv, bias, dout = j
+        self.c_ref.scan_fwd(u, delta, A, Bm, Cm, Dv, bias, True)
+        self.c_ref.scan_bwd(u, delta, A, Bm, Cm, Dv, bias, True, dout)
+
+    def run(self, steps, warmup):
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(self.threads) as ex:
+            for _ in range(warmup):
+                list(ex.map(self._job, self.jobs))
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                list(ex.map(self._job, self.jobs))
+            dt = (time.perf_counter() - t0) / steps
+        return self.bytes / dt / 1e9, dt * 1e3, min(self.threads, len(self.jobs))
+
+
+def workload_config(wl):
+    """The ``config`` object both arms print (the driver compares them)."""
+    return {"workload": f"{wl.yaml}: SS2D selective-scan forward + backward of one training step (34 + 34 calls), "
+                        f"batch {wl.batch} per GPU, fp32, d_state 1, 4 B/C groups"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def stft_times(wl, device, reps=20):
+    """Kernel times (CUDA graph of `reps` calls, CUDA events) of the three STFT entry points next to the torch chains."""
+    from vm_asr_b200 import stft
+    out = {}
+    B, T, F_, Nf = wl.batch, wl.T, wl.n_fft // 2 + 1, 1 + wl.T // wl.hop
+    wave = [0.1 * torch.randn(B, 1, T, device=device) for _ in range(4)]
+    mp = [stft.wav2spectro(w, wl.n_fft, wl.hop, wl.win, "log2") for w in wave]
+    win = torch.hann_window(wl.win, device=device)
+    k = [0]
+
+    def rot():
+        k[0] = (k[0] + 1) % 4
+        return k[0]
+
+    def ours_stft():
+        for _ in range(reps):
+            stft.wav2spectro(wave[rot()], wl.n_fft, wl.hop, wl.win, "log2")
+
+    def torch_stft():
+        for _ in range(reps):
+            s = torch.stft(wave[rot()].reshape(-1, T), wl.n_fft, wl.hop, wl.win, win, normalized=True, return_complex=True)
+            torch.log2(s.abs() + 1e-8), torch.angle(s)
+
+    def ours_istft():
+        for _ in range(reps):
+            m, p = mp[rot()]
+            stft.spectro2wav(m, p, wl.n_fft, wl.hop, wl.win, "log2")
+
+    def torch_istft():
+        for _ in range(reps):
+            m, p = mp[rot()]
+            X = torch.exp2(m.reshape(-1, F_, Nf)) * torch.exp(1j * p.reshape(-1, F_, Nf))
+            torch.istft(X, wl.n_fft, wl.hop, wl.win, win, normalized=True)
+
+    def ours_istft_fb():
+        for _ in range(reps):
+            m, p = mp[rot()]
+            m, p = m.detach().requires_grad_(), p.detach().requires_grad_()
+            w = stft.spectro2wav(m, p, wl.n_fft, wl.hop, wl.win, "log2")
+            torch.autograd.grad(w, (m, p), torch.ones_like(w))
+
+    def torch_istft_fb():
+        for _ in range(reps):
+            m, p = mp[rot()]
+            m, p = m.detach().requires_grad_(), p.detach().requires_grad_()
+            X = torch.exp2(m.reshape(-1, F_, Nf)) * torch.exp(1j * p.reshape(-1, F_, Nf))
+            w = torch.istft(X, wl.n_fft, wl.hop, wl.win, win, normalized=True)
+            torch.autograd.grad(w, (m, p), torch.ones_like(w))
+
+    nb = 4 * B * T + 8 * B * F_ * Nf
+    for name, fn, nbytes in (("stft", ours_stft, nb), ("torch_stft_chain", torch_stft, nb), ("istft", ours_istft, nb),
+                             ("torch_istft_chain", torch_istft, nb), ("istft_fwd_bwd", ours_istft_fb, 2 * nb + 8 * B * F_ * Nf),
+                             ("torch_istft_fwd_bwd", torch_istft_fb, 2 * nb + 8 * B * F_ * Nf)):
+        try:
+            ms = time_graph(graph_of(fn), 5, 3) / reps
+            out[name] = {"us": round(ms * 1e3, 2), "GBps": round(nbytes / ms / 1e6, 1)}
+        except Exception as e:  # a torch op that cannot be captured must not take the bench line down
+            out[name] = {"error": str(e)[:120]}
+    for a, b in (("stft", "torch_stft_chain"), ("istft", "torch_istft_chain"), ("istft_fwd_bwd", "torch_istft_fwd_bwd")):
+        if "us" in out.get(a, {}) and "us" in out.get(b, {}):
+            out[a]["vs_torch"] = round(out[b]["us"] / out[a]["us"], 2)
+    out["shape"] = f"B={B} T={T} n_fft={wl.n_fft} hop={wl.hop} win={wl.win}"
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -391,14 +514,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vm_asr_48k_MPD")
-    ap.add_argument("--e2e-steps", type=int, default=6)
-    ap.add_argument("--cpu-sample-len", type=int, default=256)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly (profiling aid)")
+    ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--pairing", default="grouped", choices=["grouped", "streams", "none"],
                     help="how the two generator streams' same-shape calls are issued: one grouped launch per pair (default), "
                          "two CUDA streams, or one call after the other")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the harness (train / infer / e2e)")
+    ap.add_argument("--no-core", action="store_true", help="skip the fused-core-vs-chain step")
+    ap.add_argument("--no-stft", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly (profiling aid)")
     args = ap.parse_args()
 
     from vm_asr_b200 import workload as W
@@ -408,21 +532,18 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     fwd_b, bwd_b = wl.scan_bytes()
     step_bytes = fwd_b + bwd_b
-    sample_desc = (f"scan fwd+bwd over the workload's 6 distinct (B, D) shapes, sequence truncated to its first "
-                   f"{args.cpu_sample_len} positions, fp32 torch ops, python loop over L (selective_scan_ref style)")
+    config = workload_config(wl)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        warm = max(1, min(args.warmup, 2))
-        steps = max(1, min(args.steps, 5))
-        gbs, ms, cores = run_cpu_reference(wl, steps, warm, args.cpu_sample_len)
+        cpu = CpuStep(wl)
+        gbs, ms, cores = cpu.run(args.steps, max(args.warmup, 1))
         print(json.dumps({
             "impl": "reference", "metric": "ss2d_scan_fwd_bwd_GBps", "value": round(gbs, 4), "unit": "GB/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": warm, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{wl.yaml} SS2D selective-scan fwd+bwd (34 calls), batch {wl.batch}", "sample": sample_desc},
-            "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample_desc},
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": round(ms, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": "port", "sample": CPU_SAMPLE},
             "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
@@ -437,29 +558,20 @@ def main():
     peak, peak_src = load_peaks()
 
     cpu_base = None
-    if rank == 0 and not args.no_cpu_baseline:
-        gbs, ms, cores = run_cpu_reference(wl, 2, 1, args.cpu_sample_len)
-        cpu_base = {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample_desc,
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        gbs, ms, cores = CpuStep(wl).run(3, 1)
+        cpu_base = {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": "port", "sample": CPU_SAMPLE,
                     "ms_per_sample_step": round(ms, 1)}
 
+    # ---- headline: the scan step ----
     ds = DeviceStep(wl, device, args.pairing)
     if args.no_graph:
         ds.step = ds.run_eager
         ds.run_eager()
     else:
         ds.capture()
-    grad_flat = torch.zeros(GEN_PARAMS, dtype=torch.float32, device=device) if world > 1 else None
-
-    def one_step():
-        ds.step()
-        if world > 1:
-            return dist.all_reduce(grad_flat, async_op=True)
-        return None
-
     for _ in range(max(args.warmup, 3)):
-        h = one_step()
-        if h is not None:
-            h.wait()
+        ds.step()
     sampler = ClockSampler(local_rank)
     sampler.start()
     torch.cuda.synchronize()
@@ -469,77 +581,121 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     e0.record()
-    handles = []
     for _ in range(args.steps):
-        handles.append(one_step())
-    for h in handles:
-        if h is not None:
-            h.wait()
+        ds.step()
     e1.record()
     torch.cuda.synchronize()
     t_wall1 = time.perf_counter()
     if world > 1:
         dist.barrier()
     sampler.stop()
-    elapsed_ms = e0.elapsed_time(e1)
-    elapsed_ms = vdist.max_over_ranks(elapsed_ms, device)  # timing rule: max over ranks
-    ms_per_step = elapsed_ms / args.steps
+    ms_per_step = vdist.max_over_ranks(e0.elapsed_time(e1), device) / args.steps  # timing rule: max over ranks
     value = world * step_bytes / (ms_per_step * 1e-3) / 1e9
     clocks = sampler.summary(t_wall0, t_wall1)
 
-    # dominant kernel, launch by launch
     k_ms, k_bytes, k_per_step = time_dominant_kernel(ds, max(2, min(args.steps, 5)))
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
-        except Exception:
-            traffic = None
+    eager = time_eager(ds, 5) if rank == 0 else None
+    del ds
+    torch.cuda.empty_cache()
 
-    e2e = None
+    # ---- fused SS2D core vs the chain ----
+    core = None
+    if not args.no_core:
+        cs = CoreStep(wl, device)
+        fused_b, chain_b = cs.bytes()
+        t_fused = time_graph(graph_of(cs.fused_step), max(3, min(args.steps, 10)), 3)
+        t_chain = time_graph(graph_of(cs.chain_step), max(3, min(args.steps, 10)), 3)
+        t_fused, t_chain = vdist.max_over_ranks(t_fused, device), vdist.max_over_ranks(t_chain, device)
+        core = {"fused_ms_per_step": round(t_fused, 4), "chain_ms_per_step": round(t_chain, 4),
+                "fused_algorithmic_GBps": round(world * fused_b / t_fused / 1e6, 1),
+                "effective_GBps_vs_chain_bytes": round(world * chain_b / t_fused / 1e6, 1),
+                "chain_GBps": round(world * chain_b / t_chain / 1e6, 1), "speedup_vs_chain": round(t_chain / t_fused, 3),
+                "fused_frac_of_hbm_peak": round(fused_b / t_fused / 1e6 / peak, 4),
+                "what": "34 SS2D cores (CrossScan -> selective scan -> CrossMerge) forward + backward under autograd in one CUDA graph; "
+                        "fused: vmasr_ss2d_core_fwd/bwd, the two streams' cores of a pair in one grid, no xs / ys copies; "
+                        "chain: vmasr_cross_scan -> vmasr_scan_* -> vmasr_cross_merge per call"}
+        del cs
+        torch.cuda.empty_cache()
+
+    # ---- the step harness: training / inference throughput and the end-to-end number ----
+    train = infer = e2e = None
     if not args.no_e2e:
-        hs = HostStep(wl, device)
-        hs.step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            hs.step()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        dt = vdist.max_over_ranks(dt, device)
-        e2e = {"value": round(world * step_bytes / dt / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": hs.h2d,
-               "d2h_bytes_per_step": hs.d2h, "ms_per_step": round(dt * 1e3, 2), "steps": args.e2e_steps,
-               "api": "vm_asr_b200.scan.fwd/bwd (selective_scan_cuda_core surface), pinned host buffers, copies on side streams"}
-        del hs
+        from vm_asr_b200 import harness
+        ts = harness.TrainStep(wl, device, world=world)
+        host_in, host_tgt = harness.synthetic_batch(wl, device, rank, pinned=True)
+
+        def e2e_step(comm=True):
+            x = host_in.to(device, non_blocking=True)
+            y = host_tgt.to(device, non_blocking=True)
+            return ts(x, y, comm=comm).item()   # the loss is read back to the host: the step's result
+
+        for _ in range(3):
+            e2e_step()
+        n_train = max(3, args.train_steps)
+
+        def timed(fn, n):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            torch.cuda.synchronize()
+            return vdist.max_over_ranks((time.perf_counter() - t0) / n, device)
+
+        t_train = timed(e2e_step, n_train)
+        t_nocomm = timed(lambda: e2e_step(False), n_train) if world > 1 else t_train
+        dev_in = host_in.to(device)
+        t_infer = timed(lambda: ts.infer(dev_in), n_train)
+        secs = wl.batch * wl.clip_seconds
+        train = {"audio_sec_per_s": round(world * secs / t_train, 1), "ms_per_step": round(t_train * 1e3, 2), "steps": n_train,
+                 "launch": "eager (Python, autograd)", "parameters": ts.n_params,
+                 "collective": (f"NCCL all-reduce of the {ts.n_params}-float gradient buffer in {len(ts.grads.buckets)} buckets from autograd hooks "
+                                f"+ a {harness.MPD_PARAMS}-float zero payload standing in for the MPD gradients (not built), overlapped with backward")
+                 if world > 1 else "none",
+                 "exposed_comm_ms": round((t_train - t_nocomm) * 1e3, 3) if world > 1 else 0.0}
+        infer = {"audio_sec_per_s": round(world * secs / t_infer, 1), "ms_per_step": round(t_infer * 1e3, 2),
+                 "what": "torch.no_grad forward of the harness (STFT -> 34 fused cores -> iSTFT), inputs on the device"}
+        e2e = {"value": round(world * step_bytes / t_train / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": 2 * host_in.numel() * 4,
+               "d2h_bytes_per_step": 4, "ms_per_step": round(t_train * 1e3, 2), "steps": n_train,
+               "api": "vm_asr_b200.harness.TrainStep: pinned host waveforms -> device, wav2spectro, 34 x ss2d_core (fused, paired) forward + "
+                      "backward, spectro2wav (+ backward), L1 loss read back to the host, gradient all-reduce, AdamW; the step's "
+                      "algorithmic scan bytes over its wall time"}
+        del ts
+        torch.cuda.empty_cache()
+
+    stft_t = None
+    if not args.no_stft and rank == 0:
+        try:
+            stft_t = stft_times(wl, device)
+        except Exception as e:
+            stft_t = {"error": str(e)[:200]}
 
     if rank == 0:
         out = {
             "metric": "ss2d_scan_fwd_bwd_GBps", "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": f"{wl.yaml} SS2D selective-scan fwd+bwd of one training step (34 fwd + 34 bwd calls), "
-                            f"batch {wl.batch} per GPU, d_state 1, 4 groups",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "run": {
                 "algorithmic_bytes_per_step": step_bytes, "scan_elements_per_step": wl.scan_elements(),
                 "l2": "inputs larger than L2: every call has its own buffers, ~5.4 GB touched per step vs 126 MB L2",
-                "launch": "eager launches" if args.no_graph else "one CUDA graph per step", "pairing": args.pairing, "parallelism": f"dp{world}" if world > 1 else "single",
-                "collective": "NCCL all-reduce of a 3.01M-float gradient buffer per step" if world > 1 else "none",
+                "launch": "eager launches" if args.no_graph else "one CUDA graph per step", "pairing": args.pairing,
+                "parallelism": f"dp{world}: one rank per GPU on its own batch shard, no data-path collective" if world > 1 else "single",
             },
             "frac_of_hbm_peak": round(value / world / peak, 4), "hbm_peak_gbs": peak, "hbm_peak_source": peak_src,
-            "audio_sec_per_s_hot_path": round(world * wl.batch * wl.clip_seconds / (ms_per_step * 1e-3), 1),
             "clocks": clocks,
-            "gpu_launches": ds.gpu_launches_per_step * args.steps,
+            "gpu_launches": (len(wl.calls) if args.pairing == "grouped" else 2 * len(wl.calls)) * args.steps,
             "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": traffic,
-                         "kernel": "scan_bwd_pipe_kernel<softplus> (csrc/scan_bwd_pipe.cu), every backward call with seqlen > 2048 (18 of the 34 calls, 85 % of the backward bytes)", "launches_per_step": k_per_step,
-                         "avg_launch_ms": round(k_ms, 5), "avg_algorithmic_bytes_per_launch": int(k_bytes),
-                         "peak_source": peak_src},
+                         "frac": round(achieved / peak, 4), "traffic": None,
+                         "kernel": "scan_bwd_pipe_kernel<softplus> (csrc/scan_bwd_pipe.cu), every backward launch with seqlen > 2048 "
+                                   "(grouped: one launch per pair of calls)",
+                         "launches_per_step": k_per_step, "avg_launch_ms": round(k_ms, 5),
+                         "avg_algorithmic_bytes_per_launch": int(k_bytes), "peak_source": peak_src,
+                         "traffic_note": "per-launch DRAM bytes are in the ncu launch lists under profiles/ (not measured inside this run)"},
             "cpu_baseline": cpu_base,
+            "ss2d_core": core, "train": train, "infer": infer, "eager": eager, "stft": stft_t,
         }
         print(json.dumps(out))
     if world > 1:

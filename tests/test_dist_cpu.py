@@ -81,3 +81,43 @@ def test_single_process_is_a_no_op():
     vdist.allreduce_grads_(g)
     assert torch.equal(g[0], torch.ones(4))
     assert vdist.max_over_ranks(3.5) == 3.5
+
+
+def _flat_worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vm_asr_b200.harness import FlatGrads
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4))
+        unused = torch.nn.Parameter(torch.ones(7))   # never receives a gradient (cf. the reference's unused phase decoder)
+        params = list(net.parameters()) + [unused]
+        fg = FlatGrads(params, bucket_floats=100, payload_floats=1000, payload_chunks=3)
+        assert len(fg.buckets) >= 3 and fg.enabled
+        x_all = torch.randn(8, 16)
+        for _ in range(2):   # two steps: the hooks re-arm
+            fg.zero()
+            fg.start_payload()
+            lo, hi = vdist.shard_range(8, rank, world)
+            net(x_all[lo:hi]).square().sum().backward()
+            fg.finish(world)
+        ref = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4))
+        ref.load_state_dict(net.state_dict())
+        (ref(x_all).square().sum() / world).backward()   # mean over ranks of the per-shard sums
+        for p, q in zip(net.parameters(), ref.parameters()):
+            np.testing.assert_allclose(p.grad.numpy(), q.grad.numpy(), rtol=1e-5, atol=1e-6)
+        assert torch.equal(unused.grad, torch.zeros(7))
+        assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in params)   # gradients are views of the flat buffer
+        open(os.path.join(tmp, f"flat{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_flat_bucketed_gradient_allreduce(tmp_path):
+    """The harness's gradient plumbing (one flat buffer, buckets reduced from autograd hooks as they fill, a payload going out
+    first, a bucket whose parameter got no gradient) on two gloo ranks: equal to the full-batch gradient divided by world."""
+    world, port = 2, _free_port()
+    mp.spawn(_flat_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"flat{r}").exists() for r in range(world))

@@ -54,11 +54,13 @@ def rel_err(got, ref):
 # therefore relative to each element's own conditioning scale  s_l = |C_l| sum_m (prod a) dt_m |B_m| |u_m| + |D| |u_l|  -- the
 # same scan run by the float64 oracle over absolute values (s_l >= |y_l|) -- plus a small floor:
 #       |got_l - ref_l| <= ELEM_TOL * (s_l + ELEM_FLOOR * rms(s)).
-# du and ddelta get the scales of the adjoint recurrence in the same way (cond_scales).  ELEM_TOL is looser than the max-norm
-# bar because the decay exp2(dt * A) comes from the MUFU (ex2.approx, as in the reference's --use_fast_math build): its 2^-22
-# relative error per position accumulates over the memory length of slowly decaying channels (|A| -> 0).
-ELEM_TOL = 1e-3
+# du and ddelta get the scales of the adjoint recurrence in the same way (cond_scales), and the three per-channel sums (dA, dD,
+# ddelta_bias: fp32 atomic sums over batch x seqlen terms, as in the reference) are held to SUM_TOL of the sum of their terms'
+# magnitudes.  Measured worst ratios over the whole suite (gpurun_out/elementwise.json): 2e-6 for out / du / ddelta.
+ELEM_TOL = 2e-5
 ELEM_FLOOR = 0.01
+SUM_TOL = 1e-4    # dA, dD, ddelta_bias relative to sum |terms|
+SUM_MAXNORM_TOL = 3e-4   # the same three sums relative to the largest |ref| (they cancel: sum |terms| >> |sum|)
 ELEM_LOG = []   # (tag, tensor, worst ratio) -- written to gpurun_out/elementwise.json at the end of the session
 
 
@@ -89,16 +91,26 @@ def cond_scales(cpu, softplus):
         dt, sig = x, np.ones_like(x)
     ddout = 0.0 if Dv is None else Dv.astype(np.float64)[None, :, None] * dout
     T1 = (s_du - ddout) * u * sig / np.maximum(np.abs(dt), 1e-30)
-    return s_out, s_du, np.abs(2.0 * T1 - R)
+    s_dd = np.abs(2.0 * T1 - R)
+    sums = dict(dA=np.asarray(g[2], dtype=np.float64), dD=None if g[5] is None else np.asarray(g[5], dtype=np.float64),
+                dbias=None if g[6] is None else s_dd.sum(axis=(0, 2)))
+    return s_out, s_du, s_dd, sums
 
 
 def check_elementwise(got, ref, cpu, softplus, tag):
     (out, _, grads), (ref_out, _, _, ref_grads) = got, ref
-    s_out, s_du, s_dd = cond_scales(cpu, softplus)
+    s_out, s_du, s_dd, sums = cond_scales(cpu, softplus)
     for name, a, b, sc in (("out", out, ref_out, s_out), ("du", grads[0], ref_grads[0], s_du), ("ddelta", grads[1], ref_grads[1], s_dd)):
         e = elem_err(a.float(), b, sc)
         ELEM_LOG.append((tag, name, e))
         assert e < ELEM_TOL, f"{name}, elementwise {tag}: {e}"
+    for name, idx in (("dA", 2), ("dD", 5), ("dbias", 6)):
+        if ref_grads[idx] is None:
+            continue
+        sc = np.abs(sums[name]).reshape(np.asarray(ref_grads[idx]).shape)
+        e = float((np.abs(grads[idx].double().cpu().numpy() - np.asarray(ref_grads[idx], dtype=np.float64)) / (sc + 1e-30)).max())
+        ELEM_LOG.append((tag, name, e))
+        assert e < SUM_TOL, f"{name}, relative to the sum of its terms' magnitudes, {tag}: {e}"
 
 
 @pytest.fixture(scope="session", autouse=True)
@@ -144,7 +156,7 @@ def assert_parity(got, ref, itype, tag=""):
             assert g is None, name
             continue
         # parameter gradients are fp32 sums in every dtype mode
-        t = tol if name in ("du", "ddelta", "dB", "dC") else max(REL_FP32, tol / 10)
+        t = tol if name in ("du", "ddelta", "dB", "dC") else max(SUM_MAXNORM_TOL, tol / 10)
         assert rel_err(g, r) < t, f"{name} {tag}: {rel_err(g, r)}"
 
 

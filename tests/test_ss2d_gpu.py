@@ -110,7 +110,9 @@ def test_fused_core_against_oracle_chain(Bsz, C, H, W):
     y_ref, g_ref = _run_oracle(*inp)
     assert rel_err(y, y_ref) < REL_FP32
     for name in ("dx", "ddelta", "dB", "dC", "dA", "dD", "dbias"):
-        assert rel_err(grads[name], g_ref[name]) < REL_FP32, f"{name}: {rel_err(grads[name], g_ref[name])}"
+        # the three per-channel sums are fp32 atomic sums over batch x L terms that cancel (tests/test_scan_gpu.py: SUM_MAXNORM_TOL)
+        tol = 3e-4 if name in ("dA", "dD", "dbias") else REL_FP32
+        assert rel_err(grads[name], g_ref[name]) < tol, f"{name}: {rel_err(grads[name], g_ref[name])}"
 
 
 @pytest.mark.parametrize("Bsz,C,H,W", [(2, 4, 16, 16), (2, 8, 64, 48), (1, 4, 128, 96)])

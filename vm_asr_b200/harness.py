@@ -1,0 +1,246 @@
+"""Step harness of the hot path (SURVEY.md 8d "Throughput metric", 8e): the SHAPE of one VM-ASR generator step, with every
+hot-path operator on this library's kernels and nothing else of the model rebuilt.
+
+    wave --wav2spectro--> (mag, phase) --drop DC bin--> two streams of 17 SS2D cores each (the 34 calls of the config, at the
+    config's map sizes, in the generator's order: model/model.py:1103-1227) --add DC bin back--> spectro2wav --> wave_out
+
+Between two SS2D cores the real generator runs in_proj / depthwise conv / LayerNorm / MLP / patch merging on cuBLAS / cuDNN
+(out of scope: BASELINE.json north_star keeps them on PyTorch).  Here they are replaced by the cheapest differentiable glue
+that produces a map of the next call's shape -- residual add, a one-group normalisation, nearest / average resampling and a
+1x1 convolution when the channel count changes -- so that one autograd graph links all 34 calls, the STFT and the iSTFT, and
+the two streams interact after every pair as in the reference (``mag = mag + phase; phase = phase + mag``, model.py:1129-1131).
+The cores' parameters use the reference's initialisers (vmamba.py:1204-1267).
+
+``TrainStep`` adds what a data-parallel trainer adds (trainer/trainer.py:138-156 has no multi-GPU path at all, README.md:31):
+  * all gradients live in ONE flat buffer, cut into buckets; a bucket's NCCL all-reduce is issued on a side stream from the
+    autograd hook of its last parameter, so it overlaps the rest of the backward;
+  * the multi-period discriminator is not built here; its 41.09 M-float gradient payload is carried as a
+    zero buffer of that size, all-reduced in chunks alongside -- stated as synthetic wherever it is reported;
+  * fused AdamW on the real parameters.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ss2d, stft
+from .workload import Workload
+
+MPD_PARAMS = 41_090_000  # MultiPeriodDiscriminator(hidden=32), SURVEY.md 8e
+
+
+class SS2DCoreParams(nn.Module):
+    """Parameters of one SS2D core, initialised as SS2D.__initv2__ does (vmamba.py:772-850 with dt_init :1204-1236,
+    A_log_init :1241-1255, D_init :1258-1267); d_state 1, 4 directions, dt_rank = ceil(d_model / 16) with d_model = d_inner / 2."""
+
+    def __init__(self, d_inner: int, generator: torch.Generator):
+        super().__init__()
+        K, N = 4, 1
+        R = max(1, math.ceil((d_inner // 2) / 16))
+        self.d_inner, self.R = d_inner, R
+        bound = 1.0 / math.sqrt(d_inner)
+        self.x_proj_weight = nn.Parameter((torch.rand(K, R + 2 * N, d_inner, generator=generator) * 2 - 1) * bound)
+        std = R ** -0.5
+        self.dt_projs_weight = nn.Parameter((torch.rand(K, d_inner, R, generator=generator) * 2 - 1) * std)
+        dt = torch.exp(torch.rand(K, d_inner, generator=generator) * (math.log(0.1) - math.log(0.001)) + math.log(0.001)).clamp(min=1e-4)
+        self.dt_projs_bias = nn.Parameter(dt + torch.log(-torch.expm1(-dt)))
+        self.A_logs = nn.Parameter(torch.zeros(K * d_inner, N))   # log(arange(1, N + 1)) with N = 1
+        self.Ds = nn.Parameter(torch.ones(K * d_inner))
+
+    def tensors(self):
+        return (self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds)
+
+
+class HotPathNet(nn.Module):
+    """STFT -> 17 pairs of SS2D cores (magnitude stream, phase stream) -> iSTFT, see the module docstring."""
+
+    def __init__(self, wl: Workload, seed: int = 123, pair: bool = True):
+        super().__init__()
+        self.wl, self.pair = wl, pair
+        gen = torch.Generator().manual_seed(seed)
+        assert len(wl.calls) % 2 == 0
+        self.steps = [wl.calls[i] for i in range(0, len(wl.calls), 2)]   # calls 2j, 2j + 1: the two streams' same-shape pair
+        self.cores = nn.ModuleList()
+        self.glue = nn.ModuleList()
+        c_prev = 1
+        for call in self.steps:
+            self.cores.append(nn.ModuleList([SS2DCoreParams(call.d_inner, gen), SS2DCoreParams(call.d_inner, gen)]))
+            if call.d_inner != c_prev:
+                convs = nn.ModuleList([nn.Conv2d(c_prev, call.d_inner, 1), nn.Conv2d(c_prev, call.d_inner, 1)])
+            else:
+                convs = nn.ModuleList()
+            self.glue.append(convs)
+            c_prev = call.d_inner
+        self.head = nn.ModuleList([nn.Conv2d(c_prev, 1, 1), nn.Conv2d(c_prev, 1, 1)])
+
+    @staticmethod
+    def _resample(x, H, W):
+        h, w = x.shape[-2:]
+        if (h, w) == (H, W):
+            return x
+        if h >= H and w >= W and h % H == 0 and w % W == 0:
+            return F.avg_pool2d(x, (h // H, w // W))
+        return F.interpolate(x, size=(H, W), mode="nearest")
+
+    def forward(self, wave: torch.Tensor) -> torch.Tensor:
+        wl = self.wl
+        Bsz = wave.shape[0]
+        mag, phase = stft.wav2spectro(wave, wl.n_fft, wl.hop, wl.win, "log2")   # (B, 1, F, Nf); model.py:424-434
+        dc = (mag[..., :1, :], phase[..., :1, :])
+        streams = [mag[..., 1:, :], phase[..., 1:, :]]                            # model.py:1110-1111
+        residual_mag = streams[0]
+        for call, cores, convs in zip(self.steps, self.cores, self.glue):
+            xs = []
+            for s in range(2):
+                x = self._resample(streams[s], call.H, call.W)
+                if len(convs):
+                    x = convs[s](x)
+                xs.append(x.contiguous())
+            if self.pair and call.H % 4 == 0 and call.W % 4 == 0:
+                ys = ss2d.ss2d_core_pair(xs[0], cores[0].tensors(), xs[1], cores[1].tensors())
+            else:
+                ys = [ss2d.ss2d_core(xs[s], *cores[s].tensors()) for s in range(2)]
+            outs = []
+            for s in range(2):
+                y = ys[s].view(Bsz, call.d_inner, call.H, call.W)
+                outs.append(xs[s] + F.group_norm(y, 1))                          # VSSBlock: x + SS2D(LN(x)) (vmamba.py:1826-1837)
+            m = outs[0] + outs[1]                                                # model.py:1129-1131
+            streams = [m, outs[1] + m]
+        full_h, full_w = residual_mag.shape[-2:]
+        out = [self.head[s](self._resample(streams[s], full_h, full_w)) for s in range(2)]
+        mag_out = torch.cat([dc[0], out[0] + residual_mag], dim=-2)              # model.py:1205-1215
+        phase_out = torch.cat([dc[1], out[1]], dim=-2)
+        wav = stft.spectro2wav(mag_out, phase_out, wl.n_fft, wl.hop, wl.win, "log2")   # model.py:436-445
+        return wav[..., : wave.shape[-1]]
+
+
+class FlatGrads:
+    """All parameter gradients as views of one flat fp32 buffer, cut into buckets of ``bucket_floats``; the all-reduce of a
+    bucket is issued from the post-accumulate hook of the LAST of its parameters to receive a gradient."""
+
+    def __init__(self, params: List[nn.Parameter], bucket_floats: int = 1 << 20, payload_floats: int = 0, payload_chunks: int = 4):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.buckets = []   # (lo, hi, pending count)
+        off, lo, members = 0, 0, 0
+        self._bucket_of = {}
+        # buckets in REVERSE registration order: the last layers' gradients are ready first
+        for p in reversed(self.params):
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            self._bucket_of[p] = len(self.buckets)
+            off += n
+            members += 1
+            if off - lo >= bucket_floats:
+                self.buckets.append([lo, off, members])
+                lo, members = off, 0
+        if members:
+            self.buckets.append([lo, off, members])
+        self.payload = torch.zeros(payload_floats, dtype=torch.float32, device=dev) if payload_floats else None
+        self.payload_chunks = payload_chunks
+        self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None   # CPU (gloo) in the unit tests
+        self._pending = [b[2] for b in self.buckets]
+        self._handles = []
+        self.enabled = dist.is_initialized() and dist.get_world_size() > 1
+        for p in self.params:
+            p.register_post_accumulate_grad_hook(self._hook)
+
+    def _on_comm_stream(self):
+        import contextlib
+        if self.comm_stream is None:
+            return contextlib.nullcontext()
+        self.comm_stream.wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(self.comm_stream)
+
+    def zero(self):
+        self.flat.zero_()
+        self._pending = [b[2] for b in self.buckets]
+        self._handles = []
+
+    def start_payload(self):
+        """The discriminator-sized payload goes out first, in chunks, on the communication stream (it has no dependency on
+        this step's backward): it overlaps the whole backward."""
+        if not self.enabled or self.payload is None:
+            return
+        with self._on_comm_stream():
+            for chunk in self.payload.chunk(self.payload_chunks):
+                self._handles.append(dist.all_reduce(chunk, async_op=True))
+
+    def _hook(self, p):
+        if not self.enabled:
+            return
+        b = self._bucket_of[p]
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            lo, hi, _ = self.buckets[b]
+            with self._on_comm_stream():
+                self._handles.append(dist.all_reduce(self.flat[lo:hi], async_op=True))
+
+    def finish(self, world: int):
+        if not self.enabled:
+            return
+        # buckets with a parameter that received no gradient this step (the reference has such parameters: the phase decoder
+        # is never run with CONCAT_SKIP, model/model.py:1186-1187) were never triggered: their zeros are reduced now
+        for b, left in enumerate(self._pending):
+            if left > 0:
+                lo, hi, _ = self.buckets[b]
+                with self._on_comm_stream():
+                    self._handles.append(dist.all_reduce(self.flat[lo:hi], async_op=True))
+                self._pending[b] = 0
+        for h in self._handles:
+            h.wait()
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.flat.div_(world)
+
+
+class TrainStep:
+    """forward -> L1 waveform loss -> backward (bucketed all-reduce overlapped) -> fused AdamW.  ``comm=False`` runs the
+    same step without any collective (to state the exposed communication time)."""
+
+    def __init__(self, wl: Workload, device, world: int = 1, pair: bool = True, mpd_payload: bool = True, lr: float = 1e-3):
+        self.wl, self.world, self.device = wl, world, device
+        self.net = HotPathNet(wl, pair=pair).to(device)
+        if world > 1:
+            for p in self.net.parameters():
+                dist.broadcast(p.data, 0)
+        self.grads = FlatGrads(list(self.net.parameters()), payload_floats=MPD_PARAMS if (mpd_payload and world > 1) else 0)
+        self.opt = torch.optim.AdamW(self.net.parameters(), lr=lr, weight_decay=0.0, fused=True)   # config.py:131-154
+        self.n_params = sum(p.numel() for p in self.net.parameters())
+
+    def __call__(self, wave_in: torch.Tensor, wave_target: torch.Tensor, comm: bool = True) -> torch.Tensor:
+        g = self.grads
+        g.zero()
+        was = g.enabled
+        g.enabled = was and comm
+        g.start_payload()
+        out = self.net(wave_in)
+        loss = (out - wave_target).abs().mean()
+        loss.backward()
+        g.finish(self.world)
+        g.enabled = was
+        self.opt.step()
+        return loss
+
+    @torch.no_grad()
+    def infer(self, wave_in: torch.Tensor) -> torch.Tensor:
+        return self.net(wave_in)
+
+
+def synthetic_batch(wl: Workload, device, rank: int = 0, pinned: bool = False):
+    """wave_target = 0.1 randn(B, 1, T); the input is a crudely band-limited copy (box filter: the data loader's
+    resampling chain is out of scope)."""
+    gen = torch.Generator().manual_seed(1000 + rank)
+    target = 0.1 * torch.randn(wl.batch, 1, wl.T, generator=gen)
+    k = 6
+    inp = F.avg_pool1d(F.pad(target, (k // 2, k - 1 - k // 2), mode="replicate"), k, stride=1)
+    if pinned:
+        return inp.pin_memory(), target.pin_memory()
+    return inp.to(device), target.to(device)

@@ -219,7 +219,9 @@ def _prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_pro
     x32 = x.to(torch.float32).contiguous()
     xT = MapTranspose.apply(x32)
     (dts_rm, Bs_rm, Cs_rm), (dts_cm, Bs_cm, Cs_cm) = _projections(x32, xT, x_proj_weight, x_proj_bias, dt_projs_weight, R, N)
-    f = lambda t: t.to(torch.float32)   # force_fp32 (vmamba.py:1487-1491); a no-op outside autocast
+    # force_fp32 (vmamba.py:1487-1491; a no-op outside autocast); einsum is free to return any strides: the kernels need
+    # unit stride along L only (the reference makes Bs / Cs / dts contiguous unconditionally, vmamba.py:1480-1483)
+    f = lambda t: t.to(torch.float32) if t.stride(-1) == 1 else t.to(torch.float32).contiguous()
     As = -torch.exp(A_logs.to(torch.float))                           # vmamba.py:1481
     return (x32, xT, f(dts_rm).contiguous(), f(dts_cm).contiguous(), f(Bs_rm), f(Bs_cm), f(Cs_rm), f(Cs_cm), As.contiguous(),
             Ds.to(torch.float).contiguous(), dt_projs_bias.reshape(-1).to(torch.float).contiguous())
