@@ -441,11 +441,11 @@ def workload_config(wl):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def stft_times(wl, device, reps=20):
-    """Kernel times (CUDA graph of `reps` calls, CUDA events) of the three STFT entry points next to the torch chains."""
+def stft_times(wl, device, batch, reps=20):
+    """Device times (CUDA events, calls queued behind a device-side delay) of the STFT entry points next to the torch chains."""
     from vm_asr_b200 import stft
     out = {}
-    B, T, F_, Nf = wl.batch, wl.T, wl.n_fft // 2 + 1, 1 + wl.T // wl.hop
+    B, T, F_, Nf = batch, wl.T, wl.n_fft // 2 + 1, 1 + wl.T // wl.hop
     wave = [0.1 * torch.randn(B, 1, T, device=device) for _ in range(4)]
     mp = [stft.wav2spectro(w, wl.n_fft, wl.hop, wl.win, "log2") for w in wave]
     win = torch.hann_window(wl.win, device=device)
@@ -490,14 +490,31 @@ def stft_times(wl, device, reps=20):
             w = torch.istft(X, wl.n_fft, wl.hop, wl.win, win, normalized=True)
             torch.autograd.grad(w, (m, p), torch.ones_like(w))
 
+    def time_queued(fn):
+        """Device time of `reps` calls enqueued behind a device-side delay (the host runs ahead, so launch gaps do not count);
+        torch.istft does not capture into a CUDA graph, so every row is timed this way."""
+        fn()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(3):
+            torch.cuda._sleep(40_000_000)   # ~20 ms
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) / reps
+            best = t if best is None else min(best, t)
+        return best
+
     nb = 4 * B * T + 8 * B * F_ * Nf
     for name, fn, nbytes in (("stft", ours_stft, nb), ("torch_stft_chain", torch_stft, nb), ("istft", ours_istft, nb),
                              ("torch_istft_chain", torch_istft, nb), ("istft_fwd_bwd", ours_istft_fb, 2 * nb + 8 * B * F_ * Nf),
                              ("torch_istft_fwd_bwd", torch_istft_fb, 2 * nb + 8 * B * F_ * Nf)):
         try:
-            ms = time_graph(graph_of(fn), 5, 3) / reps
+            ms = time_queued(fn)
             out[name] = {"us": round(ms * 1e3, 2), "GBps": round(nbytes / ms / 1e6, 1)}
-        except Exception as e:  # a torch op that cannot be captured must not take the bench line down
+        except Exception as e:
             out[name] = {"error": str(e)[:120]}
     for a, b in (("stft", "torch_stft_chain"), ("istft", "torch_istft_chain"), ("istft_fwd_bwd", "torch_istft_fwd_bwd")):
         if "us" in out.get(a, {}) and "us" in out.get(b, {}):
@@ -622,16 +639,8 @@ def main():
     train = infer = e2e = None
     if not args.no_e2e:
         from vm_asr_b200 import harness
-        ts = harness.TrainStep(wl, device, world=world)
         host_in, host_tgt = harness.synthetic_batch(wl, device, rank, pinned=True)
-
-        def e2e_step(comm=True):
-            x = host_in.to(device, non_blocking=True)
-            y = host_tgt.to(device, non_blocking=True)
-            return ts(x, y, comm=comm).item()   # the loss is read back to the host: the step's result
-
-        for _ in range(3):
-            e2e_step()
+        secs = wl.batch * wl.clip_seconds
         n_train = max(3, args.train_steps)
 
         def timed(fn, n):
@@ -644,31 +653,54 @@ def main():
             torch.cuda.synchronize()
             return vdist.max_over_ranks((time.perf_counter() - t0) / n, device)
 
-        t_train = timed(e2e_step, n_train)
-        t_nocomm = timed(lambda: e2e_step(False), n_train) if world > 1 else t_train
-        dev_in = host_in.to(device)
-        t_infer = timed(lambda: ts.infer(dev_in), n_train)
-        secs = wl.batch * wl.clip_seconds
-        train = {"audio_sec_per_s": round(world * secs / t_train, 1), "ms_per_step": round(t_train * 1e3, 2), "steps": n_train,
-                 "launch": "eager (Python, autograd)", "parameters": ts.n_params,
-                 "collective": (f"NCCL all-reduce of the {ts.n_params}-float gradient buffer in {len(ts.grads.buckets)} buckets from autograd hooks "
-                                f"+ a {harness.MPD_PARAMS}-float zero payload standing in for the MPD gradients (not built), overlapped with backward")
-                 if world > 1 else "none",
-                 "exposed_comm_ms": round((t_train - t_nocomm) * 1e3, 3) if world > 1 else 0.0}
+        def measure(graph):
+            ts = harness.TrainStep(wl, device, world=world)
+            if graph:
+                ts.capture(host_in.to(device), host_tgt.to(device))
+
+            def e2e_step(comm=True):
+                x = host_in.to(device, non_blocking=True)
+                y = host_tgt.to(device, non_blocking=True)
+                return ts(x, y, comm=comm).item()   # the loss is read back to the host: the step's result
+
+            for _ in range(3):
+                e2e_step()
+            t_train = timed(e2e_step, n_train)
+            t_nocomm = timed(lambda: e2e_step(False), n_train) if world > 1 else t_train
+            dev_in = host_in.to(device)
+            t_infer = timed(lambda: ts.infer(dev_in), n_train)
+            info = {"audio_sec_per_s": round(world * secs / t_train, 1), "ms_per_step": round(t_train * 1e3, 2), "steps": n_train,
+                    "launch": "forward + backward replayed as one CUDA graph; copies, all-reduce, AdamW eager" if graph
+                    else "eager (Python, autograd): host-bound",
+                    "parameters": ts.n_params,
+                    "collective": (f"NCCL all-reduce of the {ts.n_params}-float gradient buffer in {len(ts.grads.buckets)} buckets "
+                                   f"+ a {harness.MPD_PARAMS}-float zero payload standing in for the MPD gradients (not built); "
+                                   + ("payload overlapped with the graph replay, gradients reduced after it" if graph
+                                      else "buckets issued from autograd hooks, overlapped with backward"))
+                    if world > 1 else "none",
+                    "exposed_comm_ms": round((t_train - t_nocomm) * 1e3, 3) if world > 1 else 0.0}
+            del ts
+            torch.cuda.empty_cache()
+            return info, t_train, t_infer
+
+        train_eager, _, t_infer = measure(False)
+        try:
+            train, t_train, _ = measure(True)
+        except Exception as e:   # graph capture of the whole step is an optimisation, not a requirement of the line
+            train, t_train = dict(train_eager, graph_error=str(e)[:160]), train_eager["ms_per_step"] * 1e-3
+        train["eager"] = train_eager
         infer = {"audio_sec_per_s": round(world * secs / t_infer, 1), "ms_per_step": round(t_infer * 1e3, 2),
-                 "what": "torch.no_grad forward of the harness (STFT -> 34 fused cores -> iSTFT), inputs on the device"}
+                 "what": "torch.no_grad forward of the harness (STFT -> 34 fused cores -> iSTFT), eager, inputs on the device"}
         e2e = {"value": round(world * step_bytes / t_train / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": 2 * host_in.numel() * 4,
                "d2h_bytes_per_step": 4, "ms_per_step": round(t_train * 1e3, 2), "steps": n_train,
                "api": "vm_asr_b200.harness.TrainStep: pinned host waveforms -> device, wav2spectro, 34 x ss2d_core (fused, paired) forward + "
                       "backward, spectro2wav (+ backward), L1 loss read back to the host, gradient all-reduce, AdamW; the step's "
                       "algorithmic scan bytes over its wall time"}
-        del ts
-        torch.cuda.empty_cache()
 
     stft_t = None
     if not args.no_stft and rank == 0:
         try:
-            stft_t = stft_times(wl, device)
+            stft_t = {f"B{b}": stft_times(wl, device, b) for b in (wl.batch, 64)}
         except Exception as e:
             stft_t = {"error": str(e)[:200]}
 

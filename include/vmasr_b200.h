@@ -211,12 +211,24 @@ VMASR_API int vmasr_map_merge2(const float *p_rm, const float *p_cm, float *y, i
  *   wave  : (B, T) contiguous
  *   mag, phase : (B, n_fft/2+1, n_frames) contiguous, n_frames = 1 + T/hop
  *   istft output length = hop*(n_frames-1)
+ *   stft_bwd  : d mag, d phase -> d wave (wav2spectro is differentiable in the reference: torch.stft, abs, log2, angle)
  *   istft_bwd : d wave -> d mag, d phase (the generator loss flows through spectro2wav, model/model.py:1223)
+ *   scratch   : B * vmasr_stft_scratch_floats(n_frames, n_fft, hop) floats, caller-owned, any content: the padded
+ *               overlap-add accumulator of the synthesis kernels (istft_fwd, stft_bwd, stft_mag_bwd)
+ * Linear-magnitude STFT of the multi-resolution loss and the LSD metric (model/loss.py:17-45, model/metric.py:5-12):
+ *   stft_mag_fwd : mag = sqrt(max(|X|^2, clamp_min)), X un-normalised unless `normalized`;  stft_mag_bwd: d mag -> d wave.
  * n_fft must be a power of two in [64, 2048]; win_length <= n_fft.
  * ---------------------------------------------------------------------------------------------- */
+VMASR_API uint64_t vmasr_stft_scratch_floats(int n_frames, int n_fft, int hop);
 VMASR_API int vmasr_stft_fwd(const float *wave, float *mag, float *phase, int B, int T, int n_fft, int hop,
                    int win_length, int device, void *stream);
-VMASR_API int vmasr_istft_fwd(const float *mag, const float *phase, float *wave, int B, int n_frames, int n_fft,
+VMASR_API int vmasr_stft_bwd(const float *wave, const float *dmag, const float *dphase, float *dwave, float *scratch, int B, int T,
+                   int n_fft, int hop, int win_length, int device, void *stream);
+VMASR_API int vmasr_stft_mag_fwd(const float *wave, float *mag, int B, int T, int n_fft, int hop, int win_length, int normalized,
+                   float clamp_min, int device, void *stream);
+VMASR_API int vmasr_stft_mag_bwd(const float *wave, const float *dmag, float *dwave, float *scratch, int B, int T, int n_fft, int hop,
+                   int win_length, int normalized, float clamp_min, int device, void *stream);
+VMASR_API int vmasr_istft_fwd(const float *mag, const float *phase, float *wave, float *scratch, int B, int n_frames, int n_fft,
                     int hop, int win_length, int device, void *stream);
 VMASR_API int vmasr_istft_bwd(const float *mag, const float *phase, const float *dwave, float *dmag, float *dphase,
                     int B, int n_frames, int n_fft, int hop, int win_length, int device, void *stream);

@@ -13,7 +13,8 @@ What is executed, unmodified, from the reference tree:
   * ``kernels/selective_scan/test_selective_scan.py``  ``selective_scan_ref`` (lines 287-367), pulled out
     of the file by AST because the module itself imports a CUDA extension and runs a test at import.
     Gradients come from torch autograd through that function.
-  * ``utils/stft.py``  ``wav2spectro`` / ``spectro2wav``.
+  * ``utils/stft.py``  ``wav2spectro`` / ``spectro2wav`` (log2 and dB scales; the gradient of wav2spectro by autograd).
+  * ``model/loss.py``  ``MultiResolutionSTFTLoss`` (value and gradient), ``model/metric.py``  ``lsd`` / ``lsd_hf`` / ``lsd_lf``.
 """
 from __future__ import annotations
 
@@ -174,6 +175,42 @@ def main():
             f"{tag}_params": np.array([n_fft, hop, win]),
         })
     np.savez_compressed(os.path.join(OUT, "stft.npz"), **blob)
+
+    # ---------------- STFT backward, dB scale, multi-resolution STFT loss, LSD ----------------------------------------
+    # model/loss.py and model/metric.py import torch only; run unmodified
+    import importlib
+    ref_loss = importlib.import_module("loss")      # model/ is on sys.path
+    ref_metric = importlib.import_module("metric")
+    blob = {}
+    g = torch.Generator().manual_seed(2024)
+    T = 4800
+    x = (0.1 * torch.randn(2, T, generator=g)).requires_grad_()
+    y = 0.1 * torch.randn(2, T, generator=g)
+    sc, mg = ref_loss.MultiResolutionSTFTLoss()(x, y)
+    (sc + mg).backward()
+    blob.update(mr_x=np_(x), mr_y=np_(y), mr_sc=np_(sc), mr_mag=np_(mg), mr_dx=np_(x.grad))
+    blob["lsd"] = np.array(ref_metric.lsd(x.detach(), y))
+    hf = torch.tensor([300, 500])
+    blob["lsd_hf"] = np.array(ref_metric.lsd_hf(x.detach(), y, hf))
+    blob["lsd_lf"] = np.array(ref_metric.lsd_lf(x.detach(), y, hf))
+    blob["lsd_hf_idx"] = np_(hf)
+    # wav2spectro is differentiable in the reference (torch.stft + abs / log2 / angle): gradient of a random cotangent
+    for tag, (n_fft, hop, win) in {"48k": (1024, 240, 1024), "nfft2048": (2048, 240, 1024), "small": (256, 64, 200)}.items():
+        w = (0.1 * torch.randn(2, 1, hop * 12, generator=g)).requires_grad_()
+        mag, phase = stft.wav2spectro(w, n_fft, hop, win, "log2")
+        gm, gp = torch.randn(mag.shape, generator=g), torch.randn(phase.shape, generator=g)
+        (mag * gm).sum().backward(retain_graph=True)
+        d_from_mag = w.grad.clone()
+        w.grad = None
+        (phase * gp).sum().backward()
+        blob.update({f"bwd_{tag}_wave": np_(w), f"bwd_{tag}_gm": np_(gm), f"bwd_{tag}_gp": np_(gp),
+                     f"bwd_{tag}_dwave_mag": np_(d_from_mag), f"bwd_{tag}_dwave_phase": np_(w.grad),
+                     f"bwd_{tag}_params": np.array([n_fft, hop, win])})
+    wdb = 0.1 * torch.randn(2, 1, 240 * 10, generator=g)
+    mag_db, phase_db = stft.wav2spectro(wdb, 1024, 240, 1024, "dB")
+    back_db = stft.spectro2wav(mag_db, phase_db, 1024, 240, 1024, "dB")
+    blob.update(db_wave=np_(wdb), db_mag=np_(mag_db), db_phase=np_(phase_db), db_back=np_(back_db))
+    np.savez_compressed(os.path.join(OUT, "stft_loss.npz"), **blob)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -159,10 +159,14 @@ class FlatGrads:
         self.comm_stream.wait_stream(torch.cuda.current_stream())
         return torch.cuda.stream(self.comm_stream)
 
-    def zero(self):
-        self.flat.zero_()
+    def arm(self):
+        """host-side bookkeeping of a new step (what a CUDA-graph replay cannot do)"""
         self._pending = [b[2] for b in self.buckets]
         self._handles = []
+
+    def zero(self):
+        self.flat.zero_()
+        self.arm()
 
     def start_payload(self):
         """The discriminator-sized payload goes out first, in chunks, on the communication stream (it has no dependency on
@@ -203,7 +207,13 @@ class FlatGrads:
 
 class TrainStep:
     """forward -> L1 waveform loss -> backward (bucketed all-reduce overlapped) -> fused AdamW.  ``comm=False`` runs the
-    same step without any collective (to state the exposed communication time)."""
+    same step without any collective (to state the exposed communication time).
+
+    ``capture()`` records forward + backward (gradients into the flat buffer) as ONE CUDA graph over static input buffers: the
+    step is then a copy of the batch into those buffers, a graph replay, the all-reduce and the optimizer.  The eager step is
+    host-bound (a few hundred small PyTorch launches of glue per step); the graph is what the device can do.  In graph mode
+    the discriminator-sized payload still overlaps the whole replay (it is issued first, on the communication stream); the
+    real gradients (a few MB) are reduced after the replay."""
 
     def __init__(self, wl: Workload, device, world: int = 1, pair: bool = True, mpd_payload: bool = True, lr: float = 1e-3):
         self.wl, self.world, self.device = wl, world, device
@@ -214,17 +224,52 @@ class TrainStep:
         self.grads = FlatGrads(list(self.net.parameters()), payload_floats=MPD_PARAMS if (mpd_payload and world > 1) else 0)
         self.opt = torch.optim.AdamW(self.net.parameters(), lr=lr, weight_decay=0.0, fused=True)   # config.py:131-154
         self.n_params = sum(p.numel() for p in self.net.parameters())
+        self.graph = None
 
-    def __call__(self, wave_in: torch.Tensor, wave_target: torch.Tensor, comm: bool = True) -> torch.Tensor:
-        g = self.grads
-        g.zero()
-        was = g.enabled
-        g.enabled = was and comm
-        g.start_payload()
+    def _fwd_bwd(self, wave_in, wave_target):
+        self.grads.flat.zero_()
         out = self.net(wave_in)
         loss = (out - wave_target).abs().mean()
         loss.backward()
-        g.finish(self.world)
+        return loss
+
+    def capture(self, wave_in: torch.Tensor, wave_target: torch.Tensor):
+        g = self.grads
+        was, g.enabled = g.enabled, False        # no collectives from the autograd hooks while capturing
+        self.static_in, self.static_tgt = torch.empty_like(wave_in), torch.empty_like(wave_target)
+        self.static_in.copy_(wave_in)
+        self.static_tgt.copy_(wave_target)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._fwd_bwd(self.static_in, self.static_tgt)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                self.static_loss = self._fwd_bwd(self.static_in, self.static_tgt)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = graph
+        g.enabled = was
+
+    def __call__(self, wave_in: torch.Tensor, wave_target: torch.Tensor, comm: bool = True) -> torch.Tensor:
+        g = self.grads
+        was = g.enabled
+        g.enabled = was and comm
+        g.arm()
+        if self.graph is not None:
+            self.static_in.copy_(wave_in, non_blocking=True)
+            self.static_tgt.copy_(wave_target, non_blocking=True)
+            g.start_payload()
+            hooks, g.enabled = g.enabled, False
+            self.graph.replay()
+            g.enabled = hooks
+            loss = self.static_loss
+        else:
+            g.start_payload()
+            loss = self._fwd_bwd(wave_in, wave_target)
+        g.finish(self.world)     # reduces the buckets the hooks did not (all of them in graph mode)
         g.enabled = was
         self.opt.step()
         return loss
