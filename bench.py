@@ -17,7 +17,7 @@ One JSON line.  What each key is:
 * ``ss2d_core``: the same 34 calls as FUSED SS2D cores (CrossScan -> scan -> CrossMerge in ``vmasr_ss2d_core_fwd/bwd``, no
   xs / ys copies) against the chain of the three operators, both under autograd in one CUDA graph: fused algorithmic GB/s
   (SURVEY.md 8d fused formula) and "effective" GB/s (the chain's algorithmic bytes over the fused time).
-* ``train`` / ``infer``: the step harness (vm_asr_b200/harness.py: STFT -> 34 fused cores with glue -> iSTFT -> L1 loss ->
+* ``train`` / ``infer``: the step harness (vm_asr_b200/harness.py: STFT -> 34 fused cores with glue -> iSTFT -> L1 + multi-resolution STFT loss ->
   backward -> bucketed, overlapped NCCL all-reduce of the real gradients + an MPD-sized 164 MB payload -> fused AdamW),
   launched eagerly: audio-seconds per second (SURVEY.md 8d "Throughput metric"), exposed communication time.
 * ``e2e``: the headline metric END TO END through the public operator API: one harness training step per step with the
@@ -306,20 +306,52 @@ def time_dominant_kernel(ds: DeviceStep, steps: int):
 
 def time_eager(ds: DeviceStep, steps: int):
     """The step launched call by call from Python, wall clock with a device sync at both ends: host-bound when the host
-    cost per call exceeds the kernel time."""
-    ds.run_eager()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        ds.run_eager()
-    t_host = (time.perf_counter() - t0) / steps   # host enqueue time (the device may lag behind)
-    torch.cuda.synchronize()
-    t_all = (time.perf_counter() - t0) / steps
+    cost per call exceeds the kernel time.  Twice: through the plain entry points (validated call-site cache, outputs
+    pre-allocated) and through PreparedCalls (parameter blocks filled once; what a fixed-buffer caller would use)."""
+    def run(fn):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        t_host = (time.perf_counter() - t0) / steps   # host enqueue time (the device may lag behind)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / steps, t_host
+
     launches = ds.gpu_launches_per_step
-    return {"ms_per_step": round(t_all * 1e3, 3), "host_ms_per_step": round(t_host * 1e3, 3),
-            "host_us_per_launch": round(t_host * 1e6 / launches, 2), "launches_per_step": launches,
-            "note": "Python -> ctypes -> C ABI -> cudaLaunchKernelEx per launch (grouped: one launch per pair of calls); "
-                    "the reference's pybind entry costs ~9 us per call (round-1 measurement on the same box)"}
+    t_all, t_host = run(ds.run_eager)
+    out = {"ms_per_step": round(t_all * 1e3, 3), "host_ms_per_step": round(t_host * 1e3, 3),
+           "host_us_per_launch": round(t_host * 1e6 / launches, 2), "launches_per_step": launches,
+           "note": "Python -> ctypes -> C ABI -> cudaLaunchKernelEx per launch (grouped: one launch per pair of calls); "
+                   "the reference's pybind entry costs ~9 us per call (round-1 measurement on the same box)"}
+    if ds.pairing == "grouped":
+        plans = []
+        n = len(ds.calls)
+        for i in range(0, n, 2):
+            args, outs = [], []
+            for k in (i, i + 1):
+                c, inp, b = ds.calls[k]
+                args.append((inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], True))
+                outs.append((b["out"], b["x"]))
+            plans.append(ds.scan.prepare_fwd(args, outs))
+        for i in reversed(range(0, n, 2)):
+            args, outs = [], []
+            for k in (i, i + 1):
+                c, inp, b = ds.calls[k]
+                args.append((inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], inp["dout"], b["x"], True))
+                outs.append((b["du"], b["ddelta"], b["dA"], b["dB"], b["dC"], b["dD"], b["dbias"]))
+            plans.append(ds.scan.prepare_bwd(args, outs))
+
+        def prepared():
+            ds.arena.zero_()
+            for p in plans:
+                p()
+
+        t_all, t_host = run(prepared)
+        out["prepared"] = {"ms_per_step": round(t_all * 1e3, 3), "host_ms_per_step": round(t_host * 1e3, 3),
+                           "host_us_per_launch": round(t_host * 1e6 / launches, 2),
+                           "host_us_per_call": round(t_host * 1e6 / (2 * launches), 2)}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -694,7 +726,7 @@ def main():
         e2e = {"value": round(world * step_bytes / t_train / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": 2 * host_in.numel() * 4,
                "d2h_bytes_per_step": 4, "ms_per_step": round(t_train * 1e3, 2), "steps": n_train,
                "api": "vm_asr_b200.harness.TrainStep: pinned host waveforms -> device, wav2spectro, 34 x ss2d_core (fused, paired) forward + "
-                      "backward, spectro2wav (+ backward), L1 loss read back to the host, gradient all-reduce, AdamW; the step's "
+                      "backward, spectro2wav (+ backward), L1 + multi-resolution STFT loss read back to the host, gradient all-reduce, AdamW; the step's "
                       "algorithmic scan bytes over its wall time"}
 
     stft_t = None

@@ -37,6 +37,10 @@ SHAPES = [
     (2, 3, 56, 57),      # the odd shape of CHECKS.check_csm_triton (vmamba.py:2560)
     (1, 2, 64, 64), (2, 4, 128, 32), (1, 3, 20, 132), (2, 2, 4, 4), (1, 1, 1, 7), (1, 2, 9, 1),
     (4, 2, 512, 512), (8, 2, 1024, 512), (4, 16, 256, 256), (4, 256, 16, 16), (8, 64, 128, 64),
+    # the VSSM32 maps (DIMS 32, batch 8) and the two small-map families that take several channels per CTA
+    (8, 32, 256, 256), (8, 64, 128, 128), (8, 128, 64, 64), (8, 256, 32, 32), (8, 512, 16, 16), (4, 128, 32, 32),
+    (3, 7, 24, 32), (2, 5, 8, 16),   # vector path with a partial plane group / tile
+    (70000, 1, 4, 4),                # more planes than the old gridDim.z limit (65535)
 ]
 
 
@@ -78,3 +82,22 @@ def test_errors():
         cross.cross_scan(torch.randn(1, 2, 4, 4))           # CPU tensor
     with pytest.raises(RuntimeError):
         cross.cross_scan(torch.randn(1, 2, 4, 4, device="cuda").double())
+
+
+def test_matches_the_references_triton_kernels():
+    """CrossScanTriton / CrossMergeTriton (model/csm_triton.py:311-366, staged by oracle/stage_ref_py.py) on the same device:
+    the scan is a permutation, so identical; the merge differs only by the association of its four-term sum."""
+    from oracle import stage_ref_py
+    if not stage_ref_py.available():
+        pytest.skip("reference sources not staged")
+    stage_ref_py.load("vmamba")
+    import csm_triton
+    from vm_asr_b200 import cross
+    for shape, dt in (((2, 8, 64, 64), torch.float32), ((2, 5, 56, 57), torch.float32), ((1, 16, 128, 64), torch.float16), ((4, 64, 16, 16), torch.bfloat16)):
+        x = torch.randn(*shape, device="cuda").to(dt)
+        a, b = cross.cross_scan(x), csm_triton.CrossScanTriton.apply(x)
+        assert torch.equal(a, b.view_as(a))
+        ys = torch.randn(shape[0], 4, *shape[1:], device="cuda").to(dt)
+        m0, m1 = cross.cross_merge(ys, shape[2], shape[3]), csm_triton.CrossMergeTriton.apply(ys)
+        tol = 1e-5 if dt == torch.float32 else 5e-2
+        assert (m0.float() - m1.view_as(m0).float()).abs().max().item() < tol

@@ -517,3 +517,38 @@ def test_grouped_launch_rejects_shared_workspace():
         ctypes.memmove(ctypes.addressof(arr[i]), ctypes.addressof(s.p), ctypes.sizeof(_lib.ScanParams))
     with pytest.raises(RuntimeError, match="share a carry workspace"):
         _lib.check(_lib.load_library().vmasr_scan_fwd_grouped(2, arr))
+
+
+def test_prepared_calls_equal_plain_calls():
+    """PreparedCalls (parameter blocks filled once, only stream / workspace refreshed per launch) give bit-identical results
+    to the plain entry points, on the current stream and on another one, call after call."""
+    scan = _ops()
+    gs = [make_inputs(2, 16, L, 4, 1, torch.float32, seed=30 + i)[1] for i, L in enumerate((4096, 4096))]
+    ref = []
+    for g in gs:
+        out, x = scan.fwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], g["bias"], True, 1)
+        ref.append((out, x, scan.bwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], g["bias"], g["dout"], x, True, 1)))
+    outs_f = [(torch.empty_like(g["u"]), torch.empty(2, 16, 2, 2, device="cuda")) for g in gs]
+    fwd = scan.prepare_fwd([(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], g["bias"], True) for g in gs], outs_f)
+    bufs = []
+    for g in gs:
+        dA, dB, dC, dD, dbias = scan._grad_buffers(g["u"], g["A"], g["D"], g["bias"], (2, 16, 4096, 1, 4))
+        bufs.append((torch.empty_like(g["u"]), torch.empty_like(g["u"]), dA, dB, dC, dD, dbias))
+    bwd = scan.prepare_bwd([(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], g["bias"], g["dout"], o[1], True)
+                            for g, o in zip(gs, outs_f)], bufs)
+    side = torch.cuda.Stream()
+    for it in range(3):
+        for b in bufs:
+            for t in b[2:]:
+                t.zero_()
+        ctx = torch.cuda.stream(side) if it == 1 else torch.cuda.stream(torch.cuda.current_stream())
+        if it == 1:
+            side.wait_stream(torch.cuda.current_stream())
+        with ctx:
+            fwd()
+            bwd()
+        torch.cuda.synchronize()
+        for (out, x, grads), (o, xs), b in zip(ref, outs_f, bufs):
+            assert torch.equal(out, o) and torch.equal(x, xs)
+            assert torch.equal(grads[0], b[0]) and torch.equal(grads[1], b[1])
+            assert rel_err(b[2], grads[2].double().cpu().numpy()) < 1e-5

@@ -29,6 +29,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ss2d, stft
+from .loss import MultiResolutionSTFTLoss
 from .workload import Workload
 
 MPD_PARAMS = 41_090_000  # MultiPeriodDiscriminator(hidden=32), SURVEY.md 8e
@@ -206,7 +207,7 @@ class FlatGrads:
 
 
 class TrainStep:
-    """forward -> L1 waveform loss -> backward (bucketed all-reduce overlapped) -> fused AdamW.  ``comm=False`` runs the
+    """forward -> L1 + multi-resolution STFT loss -> backward (bucketed all-reduce overlapped) -> fused AdamW.  ``comm=False`` runs the
     same step without any collective (to state the exposed communication time).
 
     ``capture()`` records forward + backward (gradients into the flat buffer) as ONE CUDA graph over static input buffers: the
@@ -225,11 +226,18 @@ class TrainStep:
         self.opt = torch.optim.AdamW(self.net.parameters(), lr=lr, weight_decay=0.0, fused=True)   # config.py:131-154
         self.n_params = sum(p.numel() for p in self.net.parameters())
         self.graph = None
+        # generator loss of the reference step without the adversarial terms (trainer/trainer.py:318-333): L1 + the
+        # multi-resolution STFT loss with factors 0.5 / 0.5 (config.py:176-191), on this library's STFT kernel
+        self.stft_loss = MultiResolutionSTFTLoss(factor_sc=0.5, factor_mag=0.5)
+
+    def loss_fn(self, out, target):
+        sc, mag = self.stft_loss(out.flatten(0, -2), target.flatten(0, -2))
+        return (out - target).abs().mean() + sc + mag
 
     def _fwd_bwd(self, wave_in, wave_target):
         self.grads.flat.zero_()
         out = self.net(wave_in)
-        loss = (out - wave_target).abs().mean()
+        loss = self.loss_fn(out, wave_target)
         loss.backward()
         return loss
 

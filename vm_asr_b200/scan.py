@@ -328,6 +328,70 @@ def bwd_grouped(calls, outs=None):
     return results
 
 
+class PreparedCalls:
+    """One (grouped) launch with its parameter blocks filled ONCE -- for call sites that launch the same tensors again and
+    again (a captured step, a benchmark loop, an inference server's fixed buffers).  The tensors must stay alive and keep
+    their storage; a call only refreshes the stream handle and the carry-workspace pointers and launches: no validation, no
+    allocation, no per-tensor work.  ``prepare_fwd`` / ``prepare_bwd`` build it from the arguments of ``fwd_grouped`` /
+    ``bwd_grouped`` with pre-allocated outputs."""
+
+    def __init__(self, kind, calls, outs):
+        _check(outs is not None and len(outs) == len(calls), "prepare: pre-allocated outputs are required")
+        _check(0 < len(calls) <= _lib.SCAN_MAX_GROUP, f"prepare: 1..{_lib.SCAN_MAX_GROUP} calls")
+        lib = _lib.load_library()
+        self._fn = lib.vmasr_scan_fwd_grouped if kind == "fwd" else lib.vmasr_scan_bwd_grouped
+        self._keep = (calls, outs)
+        self.device = calls[0][0].device
+        self._dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        n = self.n = len(calls)
+        self.arr = (ScanParams * n)()
+        size = ctypes.sizeof(ScanParams)
+        self._ws_bytes, self._total = [], 0
+        for i, (c, o) in enumerate(zip(calls, outs)):
+            if kind == "fwd":
+                u, delta, A, B, C, D, bias, sp = c[:8]
+                flags = c[8] if len(c) > 8 else 0
+                s = _site(u, delta, A, B, C, D, bias, sp, flags)
+                _fill_inputs(s, u, delta, A, B, C, D, bias, workspace=torch.empty(0) if s.ws_bytes else None)
+                _fill_fwd(s, o[0], o[1])
+            else:
+                u, delta, A, B, C, D, bias, dout, x, sp = c[:10]
+                flags = c[10] if len(c) > 10 else 0
+                s = _site(u, delta, A, B, C, D, bias, sp, flags)
+                _fill_inputs(s, u, delta, A, B, C, D, bias, workspace=torch.empty(0) if s.ws_bytes else None)
+                _fill_bwd(s, A, dout, x, *o)
+            ctypes.memmove(ctypes.addressof(self.arr[i]), ctypes.addressof(s.p), size)
+            self._ws_bytes.append(s.ws_bytes)
+            self._total += s.ws_bytes
+        self._layout = tuple(self._ws_bytes)
+
+    def __call__(self):
+        stream = torch._C._cuda_getCurrentRawStream(self._dev)
+        arr = self.arr
+        if self._total:
+            base = _lib.scan_workspace(self.device, self._total, layout=self._layout).data_ptr()
+            for i in range(self.n):
+                p = arr[i]
+                p.stream = stream
+                if self._ws_bytes[i]:
+                    p.workspace, p.workspace_bytes = base, self._ws_bytes[i]
+                    base += self._ws_bytes[i]
+        else:
+            for i in range(self.n):
+                arr[i].stream = stream
+        rc = self._fn(self.n, arr)
+        if rc:
+            _lib.check(rc)
+
+
+def prepare_fwd(calls, outs) -> PreparedCalls:
+    return PreparedCalls("fwd", calls, outs)
+
+
+def prepare_bwd(calls, outs) -> PreparedCalls:
+    return PreparedCalls("bwd", calls, outs)
+
+
 class SelectiveScanCore(torch.autograd.Function):
     """Drop-in for ``model.vmamba.SelectiveScanCore`` (vmamba.py:323-356); same argument list, the trailing
     ``nrows, backnrows, oflex`` are accepted and ignored exactly as there."""
