@@ -99,5 +99,5 @@ def test_matches_the_references_triton_kernels():
         assert torch.equal(a, b.view_as(a))
         ys = torch.randn(shape[0], 4, *shape[1:], device="cuda").to(dt)
         m0, m1 = cross.cross_merge(ys, shape[2], shape[3]), csm_triton.CrossMergeTriton.apply(ys)
-        tol = 1e-5 if dt == torch.float32 else 5e-2
+        tol = {torch.float32: 1e-5, torch.float16: 2e-2, torch.bfloat16: 1.3e-1}[dt]   # a couple of ulps of a sum of four N(0, 1) values
         assert (m0.float() - m1.view_as(m0).float()).abs().max().item() < tol
