@@ -102,7 +102,7 @@ typedef struct vmasr_scan_params {
     void *stream; /* cudaStream_t */
 } vmasr_scan_params;
 
-/* flags (fast path only: float32, d_state 1, seqlen a multiple of 4, 16-byte aligned rows and strides; otherwise the call
+/* flags (fast path only: float32, d_state 1, seqlen a multiple of 16, 16-byte aligned rows and strides; otherwise the call
  * fails).  They exist for the fused SS2D core, whose directions 2 and 3 are directions 0 and 1 run back to front
  * (model/vmamba.py:33, 54-55), and whose four outputs are summed (vmamba.py:55-60).
  *   VMASR_SCAN_REVERSE    : time runs against memory order: position l of the recurrence is element seqlen-1-l of u, delta,

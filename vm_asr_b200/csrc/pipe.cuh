@@ -35,6 +35,14 @@ __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, 
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// tile of a 4-D tensor map (line, lines, row, batch) -> shared memory, completion counted in bytes (the FULL box) on `bar`
+__device__ __forceinline__ void tensor_load(void *dst_smem, const CUtensorMap *tm, int line0, int row, int batch, unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tm), "r"(0), "r"(line0), "r"(row), "r"(batch), "r"(smem_u32(bar))
+        : "memory");
+}
 // ---- two-level chunk-carry look-back ---------------------------------------------------------------
 // Level 1: one entry per chunk, the chunk's own affine map, published as soon as its local scan is done.
 // Level 2: one entry per GROUP of 16 consecutive chunks (in scan order), the composite map of the group,

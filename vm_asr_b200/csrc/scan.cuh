@@ -8,6 +8,8 @@
 // over HBM is enough.  Inside a tile every thread owns ITEMS consecutive positions and walks the tile's channels
 // serially: the positions' B/C values (and, backward, their dB/dC sums) stay in registers across channels.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched from the driver at run time, nothing links against libcuda)
+
 #include "common.cuh"
 
 namespace vmasr {
@@ -136,11 +138,27 @@ __device__ __forceinline__ void retire_tile(const ScanArgs &a) {
 // [tile_end[i - 1], tile_end[i]).  Each problem has its own carry workspace.  Used for the two streams of the generator, which
 // issue same-shape calls independently (model/model.py:1167-1176), and for the four directions of the fused SS2D core.
 constexpr int kMaxGroup = 8;
+// TMA descriptors of one problem's positional inputs.  Each (batch, channel) row of L floats is described as a 2-D array of
+// L / 16 lines of 16 floats (64 bytes) so that the copy can land in shared memory with the 64-byte swizzle: 16-byte chunk c of
+// 128-byte line r goes to chunk c ^ (r & 3) of its 64-byte half.  A thread owns 32 contiguous bytes; with the swizzle every
+// quarter-warp's 128-bit accesses cover all 32 banks once, with no address arithmetic beyond two per-thread constants and no
+// register shuffling (round 1 copied rows linearly and paid a register select per loaded float for the same effect).
+// Out-of-range lines (ragged last chunk) arrive as zeros.
+struct alignas(64) TileMaps {
+    CUtensorMap u, delta, dout, B, C;
+};
 struct GroupArgs {
+    TileMaps tm[kMaxGroup];
     ScanArgs a[kMaxGroup];
     int tile_end[kMaxGroup];
     int n;
 };
+constexpr int kTileLine = 16;  // floats per line of the tensor maps (64-byte swizzle span)
+
+// shared-memory slot (in units of a thread's 8 floats) of the thread that owns segment `tseg`, and whether its two 16-byte
+// halves are swapped: physical byte = o ^ (((o >> 7) & 3) << 4) for logical byte o = 32 tseg + 16 h
+__device__ __forceinline__ int swz_slot(int tseg) { return tseg ^ ((tseg >> 3) & 1); }
+__device__ __forceinline__ int swz_half(int tseg) { return (tseg >> 2) & 1; }
 // problem of this CTA and its tile index inside the problem
 __device__ __forceinline__ int group_problem(const GroupArgs &ga, int &tile) {
     int prob = 0, start = 0;

@@ -33,7 +33,7 @@ constexpr int kBPipeThreads = 288;     // 8 compute warps + the exchange warp
 
 // `chunk` is the chunk's index in TIME order (the forward scan's order); with REV it sits at the mirrored place in memory.
 template <bool TAIL, bool SP, int STAGES, bool REV>
-__device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned char *smem, const int chunk, const int rg,
+__device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const TileMaps &tm, unsigned char *smem, const int chunk, const int rg,
                                                    const unsigned epoch) {
     constexpr int NC = 256, ITEMS = 8, WPR = 8, SEG = NC * ITEMS;
 
@@ -61,23 +61,19 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
     const bool exchange = warp == WPR;
     const int L = a.seqlen;
     const int seg0 = (REV ? a.n_chunks - 1 - chunk : chunk) * SEG;  // first MEMORY position of the tile
-    const int seg_len = min(SEG, L - seg0);
-    const unsigned seg_bytes = (unsigned)seg_len * 4u;
+    const int line0 = seg0 / kTileLine;                             // ... and its first line in the tensor maps
+    constexpr unsigned seg_bytes = SEG * 4u;                        // a box always counts in full (lines past the end arrive as zeros)
 
     const int c_begin = ctile * a.chan_per_tile;
     const int n_iter = min(a.chan_per_group, c_begin + a.chan_per_tile) - c_begin;  // <= STAGES
     const int d0 = g * a.chan_per_group + c_begin;
 
-    const float *u_src = reinterpret_cast<const float *>(a.u) + b * a.u_bs + (long long)d0 * a.u_ds + seg0;
-    const float *dl_src = reinterpret_cast<const float *>(a.delta) + b * a.delta_bs + (long long)d0 * a.delta_ds + seg0;
-    const float *dy_src = reinterpret_cast<const float *>(a.dout) + b * a.dout_bs + (long long)d0 * a.dout_ds + seg0;
-
     auto issue_stage = [&](int it) {  // lane 0 of the exchange warp only
         float *dst = s_stage + (size_t)it * 3 * SEG;
         mbar_expect_tx(&bar_full[it], 3u * seg_bytes);
-        bulk_load(dst, u_src + it * a.u_ds, seg_bytes, &bar_full[it]);
-        bulk_load(dst + SEG, dl_src + it * a.delta_ds, seg_bytes, &bar_full[it]);
-        bulk_load(dst + 2 * SEG, dy_src + it * a.dout_ds, seg_bytes, &bar_full[it]);
+        tensor_load(dst, &tm.u, line0, d0 + it, b, &bar_full[it]);
+        tensor_load(dst + SEG, &tm.delta, line0, d0 + it, b, &bar_full[it]);
+        tensor_load(dst + 2 * SEG, &tm.dout, line0, d0 + it, b, &bar_full[it]);
     };
     // the bulk copies go out first: they do not depend on the per-channel parameters staged below
     if (threadIdx.x == NC) {
@@ -90,11 +86,9 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
         }
         mbar_init(bar_done, WPR);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const float *Bg = reinterpret_cast<const float *>(a.B) + b * a.B_bs + g * a.B_gs + seg0;
-        const float *Cg = reinterpret_cast<const float *>(a.C) + b * a.C_bs + g * a.C_gs + seg0;
         mbar_expect_tx(bar_bc, 2u * seg_bytes);
-        bulk_load(s_b, Bg, seg_bytes, bar_bc);
-        bulk_load(s_c, Cg, seg_bytes, bar_bc);
+        tensor_load(s_b, &tm.B, line0, g, b, bar_bc);
+        tensor_load(s_c, &tm.C, line0, g, b, bar_bc);
 #pragma unroll
         for (int s = 0; s < STAGES - 1; ++s)
             if (s < n_iter) issue_stage(s);
@@ -194,7 +188,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
         // ================= compute warps =================
         const int tseg = REV ? NC - 1 - (int)threadIdx.x : (int)threadIdx.x;  // this thread's 8-position segment of the tile (memory order)
         const int pos = seg0 + tseg * ITEMS;
-        const int sel = (tseg >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
+        const int sel = swz_half(tseg), slot = swz_slot(tseg) * ITEMS;  // where the 64-byte swizzle puts this thread's 32 bytes (scan.cuh)
         const bool accum = a.accum == 1, addm = a.accum == 2;  // red.add / load-add-store (scan.cuh)
         int nvalid = ITEMS;
         if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
@@ -202,9 +196,9 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
         float *dd_ptr = reinterpret_cast<float *>(a.ddelta) + b * a.ddelta_bs + (long long)d0 * a.ddelta_ds + pos;
 
         float2 Bv[4], dBacc[4], dCacc[4];
-        float *sC = s_c + tseg * ITEMS;  // this thread's C values (only this thread touches them)
+        float *sC = s_c + slot;  // this thread's C values (only this thread touches them)
         mbar_wait(bar_bc, 0);
-        lds8_sw(s_b + tseg * ITEMS, sel, Bv);
+        lds8_priv(s_b + slot, sel, Bv);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             dBacc[k] = f2(0.0f);
@@ -212,13 +206,13 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
         }
         if (TAIL) {  // positions past the end contribute nothing and stay finite
             float2 Cv[4];
-            lds8_sw(sC, sel, Cv);
+            lds8_priv(sC, sel, Cv);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (2 * k >= nvalid) { Bv[k].x = 0.0f; Cv[k].x = 0.0f; }
                 if (2 * k + 1 >= nvalid) { Bv[k].y = 0.0f; Cv[k].y = 0.0f; }
             }
-            stg8(sC, Cv);
+            sts8_priv(sC, sel, Cv);
         }
         __syncthreads();  // (also keeps the register allocation of the sweeps below in check: without it ptxas spills 3x more)
 
@@ -234,21 +228,21 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                 // ---- P1(j) ----
                 const float Av = s_par[j];
                 const float bias2 = s_par[2 * 4 + j];
-                float *su = s_stage + (size_t)j * 3 * SEG + tseg * ITEMS;
+                float *su = s_stage + (size_t)j * 3 * SEG + slot;
                 mbar_wait(&bar_full[j], 0);
                 float2 uv[4], dl[4], dy[4], Cv[4], dts[4];
-                lds8_sw(su, sel, uv);
-                lds8_sw(su + SEG, sel, dl);
-                lds8_sw(su + 2 * SEG, sel, dy);
-                lds8_sw(sC, sel, Cv);
+                lds8_priv(su, sel, uv);
+                lds8_priv(su + SEG, sel, dl);
+                lds8_priv(su + 2 * SEG, sel, dy);
+                lds8_priv(sC, sel, Cv);
                 if (TAIL) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (2 * k >= nvalid) { uv[k].x = 0.0f; dl[k].x = 0.0f; dy[k].x = 0.0f; }
                         if (2 * k + 1 >= nvalid) { uv[k].y = 0.0f; dl[k].y = 0.0f; dy[k].y = 0.0f; }
                     }
-                    stg8(su, uv);  // park the cleaned values for P2
-                    stg8(su + 2 * SEG, dy);
+                    sts8_priv(su, sel, uv);  // park the cleaned values for P2
+                    sts8_priv(su + 2 * SEG, sel, dy);
                 }
                 float p = 1.0f, q = 0.0f, qr = 0.0f;
 #pragma unroll
@@ -306,12 +300,12 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
                 float *o_dd = dd_ptr + (long long)j * a.ddelta_ds;
                 mbar_wait(&bar_in[j], 0);
                 const float2 in = s_in[j * WPR + warp];
-                const float *su = s_stage + (size_t)j * 3 * SEG + tseg * ITEMS;
+                const float *su = s_stage + (size_t)j * 3 * SEG + slot;
                 float2 uv[4], dts[4], dy[4], Cv[4];
-                lds8_sw(su, sel, uv);
+                lds8_priv(su, sel, uv);
                 lds8_priv(su + SEG, sel, dts);
-                lds8_sw(su + 2 * SEG, sel, dy);
-                lds8_sw(sC, sel, Cv);
+                lds8_priv(su + 2 * SEG, sel, dy);
+                lds8_priv(sC, sel, Cv);
                 float2 av[4], bu[4], dtn[4], hs[4], gl[4];
                 // forward states of this thread's positions
                 {
@@ -425,11 +419,13 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, unsigned c
 
 template <bool SP, int STAGES>
 __global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const __grid_constant__ GroupArgs ga) {
-    extern __shared__ __align__(128) unsigned char smem_bwd_pipe[];
+    extern __shared__ __align__(1024) unsigned char smem_bwd_pipe[];  // swizzled tiles need 512-byte aligned slots
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
     pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
     int tile;
-    const ScanArgs &a = ga.a[group_problem(ga, tile)];
+    const int prob = group_problem(ga, tile);
+    const ScanArgs &a = ga.a[prob];
+    const TileMaps &tm = ga.tm[prob];
     // adjoint: late chunks first; block order = the adjoint's scan order, so a tile only waits on tiles dispatched before it
     const unsigned epoch = *reinterpret_cast<volatile unsigned *>(a.ws_header + 2) % 0xfffffffeu + 1u;
     const int chunk = a.n_chunks - 1 - tile / a.n_rowgroups;
@@ -437,11 +433,11 @@ __global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const _
     const int mchunk = a.rev ? a.n_chunks - 1 - chunk : chunk;
     const bool tail = (mchunk + 1) * 2048 > a.seqlen;
     if (a.rev) {
-        if (tail) scan_bwd_pipe_body<true, SP, STAGES, true>(a, smem_bwd_pipe, chunk, rg, epoch);
-        else scan_bwd_pipe_body<false, SP, STAGES, true>(a, smem_bwd_pipe, chunk, rg, epoch);
+        if (tail) scan_bwd_pipe_body<true, SP, STAGES, true>(a, tm, smem_bwd_pipe, chunk, rg, epoch);
+        else scan_bwd_pipe_body<false, SP, STAGES, true>(a, tm, smem_bwd_pipe, chunk, rg, epoch);
     } else {
-        if (tail) scan_bwd_pipe_body<true, SP, STAGES, false>(a, smem_bwd_pipe, chunk, rg, epoch);
-        else scan_bwd_pipe_body<false, SP, STAGES, false>(a, smem_bwd_pipe, chunk, rg, epoch);
+        if (tail) scan_bwd_pipe_body<true, SP, STAGES, false>(a, tm, smem_bwd_pipe, chunk, rg, epoch);
+        else scan_bwd_pipe_body<false, SP, STAGES, false>(a, tm, smem_bwd_pipe, chunk, rg, epoch);
     }
 }
 

@@ -20,7 +20,7 @@ constexpr int kBwdMaxTileChannels = 64;
 
 // REV (time runs against memory order) is supported for single-chunk sequences, which is all the host sends here.
 template <int TPR, bool TAIL, bool SP, bool REV>
-__device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned char *smem, const int chunk, const int rg,
+__device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, const TileMaps &tm, unsigned char *smem, const int chunk, const int rg,
                                                   const unsigned epoch) {
     constexpr int NT = 256, ITEMS = 8, STAGES = kBwdStages;
     constexpr int ROWS = NT / TPR;
@@ -48,13 +48,13 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
     const int warp_slot = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int tseg = REV ? TPR - 1 - t_in_row : t_in_row;  // this thread's 8-position segment of the row segment (memory order)
-    const int sel = (tseg >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
+    const int sel = swz_half(tseg), slot = swz_slot(tseg) * ITEMS;  // where the 64-byte swizzle puts this thread's 32 bytes (scan.cuh)
     const int L = a.seqlen;
     const int seg0 = chunk * SEG;
     const int pos = seg0 + tseg * ITEMS;
     const bool accum = a.accum == 1, addm = a.accum == 2;  // red.add / load-add-store (scan.cuh)
-    const int seg_len = min(SEG, L - seg0);
-    const unsigned seg_bytes = (unsigned)seg_len * 4u;
+    const int line0 = seg0 / kTileLine;        // first line of the tile in the tensor maps
+    constexpr unsigned seg_bytes = SEG * 4u;   // a box always counts in full (lines past the end arrive as zeros)
     int nvalid = ITEMS;
     if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
 
@@ -63,12 +63,8 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
     const int n_iter = (n_chan - row + ROWS - 1) / ROWS;  // iterations of THIS row segment (may be 0)
     const int d0 = g * a.chan_per_group + c_begin;
 
-    const float *u_src = reinterpret_cast<const float *>(a.u) + b * a.u_bs + (long long)(d0 + row) * a.u_ds + seg0;
-    const float *dl_src = reinterpret_cast<const float *>(a.delta) + b * a.delta_bs + (long long)(d0 + row) * a.delta_ds + seg0;
-    const float *dy_src = reinterpret_cast<const float *>(a.dout) + b * a.dout_bs + (long long)(d0 + row) * a.dout_ds + seg0;
     float *du_ptr = reinterpret_cast<float *>(a.du) + b * a.du_bs + (long long)(d0 + row) * a.du_ds + pos;
     float *dd_ptr = reinterpret_cast<float *>(a.ddelta) + b * a.ddelta_bs + (long long)(d0 + row) * a.ddelta_ds + pos;
-    const long long u_step = (long long)ROWS * a.u_ds, dl_step = (long long)ROWS * a.delta_ds, dy_step = (long long)ROWS * a.dout_ds;
     const long long du_step = (long long)ROWS * a.du_ds, dd_step = (long long)ROWS * a.ddelta_ds;
 
     if (threadIdx.x == 0) {
@@ -96,16 +92,14 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
         float *dst = my_stage + (size_t)s * ROWS * 3 * SEG;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was written through the generic proxy (sigmoid)
         mbar_expect_tx(bar, 3u * seg_bytes);
-        bulk_load(dst, u_src + it * u_step, seg_bytes, bar);
-        bulk_load(dst + SEG, dl_src + it * dl_step, seg_bytes, bar);
-        bulk_load(dst + 2 * SEG, dy_src + it * dy_step, seg_bytes, bar);
+        tensor_load(dst, &tm.u, line0, d0 + row + it * ROWS, b, bar);
+        tensor_load(dst + SEG, &tm.delta, line0, d0 + row + it * ROWS, b, bar);
+        tensor_load(dst + 2 * SEG, &tm.dout, line0, d0 + row + it * ROWS, b, bar);
     };
     if (threadIdx.x == 0) {
-        const float *Bg = reinterpret_cast<const float *>(a.B) + b * a.B_bs + g * a.B_gs + seg0;
-        const float *Cg = reinterpret_cast<const float *>(a.C) + b * a.C_bs + g * a.C_gs + seg0;
         mbar_expect_tx(bar_bc, 2u * seg_bytes);
-        bulk_load(s_bc, Bg, seg_bytes, bar_bc);
-        bulk_load(s_bc + SEG, Cg, seg_bytes, bar_bc);
+        tensor_load(s_bc, &tm.B, line0, g, b, bar_bc);
+        tensor_load(s_bc + SEG, &tm.C, line0, g, b, bar_bc);
     }
     if (t_in_row == 0) {
 #pragma unroll
@@ -120,7 +114,7 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
 
     float2 Bv[4], dBacc[4], dCacc[4];
     mbar_wait(bar_bc, 0);
-    lds8_sw(s_bc + tseg * ITEMS, sel, Bv);
+    lds8_priv(s_bc + slot, sel, Bv);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         dBacc[j] = f2(0.0f);
@@ -166,22 +160,22 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
         mbar_wait(my_bars + s * ROWS, (unsigned)((it / STAGES) & 1));
         // The stage stays valid for the whole iteration (it is refilled one iteration later), so u and dout are read
         // again where they are needed instead of being held in registers, and sigmoid is parked in delta's slot.
-        float *su = my_stage + (size_t)s * ROWS * 3 * SEG + tseg * ITEMS;
+        float *su = my_stage + (size_t)s * ROWS * 3 * SEG + slot;
         float2 dtn[4], av[4], bx[4], cdy[4];
         {
             float2 uv[4], dl[4], dy[4], Cv[4], sig[4];
-            lds8_sw(su, sel, uv);
-            lds8_sw(su + SEG, sel, dl);
-            lds8_sw(su + 2 * SEG, sel, dy);
-            lds8_sw(s_bc + SEG + tseg * ITEMS, sel, Cv);
+            lds8_priv(su, sel, uv);
+            lds8_priv(su + SEG, sel, dl);
+            lds8_priv(su + 2 * SEG, sel, dy);
+            lds8_priv(s_bc + SEG + slot, sel, Cv);
             if (TAIL) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (2 * j >= nvalid) { uv[j].x = 0.0f; dl[j].x = 0.0f; dy[j].x = 0.0f; Cv[j].x = 0.0f; }
                     if (2 * j + 1 >= nvalid) { uv[j].y = 0.0f; dl[j].y = 0.0f; dy[j].y = 0.0f; Cv[j].y = 0.0f; }
                 }
-                stg8(su, uv);  // park the cleaned values for the second read
-                stg8(su + 2 * SEG, dy);
+                sts8_priv(su, sel, uv);  // park the cleaned values for the second read
+                sts8_priv(su + 2 * SEG, sel, dy);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -291,8 +285,8 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
         }
         // gradients, position pairs
         float2 du[4], ddl[4], uv[4], dy[4], sig[4];
-        lds8_sw(su, sel, uv);
-        lds8_sw(su + 2 * SEG, sel, dy);
+        lds8_priv(su, sel, uv);
+        lds8_priv(su + 2 * SEG, sel, dy);
         lds8_priv(su + SEG, sel, sig);
         float2 sA = f2(0.0f), sD = f2(0.0f), sB = f2(0.0f);
 #pragma unroll
@@ -398,23 +392,25 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, unsigned ch
 
 template <int TPR, bool SP>
 __global__ void __launch_bounds__(256, 2) scan_bwd_tma_kernel(const __grid_constant__ GroupArgs ga) {
-    extern __shared__ __align__(128) unsigned char smem_bwd_tma[];
+    extern __shared__ __align__(1024) unsigned char smem_bwd_tma[];  // swizzled tiles need 512-byte aligned slots
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
     pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
     constexpr int SEG = TPR * 8;
     int gtile;
-    const ScanArgs &a = ga.a[group_problem(ga, gtile)];
+    const int prob = group_problem(ga, gtile);
+    const ScanArgs &a = ga.a[prob];
+    const TileMaps &tm = ga.tm[prob];
     unsigned tile = (unsigned)gtile, epoch = 0;
     if (a.n_chunks > 1) claim_tile(a, reinterpret_cast<unsigned *>(smem_bwd_tma + 384), tile, epoch);  // VMASR_TUNING builds only
     const int chunk = a.n_chunks - 1 - (int)(tile / a.n_rowgroups);  // adjoint: late chunks first
     const int rg = tile % a.n_rowgroups;
     const bool tail = (chunk + 1) * SEG > a.seqlen;
     if (a.rev) {  // single chunk only (host-checked)
-        if (tail) scan_bwd_tma_body<TPR, true, SP, true>(a, smem_bwd_tma, chunk, rg, epoch);
-        else scan_bwd_tma_body<TPR, false, SP, true>(a, smem_bwd_tma, chunk, rg, epoch);
+        if (tail) scan_bwd_tma_body<TPR, true, SP, true>(a, tm, smem_bwd_tma, chunk, rg, epoch);
+        else scan_bwd_tma_body<TPR, false, SP, true>(a, tm, smem_bwd_tma, chunk, rg, epoch);
     } else {
-        if (tail) scan_bwd_tma_body<TPR, true, SP, false>(a, smem_bwd_tma, chunk, rg, epoch);
-        else scan_bwd_tma_body<TPR, false, SP, false>(a, smem_bwd_tma, chunk, rg, epoch);
+        if (tail) scan_bwd_tma_body<TPR, true, SP, false>(a, tm, smem_bwd_tma, chunk, rg, epoch);
+        else scan_bwd_tma_body<TPR, false, SP, false>(a, tm, smem_bwd_tma, chunk, rg, epoch);
     }
 }
 

@@ -35,7 +35,7 @@ constexpr int kPipeThreads = 288;     // 8 compute warps + the exchange warp
 
 // `chunk` is the chunk's index in TIME order; with REV (time runs against memory order) it sits at the mirrored place in memory.
 template <bool TAIL, bool SP, bool REV>
-__device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned char *smem, const int chunk, const int rg) {
+__device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const TileMaps &tm, unsigned char *smem, const int chunk, const int rg) {
     constexpr int NC = 256, ITEMS = 8, WPR = 8, SEG = NC * ITEMS, STAGES = kPipeStages;
 
     // shared memory carve-up (header 2048 bytes)
@@ -49,6 +49,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
     float *s_par = reinterpret_cast<float *>(smem + 1024);                        // [3][STAGES]
     float *s_stage = reinterpret_cast<float *>(smem + 2048);                      // [STAGES][2][SEG]
     float *s_bc = s_stage + (size_t)(STAGES - 1) * 2 * SEG;                       // B, C: borrowed from the last stage
+    float2 *s_exc = reinterpret_cast<float2 *>(s_stage + (size_t)STAGES * 2 * SEG);  // [STAGES][NC] warp-exclusive prefix of every thread
 
     const int ctile = rg % a.n_ctiles;
     const int bg = rg / a.n_ctiles;
@@ -60,21 +61,18 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
     const bool exchange = warp == WPR;  // the ninth warp
     const int L = a.seqlen;
     const int seg0 = (REV ? a.n_chunks - 1 - chunk : chunk) * SEG;  // first MEMORY position of the tile
-    const int seg_len = min(SEG, L - seg0);  // multiple of 4
-    const unsigned seg_bytes = (unsigned)seg_len * 4u;
+    const int line0 = seg0 / kTileLine;                             // ... and its first line in the tensor maps
+    constexpr unsigned seg_bytes = SEG * 4u;                        // a box always counts in full (lines past the end arrive as zeros)
 
     const int c_begin = ctile * a.chan_per_tile;
     const int n_iter = min(a.chan_per_group, c_begin + a.chan_per_tile) - c_begin;  // channels of this tile (<= STAGES)
     const int d0 = g * a.chan_per_group + c_begin;
 
-    const float *u_src = reinterpret_cast<const float *>(a.u) + b * a.u_bs + (long long)d0 * a.u_ds + seg0;
-    const float *dl_src = reinterpret_cast<const float *>(a.delta) + b * a.delta_bs + (long long)d0 * a.delta_ds + seg0;
-
     auto issue_stage = [&](int it) {  // lane 0 of the exchange warp only
         float *dst = s_stage + (size_t)it * 2 * SEG;
         mbar_expect_tx(&bar_full[it], 2u * seg_bytes);
-        bulk_load(dst, u_src + it * a.u_ds, seg_bytes, &bar_full[it]);
-        bulk_load(dst + SEG, dl_src + it * a.delta_ds, seg_bytes, &bar_full[it]);
+        tensor_load(dst, &tm.u, line0, d0 + it, b, &bar_full[it]);
+        tensor_load(dst + SEG, &tm.delta, line0, d0 + it, b, &bar_full[it]);
     };
     // the bulk copies go out first: they do not depend on the per-channel parameters staged below
     if (threadIdx.x == NC) {
@@ -87,11 +85,9 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
         }
         mbar_init(bar_free, WPR);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const float *Bg = reinterpret_cast<const float *>(a.B) + b * a.B_bs + g * a.B_gs + seg0;
-        const float *Cg = reinterpret_cast<const float *>(a.C) + b * a.C_bs + g * a.C_gs + seg0;
         mbar_expect_tx(bar_bc, 2u * seg_bytes);
-        bulk_load(s_bc, Bg, seg_bytes, bar_bc);
-        bulk_load(s_bc + SEG, Cg, seg_bytes, bar_bc);
+        tensor_load(s_bc, &tm.B, line0, g, b, bar_bc);
+        tensor_load(s_bc + SEG, &tm.C, line0, g, b, bar_bc);
 #pragma unroll
         for (int s = 0; s < STAGES - 1; ++s)
             if (s < n_iter) issue_stage(s);
@@ -174,7 +170,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
         // ================= compute warps =================
         const int tseg = REV ? NC - 1 - (int)threadIdx.x : (int)threadIdx.x;  // this thread's 8-position segment of the tile (memory order)
         const int pos = seg0 + tseg * ITEMS;
-        const int sel = (tseg >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
+        const int sel = swz_half(tseg), slot = swz_slot(tseg) * ITEMS;  // where the 64-byte swizzle puts this thread's 32 bytes (scan.cuh)
         int nvalid = ITEMS;
         if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
         float *out_ptr = reinterpret_cast<float *>(a.out) + b * a.out_bs + (long long)d0 * a.out_ds + pos;
@@ -182,8 +178,8 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
 
         float2 Bl[4], Cv[4];  // ln2 * B (the scan runs on dt in the log2 domain) and C of this thread's positions
         mbar_wait(bar_bc, 0);
-        lds8_sw(s_bc + tseg * ITEMS, sel, Bl);
-        lds8_sw(s_bc + SEG + tseg * ITEMS, sel, Cv);
+        lds8_priv(s_bc + slot, sel, Bl);
+        lds8_priv(s_bc + SEG + slot, sel, Cv);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free);
 #pragma unroll
@@ -195,9 +191,6 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
             }
         }
 
-        Aff exc[STAGES];  // warp-exclusive prefix of this thread, per channel (registers: only constant indices below)
-#pragma unroll
-        for (int i = 0; i < STAGES; ++i) exc[i] = Aff{1.0f, 0.0f};
 #pragma unroll 1
         for (int j = 0; j < n_iter; ++j) {
             {
@@ -205,11 +198,11 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
                 const float Av = s_par[j];
                 const float Dv = s_par[STAGES + j];
                 const float bias2 = s_par[2 * STAGES + j];
-                float *su = s_stage + (size_t)j * 2 * SEG + tseg * ITEMS;
+                float *su = s_stage + (size_t)j * 2 * SEG + slot;
                 mbar_wait(&bar_full[j], 0);
                 float2 uv[4], dl[4], Y0[4], Y1[4];
-                lds8_sw(su, sel, uv);
-                lds8_sw(su + SEG, sel, dl);
+                lds8_priv(su, sel, uv);
+                lds8_priv(su + SEG, sel, dl);
                 float p = 1.0f, q = 0.0f;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
@@ -239,9 +232,8 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
                 sts8_priv(su + SEG, sel, Y1);
                 const Aff inc = warp_scan_up_fast<32>(Aff{p, q});
                 const Aff ex = shift_up1(inc, lane);
-#pragma unroll
-                for (int i = 0; i < STAGES; ++i)
-                    if (i == j) exc[i] = ex;
+                s_exc[j * NC + threadIdx.x] = make_float2(ex.p, ex.q);  // read back by this thread in P2(j): parked in shared memory, not in
+                                                                        // STAGES register pairs picked by predicated selects in a rolled loop
                 if (lane == 31) s_tot[j * WPR + warp] = make_float2(inc.p, inc.q);
                 __syncwarp();
                 if (lane == 31) mbar_arrive(&bar_tot[j]);
@@ -251,16 +243,14 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
         for (int j = 0; j < n_iter; ++j) {
             {
                 // ---- P2(j) ----
-                Aff ex = exc[0];
-#pragma unroll
-                for (int i = 1; i < STAGES; ++i)
-                    if (i == j) ex = exc[i];
+                const float2 exv = s_exc[j * NC + threadIdx.x];
+                const Aff ex = {exv.x, exv.y};
                 float *o = out_ptr + (long long)j * a.out_ds;
                 float2 old[4];
                 if (addm && (!TAIL || nvalid == ITEMS)) ldg8(o, old);  // in flight while this warp waits for its entering state
                 mbar_wait(&bar_in[j], 0);
                 const float h_in = fmaf(ex.p, s_in[j * WPR + warp], ex.q);
-                const float *sy = s_stage + (size_t)j * 2 * SEG + tseg * ITEMS;
+                const float *sy = s_stage + (size_t)j * 2 * SEG + slot;
                 float2 Y0[4], Y1[4], y[4];
                 lds8_priv(sy, sel, Y0);
                 lds8_priv(sy + SEG, sel, Y1);
@@ -296,27 +286,29 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, unsigned c
 
 template <bool SP>
 __global__ void __launch_bounds__(kPipeThreads, 3) scan_fwd_pipe_kernel(const __grid_constant__ GroupArgs ga) {
-    extern __shared__ __align__(128) unsigned char smem_fwd_pipe[];
+    extern __shared__ __align__(1024) unsigned char smem_fwd_pipe[];  // swizzled tiles need 512-byte aligned slots
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
     pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
     int tile;
-    const ScanArgs &a = ga.a[group_problem(ga, tile)];
+    const int prob = group_problem(ga, tile);
+    const ScanArgs &a = ga.a[prob];
+    const TileMaps &tm = ga.tm[prob];
     const int chunk = tile / a.n_rowgroups;  // chunk-major in TIME order: a tile only waits on tiles dispatched before it
     const int rg = tile - chunk * a.n_rowgroups;
     const int mchunk = a.rev ? a.n_chunks - 1 - chunk : chunk;
     const bool tail = (mchunk + 1) * 2048 > a.seqlen;
     if (a.rev) {
-        if (tail) scan_fwd_pipe_body<true, SP, true>(a, smem_fwd_pipe, chunk, rg);
-        else scan_fwd_pipe_body<false, SP, true>(a, smem_fwd_pipe, chunk, rg);
+        if (tail) scan_fwd_pipe_body<true, SP, true>(a, tm, smem_fwd_pipe, chunk, rg);
+        else scan_fwd_pipe_body<false, SP, true>(a, tm, smem_fwd_pipe, chunk, rg);
     } else {
-        if (tail) scan_fwd_pipe_body<true, SP, false>(a, smem_fwd_pipe, chunk, rg);
-        else scan_fwd_pipe_body<false, SP, false>(a, smem_fwd_pipe, chunk, rg);
+        if (tail) scan_fwd_pipe_body<true, SP, false>(a, tm, smem_fwd_pipe, chunk, rg);
+        else scan_fwd_pipe_body<false, SP, false>(a, tm, smem_fwd_pipe, chunk, rg);
     }
 }
 
 template <bool SP>
 static int launch_fwd_pipe(const GroupArgs &ga, int grid, cudaStream_t stream) {
-    const size_t smem = 2048 + sizeof(float) * ((size_t)kPipeStages * 2 * 2048);
+    const size_t smem = 2048 + sizeof(float) * ((size_t)kPipeStages * 2 * 2048) + sizeof(float2) * kPipeStages * 256;
     static PerDeviceOnce configured;  // the attribute is per function and per device
     if (!configured()) {
         if (int rc = check_cuda(cudaFuncSetAttribute(scan_fwd_pipe_kernel<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),

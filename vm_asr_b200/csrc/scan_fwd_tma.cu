@@ -22,7 +22,7 @@ constexpr int kMaxTileChannels = 64;
 
 // REV (time runs against memory order) is supported for single-chunk sequences, which is all the host sends here.
 template <int TPR, bool TAIL, bool SP, int STAGES, bool REV>
-__device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned char *smem, const int chunk, const int rg) {
+__device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, const TileMaps &tm, unsigned char *smem, const int chunk, const int rg) {
     constexpr int NT = 256, ITEMS = 8;
     constexpr int ROWS = NT / TPR;
     constexpr int WPR = TPR / 32;
@@ -48,13 +48,13 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
     const int warp_slot = threadIdx.x >> 5;  // row * WPR + warp_in_row
     const int lane = threadIdx.x & 31;
     const int tseg = REV ? TPR - 1 - t_in_row : t_in_row;  // this thread's 8-position segment of the row segment (memory order)
-    const int sel = (tseg >> 2) & 1;  // bank-conflict-free access order (fast.cuh)
+    const int sel = swz_half(tseg), slot = swz_slot(tseg) * ITEMS;  // where the 64-byte swizzle puts this thread's 32 bytes (scan.cuh)
     const int L = a.seqlen;
     const int seg0 = chunk * SEG;                       // first position of the tile
     const int pos = seg0 + tseg * ITEMS;
     const bool accum = a.accum == 1, addm = a.accum == 2;  // red.add / load-add-store (scan.cuh)
-    const int seg_len = min(SEG, L - seg0);             // valid positions in this tile (multiple of 4)
-    const unsigned seg_bytes = (unsigned)seg_len * 4u;
+    const int line0 = seg0 / kTileLine;                 // first line of the tile in the tensor maps
+    constexpr unsigned seg_bytes = SEG * 4u;            // a box always counts in full (lines past the end arrive as zeros)
     int nvalid = ITEMS;
     if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
 
@@ -63,10 +63,8 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
     const int n_iter = (n_chan - row + ROWS - 1) / ROWS;  // iterations of THIS row segment (may be 0)
     const int d0 = g * a.chan_per_group + c_begin;        // first scan channel of the tile
 
-    const float *u_src = reinterpret_cast<const float *>(a.u) + b * a.u_bs + (long long)(d0 + row) * a.u_ds + seg0;
-    const float *dl_src = reinterpret_cast<const float *>(a.delta) + b * a.delta_bs + (long long)(d0 + row) * a.delta_ds + seg0;
     float *out_ptr = reinterpret_cast<float *>(a.out) + b * a.out_bs + (long long)(d0 + row) * a.out_ds + pos;
-    const long long u_step = (long long)ROWS * a.u_ds, dl_step = (long long)ROWS * a.delta_ds, out_step = (long long)ROWS * a.out_ds;
+    const long long out_step = (long long)ROWS * a.out_ds;
 
     unsigned epoch = 0;
     if (threadIdx.x == 0) {
@@ -95,15 +93,13 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
         float *dst = my_stage + (size_t)s * ROWS * 2 * SEG;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of the slot are ordered before the refill
         mbar_expect_tx(bar, 2u * seg_bytes);
-        bulk_load(dst, u_src + it * u_step, seg_bytes, bar);
-        bulk_load(dst + SEG, dl_src + it * dl_step, seg_bytes, bar);
+        tensor_load(dst, &tm.u, line0, d0 + row + it * ROWS, b, bar);
+        tensor_load(dst + SEG, &tm.delta, line0, d0 + row + it * ROWS, b, bar);
     };
     if (threadIdx.x == 0) {
-        const float *Bg = reinterpret_cast<const float *>(a.B) + b * a.B_bs + g * a.B_gs + seg0;
-        const float *Cg = reinterpret_cast<const float *>(a.C) + b * a.C_bs + g * a.C_gs + seg0;
         mbar_expect_tx(bar_bc, 2u * seg_bytes);
-        bulk_load(s_bc, Bg, seg_bytes, bar_bc);
-        bulk_load(s_bc + SEG, Cg, seg_bytes, bar_bc);
+        tensor_load(s_bc, &tm.B, line0, g, b, bar_bc);
+        tensor_load(s_bc + SEG, &tm.C, line0, g, b, bar_bc);
     }
     if (t_in_row == 0) {
 #pragma unroll
@@ -118,8 +114,8 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
 
     float2 Bl[4], Cv[4];  // ln2 * B (the scan runs on dt in the log2 domain) and C of this thread's positions
     mbar_wait(bar_bc, 0);
-    lds8_sw(s_bc + tseg * ITEMS, sel, Bl);
-    lds8_sw(s_bc + SEG + tseg * ITEMS, sel, Cv);
+    lds8_priv(s_bc + slot, sel, Bl);
+    lds8_priv(s_bc + SEG + slot, sel, Cv);
     __syncthreads();  // B / C are in registers: the last stage is free for data now
     if (t_in_row == 0 && STAGES - 1 < n_iter) issue_stage(STAGES - 1);
 #pragma unroll
@@ -146,10 +142,10 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
         mbar_wait(my_bars + s * ROWS, (unsigned)((it / STAGES) & 1));
         float2 uv[4], av[4], bx[4];
         {
-            const float *su = my_stage + (size_t)s * ROWS * 2 * SEG + tseg * ITEMS;
+            const float *su = my_stage + (size_t)s * ROWS * 2 * SEG + slot;
             float2 dl[4];
-            lds8_sw(su, sel, uv);
-            lds8_sw(su + SEG, sel, dl);
+            lds8_priv(su, sel, uv);
+            lds8_priv(su + SEG, sel, dl);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float2 dt2 = fma2(dl[j], f2(kLog2e), f2(bias2));
@@ -281,21 +277,23 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, unsigned ch
 
 template <int TPR, bool SP, int STAGES>
 __global__ void __launch_bounds__(256, 3) scan_fwd_tma_kernel(const __grid_constant__ GroupArgs ga) {
-    extern __shared__ __align__(128) unsigned char smem_fwd_tma[];
+    extern __shared__ __align__(1024) unsigned char smem_fwd_tma[];  // swizzled tiles need 512-byte aligned slots
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
     pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
     constexpr int SEG = TPR * 8;
     int tile;
-    const ScanArgs &a = ga.a[group_problem(ga, tile)];
+    const int prob = group_problem(ga, tile);
+    const ScanArgs &a = ga.a[prob];
+    const TileMaps &tm = ga.tm[prob];
     const int chunk = tile / a.n_rowgroups;
     const int rg = tile - chunk * a.n_rowgroups;
     const bool tail = (chunk + 1) * SEG > a.seqlen;
     if (a.rev) {  // single chunk only (host-checked)
-        if (tail) scan_fwd_tma_body<TPR, true, SP, STAGES, true>(a, smem_fwd_tma, chunk, rg);
-        else scan_fwd_tma_body<TPR, false, SP, STAGES, true>(a, smem_fwd_tma, chunk, rg);
+        if (tail) scan_fwd_tma_body<TPR, true, SP, STAGES, true>(a, tm, smem_fwd_tma, chunk, rg);
+        else scan_fwd_tma_body<TPR, false, SP, STAGES, true>(a, tm, smem_fwd_tma, chunk, rg);
     } else {
-        if (tail) scan_fwd_tma_body<TPR, true, SP, STAGES, false>(a, smem_fwd_tma, chunk, rg);
-        else scan_fwd_tma_body<TPR, false, SP, STAGES, false>(a, smem_fwd_tma, chunk, rg);
+        if (tail) scan_fwd_tma_body<TPR, true, SP, STAGES, false>(a, tm, smem_fwd_tma, chunk, rg);
+        else scan_fwd_tma_body<TPR, false, SP, STAGES, false>(a, tm, smem_fwd_tma, chunk, rg);
     }
 }
 

@@ -16,6 +16,53 @@ constexpr int kMultiChunkTileChannels = 4;  // the multi-chunk kernels keep the 
 
 static size_t dtype_size(int dt) { return dt == VMASR_F32 ? 4 : 2; }
 
+// ---- TMA descriptors of the fast path ------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point; it is looked up through the runtime so that the library links against
+// nothing but the (static) CUDA runtime.  Encoding is pure host arithmetic (no driver call).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// rows of `len` floats (unit stride, len % 16 == 0) indexed by (row, batch) with element strides -> (16, len / 16, rows, batch),
+// boxes of `box_lines` lines of one row, 64-byte swizzle, zeros past the end
+static int make_tile_map(CUtensorMap *tm, const void *base, long long len, long long rows, long long row_stride, long long batch,
+                         long long batch_stride, int box_lines, const char *what) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail("selective_scan: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[4] = {(cuuint64_t)kTileLine, (cuuint64_t)(len / kTileLine), (cuuint64_t)rows, (cuuint64_t)batch};
+    // a dimension of extent 1 may carry any stride in the caller's tensor: give it the natural one
+    const cuuint64_t line_bytes = kTileLine * sizeof(float);
+    const cuuint64_t rs = rows > 1 ? (cuuint64_t)row_stride * sizeof(float) : line_bytes * dims[1];
+    const cuuint64_t bs = batch > 1 ? (cuuint64_t)batch_stride * sizeof(float) : rs * dims[2];
+    const cuuint64_t strides[3] = {line_bytes, rs, bs};
+    const cuuint32_t box[4] = {(cuuint32_t)kTileLine, (cuuint32_t)box_lines, 1u, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("selective_scan: cannot describe %s to the TMA (cuTensorMapEncodeTiled error %d)", what, (int)r);
+    return 0;
+}
+
+static int make_tile_maps(TileMaps &tm, const vmasr_scan_params *p, bool bwd, int box_lines) {
+    const long long L = p->seqlen;
+    if (int rc = make_tile_map(&tm.u, p->u, L, p->dim, p->u_d_stride, p->batch, p->u_batch_stride, box_lines, "u")) return rc;
+    if (int rc = make_tile_map(&tm.delta, p->delta, L, p->dim, p->delta_d_stride, p->batch, p->delta_batch_stride, box_lines, "delta")) return rc;
+    if (int rc = make_tile_map(&tm.B, p->B, L, p->ngroups, p->B_group_stride, p->batch, p->B_batch_stride, box_lines, "B")) return rc;
+    if (int rc = make_tile_map(&tm.C, p->C, L, p->ngroups, p->C_group_stride, p->batch, p->C_batch_stride, box_lines, "C")) return rc;
+    if (bwd)
+        if (int rc = make_tile_map(&tm.dout, p->dout, L, p->dim, p->dout_d_stride, p->batch, p->dout_batch_stride, box_lines, "dout")) return rc;
+    return 0;
+}
+
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int validate(const vmasr_scan_params *p, bool bwd) {
@@ -169,6 +216,8 @@ static int decide(const vmasr_scan_params *p, bool bwd, int peers, ScanPlan &pl,
                  aligned16(p->dC) && mult(p->dout_batch_stride) && mult(p->dout_d_stride) && mult(p->du_batch_stride) &&
                  mult(p->du_d_stride) && mult(p->ddelta_batch_stride) && mult(p->ddelta_d_stride) && (p->seqlen % 4 == 0);
     }
+    // the fast kernels stage rows through TMA descriptors whose lines are 16 floats (64-byte swizzle, scan.cuh)
+    pl.vec = pl.vec && (p->seqlen % kTileLine == 0);
     // fast path: fp32, d_state 1, 16-byte aligned rows -> TMA-staged packed-fp32x2 kernels; more than one chunk: the
     // kernels with the exchange warp (scan_*_pipe.cu).  VMASR_TUNING builds: VMASR_SCAN_FWD / VMASR_SCAN_BWD = generic | tma
     const char *force_env = tuning_env(bwd ? "VMASR_SCAN_BWD" : "VMASR_SCAN_FWD");
@@ -178,7 +227,7 @@ static int decide(const vmasr_scan_params *p, bool bwd, int peers, ScanPlan &pl,
     else if (n_chunks > 1 && !(force == 't' && p->flags == 0)) variant = kMultiChunk;
     else variant = kSingleChunk;
     if (variant == kGeneric && p->flags != 0)
-        return fail("selective_scan: VMASR_SCAN_REVERSE / _ACCUMULATE / _ADD need the fast path (float32, d_state 1, seqlen a multiple of 4, "
+        return fail("selective_scan: VMASR_SCAN_REVERSE / _ACCUMULATE / _ADD need the fast path (float32, d_state 1, seqlen a multiple of 16, "
                     "16-byte aligned rows and strides)");
     return 0;
 }
@@ -226,6 +275,9 @@ int scan_run_group(int n, const vmasr_scan_params *ps, bool bwd) {
             if (done[j] || key[j] != key[i]) continue;
             done[j] = true;
             ga.a[ga.n] = a[j];
+            // boxes: one 2048-position chunk (multi-chunk kernels) or one row segment of 8 positions per thread (single-chunk kernels)
+            const int box_lines = (variant[i] == kMultiChunk ? VMASR_SCAN_CHUNK : pl[j].tpr * 8) / kTileLine;
+            if (int rc = make_tile_maps(ga.tm[ga.n], &ps[j], bwd, box_lines)) return rc;
             grid += pl[j].grid;
             ga.tile_end[ga.n] = grid;
             ++ga.n;

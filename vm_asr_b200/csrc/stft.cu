@@ -31,6 +31,38 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
+// ---- transcendental pieces of the epilogues / prologues (MUFU based; errors far below the 1e-5 bar of the path) ----------
+// atan2 from one division and the 8-term odd polynomial of Abramowitz & Stegun 4.4.49 (|error| <= 2e-8 on [0, 1]); quadrant by
+// comparisons; signed zeros as atan2f (angle(-1 - 0i) = -pi).  atan2f itself is ~70 instructions per bin.
+__device__ __forceinline__ float fast_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = mx > 0.0f ? __fdividef(mn, mx) : 0.0f;
+    const float s = t * t;
+    float p = fmaf(s, 0.0028662257f, -0.0161657367f);
+    p = fmaf(s, p, 0.0429096138f);
+    p = fmaf(s, p, -0.0752896400f);
+    p = fmaf(s, p, 0.1065626393f);
+    p = fmaf(s, p, -0.1420889944f);
+    p = fmaf(s, p, 0.1999355085f);
+    p = fmaf(s, p, -0.3333314528f);
+    float r = fmaf(t * s, p, t);
+    if (ay > ax) r = 1.5707963267948966f - r;
+    if (x < 0.0f) r = 3.141592653589793f - r;
+    return copysignf(r, y);
+}
+// log2(sqrt(p) + 1e-8) with the MUFU square root and logarithm (2 ulp each)
+__device__ __forceinline__ float fast_log2_mag(float p) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+    return lg2_approx(r + 1e-8f);
+}
+// sin / cos of a phase: one reduction to [-pi, pi] (phases are angles, or network outputs of order 1 .. 10), then the MUFU
+__device__ __forceinline__ void fast_sincos(float x, float *sn, float *cs) {
+    x = fmaf(-6.283185307179586f, rintf(x * 0.15915494309189535f), x);
+    __sincosf(x, sn, cs);
+}
+
 // position of element n in the digit-reversed buffer (radix-4 digits, plus one radix-2 digit when log2 M odd)
 __device__ __forceinline__ int perm_index(int n, int M, int log2m) {
     int p = 0, block = M, m = log2m;
@@ -90,6 +122,7 @@ struct Tables {
     float2 *tw;   // [M]    exp(-2 pi i t / M)
     float2 *tw2;  // [M+1]  exp(-pi i k / M)
     float *wtab;  // [n_fft] padded periodic Hann * scale
+    unsigned short *perm;  // [M] perm_index(n): the digit reversal costs ~25 instructions, a frame needs M of them
 };
 
 __device__ __forceinline__ float hann_padded(const StftShape &s, int n) {
@@ -114,6 +147,7 @@ __device__ __forceinline__ void build_tables(const Tables &tb, const StftShape &
         tb.tw[k >> 1] = make_float2(cs, -sn);
     }
     for (int n = threadIdx.x; n < s.n_fft; n += blockDim.x) tb.wtab[n] = hann_padded(s, n) * s.scale;
+    for (int n = threadIdx.x; n < s.M; n += blockDim.x) tb.perm[n] = (unsigned short)perm_index(n, s.M, s.log2m);
 }
 
 // sum over the frames covering padded sample tp of window^2 (torch.istft's envelope), from the analytic window
@@ -145,18 +179,18 @@ __device__ __forceinline__ float2 unpack_rfft(const float2 *buf, const float2 *t
 // c2r packing: entries k and M - k of the buffer whose forward FFT (conjugated) is the real sequence with one-sided
 // spectrum X (imaginary parts of X[0], X[M] ignored, as a c2r transform does): x[n] = sum_k' X[k'] e^{+2 pi i k' n / N}
 // over the Hermitian extension, UN-normalised.
-__device__ __forceinline__ void pack_c2r(float2 *buf, const float2 *tw2, int M, int log2m, int k, float2 xk, float2 xm) {
+__device__ __forceinline__ void pack_c2r(float2 *buf, const float2 *tw2, const unsigned short *perm, int M, int k, float2 xk, float2 xm) {
     const int km = M - k;
     if (k == 0) { xk.y = 0.0f; xm.y = 0.0f; }
     {
         const float2 e = cadd(xk, cconj(xm));
         const float2 o = cmul(csub(xk, cconj(xm)), cconj(tw2[k]));
-        buf[perm_index(k, M, log2m)] = cconj(make_float2(e.x - o.y, e.y + o.x));
+        buf[perm[k & (M - 1)]] = cconj(make_float2(e.x - o.y, e.y + o.x));
     }
     if (k != 0 && km != k) {
         const float2 e = cadd(xm, cconj(xk));
         const float2 o = cmul(csub(xm, cconj(xk)), cconj(tw2[km]));
-        buf[perm_index(km, M, log2m)] = cconj(make_float2(e.x - o.y, e.y + o.x));
+        buf[perm[km]] = cconj(make_float2(e.x - o.y, e.y + o.x));
     }
 }
 // time sample n of the sequence packed by pack_c2r, after warp_fft
@@ -172,7 +206,7 @@ __device__ __forceinline__ void load_frame(float2 *buf, const float *__restrict_
         int t0 = start + 2 * n, t1 = t0 + 1;
         t0 = t0 < 0 ? -t0 : (t0 >= s.T ? 2 * (s.T - 1) - t0 : t0);
         t1 = t1 < 0 ? -t1 : (t1 >= s.T ? 2 * (s.T - 1) - t1 : t1);
-        buf[perm_index(n, s.M, s.log2m)] = make_float2(__ldg(row + t0) * tb.wtab[2 * n], __ldg(row + t1) * tb.wtab[2 * n + 1]);
+        buf[tb.perm[n]] = make_float2(__ldg(row + t0) * tb.wtab[2 * n], __ldg(row + t1) * tb.wtab[2 * n + 1]);
     }
 }
 
@@ -188,6 +222,7 @@ __device__ __forceinline__ Carve carve(unsigned char *smem, const StftShape &s) 
     c.tb.tw = reinterpret_cast<float2 *>(smem + off); off = align16(off + sizeof(float2) * s.M);
     c.tb.tw2 = reinterpret_cast<float2 *>(smem + off); off = align16(off + sizeof(float2) * (s.M + 1));
     c.tb.wtab = reinterpret_cast<float *>(smem + off); off = align16(off + sizeof(float) * s.n_fft);
+    c.tb.perm = reinterpret_cast<unsigned short *>(smem + off); off = align16(off + sizeof(unsigned short) * s.M);
     c.bufs = reinterpret_cast<float2 *>(smem + off); off = align16(off + sizeof(float2) * s.M * kFramesPerCta);
     c.st_a = reinterpret_cast<float *>(smem + off); off = align16(off + sizeof(float) * s.F * kStageStride);
     c.st_b = reinterpret_cast<float *>(smem + off); off = align16(off + sizeof(float) * s.F * kStageStride);
@@ -251,8 +286,8 @@ __global__ void __launch_bounds__(256) stft_fwd_kernel(const float *__restrict__
             if (LINEAR) {
                 c.st_a[k * kStageStride + warp] = sqrtf(fmaxf(p, clamp));
             } else {
-                c.st_a[k * kStageStride + warp] = log2f(sqrtf(p) + 1e-8f);
-                c.st_b[k * kStageStride + warp] = atan2f(X.y, X.x);
+                c.st_a[k * kStageStride + warp] = fast_log2_mag(p);
+                c.st_b[k * kStageStride + warp] = fast_atan2(X.y, X.x);
             }
         }
     }
@@ -326,17 +361,17 @@ __global__ void __launch_bounds__(256) synth_kernel(const float *__restrict__ in
                 float2 xk, xm;
                 if (MODE == 0) {
                     float sk, ck, sm, cm;
-                    sincosf(c.st_b[k * kStageStride + warp], &sk, &ck);
-                    sincosf(c.st_b[km * kStageStride + warp], &sm, &cm);
-                    const float ak = exp2f(c.st_a[k * kStageStride + warp]);
-                    const float am = exp2f(c.st_a[km * kStageStride + warp]);
+                    fast_sincos(c.st_b[k * kStageStride + warp], &sk, &ck);
+                    fast_sincos(c.st_b[km * kStageStride + warp], &sm, &cm);
+                    const float ak = ex2_approx(c.st_a[k * kStageStride + warp]);
+                    const float am = ex2_approx(c.st_a[km * kStageStride + warp]);
                     xk = make_float2(ak * ck, ak * sk);
                     xm = make_float2(am * cm, am * sm);
                 } else {
                     xk = make_float2(c.st_a[k * kStageStride + warp], c.st_b[k * kStageStride + warp]);
                     xm = make_float2(c.st_a[km * kStageStride + warp], c.st_b[km * kStageStride + warp]);
                 }
-                pack_c2r(buf, c.tb.tw2, M, s.log2m, k, xk, xm);
+                pack_c2r(buf, c.tb.tw2, c.tb.perm, M, k, xk, xm);
             }
             __syncwarp();
             warp_fft(buf, c.tb.tw, M, s.log2m, lane);
@@ -421,7 +456,7 @@ __global__ void __launch_bounds__(256) istft_bwd_kernel(const float *__restrict_
     if (f < s.n_frames) {
         const float *g = genv + warp * s.hop;
         for (int n = lane; n < M; n += 32)
-            buf[perm_index(n, M, s.log2m)] = make_float2(g[2 * n] * c.tb.wtab[2 * n], g[2 * n + 1] * c.tb.wtab[2 * n + 1]);
+            buf[c.tb.perm[n]] = make_float2(g[2 * n] * c.tb.wtab[2 * n], g[2 * n + 1] * c.tb.wtab[2 * n + 1]);
         __syncwarp();
         warp_fft(buf, c.tb.tw, M, s.log2m, lane);
         for (int k = lane; k <= M; k += 32) {
@@ -429,9 +464,9 @@ __global__ void __launch_bounds__(256) istft_bwd_kernel(const float *__restrict_
             const float cf = (k == 0 || k == M) ? 1.0f : 2.0f;
             R.x *= cf;
             R.y *= cf;
-            const float m = exp2f(c.st_a[k * kStageStride + warp]);
+            const float m = ex2_approx(c.st_a[k * kStageStride + warp]);
             float sn, cs;
-            sincosf(c.st_b[k * kStageStride + warp], &sn, &cs);
+            fast_sincos(c.st_b[k * kStageStride + warp], &sn, &cs);
             c.st_a[k * kStageStride + warp] = 0.6931471805599453f * m * fmaf(R.x, cs, R.y * sn);
             c.st_b[k * kStageStride + warp] = m * fmaf(R.y, cs, -R.x * sn);
         }
@@ -464,6 +499,7 @@ static size_t base_smem(const StftShape &s) {
     off = a16(off + sizeof(float2) * s.M);
     off = a16(off + sizeof(float2) * (s.M + 1));
     off = a16(off + sizeof(float) * s.n_fft);
+    off = a16(off + sizeof(unsigned short) * s.M);
     off = a16(off + sizeof(float2) * s.M * kFramesPerCta);
     off = a16(off + sizeof(float) * s.F * kStageStride);
     off = a16(off + sizeof(float) * s.F * kStageStride);
