@@ -214,6 +214,8 @@ def test_reference_parametrisation(itype, seqlen, has_delta_bias, delta_softplus
     (1, 8, 40964, 4),     # 21 chunks: level-2 look-back entries, ragged last chunk, two channels per group
     (1, 28, 4104, 4),     # seven channels per group: tiles of 4 + 3 (both backward variants in one launch order)
     (1, 4, 614400, 2),    # 300 chunks: more than the 272 one look-back round covers (second round of level-2 entries)
+    # lengths that are multiples of 16 (fast kernels: TMA lines of 16 floats) but not of the chunk / row-segment size: ragged tails
+    (2, 20, 8208, 4), (1, 8, 40976, 4), (1, 28, 4112, 4), (2, 12, 304, 4), (3, 8, 1040, 2), (2, 8, 2064, 4),
 ])
 def test_ragged_shapes(Bsz, Dm, L, G):
     cpu, gpu = make_inputs(Bsz, Dm, L, G, 1, torch.float32)
@@ -411,8 +413,8 @@ def _flip(t):
 
 
 @pytest.mark.parametrize("Bsz,Dm,L,G", [
-    (2, 8, 256, 4), (2, 16, 1024, 4), (1, 12, 300, 4), (2, 8, 2048, 2),       # single-chunk kernels (32 .. 256 threads per row)
-    (2, 16, 4096, 4), (1, 8, 40964, 4), (2, 20, 8196, 4), (1, 8, 262144, 4),  # multi-chunk kernels, ragged tails, level-2 look-back
+    (2, 8, 256, 4), (2, 16, 1024, 4), (1, 12, 304, 4), (2, 8, 2048, 2),       # single-chunk kernels (32 .. 256 threads per row)
+    (2, 16, 4096, 4), (1, 8, 40976, 4), (2, 20, 8208, 4), (1, 8, 262144, 4),  # multi-chunk kernels, ragged tails, level-2 look-back
 ])
 def test_reverse_flag(Bsz, Dm, L, G):
     """VMASR_SCAN_REVERSE == flip -> scan -> flip (what CrossScan / CrossMerge do for directions 2 and 3, vmamba.py:33, 54),
@@ -468,7 +470,7 @@ def test_accumulate_flag(L):
 
 def test_flags_need_fast_path():
     scan = _ops()
-    _, g = make_inputs(1, 8, 130, 4, 1, torch.float32)  # length not a multiple of 4: generic kernels
+    _, g = make_inputs(1, 8, 132, 4, 1, torch.float32)  # length not a multiple of 16: generic kernels
     out, x = torch.empty_like(g["u"]), torch.empty(1, 8, 1, 2, device="cuda")
     with pytest.raises(RuntimeError):
         scan.fwd_out(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], g["bias"], True, out, x, flags=scan.SCAN_REVERSE)
@@ -477,8 +479,8 @@ def test_flags_need_fast_path():
 @pytest.mark.parametrize("shapes", [
     [(4, 64, 1024)] * 2,                    # two same-shape single-chunk calls (the two streams of the generator)
     [(4, 32, 16384)] * 2,                   # two multi-chunk calls
-    [(2, 16, 4096), (2, 16, 256), (2, 8, 40964), (1, 16, 1024), (2, 16, 4096)],  # mixed families: launched family by family
-    [(1, 8, 8196)] * 8,                     # the most one launch takes
+    [(2, 16, 4096), (2, 16, 256), (2, 8, 40976), (1, 16, 1024), (2, 16, 4100), (2, 16, 4096)],  # mixed families (one generic): launched family by family
+    [(1, 8, 8208)] * 8,                     # the most one launch takes
 ])
 def test_grouped_launch_equals_separate_calls(shapes):
     """vmasr_scan_fwd_grouped / _bwd_grouped: one grid over several calls, bit-identical to the calls made one by one
