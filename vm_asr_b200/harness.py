@@ -229,7 +229,7 @@ class TrainStep:
         # the reference trains under fp16 autocast with a GradScaler (config.py:217, trainer/trainer.py:106-107, 138): the two small
         # einsums of the core and the glue then run on tensor cores, the scan is forced to fp32 (vmamba.py:1487-1491) as here
         self.amp = amp
-        self.scaler = torch.amp.GradScaler("cuda", enabled=amp)
+        self.scaler = torch.amp.GradScaler("cuda", init_scale=1024.0, enabled=amp)
         self.net = HotPathNet(wl, pair=pair).to(device)
         if world > 1:
             for p in self.net.parameters():
