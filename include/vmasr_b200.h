@@ -145,6 +145,12 @@ VMASR_API int vmasr_scan_bwd_grouped(int n, const vmasr_scan_params *p);
  * ---------------------------------------------------------------------------------------------- */
 VMASR_API int vmasr_cross_scan(const void *x, void *xs, int B, int C, int H, int W, int dtype, int device, void *stream);
 VMASR_API int vmasr_cross_merge(const void *ys, void *y, int B, int C, int H, int W, int dtype, int device, void *stream);
+/* One-by-one variants: replace CrossScanTriton1b1 and its kernels triton_cross_scan_1b1 / triton_cross_merge_1b1
+ * (model/csm_triton.py:157-308, 369-395; reached only from SS2D.forwardxv, which no shipped config selects).
+ *   cross_scan_1b1 : x (B, 4, C, H, W) -> y (B, 4, C, H*W), direction k of y is direction k's walk over map k of x
+ *   cross_merge_1b1: the inverse permutation, y (B, 4, C, H*W) -> x (B, 4, C, H, W) */
+VMASR_API int vmasr_cross_scan_1b1(const void *x, void *y, int B, int C, int H, int W, int dtype, int device, void *stream);
+VMASR_API int vmasr_cross_merge_1b1(const void *y, void *x, int B, int C, int H, int W, int dtype, int device, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused SS2D core: CrossScan -> selective scan -> CrossMerge of SS2D.forward_corev2 (model/vmamba.py:1472-1497; the Triton

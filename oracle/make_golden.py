@@ -15,6 +15,7 @@ What is executed, unmodified, from the reference tree:
     Gradients come from torch autograd through that function.
   * ``utils/stft.py``  ``wav2spectro`` / ``spectro2wav`` (log2 and dB scales; the gradient of wav2spectro by autograd).
   * ``model/loss.py``  ``MultiResolutionSTFTLoss`` (value and gradient), ``model/metric.py``  ``lsd`` / ``lsd_hf`` / ``lsd_lf``.
+  * ``utils/post_processing.py``  ``unfold_audio`` / ``fold_audio``.
 """
 from __future__ import annotations
 
@@ -211,6 +212,16 @@ def main():
     back_db = stft.spectro2wav(mag_db, phase_db, 1024, 240, 1024, "dB")
     blob.update(db_wave=np_(wdb), db_mag=np_(mag_db), db_phase=np_(phase_db), db_back=np_(back_db))
     np.savez_compressed(os.path.join(OUT, "stft_loss.npz"), **blob)
+
+    # ---------------- overlapped segments (utils/post_processing.py, torch only) --------------------------------------------
+    pp = importlib.import_module("utils.post_processing")
+    audio = torch.randn(2, 1, 9000, generator=g)
+    seg, ov = 2500, 300
+    segs = pp.unfold_audio(audio, seg, ov)
+    processed = torch.tanh(segs) + 0.1 * torch.randn(segs.shape, generator=g)
+    folded = pp.fold_audio(processed, audio.shape[-1], seg, ov)
+    np.savez_compressed(os.path.join(OUT, "segments.npz"), audio=np_(audio), segments=np_(segs.contiguous()), processed=np_(processed),
+                        folded=np_(folded), params=np.array([seg, ov]))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

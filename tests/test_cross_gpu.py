@@ -101,3 +101,21 @@ def test_matches_the_references_triton_kernels():
         m0, m1 = cross.cross_merge(ys, shape[2], shape[3]), csm_triton.CrossMergeTriton.apply(ys)
         tol = {torch.float32: 1e-5, torch.float16: 2e-2, torch.bfloat16: 1.3e-1}[dt]   # a couple of ulps of a sum of four N(0, 1) values
         assert (m0.float() - m1.view_as(m0).float()).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 3, 8, 8), (1, 5, 56, 57), (2, 4, 64, 32), (1, 2, 33, 100)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_one_by_one_variant(B, C, H, W, dtype):
+    """CrossScanTriton1b1 (csm_triton.py:369-395): every direction walks its OWN map; defined here by the pure-PyTorch
+    CrossScan applied to each of the four maps (direction k of CrossScan(x_k)); the backward is the inverse permutation."""
+    cross = _ops()
+    x = torch.randn(B, 4, C, H, W, generator=torch.Generator().manual_seed(H + W)).to(dtype)
+    ref = torch.stack([ss2d_ref.cross_scan(x[:, k])[:, k] for k in range(4)], dim=1)
+    xg = x.cuda().requires_grad_()
+    y = cross.CrossScanTriton1b1.apply(xg)
+    assert y.shape == (B, 4, C, H * W) and torch.equal(y.detach().cpu(), ref)
+    gy = torch.randn(B, 4, C, H * W, generator=torch.Generator().manual_seed(1)).to(dtype)
+    y.backward(gy.cuda())
+    xs = [x[:, k].float().requires_grad_() for k in range(4)]
+    gref = torch.autograd.grad(torch.stack([ss2d_ref.cross_scan(xr)[:, k] for k, xr in enumerate(xs)], dim=1), xs, gy.float())
+    assert torch.equal(xg.grad.float().cpu(), torch.stack(gref, dim=1))

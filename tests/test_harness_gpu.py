@@ -63,3 +63,27 @@ def test_graph_captured_step_matches_eager():
     lb = [b(x, y).item() for _ in range(4)]
     for u, v in zip(la, lb):
         assert abs(u - v) < 1e-4 * max(1.0, abs(u)), (la, lb)
+
+
+def test_batched_long_clip_inference_matches_segment_by_segment():
+    """segment.infer_long: all segments of all clips as ONE batch through the harness generator, cross-faded on the device,
+    equals the reference's procedure (one segment at a time, tester.py:106-131; the oracle's fold) -- and reports an RTF from
+    CUDA events."""
+    from oracle import segment_ref
+    from vm_asr_b200 import harness, segment
+    wl = _small_workload()
+    dev = torch.device("cuda")
+    net = harness.HotPathNet(wl).to(dev).eval()
+    T, ov = wl.T, 200
+    long_clip = 0.1 * torch.randn(2, 1, 2 * (T - ov) + T + 37, generator=torch.Generator().manual_seed(3)).to(dev)
+    out, info = segment.infer_long(net, long_clip, None, segment_length=T, overlap=ov, sample_rate=wl.sr)
+    assert out.shape == long_clip.shape and info["segments"] == 2 * 3 and info["rtf"] > 0
+    segs = segment_ref.unfold_audio(long_clip, T, ov)
+    done = torch.zeros_like(segs)
+    with torch.no_grad():
+        for i in range(segs.shape[2]):
+            done[:, :, i] = net(segs[:, :, i].contiguous())
+    ref = segment_ref.fold_audio(done.cpu(), long_clip.shape[-1], T, ov)
+    assert torch.allclose(out.cpu(), ref, rtol=1e-4, atol=1e-5)
+    short, info1 = segment.infer_long(net, long_clip[..., :T].contiguous(), None, segment_length=T, overlap=ov, sample_rate=wl.sr)
+    assert short.shape[-1] == T and info1["segments"] == 2

@@ -81,6 +81,8 @@ EXPORTS = {
     "vmasr_map_merge2": (ctypes.c_int, [_vp, _vp, _vp, _i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "vmasr_cross_scan": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
     "vmasr_cross_merge": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
+    "vmasr_cross_scan_1b1": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
+    "vmasr_cross_merge_1b1": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
     "vmasr_stft_scratch_floats": (_u64, [ctypes.c_int] * 3),
     "vmasr_stft_fwd": (ctypes.c_int, [_vp, _vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
     "vmasr_stft_bwd": (ctypes.c_int, [_vp] * 5 + [ctypes.c_int] * 6 + [_vp]),

@@ -263,6 +263,81 @@ __global__ void __launch_bounds__(256) cross_merge_any(const T *__restrict__ ys,
     }
 }
 
+// ---- one-by-one variants (csm_triton.py:157-308): every direction has its OWN map --------------------------------------
+//   scan_1b1 : x (B, 4, C, H, W) -> y (B, 4, C, L):  y0 = x0 row-major, y1 = x1 column-major, y2 / y3 = the same of x2 / x3 reversed
+//   merge_1b1: the inverse permutation, y (B, 4, C, L) -> x (B, 4, C, H, W)   (no sum: four separate maps)
+// Reached only from SS2D.forwardxv (vmamba.py:1618-1690), which no shipped config selects: a plain 32 x 32 tile kernel.
+template <typename T, bool INVERSE>
+__global__ void __launch_bounds__(256) cross_1b1_any(const T *__restrict__ src, T *__restrict__ dst, long long planes, int C, int H, int W) {
+    __shared__ T s[32][33];
+    const TileJob<32, 1> job(planes, H, W);  // planes = B * 4 * C; direction k = (plane / C) % 4
+    const long long pl = job.plane0;
+    const int k = (int)((pl / C) & 3);
+    const long long L = (long long)H * W;
+    const T *in = src + pl * L;
+    T *out = dst + pl * L;
+    const int h0 = job.h0, w0 = job.w0;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const bool rev = k >= 2;
+    if (!(k & 1)) {  // row-major directions: a copy, possibly reversed
+        for (int r = ty; r < 32; r += 8) {
+            const int h = h0 + r, w = w0 + tx;
+            if (h < H && w < W) {
+                const long long l = (long long)h * W + w, m = rev ? L - 1 - l : l;
+                if (INVERSE) out[l] = in[m];
+                else out[m] = in[l];
+            }
+        }
+        return;
+    }
+    // column-major directions through a shared-memory transpose: map position (h, w) <-> sequence index w * H + h
+    for (int r = ty; r < 32; r += 8) {
+        if (!INVERSE) {
+            const int h = h0 + r, w = w0 + tx;
+            if (h < H && w < W) s[r][tx] = in[(long long)h * W + w];
+        } else {
+            const int w = w0 + r, h = h0 + tx;
+            if (h < H && w < W) {
+                const long long l = (long long)w * H + h;
+                s[tx][r] = in[rev ? L - 1 - l : l];
+            }
+        }
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        if (!INVERSE) {
+            const int w = w0 + r, h = h0 + tx;
+            if (h < H && w < W) {
+                const long long l = (long long)w * H + h;
+                out[rev ? L - 1 - l : l] = s[tx][r];
+            }
+        } else {
+            const int h = h0 + r, w = w0 + tx;
+            if (h < H && w < W) out[(long long)h * W + w] = s[r][tx];
+        }
+    }
+}
+
+template <bool INVERSE>
+static int run_1b1(const void *in, void *out, int B, int C, int H, int W, int dtype, int device, void *stream_) {
+    const char *who = INVERSE ? "cross_merge_1b1" : "cross_scan_1b1";
+    if (!in || !out) return fail("%s: null tensor", who);
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail("%s: sizes must be positive (B %d C %d H %d W %d)", who, B, C, H, W);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail("%s: cannot select CUDA device %d", who, device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long planes = (long long)B * 4 * C;
+    const long long g = planes * ((H + 31) / 32) * ((W + 31) / 32);
+    if (g > 0x7fffffffll) return fail("%s: %lld tiles exceed the grid limit", who, g);
+    switch (dtype) {
+        case VMASR_F32: cross_1b1_any<float, INVERSE><<<(unsigned)g, 256, 0, stream>>>(static_cast<const float *>(in), static_cast<float *>(out), planes, C, H, W); break;
+        case VMASR_F16: cross_1b1_any<__half, INVERSE><<<(unsigned)g, 256, 0, stream>>>(static_cast<const __half *>(in), static_cast<__half *>(out), planes, C, H, W); break;
+        case VMASR_BF16: cross_1b1_any<__nv_bfloat16, INVERSE><<<(unsigned)g, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(in), static_cast<__nv_bfloat16 *>(out), planes, C, H, W); break;
+        default: return fail("%s: unsupported dtype %d", who, dtype);
+    }
+    return check_cuda(cudaGetLastError(), who);
+}
+
 static int check_shape(const void *a, const void *b, int B, int C, int H, int W, int dtype, const char *who) {
     if (!a || !b) return fail("%s: null tensor", who);
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail("%s: sizes must be positive (B %d C %d H %d W %d)", who, B, C, H, W);
@@ -349,4 +424,10 @@ extern "C" int vmasr_cross_scan(const void *x, void *xs, int B, int C, int H, in
 }
 extern "C" int vmasr_cross_merge(const void *ys, void *y, int B, int C, int H, int W, int dtype, int device, void *stream) {
     return vmasr::run_cross<true>(ys, y, B, C, H, W, dtype, device, stream);
+}
+extern "C" int vmasr_cross_scan_1b1(const void *x, void *y, int B, int C, int H, int W, int dtype, int device, void *stream) {
+    return vmasr::run_1b1<false>(x, y, B, C, H, W, dtype, device, stream);
+}
+extern "C" int vmasr_cross_merge_1b1(const void *y, void *x, int B, int C, int H, int W, int dtype, int device, void *stream) {
+    return vmasr::run_1b1<true>(y, x, B, C, H, W, dtype, device, stream);
 }
