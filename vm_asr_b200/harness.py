@@ -109,14 +109,18 @@ class HotPathNet(nn.Module):
                 if len(convs):
                     x = convs[s](x)
                 xs.append(x.contiguous())
+            # VSSBlock: x + SS2D(LN(x)), and SS2D normalises its own output (out_norm) -- vmamba.py:1826-1837, 1527-1531.  The
+            # core is cubic in the scale of its input (B, C and u are all linear in it), so the pre-normalisation is what keeps
+            # the activations (and the fp16 gradients under autocast) in range, exactly as in the reference.
+            xn = [self._rms(x) for x in xs]
             if self.pair and call.H % 4 == 0 and call.W % 4 == 0:
-                ys = ss2d.ss2d_core_pair(xs[0], cores[0].tensors(), xs[1], cores[1].tensors())
+                ys = ss2d.ss2d_core_pair(xn[0], cores[0].tensors(), xn[1], cores[1].tensors())
             else:
-                ys = [ss2d.ss2d_core(xs[s], *cores[s].tensors()) for s in range(2)]
+                ys = [ss2d.ss2d_core(xn[s], *cores[s].tensors()) for s in range(2)]
             outs = []
             for s in range(2):
                 y = ys[s].view(Bsz, call.d_inner, call.H, call.W)
-                outs.append(xs[s] + self._rms(y))                                # VSSBlock: x + SS2D(LN(x)) (vmamba.py:1826-1837)
+                outs.append(xs[s] + self._rms(y))
             m = outs[0] + outs[1]                                                # model.py:1129-1131
             streams = [m, outs[1] + m]
         full_h, full_w = residual_mag.shape[-2:]
