@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define VMASR_ABI_VERSION 2
+#define VMASR_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define VMASR_API __attribute__((visibility("default")))
@@ -100,6 +100,29 @@ typedef struct vmasr_scan_params {
     int32_t device;         /* CUDA device ordinal the pointers live on */
     int32_t flags;          /* VMASR_SCAN_* bits below; 0 = the reference's semantics */
     void *stream; /* cudaStream_t */
+    /* ---- delta generated on the fly from the rank-R projection (model/vmamba.py:1476-1477) ----
+     * With dt_rank > 0 the kernels never see a (batch, dim, seqlen) `delta`: they are handed what dt_projs_weight is applied
+     * to, and form   delta[b, d, l] = sum_r dt_weight[d, r] * dt_rows[b, group(d), r, l]   tile by tile in shared memory
+     * (`delta` / `ddelta` are ignored and may be NULL).  The backward returns the gradients of the two factors instead of
+     * ddelta:  d_dt_rows[b, g, r, l] += sum_{d in g} dt_weight[d, r] * ddelta[b, d, l]  and
+     * d_dt_weight[d, r] += sum_{b, l} ddelta[b, d, l] * dt_rows[b, g, r, l]  (both ACCUMULATED INTO; caller zero-fills).
+     * Supported: the multi-chunk fast path (float32, d_state 1, seqlen > VMASR_SCAN_CHUNK and a multiple of 16, aligned
+     * rows) with dt_rank 1 -- the three largest maps of every config (R = 1 wherever L >= 16384 at DIMS 16);
+     * anything else fails and the caller materialises delta (vmasr_ss2d_* does that choice itself).
+     *   dt_rows, d_dt_rows : (batch, ngroups, dt_rank, seqlen), unit stride along seqlen, row (g * dt_rank + r) at
+     *                        dt_rows_row_stride, batch at dt_rows_batch_stride
+     *   dt_weight, d_dt_weight : (dim, dt_rank), unit stride along r, channel stride dt_weight_d_stride
+     *   dB_batch_stride, dC_batch_stride : 0 = contiguous (ngroups * dstate * seqlen); otherwise the batch stride of dB / dC
+     *                        (the fused core lets them land next to d_dt_rows in one d x_dbl tensor) */
+    const float *dt_rows;
+    const float *dt_weight;
+    float *d_dt_rows;
+    float *d_dt_weight;
+    int64_t dt_rows_batch_stride, dt_rows_row_stride;
+    int64_t dt_weight_d_stride;
+    int64_t dB_batch_stride, dC_batch_stride;
+    int32_t dt_rank;
+    int32_t reserved0;
 } vmasr_scan_params;
 
 /* flags (fast path only: float32, d_state 1, seqlen a multiple of 16, 16-byte aligned rows and strides; otherwise the call
@@ -201,6 +224,18 @@ typedef struct vmasr_ss2d_params {
     int32_t batch, channels, H, W;
     int32_t delta_softplus, device;
     void *stream;
+    /* ---- projected form (dt_rank > 0): delta generated inside the scan kernels, see vmasr_scan_params ----
+     * x_dbl[k] = the (R + 2) rows einsum(x_k, x_proj_weight[k]) of direction k in the memory order of its pair
+     * (vmamba.py:1473-1476): rows 0..R-1 feed dt_projs_weight[k] (C, R), row R is B_k, row R + 1 is C_k.  delta[], B[], C[]
+     * above are then ignored, as are ddelta[], dB, dC: the backward ACCUMULATES d x_dbl[k] (same layout; caller zero-fills)
+     * and d dt_weight (4, C, R).  Needs dt_rank == 1 and H * W > VMASR_SCAN_CHUNK. */
+    const float *x_dbl[4];
+    int64_t x_dbl_batch_stride[4], x_dbl_row_stride[4];
+    const float *dt_weight; /* (4, C, R) contiguous */
+    float *d_x_dbl[4];
+    float *d_dt_weight;
+    int32_t dt_rank;
+    int32_t reserved0;
 } vmasr_ss2d_params;
 
 VMASR_API uint64_t vmasr_ss2d_workspace_bytes(int batch, int channels, int H, int W);

@@ -21,7 +21,7 @@ _lock = threading.Lock()
 VMASR_F32, VMASR_F16, VMASR_BF16 = 0, 1, 2
 SCAN_REVERSE, SCAN_ACCUMULATE = 1, 2
 SCAN_MAX_GROUP = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 SCAN_CHUNK = 2048
 DTYPE_CODE = {torch.float32: VMASR_F32, torch.float16: VMASR_F16, torch.bfloat16: VMASR_BF16}
 
@@ -43,6 +43,10 @@ class ScanParams(ctypes.Structure):
             "ddelta_batch_stride", "ddelta_d_stride")]
         + [(n, _i32) for n in ("io_dtype", "delta_softplus", "device", "flags")]
         + [("stream", _vp)]
+        + [(n, _vp) for n in ("dt_rows", "dt_weight", "d_dt_rows", "d_dt_weight")]
+        + [(n, _i64) for n in ("dt_rows_batch_stride", "dt_rows_row_stride", "dt_weight_d_stride", "dB_batch_stride",
+                               "dC_batch_stride")]
+        + [("dt_rank", _i32), ("reserved0", _i32)]
     )
 
 
@@ -62,6 +66,9 @@ class SS2DParams(ctypes.Structure):
         ("batch", _i32), ("channels", _i32), ("H", _i32), ("W", _i32),
         ("delta_softplus", _i32), ("device", _i32),
         ("stream", _vp),
+        ("x_dbl", _vp * 4), ("x_dbl_batch_stride", _i64 * 4), ("x_dbl_row_stride", _i64 * 4),
+        ("dt_weight", _vp), ("d_x_dbl", _vp * 4), ("d_dt_weight", _vp),
+        ("dt_rank", _i32), ("reserved0", _i32),
     ]
 
 

@@ -41,7 +41,17 @@ int sm_count(int device) {
     return cached[device];
 }
 
+#ifdef VMASR_TUNING
+static unsigned long long *g_timeline = nullptr;
+unsigned long long *debug_timeline() { return g_timeline; }
+#endif
+
 }  // namespace vmasr
+
+#ifdef VMASR_TUNING
+// measurement builds only (not in include/vmasr_b200.h): device buffer of 16 x grid timestamps, or NULL to switch it off
+extern "C" __attribute__((visibility("default"))) void vmasr_debug_timeline(unsigned long long *buf) { vmasr::g_timeline = buf; }
+#endif
 
 extern "C" int vmasr_abi_version(void) { return VMASR_ABI_VERSION; }
 extern "C" const char *vmasr_last_error(void) { return vmasr::g_err; }

@@ -53,6 +53,23 @@ inline const char *tuning_env(const char *name) {
 #endif
 }
 
+// ---- per-CTA phase timeline (VMASR_TUNING builds only) ------------------------------------------------------------------
+// tools/timeline.py hands the library a device buffer of 16 timestamps per CTA (vmasr_debug_timeline); the multi-chunk scan
+// kernels then record %globaltimer at their phase boundaries.  Compiles to nothing in the product build.
+#ifdef VMASR_TUNING
+unsigned long long *debug_timeline();
+#define VMASR_TL(args, slot)                                                                    \
+    do {                                                                                        \
+        if ((args).timeline) {                                                                  \
+            unsigned long long t_;                                                              \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                              \
+            (args).timeline[(size_t)blockIdx.x * 16 + (slot)] = t_;                             \
+        }                                                                                       \
+    } while (0)
+#else
+#define VMASR_TL(args, slot) do { } while (0)
+#endif
+
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
 // The scan kernels of a model run back to back on one stream.  Launched with the programmatic-stream-serialization
 // attribute, the CTAs of kernel N + 1 are scheduled while the last wave of kernel N drains; they park on

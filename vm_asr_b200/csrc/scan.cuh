@@ -40,8 +40,16 @@ struct ScanArgs {
     int accum;            // fast kernels only: `out` (forward) / `du` (backward) are added into instead of stored:
                           // 1 = 128-bit red.global.add (concurrent writers), 2 = load / add / store (this launch is the only writer)
     int debug_nowait;     // VMASR_TUNING builds only, timing experiment: do not wait for neighbours' aggregates -> WRONG results
+    unsigned long long *timeline;  // VMASR_TUNING builds only: 16 timestamps per CTA (common.cuh), else null
     long long u_bs, u_ds, delta_bs, delta_ds, A_ds, A_ns, B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;
     long long out_bs, out_ds, dout_bs, dout_ds, du_bs, du_ds, ddelta_bs, ddelta_ds;
+    // delta on the fly (include/vmasr_b200.h, dt_rank > 0; multi-chunk fast kernels, rank 1): delta = dt_w[d] * dt_rows[b, g, l]
+    const float *dt_w;      // (dim, dt_rank)
+    float *d_dt_rows;       // (batch, ngroups * dt_rank, seqlen) with the strides below, accumulated into
+    float *d_dt_w;          // like dt_w, accumulated into
+    long long dtr_bs, dtr_rs, dtw_ds;
+    long long dB_bs, dC_bs;  // batch strides of dB / dC (default ngroups * seqlen)
+    int dt_rank;
 };
 
 // (P, Q) represents the affine map  s -> P*s + Q  of a run of positions on the recurrence state.
@@ -145,7 +153,7 @@ constexpr int kMaxGroup = 8;
 // register shuffling (round 1 copied rows linearly and paid a register select per loaded float for the same effect).
 // Out-of-range lines (ragged last chunk) arrive as zeros.
 struct alignas(64) TileMaps {
-    CUtensorMap u, delta, dout, B, C;
+    CUtensorMap u, delta, dout, B, C;  // with dt_rank > 0 `delta` describes dt_rows: (L, ngroups * dt_rank rows, batch)
 };
 struct GroupArgs {
     TileMaps tm[kMaxGroup];

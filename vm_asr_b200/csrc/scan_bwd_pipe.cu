@@ -75,6 +75,12 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
         tensor_load(dst + SEG, &tm.delta, line0, d0 + it, b, &bar_full[it]);
         tensor_load(dst + 2 * SEG, &tm.dout, line0, d0 + it, b, &bar_full[it]);
     };
+    if (threadIdx.x == 0) {
+        VMASR_TL(a, 0);
+#ifdef VMASR_TUNING
+        if (a.timeline) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); a.timeline[(size_t)blockIdx.x * 16 + 15] = sm_; }
+#endif
+    }
     // the bulk copies go out first: they do not depend on the per-channel parameters staged below
     if (threadIdx.x == NC) {
 #pragma unroll
@@ -105,6 +111,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
         s_par[which * 4 + cc] = v;
     }
     __syncthreads();
+    if (threadIdx.x == 0) VMASR_TL(a, 1);
 
     const long long seq0 = (long long)b * a.dim + d0;
     if (exchange) {
@@ -147,6 +154,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
             CarryEntry *l1_row = a.ws_entries + seq * a.n_chunks;
             const float h_chunk = (chunk > 0) ? __ldg(a.x + (seq * a.n_chunks + (chunk - 1)) * 2 + 1) : 0.0f;
             mbar_wait(&bar_tot[j], 0);
+            if (lane == 0) VMASR_TL(a, j == 0 ? 8 : 9);
             float4 t = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
             if (lane < WPR) t = s_tot[j * WPR + lane];
             Aff cum_f = {t.x, t.y}, cum_r = {t.x, t.z};
@@ -164,6 +172,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
             p_h = h_chunk;
         }
         finish(n_iter - 1, p_look, p_cf, p_cr, p_h);
+        if (lane == 0) VMASR_TL(a, 10);
         mbar_wait(bar_done, 0);  // every compute warp is done: the channel sums are complete
         if (lane < 3 * n_iter) {
             const int c = lane / 3, which = lane - 3 * c;
@@ -198,6 +207,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
         float2 Bv[4], dBacc[4], dCacc[4];
         float *sC = s_c + slot;  // this thread's C values (only this thread touches them)
         mbar_wait(bar_bc, 0);
+        if (threadIdx.x == 0) VMASR_TL(a, 2);
         lds8_priv(s_b + slot, sel, Bv);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -230,6 +240,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
                 const float bias2 = s_par[2 * 4 + j];
                 float *su = s_stage + (size_t)j * 3 * SEG + slot;
                 mbar_wait(&bar_full[j], 0);
+                if (threadIdx.x == 0 && j == 0) VMASR_TL(a, 3);
                 float2 uv[4], dl[4], dy[4], Cv[4], dts[4];
                 lds8_priv(su, sel, uv);
                 lds8_priv(su + SEG, sel, dl);
@@ -283,6 +294,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
                 if (lane == 31) mbar_arrive(&bar_tot[j]);
             }
         }
+        if (threadIdx.x == 0) VMASR_TL(a, 4);
 #pragma unroll 1
         for (int j = 0; j < n_iter; ++j) {
             {
@@ -299,6 +311,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
                 float *o_du = du_ptr + (long long)j * a.du_ds;
                 float *o_dd = dd_ptr + (long long)j * a.ddelta_ds;
                 mbar_wait(&bar_in[j], 0);
+                if (threadIdx.x == 0) VMASR_TL(a, j == 0 ? 5 : 6);
                 const float2 in = s_in[j * WPR + warp];
                 const float *su = s_stage + (size_t)j * 3 * SEG + slot;
                 float2 uv[4], dts[4], dy[4], Cv[4];
@@ -398,6 +411,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
                 if ((lane & 7) == 0 && lane < 24) atomicAdd(s_red + j * 4 + (lane >> 3), r);
             }
         }
+        if (threadIdx.x == 0) VMASR_TL(a, 7);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_done);  // this warp's shared-memory atomics are done (release)
 

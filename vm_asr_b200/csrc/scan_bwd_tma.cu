@@ -353,8 +353,8 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, const TileM
     }
 
     // dB / dC of this tile's positions, summed over the tile's channels
-    float *dBg = a.dB + ((long long)b * a.ngroups + g) * (long long)L;
-    float *dCg = a.dC + ((long long)b * a.ngroups + g) * (long long)L;
+    float *dBg = a.dB + b * a.dB_bs + (long long)g * L;
+    float *dCg = a.dC + b * a.dC_bs + (long long)g * L;
     if (ROWS > 1) {
         __syncthreads();  // every row segment is done with the staging ring: reuse it
         float2 *sB2 = reinterpret_cast<float2 *>(s_stage) + (size_t)threadIdx.x * 4;  // [ROWS][TPR][4]

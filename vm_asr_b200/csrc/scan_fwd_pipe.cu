@@ -34,7 +34,12 @@ constexpr int kPipeStages = 4;        // channels per tile = resident stages (u 
 constexpr int kPipeThreads = 288;     // 8 compute warps + the exchange warp
 
 // `chunk` is the chunk's index in TIME order; with REV (time runs against memory order) it sits at the mirrored place in memory.
-template <bool TAIL, bool SP, bool REV>
+// F1 (delta on the fly, dt_rank 1; include/vmasr_b200.h): no delta row is copied in.  While the tile loads, the second half
+// of every stage is free (it only receives Y1 at the end of P1), so the dt row, B and C arrive in the second halves of stages
+// 0, 1, 2 and EVERY u row is requested at kernel start (no borrowed stage).  P1(j) finds the dt row in the second half of
+// stage j, forms delta = w_j * row in registers, and before its own Y1 overwrites the row hands it down to stage j + 1 (a
+// thread only ever touches its own 32 bytes of a row, so the hand-down needs no synchronisation).
+template <bool TAIL, bool SP, bool REV, bool F1>
 __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const TileMaps &tm, unsigned char *smem, const int chunk, const int rg) {
     constexpr int NC = 256, ITEMS = 8, WPR = 8, SEG = NC * ITEMS, STAGES = kPipeStages;
 
@@ -48,7 +53,8 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
     float *s_in = reinterpret_cast<float *>(smem + 512);                          // [STAGES][8] state entering each warp
     float *s_par = reinterpret_cast<float *>(smem + 1024);                        // [3][STAGES]
     float *s_stage = reinterpret_cast<float *>(smem + 2048);                      // [STAGES][2][SEG]
-    float *s_bc = s_stage + (size_t)(STAGES - 1) * 2 * SEG;                       // B, C: borrowed from the last stage
+    float *s_bc = s_stage + (size_t)(STAGES - 1) * 2 * SEG;                       // B, C: borrowed from the last stage (not F1)
+    auto y1_slot = [&](int st) { return s_stage + (size_t)st * 2 * SEG + SEG; };  // second half of stage st
     float2 *s_exc = reinterpret_cast<float2 *>(s_stage + (size_t)STAGES * 2 * SEG);  // [STAGES][NC] warp-exclusive prefix of every thread
 
     const int ctile = rg % a.n_ctiles;
@@ -74,6 +80,12 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
         tensor_load(dst, &tm.u, line0, d0 + it, b, &bar_full[it]);
         tensor_load(dst + SEG, &tm.delta, line0, d0 + it, b, &bar_full[it]);
     };
+    if (threadIdx.x == 0) {
+        VMASR_TL(a, 0);
+#ifdef VMASR_TUNING
+        if (a.timeline) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); a.timeline[(size_t)blockIdx.x * 16 + 15] = sm_; }
+#endif
+    }
     // the bulk copies go out first: they do not depend on the per-channel parameters staged below
     if (threadIdx.x == NC) {
 #pragma unroll
@@ -85,29 +97,44 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
         }
         mbar_init(bar_free, WPR);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar_bc, 2u * seg_bytes);
-        tensor_load(s_bc, &tm.B, line0, g, b, bar_bc);
-        tensor_load(s_bc + SEG, &tm.C, line0, g, b, bar_bc);
+        if (F1) {
+            mbar_expect_tx(bar_bc, 3u * seg_bytes);
+            tensor_load(y1_slot(0), &tm.delta, line0, g, b, bar_bc);  // dt row of this group (dt_rank 1: row index = group)
+            tensor_load(y1_slot(1), &tm.B, line0, g, b, bar_bc);
+            tensor_load(y1_slot(2), &tm.C, line0, g, b, bar_bc);
 #pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s)
-            if (s < n_iter) issue_stage(s);
+            for (int s = 0; s < STAGES; ++s)
+                if (s < n_iter) {
+                    mbar_expect_tx(&bar_full[s], seg_bytes);
+                    tensor_load(s_stage + (size_t)s * 2 * SEG, &tm.u, line0, d0 + s, b, &bar_full[s]);
+                }
+        } else {
+            mbar_expect_tx(bar_bc, 2u * seg_bytes);
+            tensor_load(s_bc, &tm.B, line0, g, b, bar_bc);
+            tensor_load(s_bc + SEG, &tm.C, line0, g, b, bar_bc);
+#pragma unroll
+            for (int s = 0; s < STAGES - 1; ++s)
+                if (s < n_iter) issue_stage(s);
+        }
     }
     const unsigned epoch = *reinterpret_cast<volatile unsigned *>(a.ws_header + 2) % 0xfffffffeu + 1u;
-    if (threadIdx.x < 3 * n_iter) {
+    if (threadIdx.x < (F1 ? 4 : 3) * n_iter) {
         const int which = threadIdx.x / n_iter, cc = threadIdx.x - which * n_iter;
         const int d = d0 + cc;
         float v;
         if (which == 0) v = __ldg(a.A + d * a.A_ds);
         else if (which == 1) v = a.D ? __ldg(a.D + d) : 0.0f;
-        else v = (a.delta_bias ? __ldg(a.delta_bias + d) : 0.0f) * kLog2e;
+        else if (which == 2) v = (a.delta_bias ? __ldg(a.delta_bias + d) : 0.0f) * kLog2e;
+        else v = __ldg(a.dt_w + d * a.dtw_ds) * kLog2e;  // dt weight (rank 1), log2 domain like the bias
         s_par[which * STAGES + cc] = v;
     }
     __syncthreads();
+    if (threadIdx.x == 0) VMASR_TL(a, 1);
 
     const long long seq0 = (long long)b * a.dim + d0;  // (batch, channel) row of the tile's first channel
     if (exchange) {
         // ================= exchange warp =================
-        if (STAGES - 1 < n_iter) {
+        if (!F1 && STAGES - 1 < n_iter) {
             mbar_wait(bar_free, 0);  // the compute warps hold B / C in registers: the last stage is free for data now
             if (lane == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -147,6 +174,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
             const long long seq = seq0 + j;
             CarryEntry *l1_row = a.ws_entries + seq * a.n_chunks;
             mbar_wait(&bar_tot[j], 0);
+            if (lane == 0) VMASR_TL(a, j == 0 ? 8 : 9);
             const float2 t = (lane < WPR) ? s_tot[j * WPR + lane] : make_float2(1.0f, 0.0f);
             const Aff cum = warp_scan_up_fast<WPR>(Aff{t.x, t.y});
             if (lane == WPR - 1) publish_entry(l1_row + chunk, epoch, cum.p, cum.q);
@@ -156,6 +184,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
             p_cum = cum;
         }
         finish(n_iter - 1, p_look, p_cum);
+        if (lane == 0) VMASR_TL(a, 10);
         // last CTA out recycles the carry workspace for the next launch on this stream (only this warp wrote entries)
         if (lane == 0) {
             __threadfence();
@@ -178,10 +207,13 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
 
         float2 Bl[4], Cv[4];  // ln2 * B (the scan runs on dt in the log2 domain) and C of this thread's positions
         mbar_wait(bar_bc, 0);
-        lds8_priv(s_bc + slot, sel, Bl);
-        lds8_priv(s_bc + SEG + slot, sel, Cv);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_free);
+        if (threadIdx.x == 0) VMASR_TL(a, 2);
+        lds8_priv((F1 ? y1_slot(1) : s_bc) + slot, sel, Bl);
+        lds8_priv((F1 ? y1_slot(2) : s_bc + SEG) + slot, sel, Cv);
+        if (!F1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_free);
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             Bl[k] = mul2(Bl[k], f2(kLn2));
@@ -200,9 +232,15 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
                 const float bias2 = s_par[2 * STAGES + j];
                 float *su = s_stage + (size_t)j * 2 * SEG + slot;
                 mbar_wait(&bar_full[j], 0);
+                if (threadIdx.x == 0 && j == 0) VMASR_TL(a, 3);
                 float2 uv[4], dl[4], Y0[4], Y1[4];
                 lds8_priv(su, sel, uv);
-                lds8_priv(su + SEG, sel, dl);
+                lds8_priv(su + SEG, sel, dl);  // delta, or (F1) the dt row
+                float wdt = kLog2e;
+                if (F1) {
+                    wdt = s_par[3 * STAGES + j];
+                    if (j + 1 < n_iter) sts8_priv(su + 2 * SEG + SEG, sel, dl);  // hand the row down to stage j + 1
+                }
                 float p = 1.0f, q = 0.0f;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
@@ -211,7 +249,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
                         if (2 * k >= nvalid) { uv[k].x = 0.0f; dl[k].x = 0.0f; }
                         if (2 * k + 1 >= nvalid) { uv[k].y = 0.0f; dl[k].y = 0.0f; }
                     }
-                    float2 dt2 = fma2(dl[k], f2(kLog2e), f2(bias2));
+                    float2 dt2 = fma2(dl[k], f2(wdt), f2(bias2));
                     if (SP) {
                         float2 e, sp;
                         dt2 = softplus2_pair(dt2, e, sp);
@@ -239,6 +277,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
                 if (lane == 31) mbar_arrive(&bar_tot[j]);
             }
         }
+        if (threadIdx.x == 0) VMASR_TL(a, 4);
 #pragma unroll 1
         for (int j = 0; j < n_iter; ++j) {
             {
@@ -249,6 +288,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
                 float2 old[4];
                 if (addm && (!TAIL || nvalid == ITEMS)) ldg8(o, old);  // in flight while this warp waits for its entering state
                 mbar_wait(&bar_in[j], 0);
+                if (threadIdx.x == 0) VMASR_TL(a, j == 0 ? 5 : 6);
                 const float h_in = fmaf(ex.p, s_in[j * WPR + warp], ex.q);
                 const float *sy = s_stage + (size_t)j * 2 * SEG + slot;
                 float2 Y0[4], Y1[4], y[4];
@@ -280,11 +320,12 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
                 }
             }
         }
+        if (threadIdx.x == 0) VMASR_TL(a, 7);
     }
 
 }
 
-template <bool SP>
+template <bool SP, bool F1>
 __global__ void __launch_bounds__(kPipeThreads, 3) scan_fwd_pipe_kernel(const __grid_constant__ GroupArgs ga) {
     extern __shared__ __align__(1024) unsigned char smem_fwd_pipe[];  // swizzled tiles need 512-byte aligned slots
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
@@ -298,32 +339,35 @@ __global__ void __launch_bounds__(kPipeThreads, 3) scan_fwd_pipe_kernel(const __
     const int mchunk = a.rev ? a.n_chunks - 1 - chunk : chunk;
     const bool tail = (mchunk + 1) * 2048 > a.seqlen;
     if (a.rev) {
-        if (tail) scan_fwd_pipe_body<true, SP, true>(a, tm, smem_fwd_pipe, chunk, rg);
-        else scan_fwd_pipe_body<false, SP, true>(a, tm, smem_fwd_pipe, chunk, rg);
+        if (tail) scan_fwd_pipe_body<true, SP, true, F1>(a, tm, smem_fwd_pipe, chunk, rg);
+        else scan_fwd_pipe_body<false, SP, true, F1>(a, tm, smem_fwd_pipe, chunk, rg);
     } else {
-        if (tail) scan_fwd_pipe_body<true, SP, false>(a, tm, smem_fwd_pipe, chunk, rg);
-        else scan_fwd_pipe_body<false, SP, false>(a, tm, smem_fwd_pipe, chunk, rg);
+        if (tail) scan_fwd_pipe_body<true, SP, false, F1>(a, tm, smem_fwd_pipe, chunk, rg);
+        else scan_fwd_pipe_body<false, SP, false, F1>(a, tm, smem_fwd_pipe, chunk, rg);
     }
 }
 
-template <bool SP>
+template <bool SP, bool F1>
 static int launch_fwd_pipe(const GroupArgs &ga, int grid, cudaStream_t stream) {
     const size_t smem = 2048 + sizeof(float) * ((size_t)kPipeStages * 2 * 2048) + sizeof(float2) * kPipeStages * 256;
     static PerDeviceOnce configured;  // the attribute is per function and per device
     if (!configured()) {
-        if (int rc = check_cuda(cudaFuncSetAttribute(scan_fwd_pipe_kernel<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        if (int rc = check_cuda(cudaFuncSetAttribute(scan_fwd_pipe_kernel<SP, F1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "scan_fwd_pipe smem attribute"))
             return rc;
         configured() = true;
     }
-    return launch_pdl(scan_fwd_pipe_kernel<SP>, grid, kPipeThreads, smem, stream, "scan_fwd_pipe launch", ga);
+    return launch_pdl(scan_fwd_pipe_kernel<SP, F1>, grid, kPipeThreads, smem, stream, "scan_fwd_pipe launch", ga);
 }
 
 // every problem: n_chunks > 1, at most kPipeStages channels per tile, same softplus flag (scan_host.cu groups them so)
 int scan_fwd_pipe_dispatch(const GroupArgs &ga, int grid, cudaStream_t stream) {
     for (int i = 0; i < ga.n; ++i)
         if (ga.a[i].chan_per_tile > kPipeStages) return fail("scan_fwd_pipe: %d channels per tile (max %d)", ga.a[i].chan_per_tile, kPipeStages);
-    return ga.a[0].softplus ? launch_fwd_pipe<true>(ga, grid, stream) : launch_fwd_pipe<false>(ga, grid, stream);
+    for (int i = 0; i < ga.n; ++i)
+        if ((ga.a[i].dt_rank > 0) != (ga.a[0].dt_rank > 0) || ga.a[i].dt_rank > 1) return fail("scan_fwd_pipe: mixed or unsupported dt_rank in one launch");
+    if (ga.a[0].dt_rank > 0) return ga.a[0].softplus ? launch_fwd_pipe<true, true>(ga, grid, stream) : launch_fwd_pipe<false, true>(ga, grid, stream);
+    return ga.a[0].softplus ? launch_fwd_pipe<true, false>(ga, grid, stream) : launch_fwd_pipe<false, false>(ga, grid, stream);
 }
 
 }  // namespace vmasr

@@ -55,7 +55,11 @@ static int make_tile_map(CUtensorMap *tm, const void *base, long long len, long 
 static int make_tile_maps(TileMaps &tm, const vmasr_scan_params *p, bool bwd, int box_lines) {
     const long long L = p->seqlen;
     if (int rc = make_tile_map(&tm.u, p->u, L, p->dim, p->u_d_stride, p->batch, p->u_batch_stride, box_lines, "u")) return rc;
-    if (int rc = make_tile_map(&tm.delta, p->delta, L, p->dim, p->delta_d_stride, p->batch, p->delta_batch_stride, box_lines, "delta")) return rc;
+    if (p->dt_rank > 0) {
+        if (int rc = make_tile_map(&tm.delta, p->dt_rows, L, (long long)p->ngroups * p->dt_rank, p->dt_rows_row_stride, p->batch, p->dt_rows_batch_stride,
+                                   box_lines, "dt_rows"))
+            return rc;
+    } else if (int rc = make_tile_map(&tm.delta, p->delta, L, p->dim, p->delta_d_stride, p->batch, p->delta_batch_stride, box_lines, "delta")) return rc;
     if (int rc = make_tile_map(&tm.B, p->B, L, p->ngroups, p->B_group_stride, p->batch, p->B_batch_stride, box_lines, "B")) return rc;
     if (int rc = make_tile_map(&tm.C, p->C, L, p->ngroups, p->C_group_stride, p->batch, p->C_batch_stride, box_lines, "C")) return rc;
     if (bwd)
@@ -76,10 +80,15 @@ static int validate(const vmasr_scan_params *p, bool bwd) {
     if (p->dstate > 256) return fail("selective_scan only supports state dimension <= 256");
     if (p->flags & ~(VMASR_SCAN_REVERSE | VMASR_SCAN_ACCUMULATE | VMASR_SCAN_ADD)) return fail("selective_scan: unknown flag bits 0x%x", p->flags);
     if ((p->flags & VMASR_SCAN_ACCUMULATE) && (p->flags & VMASR_SCAN_ADD)) return fail("selective_scan: VMASR_SCAN_ACCUMULATE and VMASR_SCAN_ADD exclude each other");
-    if (!p->u || !p->delta || !p->A || !p->B || !p->C) return fail("selective_scan: u, delta, A, B, C must be non-null");
+    if (p->dt_rank < 0) return fail("selective_scan: dt_rank must not be negative");
+    if (!p->u || (!p->delta && p->dt_rank == 0) || !p->A || !p->B || !p->C) return fail("selective_scan: u, delta, A, B, C must be non-null");
+    if (p->dt_rank > 0) {
+        if (!p->dt_rows || !p->dt_weight) return fail("selective_scan: dt_rows and dt_weight must be non-null when dt_rank > 0");
+        if (bwd && (!p->d_dt_rows || !p->d_dt_weight)) return fail("selective_scan_bwd: d_dt_rows and d_dt_weight must be non-null when dt_rank > 0");
+    }
     if (!bwd && (!p->out || !p->x)) return fail("selective_scan_fwd: out and x must be non-null");
     if (bwd) {
-        if (!p->dout || !p->du || !p->ddelta || !p->dA || !p->dB || !p->dC)
+        if (!p->dout || !p->du || (!p->ddelta && p->dt_rank == 0) || !p->dA || !p->dB || !p->dC)
             return fail("selective_scan_bwd: dout, du, ddelta, dA, dB, dC must be non-null");
         if ((p->D != nullptr) != (p->dD != nullptr)) return fail("selective_scan_bwd: dD must be given exactly when D is");
         if ((p->delta_bias != nullptr) != (p->ddelta_bias != nullptr))
@@ -109,6 +118,7 @@ static int plan_channels(const vmasr_scan_params *p, int n_chunks, bool bwd, int
     if (n_chunks > 1) {
         int cap = kMultiChunkTileChannels;
         if (const char *e = tuning_env(bwd ? "VMASR_SCAN_CPT" : "VMASR_SCAN_CPT_FWD")) cap = atoi(e) < 1 ? 1 : atoi(e) > 4 ? 4 : atoi(e);
+        if (bwd && p->dt_rank > 0 && cap > 3) cap = 3;  // the fourth stage of the resident tile keeps the dt row (scan_bwd_pipe.cu)
         return cpg < cap ? cpg : cap;
     }
     const long long base_tiles = (long long)p->batch * p->ngroups * (peers < 1 ? 1 : peers);
@@ -154,8 +164,10 @@ static ScanPlan make_plan(const vmasr_scan_params *p, int n_chunks, bool bwd, in
     const size_t es = dtype_size(p->io_dtype);
     const long long vec_elems = 16 / (long long)es;
     auto mult = [&](long long s) { return s % vec_elems == 0; };
-    pl.vec = (L % vec_elems == 0) && aligned16(p->u) && aligned16(p->delta) && aligned16(p->B) && aligned16(p->C) &&
-             mult(p->u_batch_stride) && mult(p->u_d_stride) && mult(p->delta_batch_stride) && mult(p->delta_d_stride) &&
+    const bool delta_ok = p->dt_rank > 0 ? (aligned16(p->dt_rows) && mult(p->dt_rows_batch_stride) && mult(p->dt_rows_row_stride))
+                                         : (aligned16(p->delta) && mult(p->delta_batch_stride) && mult(p->delta_d_stride));
+    pl.vec = (L % vec_elems == 0) && aligned16(p->u) && delta_ok && aligned16(p->B) && aligned16(p->C) &&
+             mult(p->u_batch_stride) && mult(p->u_d_stride) &&
              mult(p->B_batch_stride) && mult(p->B_group_stride) && mult(p->B_dstate_stride) && mult(p->C_batch_stride) &&
              mult(p->C_group_stride) && mult(p->C_dstate_stride);
     return pl;
@@ -185,6 +197,9 @@ static ScanArgs make_args(const vmasr_scan_params *p, int n_chunks, int chan_per
     a.accum = (p->flags & VMASR_SCAN_ACCUMULATE) ? 1 : (p->flags & VMASR_SCAN_ADD) ? 2 : 0;
     const char *nowait = tuning_env("VMASR_DEBUG_NOWAIT");
     a.debug_nowait = nowait ? atoi(nowait) : 0;
+#ifdef VMASR_TUNING
+    a.timeline = debug_timeline();
+#endif
     a.u_bs = p->u_batch_stride; a.u_ds = p->u_d_stride;
     a.delta_bs = p->delta_batch_stride; a.delta_ds = p->delta_d_stride;
     a.A_ds = p->A_d_stride; a.A_ns = p->A_dstate_stride;
@@ -194,6 +209,11 @@ static ScanArgs make_args(const vmasr_scan_params *p, int n_chunks, int chan_per
     a.dout_bs = p->dout_batch_stride; a.dout_ds = p->dout_d_stride;
     a.du_bs = p->du_batch_stride; a.du_ds = p->du_d_stride;
     a.ddelta_bs = p->ddelta_batch_stride; a.ddelta_ds = p->ddelta_d_stride;
+    a.dt_rank = p->dt_rank;
+    a.dt_w = p->dt_weight; a.d_dt_rows = p->d_dt_rows; a.d_dt_w = p->d_dt_weight;
+    a.dtr_bs = p->dt_rows_batch_stride; a.dtr_rs = p->dt_rows_row_stride; a.dtw_ds = p->dt_weight_d_stride;
+    a.dB_bs = p->dB_batch_stride ? p->dB_batch_stride : (long long)p->ngroups * p->dstate * p->seqlen;
+    a.dC_bs = p->dC_batch_stride ? p->dC_batch_stride : (long long)p->ngroups * p->dstate * p->seqlen;
     return a;
 }
 
@@ -212,9 +232,10 @@ static int decide(const vmasr_scan_params *p, bool bwd, int peers, ScanPlan &pl,
     if (!bwd) {
         pl.vec = pl.vec && aligned16(p->out) && mult(p->out_batch_stride) && mult(p->out_d_stride);
     } else {
-        pl.vec = pl.vec && aligned16(p->dout) && aligned16(p->du) && aligned16(p->ddelta) && aligned16(p->dB) &&
+        const bool ddelta_ok = p->dt_rank > 0 ? aligned16(p->d_dt_rows) : (aligned16(p->ddelta) && mult(p->ddelta_batch_stride) && mult(p->ddelta_d_stride));
+        pl.vec = pl.vec && aligned16(p->dout) && aligned16(p->du) && ddelta_ok && aligned16(p->dB) &&
                  aligned16(p->dC) && mult(p->dout_batch_stride) && mult(p->dout_d_stride) && mult(p->du_batch_stride) &&
-                 mult(p->du_d_stride) && mult(p->ddelta_batch_stride) && mult(p->ddelta_d_stride) && (p->seqlen % 4 == 0);
+                 mult(p->du_d_stride) && mult(p->dB_batch_stride) && mult(p->dC_batch_stride) && (p->seqlen % 4 == 0);
     }
     // the fast kernels stage rows through TMA descriptors whose lines are 16 floats (64-byte swizzle, scan.cuh)
     pl.vec = pl.vec && (p->seqlen % kTileLine == 0);
@@ -226,6 +247,10 @@ static int decide(const vmasr_scan_params *p, bool bwd, int peers, ScanPlan &pl,
     if (!fast || force == 'g') variant = kGeneric;
     else if (n_chunks > 1 && !(force == 't' && p->flags == 0)) variant = kMultiChunk;
     else variant = kSingleChunk;
+    if (p->dt_rank > 0 && (variant != kMultiChunk || p->dt_rank != 1))
+        return fail("selective_scan: delta on the fly (dt_rank %d) needs dt_rank 1 on the multi-chunk fast path (float32, d_state 1, seqlen > %d and a "
+                    "multiple of 16, 16-byte aligned rows and strides)", p->dt_rank, VMASR_SCAN_CHUNK);
+    if (p->dB_batch_stride != 0 && variant == kGeneric) return fail("selective_scan: dB / dC batch strides need the fast path");
     if (variant == kGeneric && p->flags != 0)
         return fail("selective_scan: VMASR_SCAN_REVERSE / _ACCUMULATE / _ADD need the fast path (float32, d_state 1, seqlen a multiple of 16, "
                     "16-byte aligned rows and strides)");
@@ -236,7 +261,8 @@ static int decide(const vmasr_scan_params *p, bool bwd, int peers, ScanPlan &pl,
 static long long launch_key(int variant, const ScanArgs &a, const ScanPlan &pl, bool bwd) {
     long long k = variant * 1000 + (a.softplus ? 500 : 0);
     if (variant == kSingleChunk) k += pl.tpr;
-    if (variant == kMultiChunk && bwd) k += (a.chan_per_tile <= 3) ? 1 : 2;
+    if (variant == kMultiChunk && bwd) k += (a.dt_rank > 0) ? 3 : (a.chan_per_tile <= 3) ? 1 : 2;
+    if (variant == kMultiChunk && !bwd && a.dt_rank > 0) k += 3;
     return k;
 }
 
