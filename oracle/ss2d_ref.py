@@ -183,14 +183,16 @@ def selective_scan_bwd(u, delta, A, B, C, D, delta_bias, delta_softplus, dout, d
 # ----------------------------------------------------------------------------------------------
 # the SS2D core chain the way SS2D.forward_corev2 strings it together (vmamba.py:1472-1497)
 # ----------------------------------------------------------------------------------------------
-def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, dtype=torch.float32):
-    """x: (B, C, H, W) -> y: (B, C, H*W).  CrossScan -> two einsums -> scan -> CrossMerge."""
+def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, dtype=torch.float32, x_proj_bias=None):
+    """x: (B, C, H, W) -> y: (B, C, H*W).  CrossScan -> two einsums -> scan -> CrossMerge (x_proj_bias: vmamba.py:1474-1475)."""
     Bsz, C, H, W = x.shape
     K, _, R = dt_projs_weight.shape
     N = A_logs.shape[1]
     L = H * W
     xs = cross_scan(x)
     x_dbl = torch.einsum("bkdl,kcd->bkcl", xs, x_proj_weight)
+    if x_proj_bias is not None:
+        x_dbl = x_dbl + x_proj_bias.view(1, K, -1, 1)
     dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
     dts = torch.einsum("bkrl,kdr->bkdl", dts, dt_projs_weight)
     As = -torch.exp(A_logs.float())

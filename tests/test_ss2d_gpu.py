@@ -240,3 +240,103 @@ def test_fused_core_rejects_unsupported_maps():
         ss2d.ss2d_core(x, *prm, fused=True)
     y = ss2d.ss2d_core(x, *prm)  # falls back to the chain of this library's operators
     assert y.shape == (1, 2, 60)
+
+
+# ---- delta generated inside the scan kernels (vmamba.py:1476-1477) --------------------------------------------
+# maps of more than one chunk with dt_rank 1: ragged last chunk (72x64, 100x84), 2 / 3 / 7 / 16 channels (tiles of 2, 3, 3+3+1 and
+# 5x3+1 channels), and the three largest maps of the 48 kHz config (R = 1 wherever L >= 16384) + the largest of all
+PROJ_MAPS = [(2, 2, 64, 48), (1, 3, 72, 64), (2, 16, 64, 80), (1, 7, 100, 84), (4, 2, 512, 512), (4, 16, 256, 256), (4, 32, 128, 128),
+             (8, 2, 1024, 512)]
+
+
+@pytest.mark.parametrize("Bsz,C,H,W", PROJ_MAPS)
+def test_projected_core_matches_materialised_delta(Bsz, C, H, W):
+    """ss2d_core with the dt projection inside the kernels (x_dbl and dt_projs_weight handed to vmasr_ss2d_core_*) against the
+    same fused core fed a materialised delta, outputs and the gradients of the map and of every parameter; small maps also
+    against the float64 torch oracle of forward_corev2."""
+    from vm_asr_b200 import ss2d
+    names = ("x", "xw", "dw", "db", "A_logs", "Ds")
+    vals = (torch.randn(Bsz, C, H, W, generator=torch.Generator().manual_seed(15)),) + _core_params(C, 1, seed=16)
+    xb = 0.2 * torch.randn(4, 3, generator=torch.Generator().manual_seed(17))
+    dy = torch.randn(Bsz, C, H * W, generator=torch.Generator().manual_seed(18))
+    runs = {}
+    for projected in (True, False):
+        ins = [v.cuda().requires_grad_() for v in vals]
+        bias = xb.cuda().requires_grad_()
+        y = ss2d.ss2d_core(*ins, x_proj_bias=bias, fused=True, projected=projected)
+        y.backward(dy.cuda())
+        runs[projected] = (y, ins + [bias])
+    assert rel_err(runs[True][0], runs[False][0]) < 2e-5
+    for n, g, c in zip(names + ("x_proj_bias",), runs[True][1], runs[False][1]):
+        assert rel_err(g.grad, c.grad) < 1e-4, (n, rel_err(g.grad, c.grad))
+    if Bsz * C * H * W <= 1 << 17:
+        ref_in = [v.double().requires_grad_() for v in vals]
+        rb = xb.double().requires_grad_()
+        ref = ss2d_ref.ss2d_core(*ref_in, x_proj_bias=rb, dtype=torch.float64)
+        ref.backward(dy.double())
+        assert rel_err(runs[True][0], ref) < 2e-4
+        for n, g, r in zip(names + ("x_proj_bias",), runs[True][1], ref_in + [rb]):
+            assert rel_err(g.grad, r.grad) < 5e-4, n
+
+
+def test_projected_pair_and_activation_memory():
+    """Both streams' cores in one grid in the projected form equal two single calls bit for bit; and the projected form never
+    allocates a (B, 4C, L) delta: the forward's extra memory stays below the map-sized buffers it needs (x^T, y, two planes)
+    plus the 12 rows of x_dbl."""
+    from vm_asr_b200 import ss2d
+    Bsz, C, H, W = 2, 16, 128, 128
+    maps = [torch.randn(Bsz, C, H, W, generator=torch.Generator().manual_seed(s)).cuda() for s in (21, 22)]
+    prms = [[t.cuda() for t in _core_params(C, 1, seed=s)] for s in (23, 24)]
+    singles = [ss2d.ss2d_core(x, *p, projected=True) for x, p in zip(maps, prms)]
+    pair = ss2d.ss2d_core_pair(maps[0], prms[0], maps[1], prms[1])
+    for a, b in zip(singles, pair):
+        assert torch.equal(a, b)
+    map_bytes = Bsz * C * H * W * 4
+    del singles, pair
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    with torch.no_grad():
+        y = ss2d.ss2d_core(maps[0], *prms[0], projected=True)
+    torch.cuda.synchronize()
+    peak = torch.cuda.max_memory_allocated() - base
+    assert peak < (4 + 12 / C + 0.5) * map_bytes, peak / map_bytes   # a materialised delta alone is 4 map sizes more
+    assert y.shape == (Bsz, C, H * W)
+
+
+@pytest.mark.parametrize("batch,dim,ngroups,L,rev", [(2, 8, 4, 4096 + 512, False), (1, 12, 2, 3 * 2048, True), (2, 20, 4, 8192 + 16, False)])
+def test_scan_level_projected_form(batch, dim, ngroups, L, rev):
+    """vmasr_scan_fwd / _bwd with dt_rank 1 and several B / C groups (dt row index = group), forward and time-reversed,
+    against the same kernels fed delta = dt_weight * dt_rows: out, chunk states, du, dA, dB, dC, dD, ddelta_bias, and the two
+    factor gradients d_dt_rows = sum_d w_d ddelta_d, d_dt_weight = sum_{b,l} ddelta * row."""
+    from vm_asr_b200 import scan
+    g = torch.Generator().manual_seed(31)
+    cpg = dim // ngroups
+    u = torch.randn(batch, dim, L, generator=g).cuda()
+    rows = (0.5 * torch.randn(batch, ngroups, 1, L, generator=g)).cuda()
+    w = (0.5 * torch.randn(dim, 1, generator=g)).cuda()
+    A = (-0.5 * torch.rand(dim, 1, generator=g)).cuda()
+    Bm, Cm = torch.randn(batch, ngroups, 1, L, generator=g).cuda(), torch.randn(batch, ngroups, 1, L, generator=g).cuda()
+    D, bias = torch.randn(dim, generator=g).cuda(), (0.5 * torch.rand(dim, generator=g)).cuda()
+    dout = torch.randn(batch, dim, L, generator=g).cuda()
+    flags = scan.SCAN_REVERSE if rev else 0
+    delta = (rows[:, :, 0].repeat_interleave(cpg, dim=1) * w.view(1, dim, 1)).contiguous()
+    out_ref = torch.empty_like(u)
+    x_ref = torch.empty(batch, dim, (L + 2047) // 2048, 2, device="cuda")
+    scan.fwd_out(u, delta, A, Bm, Cm, D, bias, True, out_ref, x_ref, flags=flags)
+    out, x = scan.fwd_projected(u, rows, w, A, Bm, Cm, D, bias, True, flags=flags)
+    assert rel_err(out, out_ref) < 2e-5 and rel_err(x, x_ref) < 2e-5
+    du_r, dd_r = torch.empty_like(u), torch.empty_like(u)
+    dA_r, dB_r, dC_r, dD_r, db_r = scan._grad_buffers(u, A, D, bias, (batch, dim, L, 1, ngroups))
+    scan.bwd_out(u, delta, A, Bm, Cm, D, bias, dout, x_ref, True, du_r, dd_r, dA_r, dB_r, dC_r, dD_r, db_r, flags=flags)
+    du, d_rows, d_w, dA, dB, dC, dD, db = scan.bwd_projected(u, rows, w, A, Bm, Cm, D, bias, dout, x, True, flags=flags)
+    d_rows_ref = (dd_r.double() * w.double().view(1, dim, 1)).view(batch, ngroups, cpg, L).sum(2).unsqueeze(2)
+    d_w_ref = (dd_r.double() * rows[:, :, 0].double().repeat_interleave(cpg, dim=1)).sum((0, 2)).view(dim, 1)
+    for name, got, ref, tol in (("du", du, du_r, 1e-4), ("dA", dA, dA_r, 3e-4), ("dB", dB, dB_r, 1e-4), ("dC", dC, dC_r, 1e-4),
+                                ("dD", dD, dD_r, 3e-4), ("dbias", db, db_r, 3e-4), ("d_dt_rows", d_rows, d_rows_ref, 1e-4),
+                                ("d_dt_weight", d_w, d_w_ref, 3e-4)):
+        assert rel_err(got, ref) < tol, (name, rel_err(got, ref))
+    # anything the multi-chunk fast kernels do not take is refused, not silently materialised
+    with pytest.raises(RuntimeError):
+        scan.fwd_projected(u[..., :1024].contiguous(), rows[..., :1024].contiguous(), w, A, Bm[..., :1024].contiguous(),
+                           Cm[..., :1024].contiguous(), D, bias, True)

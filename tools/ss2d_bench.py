@@ -27,6 +27,8 @@ def make_set(B, C, H, W_, dev, gen):
     # the chain's inputs: time-order tensors (values do not matter for timing)
     d["dts4"] = 0.5 * u(B, 4 * C, L)
     d["Bs4"], d["Cs4"] = r(B, 4, 1, L), r(B, 4, 1, L)
+    # the projected form (delta generated inside the kernels): x_dbl rows (dt, B, C) per pair, dt_projs_weight (4, C, 1)
+    d["xd_rm"], d["xd_cm"], d["dt_w"] = 0.5 * r(B, 2, 3, L), 0.5 * r(B, 2, 3, L), 0.5 * r(4, C, 1)
     return d
 
 
@@ -35,6 +37,8 @@ def main():
     ap.add_argument("--workload", default="vm_asr_48k_MPD")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--pair", action="store_true", help="fused: the two streams' cores in one grid (ss2d pair)")
+    ap.add_argument("--projected", action="store_true", help="also time the projected form (dt_rank 1, L > 2048) against the fused "
+                    "core preceded by the dt einsum it replaces")
     ap.add_argument("--only", default="", help="comma-separated d_inner values to run (default: every shape)")
     args = ap.parse_args()
     wl = W.WORKLOADS[args.workload]
@@ -77,6 +81,37 @@ def main():
             ys, ts, dys = fused_f(i, True)
             torch.autograd.grad(ys, ts, dys)
 
+        pnames = ("x", "xd_rm", "xd_cm", "dt_w", "As", "Ds", "bias")
+
+        def proj_f(i, grad=False):
+            d = sets[i]
+            ts = [d[k].requires_grad_(grad) for k in pnames]
+            xT = ss2d.MapTranspose.apply(ts[0])
+            y = ss2d._SS2DScanProj.apply(True, 1, ts[0], xT, *ts[1:])
+            return (y,), ts, (d["dy"],)
+
+        def einsum_f(i, grad=False):  # what the projected form replaces: dts = einsum(dt rows, dt_projs_weight), then the fused core
+            d = sets[i]
+            ts = [d[k].requires_grad_(grad) for k in pnames]
+            xT = ss2d.MapTranspose.apply(ts[0])
+            w = ts[3]
+            dts = [torch.einsum("bkrl,kdr->bkdl", xd[:, :, :1], w[par::2]) for par, xd in ((0, ts[1]), (1, ts[2]))]
+            bc = [xd[:, :, j:j + 1] for j in (1, 2) for xd in (ts[1], ts[2])]
+            y = ss2d._SS2DScan.apply(True, 1, ts[0], xT, dts[0], dts[1], *bc, *ts[4:])
+            return (y,), ts, (d["dy"],)
+
+        def both_of(f):
+            def run(i):
+                ys, ts, dys = f(i, True)
+                torch.autograd.grad(ys, ts, dys)
+            return run
+
+        def fwd_of(f):
+            def run(i):
+                with torch.no_grad():
+                    f(i)
+            return run
+
         def chain_f(i, grad=False):
             d = sets[i]
             ts = [d[k].requires_grad_(grad) for k in ("x", "dts4", "As", "Bs4", "Cs4", "Ds", "bias")]
@@ -104,6 +139,12 @@ def main():
             row[name + "_GBps"] = round(alg / ms / 1e6, 1)
             if name.startswith("fused"):
                 row[name + "_effective_GBps"] = round(eff / ms / 1e6, 1)
+        if args.projected and L > 2048 and L % 16 == 0 and not args.pair:
+            for name, fn in (("proj_fwd", fwd_of(proj_f)), ("proj_fwd_bwd", both_of(proj_f)), ("einsum_fused_fwd", fwd_of(einsum_f)),
+                             ("einsum_fused_fwd_bwd", both_of(einsum_f))):
+                row[name + "_ms"] = round(timeit(fn, args.reps, n_sets), 5)
+            row["proj_speedup_fwd"] = round(row["einsum_fused_fwd_ms"] / row["proj_fwd_ms"], 3)
+            row["proj_speedup_fwd_bwd"] = round(row["einsum_fused_fwd_bwd_ms"] / row["proj_fwd_bwd_ms"], 3)
         row["speedup_fwd"] = round(row["chain_fwd_ms"] / row["fused_fwd_ms"], 3)
         row["speedup_fwd_bwd"] = round(row["chain_fwd_bwd_ms"] / row["fused_fwd_bwd_ms"], 3)
         row["fused_fwd_bwd_frac_of_peak"] = round(row["fused_fwd_bwd_GBps"] / peak, 3)

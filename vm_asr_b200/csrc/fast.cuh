@@ -224,6 +224,23 @@ __device__ __forceinline__ float warp_sum3(float v0, float v1, float v2, int lan
     return k;  // lane bits (4,3): 00 -> slot 0, 01 -> slot 1, 10 -> slot 2, 11 -> slot 3 (zero)
 }
 
+// The same tree with the fourth slot in use: lanes 0, 8, 16, 24 hold the sums of v0 .. v3.
+__device__ __forceinline__ float warp_sum4(float v0, float v1, float v2, float v3, int lane) {
+    const bool hi = lane & 16;
+    const float send0 = hi ? v0 : v2, send1 = hi ? v1 : v3;
+    float k0 = hi ? v2 : v0, k1 = hi ? v3 : v1;
+    k0 += __shfl_xor_sync(0xffffffffu, send0, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, send1, 16);
+    const bool mid = lane & 8;
+    const float send = mid ? k0 : k1;
+    float k = mid ? k1 : k0;
+    k += __shfl_xor_sync(0xffffffffu, send, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    return k;
+}
+
 // named barrier over the `count` threads of one row segment (ids 1..8; id 0 is __syncthreads)
 __device__ __forceinline__ void row_barrier(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");

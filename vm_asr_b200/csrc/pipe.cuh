@@ -149,6 +149,27 @@ __device__ __forceinline__ Aff look_finish(CarryLook &c, Aff acc, bool ok, const
     return acc;
 }
 
+// Epoch tag of this launch (never 0), read once per CTA by the exchange warp, and the recycling of the workspace for the next
+// launch.  A CTA counts itself in `done` right AFTER it has read the epoch (the acquire load orders the two), so the CTA that
+// completes the count knows that every CTA of the launch holds the current epoch and bumps it there and then: entries of this
+// launch keep the old tag and never validate in the next one.  Nothing is left to do at the END of a tile, where a fence and an
+// atomic round trip used to hold the CTA's shared memory for another microsecond; and only one lane waits for the header (the
+// compute warps used to, before their first barrier).  Whole warp; call it after the tile's last bulk copy has been issued.
+__device__ __forceinline__ unsigned launch_epoch(const ScanArgs &a, int lane) {
+    unsigned raw = 0;
+    if (lane == 0) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(raw) : "l"(a.ws_header + 2) : "memory");
+        const unsigned prev = atomicAdd(a.ws_header + 1, 1u);
+        if (prev == (unsigned)(a.n_chunks * a.n_rowgroups) - 1u) {
+            a.ws_header[0] = 0u;
+            a.ws_header[1] = 0u;
+            a.ws_header[2] = raw + 1u;
+        }
+    }
+    raw = __shfl_sync(0xffffffffu, raw, 0);
+    return raw % 0xfffffffeu + 1u;
+}
+
 __device__ __forceinline__ void publish_entry(CarryEntry *e, unsigned tag, float p, float q) {
     asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(e), "r"(__float_as_uint(p)), "r"(tag),
                  "r"(__float_as_uint(q)), "r"(tag)

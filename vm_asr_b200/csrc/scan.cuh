@@ -91,8 +91,9 @@ __device__ __forceinline__ Aff warp_scan_down(Aff v, int lane) {
 // An entry is valid when both tags equal the current tag; 8-byte accesses are single-copy atomic, so a
 // half-written entry can never validate with stale numbers and no fence is needed on either side (the data
 // validates itself, there is no separate flag to order against).  The workspace is zero-filled once; every
-// launch that uses it reads the epoch from the header and the last CTA to finish bumps it, so entries of
-// earlier launches never validate and nothing has to be cleared between launches.  How the entries are
+// launch that uses it reads the epoch from the header and bumps it once every CTA of the launch has read it (the multi-chunk
+// fast kernels: launch_epoch() in pipe.cuh, at the start of a tile; the generic kernels: retire_tile(), at the end), so
+// entries of earlier launches never validate and nothing has to be cleared between launches.  How the entries are
 // organised (one per chunk plus one per group of 16 chunks) and combined is in pipe.cuh.
 struct __align__(16) CarryEntry {
     float p;

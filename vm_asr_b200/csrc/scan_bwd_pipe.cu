@@ -22,6 +22,12 @@
 //                entering the chunk (from the `x` tensor the forward saved);
 //     sweep B    per channel: reduces the look-back, writes the two states entering every warp, arrives on in[j].
 //     Finally it adds the per-channel sums (dA, dD, ddelta_bias) the compute warps left in shared memory to global memory.
+//
+// F1 (delta on the fly, dt_rank 1; include/vmasr_b200.h): no delta rows are read and no ddelta rows are written.  Tiles take
+// at most 3 channels, so the fourth stage is free: the group's dt row arrives there with B (one copy per tile), P1 forms
+// delta = w_j * row in registers, and P2 folds ddelta into the gradients of the two factors -- d_dt_rows += w_j * ddelta
+// accumulated over the tile's channels in a thread-private shared-memory slot (one 128-bit red per 4 positions per tile, like
+// dB / dC), d_dt_weight[j] += sum ddelta * row as a fourth per-channel sum.
 #include <cstdlib>
 
 #include "fast.cuh"
@@ -32,9 +38,8 @@ constexpr int kBPipeStages = 4;        // most channels per tile = resident stag
 constexpr int kBPipeThreads = 288;     // 8 compute warps + the exchange warp
 
 // `chunk` is the chunk's index in TIME order (the forward scan's order); with REV it sits at the mirrored place in memory.
-template <bool TAIL, bool SP, int STAGES, bool REV>
-__device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const TileMaps &tm, unsigned char *smem, const int chunk, const int rg,
-                                                   const unsigned epoch) {
+template <bool TAIL, bool SP, int STAGES, bool REV, bool F1>
+__device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const TileMaps &tm, unsigned char *smem, const int chunk, const int rg) {
     constexpr int NC = 256, ITEMS = 8, WPR = 8, SEG = NC * ITEMS;
 
     // shared memory carve-up (header 2048 bytes)
@@ -46,10 +51,13 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
     float4 *s_tot = reinterpret_cast<float4 *>(smem + 128);                       // [STAGES][8] warp totals {p, q fwd, q adjoint, -}
     float2 *s_in = reinterpret_cast<float2 *>(smem + 640);                        // [STAGES][8] {h, g} entering each warp
     float *s_red = reinterpret_cast<float *>(smem + 896);                         // [STAGES][4] channel sums dA, dD, dbias
-    float *s_par = reinterpret_cast<float *>(smem + 960);                         // [3][4]
+    float *s_par = reinterpret_cast<float *>(smem + 960);                         // [4][4]  A, D, bias * log2 e, (F1) dt weight
     float *s_c = reinterpret_cast<float *>(smem + 2048);                          // [SEG]   C
     float *s_stage = s_c + SEG;                                                   // [STAGES][3][SEG]  u, delta -> dt, dout
     float *s_b = s_stage + (size_t)(STAGES - 1) * 3 * SEG;                        // B: borrowed from the last stage
+    float *s_row = s_b + SEG;                                                     // F1: the dt row (the last stage stays free)
+    float *s_drow = s_b + 2 * SEG;                                                // F1: its gradient, summed over the tile's channels
+    static_assert(!F1 || STAGES == 4, "delta on the fly keeps the dt row in the fourth stage");
 
     const int ctile = rg % a.n_ctiles;
     const int bg = rg / a.n_ctiles;
@@ -70,9 +78,9 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
 
     auto issue_stage = [&](int it) {  // lane 0 of the exchange warp only
         float *dst = s_stage + (size_t)it * 3 * SEG;
-        mbar_expect_tx(&bar_full[it], 3u * seg_bytes);
+        mbar_expect_tx(&bar_full[it], (F1 ? 2u : 3u) * seg_bytes);
         tensor_load(dst, &tm.u, line0, d0 + it, b, &bar_full[it]);
-        tensor_load(dst + SEG, &tm.delta, line0, d0 + it, b, &bar_full[it]);
+        if (!F1) tensor_load(dst + SEG, &tm.delta, line0, d0 + it, b, &bar_full[it]);
         tensor_load(dst + 2 * SEG, &tm.dout, line0, d0 + it, b, &bar_full[it]);
     };
     if (threadIdx.x == 0) {
@@ -92,22 +100,24 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
         }
         mbar_init(bar_done, WPR);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar_bc, 2u * seg_bytes);
+        mbar_expect_tx(bar_bc, (F1 ? 3u : 2u) * seg_bytes);
         tensor_load(s_b, &tm.B, line0, g, b, bar_bc);
         tensor_load(s_c, &tm.C, line0, g, b, bar_bc);
+        if (F1) tensor_load(s_row, &tm.delta, line0, g, b, bar_bc);  // dt_rank 1: row index = group
 #pragma unroll
         for (int s = 0; s < STAGES - 1; ++s)
             if (s < n_iter) issue_stage(s);
     }
     if (threadIdx.x < STAGES * 4) s_red[threadIdx.x] = 0.0f;
-    if (threadIdx.x >= 32 && threadIdx.x < 32 + 3 * n_iter) {
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + (F1 ? 4 : 3) * n_iter) {
         const int i = threadIdx.x - 32;
         const int which = i / n_iter, cc = i - which * n_iter;
         const int d = d0 + cc;
         float v;
         if (which == 0) v = __ldg(a.A + d * a.A_ds);
         else if (which == 1) v = a.D ? __ldg(a.D + d) : 0.0f;
-        else v = (a.delta_bias ? __ldg(a.delta_bias + d) : 0.0f) * kLog2e;
+        else if (which == 2) v = (a.delta_bias ? __ldg(a.delta_bias + d) : 0.0f) * kLog2e;
+        else v = __ldg(a.dt_w + d * a.dtw_ds);
         s_par[which * 4 + cc] = v;
     }
     __syncthreads();
@@ -121,6 +131,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue_stage(STAGES - 1);
         }
+        const unsigned epoch = launch_epoch(a, lane);  // (also recycles the carry workspace for the next launch: pipe.cuh)
         const int n_groups16 = (a.n_chunks + 15) >> 4;
         const int jrev = a.n_chunks - 1 - chunk;  // position of this chunk in the adjoint's scan order
         // per channel: publish the chunk's adjoint aggregate as soon as it exists and start its look-back; finish the
@@ -174,23 +185,15 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
         finish(n_iter - 1, p_look, p_cf, p_cr, p_h);
         if (lane == 0) VMASR_TL(a, 10);
         mbar_wait(bar_done, 0);  // every compute warp is done: the channel sums are complete
-        if (lane < 3 * n_iter) {
-            const int c = lane / 3, which = lane - 3 * c;
-            const float v = s_red[c * 4 + which];
-            const int d = d0 + c;
-            if (which == 0) atomicAdd(a.dA + d * a.A_ds, v);
-            else if (which == 1) { if (a.dD) atomicAdd(a.dD + d, v); }
-            else { if (a.ddelta_bias) atomicAdd(a.ddelta_bias + d, v); }
-        }
-        // last CTA out recycles the carry workspace for the next launch on this stream (only this warp wrote entries)
-        if (lane == 0) {
-            __threadfence();
-            const unsigned prev = atomicAdd(a.ws_header + 1, 1u);
-            if (prev == (unsigned)(a.n_chunks * a.n_rowgroups) - 1u) {
-                a.ws_header[0] = 0u;
-                a.ws_header[1] = 0u;
-                a.ws_header[2] = a.ws_header[2] + 1u;
-                __threadfence();
+        {
+            const int c = lane >> 2, which = lane & 3;
+            if (c < n_iter && which < (F1 ? 4 : 3)) {
+                const float v = s_red[c * 4 + which];
+                const int d = d0 + c;
+                if (which == 0) atomicAdd(a.dA + d * a.A_ds, v);
+                else if (which == 1) { if (a.dD) atomicAdd(a.dD + d, v); }
+                else if (which == 2) { if (a.ddelta_bias) atomicAdd(a.ddelta_bias + d, v); }
+                else atomicAdd(a.d_dt_w + d * a.dtw_ds, v);
             }
         }
     } else {
@@ -202,7 +205,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
         int nvalid = ITEMS;
         if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
         float *du_ptr = reinterpret_cast<float *>(a.du) + b * a.du_bs + (long long)d0 * a.du_ds + pos;
-        float *dd_ptr = reinterpret_cast<float *>(a.ddelta) + b * a.ddelta_bs + (long long)d0 * a.ddelta_ds + pos;
+        float *dd_ptr = F1 ? nullptr : reinterpret_cast<float *>(a.ddelta) + b * a.ddelta_bs + (long long)d0 * a.ddelta_ds + pos;
 
         float2 Bv[4], dBacc[4], dCacc[4];
         float *sC = s_c + slot;  // this thread's C values (only this thread touches them)
@@ -225,6 +228,10 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
             sts8_priv(sC, sel, Cv);
         }
         __syncthreads();  // (also keeps the register allocation of the sweeps below in check: without it ptxas spills 3x more)
+        if (F1) {
+            const float2 zero[4] = {f2(0.0f), f2(0.0f), f2(0.0f), f2(0.0f)};
+            sts8_priv(s_drow + slot, sel, zero);  // thread-private accumulator of d_dt_rows
+        }
 
         Aff excf[STAGES], excr[STAGES];  // registers: only constant indices below
 #pragma unroll
@@ -243,9 +250,10 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
                 if (threadIdx.x == 0 && j == 0) VMASR_TL(a, 3);
                 float2 uv[4], dl[4], dy[4], Cv[4], dts[4];
                 lds8_priv(su, sel, uv);
-                lds8_priv(su + SEG, sel, dl);
+                lds8_priv(F1 ? s_row + slot : su + SEG, sel, dl);  // delta, or (F1) the dt row
                 lds8_priv(su + 2 * SEG, sel, dy);
                 lds8_priv(sC, sel, Cv);
+                const float wdt = F1 ? s_par[3 * 4 + j] * kLog2e : kLog2e;
                 if (TAIL) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -259,7 +267,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     const int k = pair_at<REV>(kk);  // pairs in time order
-                    float2 dt2 = fma2(dl[k], f2(kLog2e), f2(bias2));
+                    float2 dt2 = fma2(dl[k], f2(wdt), f2(bias2));
                     if (SP) {
                         float2 e, sp;
                         dt2 = softplus2_pair(dt2, e, sp);
@@ -309,7 +317,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
                 const float Av = s_par[j];
                 const float Dv = s_par[4 + j];
                 float *o_du = du_ptr + (long long)j * a.du_ds;
-                float *o_dd = dd_ptr + (long long)j * a.ddelta_ds;
+                float *o_dd = F1 ? nullptr : dd_ptr + (long long)j * a.ddelta_ds;
                 mbar_wait(&bar_in[j], 0);
                 if (threadIdx.x == 0) VMASR_TL(a, j == 0 ? 5 : 6);
                 const float2 in = s_in[j * WPR + warp];
@@ -346,7 +354,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
                 }
                 // gradients, position pairs
                 float2 du[4], ddl[4];
-                float2 sA = f2(0.0f), sD = f2(0.0f), sB = f2(0.0f);
+                float2 sA = f2(0.0f), sD = f2(0.0f), sB = f2(0.0f), sW = f2(0.0f);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float2 carried = fma2(mul2(dtn[k], bu[k]), f2(-1.0f), hs[k]);  // a_l h_{l-1}
@@ -378,6 +386,18 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
                     sD = fma2(dy[k], uv[k], sD);
                     sB = add2(sB, ddl[k]);
                 }
+                if (F1) {  // ddelta = w * d(row) and row * d(w): neither is stored per channel
+                    const float w = s_par[3 * 4 + j];
+                    float2 rowv[4], dr[4];
+                    lds8_priv(s_row + slot, sel, rowv);
+                    lds8_priv(s_drow + slot, sel, dr);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        sW = fma2(ddl[k], rowv[k], sW);
+                        dr[k] = fma2(ddl[k], f2(w), dr[k]);
+                    }
+                    sts8_priv(s_drow + slot, sel, dr);
+                }
                 {
                     if (!TAIL || nvalid == ITEMS) {
                         if (accum) {
@@ -391,24 +411,24 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
                             }
                             stg8(o_du, du);
                         }
-                        stg8(o_dd, ddl);
+                        if (!F1) stg8(o_dd, ddl);
                     } else {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             if (2 * k < nvalid) {
                                 if (accum || addm) atomicAdd(o_du + 2 * k, du[k].x); else o_du[2 * k] = du[k].x;
-                                o_dd[2 * k] = ddl[k].x;
+                                if (!F1) o_dd[2 * k] = ddl[k].x;
                             }
                             if (2 * k + 1 < nvalid) {
                                 if (accum || addm) atomicAdd(o_du + 2 * k + 1, du[k].y); else o_du[2 * k + 1] = du[k].y;
-                                o_dd[2 * k + 1] = ddl[k].y;
+                                if (!F1) o_dd[2 * k + 1] = ddl[k].y;
                             }
                         }
                     }
                 }
-                // per-channel sums: dA, dD, ddelta_bias (lanes 0, 8, 16 hold them after the reduction)
-                const float r = warp_sum3(sA.x + sA.y, sD.x + sD.y, sB.x + sB.y, lane);
-                if ((lane & 7) == 0 && lane < 24) atomicAdd(s_red + j * 4 + (lane >> 3), r);
+                // per-channel sums: dA, dD, ddelta_bias, (F1) d_dt_weight (lanes 0, 8, 16, 24 hold them after the reduction)
+                const float r = warp_sum4(sA.x + sA.y, sD.x + sD.y, sB.x + sB.y, sW.x + sW.y, lane);
+                if ((lane & 7) == 0 && lane < (F1 ? 32 : 24)) atomicAdd(s_red + j * 4 + (lane >> 3), r);
             }
         }
         if (threadIdx.x == 0) VMASR_TL(a, 7);
@@ -416,8 +436,22 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
         if (lane == 0) mbar_arrive(bar_done);  // this warp's shared-memory atomics are done (release)
 
         // dB / dC of this tile's positions, summed over the tile's channels
-        float *dBg = a.dB + ((long long)b * a.ngroups + g) * (long long)L;
-        float *dCg = a.dC + ((long long)b * a.ngroups + g) * (long long)L;
+        float *dBg = a.dB + b * a.dB_bs + (long long)g * L;
+        float *dCg = a.dC + b * a.dC_bs + (long long)g * L;
+        if (F1) {
+            float2 dr[4];
+            lds8_priv(s_drow + slot, sel, dr);
+            float *dRg = a.d_dt_rows + b * a.dtr_bs + (long long)g * a.dtr_rs + pos;
+            if (!TAIL || nvalid == ITEMS) {
+                red8(dRg, dr);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (2 * k < nvalid) atomicAdd(dRg + 2 * k, dr[k].x);
+                    if (2 * k + 1 < nvalid) atomicAdd(dRg + 2 * k + 1, dr[k].y);
+                }
+            }
+        }
         if (!TAIL || nvalid == ITEMS) {
             red8(dBg + pos, dBacc);
             red8(dCg + pos, dCacc);
@@ -431,7 +465,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
     }
 }
 
-template <bool SP, int STAGES>
+template <bool SP, int STAGES, bool F1>
 __global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const __grid_constant__ GroupArgs ga) {
     extern __shared__ __align__(1024) unsigned char smem_bwd_pipe[];  // swizzled tiles need 512-byte aligned slots
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
@@ -441,31 +475,30 @@ __global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const _
     const ScanArgs &a = ga.a[prob];
     const TileMaps &tm = ga.tm[prob];
     // adjoint: late chunks first; block order = the adjoint's scan order, so a tile only waits on tiles dispatched before it
-    const unsigned epoch = *reinterpret_cast<volatile unsigned *>(a.ws_header + 2) % 0xfffffffeu + 1u;
     const int chunk = a.n_chunks - 1 - tile / a.n_rowgroups;
     const int rg = tile % a.n_rowgroups;
     const int mchunk = a.rev ? a.n_chunks - 1 - chunk : chunk;
     const bool tail = (mchunk + 1) * 2048 > a.seqlen;
     if (a.rev) {
-        if (tail) scan_bwd_pipe_body<true, SP, STAGES, true>(a, tm, smem_bwd_pipe, chunk, rg, epoch);
-        else scan_bwd_pipe_body<false, SP, STAGES, true>(a, tm, smem_bwd_pipe, chunk, rg, epoch);
+        if (tail) scan_bwd_pipe_body<true, SP, STAGES, true, F1>(a, tm, smem_bwd_pipe, chunk, rg);
+        else scan_bwd_pipe_body<false, SP, STAGES, true, F1>(a, tm, smem_bwd_pipe, chunk, rg);
     } else {
-        if (tail) scan_bwd_pipe_body<true, SP, STAGES, false>(a, tm, smem_bwd_pipe, chunk, rg, epoch);
-        else scan_bwd_pipe_body<false, SP, STAGES, false>(a, tm, smem_bwd_pipe, chunk, rg, epoch);
+        if (tail) scan_bwd_pipe_body<true, SP, STAGES, false, F1>(a, tm, smem_bwd_pipe, chunk, rg);
+        else scan_bwd_pipe_body<false, SP, STAGES, false, F1>(a, tm, smem_bwd_pipe, chunk, rg);
     }
 }
 
-template <bool SP, int STAGES>
+template <bool SP, int STAGES, bool F1>
 static int launch_bwd_pipe(const GroupArgs &ga, int grid, cudaStream_t stream) {
     const size_t smem = 2048 + sizeof(float) * (2048 + (size_t)STAGES * 3 * 2048);
     static PerDeviceOnce configured;  // the attribute is per function and per device
     if (!configured()) {
-        if (int rc = check_cuda(cudaFuncSetAttribute(scan_bwd_pipe_kernel<SP, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        if (int rc = check_cuda(cudaFuncSetAttribute(scan_bwd_pipe_kernel<SP, STAGES, F1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "scan_bwd_pipe smem attribute"))
             return rc;
         configured() = true;
     }
-    return launch_pdl(scan_bwd_pipe_kernel<SP, STAGES>, grid, kBPipeThreads, smem, stream, "scan_bwd_pipe launch", ga);
+    return launch_pdl(scan_bwd_pipe_kernel<SP, STAGES, F1>, grid, kBPipeThreads, smem, stream, "scan_bwd_pipe launch", ga);
 }
 
 // every problem: n_chunks > 1, at most kBPipeStages channels per tile, same softplus flag and the same side of the
@@ -473,9 +506,13 @@ static int launch_bwd_pipe(const GroupArgs &ga, int grid, cudaStream_t stream) {
 int scan_bwd_pipe_dispatch(const GroupArgs &ga, int grid, cudaStream_t stream) {
     for (int i = 0; i < ga.n; ++i)
         if (ga.a[i].chan_per_tile > kBPipeStages) return fail("scan_bwd_pipe: %d channels per tile (max %d)", ga.a[i].chan_per_tile, kBPipeStages);
+    for (int i = 0; i < ga.n; ++i)
+        if ((ga.a[i].dt_rank > 0) != (ga.a[0].dt_rank > 0) || ga.a[i].dt_rank > 1 || (ga.a[i].dt_rank > 0 && ga.a[i].chan_per_tile > 3))
+            return fail("scan_bwd_pipe: mixed or unsupported dt_rank in one launch");
+    if (ga.a[0].dt_rank > 0) return ga.a[0].softplus ? launch_bwd_pipe<true, 4, true>(ga, grid, stream) : launch_bwd_pipe<false, 4, true>(ga, grid, stream);
     if (ga.a[0].chan_per_tile <= 3)  // smaller tile (groups of 2 channels): 82 KB of shared memory, fewer live registers (measured +11 %)
-        return ga.a[0].softplus ? launch_bwd_pipe<true, 3>(ga, grid, stream) : launch_bwd_pipe<false, 3>(ga, grid, stream);
-    return ga.a[0].softplus ? launch_bwd_pipe<true, 4>(ga, grid, stream) : launch_bwd_pipe<false, 4>(ga, grid, stream);
+        return ga.a[0].softplus ? launch_bwd_pipe<true, 3, false>(ga, grid, stream) : launch_bwd_pipe<false, 3, false>(ga, grid, stream);
+    return ga.a[0].softplus ? launch_bwd_pipe<true, 4, false>(ga, grid, stream) : launch_bwd_pipe<false, 4, false>(ga, grid, stream);
 }
 
 }  // namespace vmasr

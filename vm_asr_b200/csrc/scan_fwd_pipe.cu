@@ -117,7 +117,6 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
                 if (s < n_iter) issue_stage(s);
         }
     }
-    const unsigned epoch = *reinterpret_cast<volatile unsigned *>(a.ws_header + 2) % 0xfffffffeu + 1u;
     if (threadIdx.x < (F1 ? 4 : 3) * n_iter) {
         const int which = threadIdx.x / n_iter, cc = threadIdx.x - which * n_iter;
         const int d = d0 + cc;
@@ -141,6 +140,7 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
                 issue_stage(STAGES - 1);
             }
         }
+        const unsigned epoch = launch_epoch(a, lane);  // (also recycles the carry workspace for the next launch: pipe.cuh)
         const int n_groups16 = (a.n_chunks + 15) >> 4;
         // per channel: publish the chunk aggregate as soon as it exists and start its look-back; finish the look-back of the
         // channel before (its loads have been in flight for one P1 of the compute warps)
@@ -185,16 +185,6 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
         }
         finish(n_iter - 1, p_look, p_cum);
         if (lane == 0) VMASR_TL(a, 10);
-        // last CTA out recycles the carry workspace for the next launch on this stream (only this warp wrote entries)
-        if (lane == 0) {
-            __threadfence();
-            const unsigned prev = atomicAdd(a.ws_header + 1, 1u);
-            if (prev == (unsigned)(a.n_chunks * a.n_rowgroups) - 1u) {
-                a.ws_header[1] = 0u;
-                a.ws_header[2] = a.ws_header[2] + 1u;
-                __threadfence();
-            }
-        }
     } else {
         // ================= compute warps =================
         const int tseg = REV ? NC - 1 - (int)threadIdx.x : (int)threadIdx.x;  // this thread's 8-position segment of the tile (memory order)

@@ -16,13 +16,29 @@ static int ss2d_check(const vmasr_ss2d_params *p, bool bwd, const char *who) {
     if (p->batch <= 0 || p->channels <= 0 || p->H <= 0 || p->W <= 0) return fail("%s: sizes must be positive", who);
     if (p->H % 4 || p->W % 4) return fail("%s: H and W must be multiples of 4 (got %d x %d)", who, p->H, p->W);
     if (!p->x || !p->xT || !p->A || !p->planes || !p->states) return fail("%s: x, xT, A, planes, states must be non-null", who);
-    for (int k = 0; k < 4; ++k)
-        if (!p->delta[k] || !p->B[k] || !p->C[k]) return fail("%s: delta / B / C of direction %d missing", who, k);
+    const bool proj = p->dt_rank != 0;  // projected form: delta generated inside the scan kernels from x_dbl and dt_weight
+    if (proj) {
+        if (p->dt_rank != 1 || (long long)p->H * p->W <= VMASR_SCAN_CHUNK)
+            return fail("%s: the projected form needs dt_rank 1 and H * W > %d (got rank %d, %d x %d)", who, VMASR_SCAN_CHUNK, p->dt_rank, p->H, p->W);
+        if (!p->dt_weight) return fail("%s: dt_weight must be non-null in the projected form", who);
+        for (int k = 0; k < 4; ++k)
+            if (!p->x_dbl[k]) return fail("%s: x_dbl of direction %d missing", who, k);
+    } else {
+        for (int k = 0; k < 4; ++k)
+            if (!p->delta[k] || !p->B[k] || !p->C[k]) return fail("%s: delta / B / C of direction %d missing", who, k);
+    }
     if (!bwd && !p->y) return fail("%s: y must be non-null", who);
     if (bwd) {
-        if (!p->dy || !p->dyT || !p->dA || !p->dB || !p->dC) return fail("%s: dy, dyT, dA, dB, dC must be non-null", who);
-        for (int k = 0; k < 4; ++k)
-            if (!p->ddelta[k]) return fail("%s: ddelta of direction %d missing", who, k);
+        if (!p->dy || !p->dyT || !p->dA) return fail("%s: dy, dyT, dA must be non-null", who);
+        if (proj) {
+            if (!p->d_dt_weight) return fail("%s: d_dt_weight must be non-null in the projected form", who);
+            for (int k = 0; k < 4; ++k)
+                if (!p->d_x_dbl[k]) return fail("%s: d_x_dbl of direction %d missing", who, k);
+        } else {
+            if (!p->dB || !p->dC) return fail("%s: dB, dC must be non-null", who);
+            for (int k = 0; k < 4; ++k)
+                if (!p->ddelta[k]) return fail("%s: ddelta of direction %d missing", who, k);
+        }
         if ((p->D != nullptr) != (p->dD != nullptr)) return fail("%s: dD must be given exactly when D is", who);
         if ((p->delta_bias != nullptr) != (p->ddelta_bias != nullptr)) return fail("%s: ddelta_bias must be given exactly when delta_bias is", who);
     }
@@ -52,18 +68,29 @@ static vmasr_scan_params direction(const vmasr_ss2d_params *p, int k, bool bwd, 
     s.u = (k & 1) ? p->xT : p->x;
     s.u_batch_stride = C * L;
     s.u_d_stride = L;
-    s.delta = p->delta[k];
-    s.delta_batch_stride = p->delta_batch_stride[k];
-    s.delta_d_stride = p->delta_d_stride[k];
+    const bool proj = p->dt_rank != 0;
+    const long long R = p->dt_rank, xd_bs = p->x_dbl_batch_stride[k], xd_rs = p->x_dbl_row_stride[k];
+    if (proj) {  // rows 0 .. R-1 of x_dbl[k] feed dt_weight, row R is B, row R + 1 is C (vmamba.py:1476)
+        s.dt_rank = p->dt_rank;
+        s.dt_rows = p->x_dbl[k];
+        s.dt_rows_batch_stride = xd_bs;
+        s.dt_rows_row_stride = xd_rs;
+        s.dt_weight = p->dt_weight + k * C * R;
+        s.dt_weight_d_stride = R;
+    } else {
+        s.delta = p->delta[k];
+        s.delta_batch_stride = p->delta_batch_stride[k];
+        s.delta_d_stride = p->delta_d_stride[k];
+    }
     s.A = p->A + k * C;
     s.A_d_stride = 1;
     s.A_dstate_stride = 1;
-    s.B = p->B[k];
-    s.B_batch_stride = p->B_batch_stride[k];
+    s.B = proj ? p->x_dbl[k] + R * xd_rs : p->B[k];
+    s.B_batch_stride = proj ? xd_bs : p->B_batch_stride[k];
     s.B_group_stride = L;
     s.B_dstate_stride = L;
-    s.C = p->C[k];
-    s.C_batch_stride = p->C_batch_stride[k];
+    s.C = proj ? p->x_dbl[k] + (R + 1) * xd_rs : p->C[k];
+    s.C_batch_stride = proj ? xd_bs : p->C_batch_stride[k];
     s.C_group_stride = L;
     s.C_dstate_stride = L;
     s.D = p->D ? p->D + k * C : nullptr;
@@ -80,12 +107,21 @@ static vmasr_scan_params direction(const vmasr_ss2d_params *p, int k, bool bwd, 
         s.du = plane;
         s.du_batch_stride = C * L;
         s.du_d_stride = L;
-        s.ddelta = p->ddelta[k];
-        s.ddelta_batch_stride = p->ddelta_batch_stride[k];
-        s.ddelta_d_stride = p->ddelta_d_stride[k];
         s.dA = p->dA + k * C;
-        s.dB = p->dB + k * Bz * L;
-        s.dC = p->dC + k * Bz * L;
+        if (proj) {  // d x_dbl[k] has the layout of x_dbl[k]: its rows receive d(dt rows), dB, dC
+            s.d_dt_rows = p->d_x_dbl[k];
+            s.d_dt_weight = p->d_dt_weight + k * C * R;
+            s.dB = p->d_x_dbl[k] + R * xd_rs;
+            s.dC = p->d_x_dbl[k] + (R + 1) * xd_rs;
+            s.dB_batch_stride = xd_bs;
+            s.dC_batch_stride = xd_bs;
+        } else {
+            s.ddelta = p->ddelta[k];
+            s.ddelta_batch_stride = p->ddelta_batch_stride[k];
+            s.ddelta_d_stride = p->ddelta_d_stride[k];
+            s.dB = p->dB + k * Bz * L;
+            s.dC = p->dC + k * Bz * L;
+        }
         s.dD = p->dD ? p->dD + k * C : nullptr;
         s.ddelta_bias = p->ddelta_bias ? p->ddelta_bias + k * C : nullptr;
     }

@@ -247,6 +247,71 @@ def bwd(u, delta, A, B, C, D, delta_bias, dout, x=None, delta_softplus=False, nr
     return [du, ddelta, dA, dB.to(B.dtype), dC.to(C.dtype), dD, dbias]
 
 
+# ---- delta generated inside the kernels (include/vmasr_b200.h, dt_rank > 0) -------------------------------
+def _projected_params(u, dt_rows, dt_weight, A, B, C, D, delta_bias, delta_softplus, flags):
+    """Parameter block of the projected form: ``delta[b, d, l] = dt_weight[d, 0] * dt_rows[b, group(d), 0, l]`` is formed tile
+    by tile inside the multi-chunk fast kernels (vmamba.py:1476-1477 with dt_rank 1); no (batch, dim, seqlen) delta exists."""
+    batch, dim, seqlen, dstate, ngroups = _validate(u, u, A, B, C, D, delta_bias)
+    _check(dt_rows.dtype == torch.float32 and dt_rows.is_cuda and tuple(dt_rows.shape) == (batch, ngroups, 1, seqlen) and dt_rows.stride(-1) == 1,
+           "selective_scan: dt_rows must be float32 CUDA (batch, n_groups, 1, seqlen) with unit stride along seqlen")
+    _check(dt_weight.dtype == torch.float32 and dt_weight.is_cuda and tuple(dt_weight.shape) == (dim, 1),
+           "selective_scan: dt_weight must be float32 CUDA (dim, 1)")
+    p = ScanParams()
+    p.batch, p.dim, p.seqlen, p.dstate, p.ngroups = batch, dim, seqlen, dstate, ngroups
+    p.u, p.A, p.B, p.C = u.data_ptr(), A.data_ptr(), B.data_ptr(), C.data_ptr()
+    p.D, p.delta_bias = _ptr(D), _ptr(delta_bias)
+    p.u_batch_stride, p.u_d_stride = u.stride(0), u.stride(1)
+    p.A_d_stride, p.A_dstate_stride = A.stride(0), A.stride(1)
+    p.B_batch_stride, p.B_group_stride, p.B_dstate_stride = B.stride(0), B.stride(1), B.stride(2)
+    p.C_batch_stride, p.C_group_stride, p.C_dstate_stride = C.stride(0), C.stride(1), C.stride(2)
+    p.dt_rows, p.dt_weight, p.dt_rank = dt_rows.data_ptr(), dt_weight.data_ptr(), 1
+    p.dt_rows_batch_stride, p.dt_rows_row_stride, p.dt_weight_d_stride = dt_rows.stride(0), dt_rows.stride(1), dt_weight.stride(0)
+    p.io_dtype = _lib.DTYPE_CODE[u.dtype]
+    p.delta_softplus = 1 if delta_softplus else 0
+    p.device = u.device.index if u.device.index is not None else torch.cuda.current_device()
+    p.flags = int(flags)
+    p.stream = torch._C._cuda_getCurrentRawStream(p.device)
+    n_chunks = (seqlen + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
+    if n_chunks > 1:
+        ws = _lib.scan_workspace(u.device, int(_lib.load_library().vmasr_scan_workspace_bytes(batch, dim, seqlen, dstate)))
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    return p, (batch, dim, seqlen, dstate, ngroups), n_chunks
+
+
+def fwd_projected(u, dt_rows, dt_weight, A, B, C, D=None, delta_bias=None, delta_softplus=True, flags=0):
+    """Forward with delta generated on the fly.  u (batch, dim, L) float32, dt_rows (batch, n_groups, 1, L), dt_weight (dim, 1);
+    the rest as ``fwd``.  Multi-chunk fast path only (float32, d_state 1, L > 2048 and a multiple of 16): anything else raises
+    and the caller materialises delta.  Returns ``[out, x]``."""
+    p, (batch, dim, seqlen, dstate, _), n_chunks = _projected_params(u, dt_rows, dt_weight, A, B, C, D, delta_bias, delta_softplus, flags)
+    out = torch.zeros_like(u) if flags & (_lib.SCAN_ACCUMULATE | 4) else torch.empty_like(u)
+    x = torch.empty((batch, dim, n_chunks, 2 * dstate), dtype=torch.float32, device=u.device)
+    p.out, p.x = out.data_ptr(), x.data_ptr()
+    p.out_batch_stride, p.out_d_stride = out.stride(0), out.stride(1)
+    with _device_of(u):
+        _lib.check(_lib.load_library().vmasr_scan_fwd(ctypes.byref(p)))
+    return [out, x]
+
+
+def bwd_projected(u, dt_rows, dt_weight, A, B, C, D, delta_bias, dout, x, delta_softplus=True, flags=0):
+    """Backward of ``fwd_projected``: returns ``[du, d_dt_rows, d_dt_weight, dA, dB, dC, dD, ddelta_bias]`` -- the gradients
+    of the two factors of delta instead of a (batch, dim, L) ddelta."""
+    p, dims, n_chunks = _projected_params(u, dt_rows, dt_weight, A, B, C, D, delta_bias, delta_softplus, flags)
+    _check(tuple(dout.shape) == tuple(u.shape) and dout.dtype == u.dtype and dout.stride(-1) == 1, "selective_scan: dout must look like u")
+    du = torch.empty_like(u)
+    d_rows = torch.zeros_like(dt_rows, memory_format=torch.contiguous_format)
+    _check(d_rows.stride() == dt_rows.stride(), "selective_scan: dt_rows must be contiguous for the backward")
+    d_w = torch.zeros_like(dt_weight)
+    dA, dB, dC, dD, dbias = _grad_buffers(u, A, D, delta_bias, dims)
+    p.dout, p.x = dout.data_ptr(), x.data_ptr()
+    p.dout_batch_stride, p.dout_d_stride = dout.stride(0), dout.stride(1)
+    p.du, p.du_batch_stride, p.du_d_stride = du.data_ptr(), du.stride(0), du.stride(1)
+    p.d_dt_rows, p.d_dt_weight = d_rows.data_ptr(), d_w.data_ptr()
+    p.dA, p.dB, p.dC, p.dD, p.ddelta_bias = dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), _ptr(dD), _ptr(dbias)
+    with _device_of(u):
+        _lib.check(_lib.load_library().vmasr_scan_bwd(ctypes.byref(p)))
+    return [du, d_rows, d_w, dA, dB, dC, dD, dbias]
+
+
 # ---- grouped launches -------------------------------------------------------------------------------------------------
 def _group_workspaces(sites, device):
     """One buffer from the stream's workspace, cut into 256-byte aligned regions (one per problem)."""

@@ -193,6 +193,118 @@ class _SS2DScan(torch.autograd.Function):
         return (None, None, *grads)
 
 
+_PER_MAP_PROJ = 8  # tensors per map of _SS2DScanProj
+
+
+def _check_map_proj(x, xT, xdbl_rm, xdbl_cm, dt_w, As, Ds, bias):
+    Bsz, C, H, W = x.shape
+    L = H * W
+    ok = x.is_contiguous() and xT.is_contiguous() and tuple(xT.shape) == (Bsz, C, W, H) and L > _lib.SCAN_CHUNK
+    for t in (xdbl_rm, xdbl_cm):
+        ok = ok and tuple(t.shape) == (Bsz, 2, 3, L) and t.is_contiguous()
+    ok = ok and tuple(dt_w.shape) == (4, C, 1) and dt_w.is_contiguous()
+    ok = ok and tuple(As.shape) == (4 * C, 1) and As.is_contiguous() and Ds.numel() == 4 * C and bias.numel() == 4 * C
+    for t in (x, xT, xdbl_rm, xdbl_cm, dt_w, As, Ds, bias):
+        ok = ok and t.is_cuda and t.dtype == torch.float32
+    if not ok:
+        raise RuntimeError("ss2d_core: the projected fused core expects float32 CUDA tensors x (B,C,H,W), xT (B,C,W,H), "
+                           "contiguous x_dbl (B,2,3,L) per pair, dt_projs_weight (4,C,1), As (4C,1), Ds / delta_bias (4C) "
+                           f"and H*W > {_lib.SCAN_CHUNK}")
+
+
+def _fill_proj(p: SS2DParams, x, xT, xdbl_rm, xdbl_cm, dt_w, As, Ds, bias, softplus):
+    Bsz, C, H, W = x.shape
+    p.x, p.xT = x.data_ptr(), xT.data_ptr()
+    for k in range(4):
+        xd = (xdbl_rm if k % 2 == 0 else xdbl_cm)[:, k // 2]
+        p.x_dbl[k], p.x_dbl_batch_stride[k], p.x_dbl_row_stride[k] = xd.data_ptr(), xd.stride(0), xd.stride(1)
+    p.dt_weight, p.dt_rank = dt_w.data_ptr(), 1
+    p.A, p.D, p.delta_bias = As.data_ptr(), Ds.data_ptr(), bias.data_ptr()
+    p.batch, p.channels, p.H, p.W = Bsz, C, H, W
+    p.delta_softplus = 1 if softplus else 0
+    p.device = _dev(x)
+    p.stream = _lib.current_stream_ptr(x.device)
+
+
+class _SS2DScanProj(torch.autograd.Function):
+    """``_SS2DScan`` with the dt projection inside the scan kernels (vmamba.py:1476-1477): the kernels are
+    handed ``x_dbl`` itself -- rows (dt, B, C) of each direction in the memory order of its pair -- and ``dt_projs_weight``,
+    and form ``delta = w_d * dt_row`` tile by tile.  No (B, 4C, L) ``delta`` is written or read, and the backward returns
+    ``d x_dbl`` (d dt-row, dB, dC side by side) and ``d dt_projs_weight`` instead of a (B, 4C, L) ``ddelta``.  dt_rank 1 and
+    more than one 2048-chunk only (the three largest maps of every config).  Per map, in order:
+    x (B,C,H,W), xT (B,C,W,H), x_dbl_rm, x_dbl_cm (B,2,3,L), dt_projs_weight (4,C,1), As (4C,1), Ds (4C), delta_bias (4C)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, softplus, n_maps, *tensors):
+        lib = _lib.load_library()
+        arr = (SS2DParams * n_maps)()
+        keep, ys = [], []
+        dev = tensors[0].device
+        wbytes = [int(lib.vmasr_ss2d_workspace_bytes(*tensors[m * _PER_MAP_PROJ].shape)) for m in range(n_maps)]
+        ws = _lib.scan_workspace(dev, sum(wbytes), layout=("ss2d",) + tuple(wbytes))
+        off = 0
+        for m in range(n_maps):
+            t = tensors[m * _PER_MAP_PROJ:(m + 1) * _PER_MAP_PROJ]
+            _check_map_proj(*t)
+            Bsz, C, H, W = t[0].shape
+            L = H * W
+            n_chunks = (L + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
+            y = torch.empty((Bsz, C, L), dtype=torch.float32, device=dev)
+            planes = torch.empty((2, Bsz, C, L), dtype=torch.float32, device=dev)
+            states = torch.empty((4, Bsz, C, n_chunks, 2), dtype=torch.float32, device=dev)
+            p = arr[m]
+            _fill_proj(p, *t, softplus)
+            p.y, p.planes, p.states = y.data_ptr(), planes.data_ptr(), states.data_ptr()
+            p.workspace, p.workspace_bytes = ws.data_ptr() + off, wbytes[m]
+            off += wbytes[m]
+            keep.append((planes, states))
+            ys.append(y)
+        with torch.cuda.device(dev):
+            _lib.check(lib.vmasr_ss2d_core_fwd(n_maps, arr))
+        ctx.softplus, ctx.n_maps = softplus, n_maps
+        ctx.save_for_backward(*tensors, *[k[1] for k in keep])
+        return tuple(ys) if n_maps > 1 else ys[0]
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, *dys):
+        lib = _lib.load_library()
+        n_maps = ctx.n_maps
+        saved = ctx.saved_tensors
+        tensors, states_all = saved[:n_maps * _PER_MAP_PROJ], saved[n_maps * _PER_MAP_PROJ:]
+        arr = (SS2DParams * n_maps)()
+        dev = tensors[0].device
+        wbytes = [int(lib.vmasr_ss2d_workspace_bytes(*tensors[m * _PER_MAP_PROJ].shape)) for m in range(n_maps)]
+        ws = _lib.scan_workspace(dev, sum(wbytes), layout=("ss2d",) + tuple(wbytes))
+        off = 0
+        grads, keep = [], []
+        for m in range(n_maps):
+            t = tensors[m * _PER_MAP_PROJ:(m + 1) * _PER_MAP_PROJ]
+            Bsz, C, H, W = t[0].shape
+            L = H * W
+            dy = dys[m].to(torch.float32).contiguous()
+            planes = torch.empty((2, Bsz, C, L), dtype=torch.float32, device=dev)
+            dyT = torch.empty((Bsz, C, L), dtype=torch.float32, device=dev)
+            dxdbl = torch.zeros((2, Bsz, 2, 3, L), dtype=torch.float32, device=dev)   # [rm | cm], accumulated into
+            small = torch.zeros((4, 4 * C), dtype=torch.float32, device=dev)          # dA, dD, ddelta_bias, d dt_weight
+            p = arr[m]
+            _fill_proj(p, *t, ctx.softplus)
+            p.planes, p.states = planes.data_ptr(), states_all[m].data_ptr()
+            p.dy, p.dyT, p.dx = dy.data_ptr(), dyT.data_ptr(), None
+            for k in range(4):
+                p.d_x_dbl[k] = dxdbl[k % 2][:, k // 2].data_ptr()
+            p.dA, p.dD, p.ddelta_bias, p.d_dt_weight = (small[i].data_ptr() for i in range(4))
+            p.workspace, p.workspace_bytes = ws.data_ptr() + off, wbytes[m]
+            off += wbytes[m]
+            keep.append((dy, dyT))
+            grads += [planes[0].view(Bsz, C, H, W), planes[1].view(Bsz, C, W, H), dxdbl[0], dxdbl[1],
+                      small[3].view(4, C, 1), small[0].view(4 * C, 1), small[1].view_as(t[6]), small[2].view_as(t[7])]
+        with torch.cuda.device(dev):
+            _lib.check(lib.vmasr_ss2d_core_bwd(n_maps, arr))
+        return (None, None, *grads)
+
+
 def _projections(x, xT, x_proj_weight, x_proj_bias, dt_projs_weight, R, N):
     """x_dbl and dts of vmamba.py:1473-1477 in memory order: the row-major pair from the map, the column-major pair from
     its transpose.  Returns dts (B,2,C,L), Bs, Cs (B,2,N,L) per pair; Bs / Cs are VIEWS of x_dbl (no contiguous copies)."""
@@ -213,6 +325,30 @@ def _fusable(x, N):
     return x.is_cuda and x.dim() == 4 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0 and N == 1
 
 
+def _projectable(x, dt_projs_weight, N):
+    """delta can be generated inside the scan kernels: fused core, dt_rank 1, more than one chunk of 16-float lines"""
+    L = x.shape[2] * x.shape[3]
+    return _fusable(x, N) and dt_projs_weight.shape[2] == 1 and L > _lib.SCAN_CHUNK and L % 16 == 0
+
+
+def _prepare_proj(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias):
+    """inputs of _SS2DScanProj: x_dbl (vmamba.py:1473-1475) of the two pairs in memory order; the dt projection (:1477) is
+    left to the kernels"""
+    Bsz, C, H, W = x.shape
+    L = H * W
+    x32 = x.to(torch.float32).contiguous()
+    xT = MapTranspose.apply(x32)
+    xd = []
+    for par, src in ((0, x32.view(Bsz, C, L)), (1, xT.view(Bsz, C, L))):
+        x_dbl = torch.einsum("bdl,kcd->bkcl", src, x_proj_weight[par::2].to(torch.float32))
+        if x_proj_bias is not None:
+            x_dbl = x_dbl + x_proj_bias[par::2].view(1, 2, -1, 1)
+        xd.append(x_dbl.to(torch.float32).contiguous())
+    As = -torch.exp(A_logs.to(torch.float))
+    return (x32, xT, xd[0], xd[1], dt_projs_weight.to(torch.float).contiguous(), As.contiguous(), Ds.to(torch.float).contiguous(),
+            dt_projs_bias.reshape(-1).to(torch.float).contiguous())
+
+
 def _prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias):
     K, _, R = dt_projs_weight.shape
     N = A_logs.shape[1]
@@ -229,10 +365,11 @@ def _prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_pro
 
 def ss2d_core(x: torch.Tensor, x_proj_weight: torch.Tensor, dt_projs_weight: torch.Tensor, dt_projs_bias: torch.Tensor,
               A_logs: torch.Tensor, Ds: torch.Tensor, delta_softplus: bool = True, force_fp32: bool = True,
-              x_proj_bias: torch.Tensor | None = None, fused: bool | None = None) -> torch.Tensor:
+              x_proj_bias: torch.Tensor | None = None, fused: bool | None = None, projected: bool | None = None) -> torch.Tensor:
     """x (B, C, H, W) -> y (B, C, H*W), float32.  Parameter layouts as in ``SS2D.__initv2__`` (vmamba.py:772-850):
     x_proj_weight (K=4, R + 2N, C), dt_projs_weight (K, C, R), dt_projs_bias (K, C), A_logs (K*C, N), Ds (K*C),
-    x_proj_bias (K, R + 2N) or None (vmamba.py:1474-1475).  ``fused=None`` picks the fused core whenever it applies."""
+    x_proj_bias (K, R + 2N) or None (vmamba.py:1474-1475).  ``fused=None`` picks the fused core whenever it applies;
+    ``projected=None`` additionally leaves the dt projection to the scan kernels wherever they take it (dt_rank 1, H*W > 2048)."""
     if x.dim() != 4:
         raise RuntimeError("ss2d_core: expected (B, C, H, W)")
     N = A_logs.shape[1]
@@ -242,19 +379,31 @@ def ss2d_core(x: torch.Tensor, x_proj_weight: torch.Tensor, dt_projs_weight: tor
         return ss2d_core_chain(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, delta_softplus, force_fp32, x_proj_bias)
     if not _fusable(x, N):
         raise RuntimeError("ss2d_core: the fused core needs a CUDA map with H, W multiples of 4 and d_state 1")
+    if projected is None:
+        projected = _projectable(x, dt_projs_weight, N)
+    if projected:
+        if not _projectable(x, dt_projs_weight, N):
+            raise RuntimeError("ss2d_core: the projected form needs the fused core, dt_rank 1 and H*W > 2048 (a multiple of 16)")
+        return _SS2DScanProj.apply(delta_softplus, 1, *_prepare_proj(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias))
     return _SS2DScan.apply(delta_softplus, 1, *_prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias))
 
 
-def ss2d_core_pair(x_a, params_a, x_b, params_b, delta_softplus: bool = True):
+def ss2d_core_pair(x_a, params_a, x_b, params_b, delta_softplus: bool = True, projected: bool | None = None):
     """The cores of the generator's two streams as one grid.  ``params_*`` = (x_proj_weight, dt_projs_weight, dt_projs_bias,
-    A_logs, Ds[, x_proj_bias]).  Returns (y_a, y_b)."""
-    args = []
+    A_logs, Ds[, x_proj_bias]).  Returns (y_a, y_b).  ``projected`` as in ``ss2d_core`` (both maps or neither)."""
     for x, prm in ((x_a, params_a), (x_b, params_b)):
         if not _fusable(x, prm[3].shape[1]):
             raise RuntimeError("ss2d_core_pair: the fused core needs CUDA maps with H, W multiples of 4 and d_state 1")
+    can = all(_projectable(x, prm[1], prm[3].shape[1]) for x, prm in ((x_a, params_a), (x_b, params_b)))
+    if projected is None:
+        projected = can
+    if projected and not can:
+        raise RuntimeError("ss2d_core_pair: the projected form needs dt_rank 1 and H*W > 2048 (a multiple of 16) on both maps")
+    args = []
+    for x, prm in ((x_a, params_a), (x_b, params_b)):
         bias = prm[5] if len(prm) > 5 else None
-        args += list(_prepare(x, prm[0], prm[1], prm[2], prm[3], prm[4], bias))
-    return _SS2DScan.apply(delta_softplus, 2, *args)
+        args += list((_prepare_proj if projected else _prepare)(x, prm[0], prm[1], prm[2], prm[3], prm[4], bias))
+    return (_SS2DScanProj if projected else _SS2DScan).apply(delta_softplus, 2, *args)
 
 
 def ss2d_core_chain(x: torch.Tensor, x_proj_weight: torch.Tensor, dt_projs_weight: torch.Tensor, dt_projs_bias: torch.Tensor,
