@@ -736,6 +736,17 @@ def main():
         except Exception as e:
             stft_t = {"error": str(e)[:200]}
 
+    # DRAM bytes per launch of the dominant kernel come from an ncu pass over THIS command (tools/gpu_profile.sh ->
+    # tools/launch_list.py), committed under profiles/: a run under a profiler is never a bench value, so it is not measured here
+    traffic, traffic_note = None, "no ncu launch list of this command under profiles/"
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_dominant_kernel_traffic.json")) as f:
+            tr = json.load(f)
+        traffic = int(tr["traffic_bytes_per_launch"])
+        traffic_note = (f"profiles/r2_dominant_kernel_traffic.json: {tr['source']}, mean of {tr['launches_averaged']} launches "
+                        "(ncu pass of this same command; not measured inside this run)")
+    except Exception:
+        pass
     if rank == 0:
         out = {
             "metric": "ss2d_scan_fwd_bwd_GBps", "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
@@ -752,12 +763,12 @@ def main():
             "gpu_launches": (len(wl.calls) if args.pairing == "grouped" else 2 * len(wl.calls)) * args.steps,
             "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None,
+                         "frac": round(achieved / peak, 4), "traffic": traffic,
                          "kernel": "scan_bwd_pipe_kernel<softplus> (csrc/scan_bwd_pipe.cu), every backward launch with seqlen > 2048 "
                                    "(grouped: one launch per pair of calls)",
                          "launches_per_step": k_per_step, "avg_launch_ms": round(k_ms, 5),
                          "avg_algorithmic_bytes_per_launch": int(k_bytes), "peak_source": peak_src,
-                         "traffic_note": "per-launch DRAM bytes are in the ncu launch lists under profiles/ (not measured inside this run)"},
+                         "traffic_note": traffic_note},
             "cpu_baseline": cpu_base,
             "ss2d_core": core, "train": train, "infer": infer, "eager": eager, "stft": stft_t,
         }

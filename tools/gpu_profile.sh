@@ -3,7 +3,7 @@
 # on three shapes.  Run under gpurun.  Keeps gpurun_out/ under the 64 MiB merge limit.
 mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep
-BENCH="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+BENCH="python bench.py --steps 2 --warmup 3 --no-e2e --no-core --no-stft --no-cpu-baseline"
 timeout -k 10 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
   --graph-profiling node -c 4000 --csv --log-file gpurun_out/launches_raw.csv $BENCH > gpurun_out/launches_run.log 2>&1
 echo "launch list rc=$? lines=$(wc -l < gpurun_out/launches_raw.csv)"

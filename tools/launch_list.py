@@ -35,7 +35,7 @@ t_all = sum(e.get("gpu__time_duration.sum", 0.0) for e in launches.values())
 t_ours = sum(e.get("gpu__time_duration.sum", 0.0) for _, e in ours)
 per = defaultdict(lambda: [0, 0.0, 0.0])
 with open(out, "w") as f:
-    f.write("# ncu launch list of `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline` (our kernels only; "
+    f.write("# ncu launch list of `python bench.py --steps 2 --warmup 3 --no-e2e --no-core --no-stft --no-cpu-baseline` (our kernels only; "
             "cold-cache, serialised: compare shares, not absolutes)\n")
     f.write("id,kernel,grid,block,time_us,dram_read_bytes,dram_write_bytes\n")
     for k, e in ours:

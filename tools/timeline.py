@@ -70,5 +70,17 @@ for name, fn in (("fwd", fwd), ("bwd", bwd)):
         m = sm == s
         busy.append(((end[m] - t[m, 0]).sum()) / max(1, (end[m].max() - t[m, 0].min())))
     print(f"   mean resident tiles per SM while it is active: {np.mean(busy):.2f}; tiles per SM {n / len(np.unique(sm)):.1f}")
+    # turn-around: on one SM the i-th exit frees the slot the (i + slots)-th entry takes
+    gaps = []
+    for s in np.unique(sm):
+        m = sm == s
+        ent, ex = np.sort(t[m, 0]), np.sort(end[m])
+        slots = int(np.searchsorted(ent, ex[0]))  # tiles that entered before the first exit = resident slots
+        if slots >= 1 and len(ent) > slots:
+            gaps.append((ent[slots:] - ex[:len(ent) - slots]) / 1e3)
+    if gaps:
+        g = np.concatenate(gaps)
+        print(f"   slot turn-around (exit of warp 0 / exchange warp -> next tile's entry on that SM): mean {g.mean():.2f} us, "
+              f"p10 {np.percentile(g, 10):.2f}, p90 {np.percentile(g, 90):.2f}")
     starts = np.sort(t[:, 0] - t0) / 1e3
     print("   tile start times (us) deciles:", [round(float(starts[int(q * (n - 1) / 10)]), 1) for q in range(11)])
