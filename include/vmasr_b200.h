@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define VMASR_ABI_VERSION 3
+#define VMASR_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define VMASR_API __attribute__((visibility("default")))
@@ -235,8 +235,11 @@ typedef struct vmasr_ss2d_params {
     float *d_x_dbl[4];
     float *d_dt_weight;
     int32_t dt_rank;
-    int32_t reserved0;
+    int32_t flags; /* VMASR_SS2D_* bits below */
 } vmasr_ss2d_params;
+/* backward: dyT already holds transpose(dy) (the caller produced both, e.g. behind vmasr_outnorm_gate_bwd): skip the
+ * internal transpose */
+#define VMASR_SS2D_DYT_GIVEN 1
 
 VMASR_API uint64_t vmasr_ss2d_workspace_bytes(int batch, int channels, int H, int W);
 VMASR_API int vmasr_ss2d_core_fwd(int n, const vmasr_ss2d_params *p);
@@ -244,6 +247,42 @@ VMASR_API int vmasr_ss2d_core_bwd(int n, const vmasr_ss2d_params *p);
 /* x (planes, H, W) -> xT (planes, W, H); y = p_rm + transpose(p_cm).  float32, H % 4 == 0, W % 4 == 0, 16-byte aligned. */
 VMASR_API int vmasr_map_transpose(const float *x, float *xT, int64_t planes, int H, int W, int device, void *stream);
 VMASR_API int vmasr_map_merge2(const float *p_rm, const float *p_cm, float *y, int64_t planes, int H, int W, int device, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tail of the SS2D block fused into the merge of the core's two planes.  Replaces, in one kernel,
+ *   y = CrossMerge's outer addition (model/vmamba.py:57-60)  ->  y.transpose(1, 2).contiguous()  ->  out_norm = nn.LayerNorm(C)
+ *   (vmamba.py:1527-1529, out_norm_shape "v0")  ->  y.to(x.dtype) (:1531)  ->  y * act(z) (forwardv2, :1536-1550).
+ *   p_rm, p_cm : (B, C, H*W) float32, the planes vmasr_ss2d_core_fwd leaves (pass y = NULL there): y0 + y2 with w fastest,
+ *                y1 + y3 with h fastest.  p_cm = NULL: p_rm is an already merged map (e.g. CrossMerge's output).
+ *   gamma, beta: (C) float32 LayerNorm weight / bias (NULL = 1 / 0);  eps as nn.LayerNorm (1e-5)
+ *   z          : (B, H*W, C) of io_dtype, the gate BEFORE its activation when z_silu = 1 (SiLU applied inside, rounded to
+ *                io_dtype as the reference's act(z) tensor is), after it when z_silu = 0; NULL = no gate
+ *   out        : (B, H*W, C) of io_dtype
+ *   y, stats   : forward OUTPUTS kept for the backward, (B, C, H*W) float32 merged map and (B, H*W, 2) float32 {mean, rstd};
+ *                either may be NULL at inference.  The backward reads them.
+ *   backward   : dout (B, H*W, C) io_dtype -> dy (B, C, H*W) float32 (row-major: what vmasr_ss2d_core_bwd takes as dy),
+ *                dz (B, H*W, C) io_dtype (required when z is given), and dgb_partial (patches, 2, C) float32: per-patch sums
+ *                of d gamma and d beta, every entry written (no zero-fill needed); the caller sums over the first axis
+ *                (patches = vmasr_outnorm_patches()); NULL = not wanted.
+ * H % 4 == 0, W % 8 == 0, float32 tensors 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vmasr_outnorm_params {
+    const float *p_rm, *p_cm, *gamma, *beta;
+    const void *z;
+    void *out;
+    float *y, *stats;
+    const void *dout;
+    float *dy;
+    void *dz;
+    float *dgb_partial;
+    float eps;
+    int32_t batch, channels, H, W;
+    int32_t io_dtype, z_silu, device;
+    void *stream;
+} vmasr_outnorm_params;
+VMASR_API int64_t vmasr_outnorm_patches(int batch, int channels, int H, int W);
+VMASR_API int vmasr_outnorm_gate_fwd(const vmasr_outnorm_params *p);
+VMASR_API int vmasr_outnorm_gate_bwd(const vmasr_outnorm_params *p);
 
 /* ------------------------------------------------------------------------------------------------
  * Magnitude/phase STFT and inverse.  Replace wav2spectro / spectro2wav (utils/stft.py:22-68, 71-115),

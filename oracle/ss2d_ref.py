@@ -204,6 +204,22 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, dtyp
     return cross_merge(ys.reshape(Bsz, K, C, H, W))
 
 
+def out_norm_gate(y, gamma, beta, z, H, W, eps=1e-5, z_silu=True, out_dtype=None):
+    """Tail of the block for the configs' layout: forward_corev2's out_norm branch (vmamba.py:1525-1531; channel_first False,
+    out_norm_shape "v0", out_norm = nn.LayerNorm(d_inner)) followed by the gate of forwardv2 (:1536-1550).
+    y (B, C, L) merged map -> (B, H, W, C); z (B, H, W, C) or None."""
+    Bsz, C, L = y.shape
+    y = y.transpose(dim0=1, dim1=2).contiguous()                         # :1527
+    y = F.layer_norm(y, (C,), gamma, beta, eps).view(Bsz, H, W, -1)      # :1528
+    if out_dtype is not None:
+        y = y.to(out_dtype)                                              # :1531
+    if z is not None:
+        if z_silu:
+            z = F.silu(z)                                                # :1538-1539
+        y = y * z                                                        # :1549-1550
+    return y
+
+
 def ss2d_core_storage_order(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, dtype=torch.float32):
     """The SS2D core computed the way the planned fused kernel will, as a check of that plan's
     algebra: no `xs` / `ys` copies.  Directions 0/2 work on the map in row-major STORAGE order, directions 1/3 on one

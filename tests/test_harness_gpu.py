@@ -16,16 +16,14 @@ def _small_workload():
 
 def test_train_step_runs_and_learns():
     """fp32 step: finite gradients for every parameter, all living in the flat buffer, and the loss goes down.  The toy net is
-    cubic in its activations (harness.py), so the LEARNING check runs without autocast: under fp16 it starts to overflow once the
-    loss moves (tools/debug_harness.py), which says nothing about the kernels; the autocast + GradScaler plumbing has its own
-    short test below."""
+    cubic in its activations (harness.py), so the LEARNING check runs without autocast; the autocast + GradScaler plumbing has
+    its own short test below."""
     from vm_asr_b200 import harness
     wl = _small_workload()
     dev = torch.device("cuda")
-    ts = harness.TrainStep(wl, dev, world=1, lr=2e-4, amp=False)
+    ts = harness.TrainStep(wl, dev, world=1, lr=1e-3, amp=False)
     x, y = harness.synthetic_batch(wl, dev)
-    # the loss only starts to move once the heads' gradients have grown (flat for ~10 steps at this rate, then 4.55 -> 2.3 by step 24)
-    losses = [ts(x, y).item() for _ in range(40)]
+    losses = [ts(x, y).item() for _ in range(30)]
     assert all(l == l and l < 1e6 for l in losses), losses
     assert min(losses[8:]) < losses[0] - 1e-3, losses
     for name, p in ts.net.named_parameters():

@@ -340,3 +340,107 @@ def test_scan_level_projected_form(batch, dim, ngroups, L, rev):
     with pytest.raises(RuntimeError):
         scan.fwd_projected(u[..., :1024].contiguous(), rows[..., :1024].contiguous(), w, A, Bm[..., :1024].contiguous(),
                            Cm[..., :1024].contiguous(), D, bias, True)
+
+
+# ---- merge + LayerNorm + cast + SiLU(z) gate in one kernel (vmamba.py:1525-1531, 1536-1550) -------------------
+def _tail_oracle(planes, gamma, beta, z, H, W, z_silu, out_dtype, dtype=torch.float64):
+    """P_rm + transpose(P_cm) (vmamba.py:57-60) -> oracle tail, in float64 (or at ``dtype``) with autograd"""
+    _, Bsz, C, L = planes.shape
+    y = planes[0] + planes[1].view(Bsz, C, W, H).transpose(2, 3).reshape(Bsz, C, L)
+    return ss2d_ref.out_norm_gate(y, gamma, beta, z, H, W, 1e-5, z_silu, out_dtype)
+
+
+TAIL_CASES = [(2, 2, 64, 64), (1, 16, 32, 48), (2, 32, 16, 16), (1, 64, 8, 16), (1, 256, 16, 16), (1, 512, 16, 16), (1, 6, 12, 24),
+              (2, 24, 20, 40), (4, 2, 512, 512), (4, 16, 256, 256), (8, 512, 16, 16)]
+
+
+@pytest.mark.parametrize("Bsz,C,H,W", TAIL_CASES)
+@pytest.mark.parametrize("gate", ["silu", "plain", "none"])
+def test_merge_norm_gate_fp32(Bsz, C, H, W, gate):
+    """forward and every gradient (both planes, gamma, beta, z) against the float64 oracle"""
+    from vm_asr_b200 import ss2d
+    if gate != "silu" and Bsz * C * H * W > 1 << 18:
+        pytest.skip("large maps once")
+    g = torch.Generator().manual_seed(40)
+    L = H * W
+    planes = torch.randn(2, Bsz, C, L, generator=g)
+    gamma, beta = 1.0 + 0.3 * torch.randn(C, generator=g), 0.3 * torch.randn(C, generator=g)
+    z = None if gate == "none" else torch.randn(Bsz, H, W, C, generator=g)
+    gout = torch.randn(Bsz, H, W, C, generator=g)
+    ins = [t.cuda().requires_grad_() if t is not None else None for t in (planes, gamma, beta, z)]
+    out = ss2d.MergeNormGate.apply(ins[0], ins[1], ins[2], ins[3], H, W, 1e-5, gate == "silu", torch.float32)
+    out.backward(gout.cuda())
+    ref_in = [t.double().requires_grad_() if t is not None else None for t in (planes, gamma, beta, z)]
+    ref = _tail_oracle(ref_in[0], ref_in[1], ref_in[2], ref_in[3], H, W, gate == "silu", None)
+    ref.backward(gout.double())
+    assert out.shape == (Bsz, H, W, C)
+    # two channels: xhat = +-1 / sqrt(1 + eps / var) with var = (y0 - y1)^2 / 4 -- where the two values nearly coincide the fp32
+    # subtraction in front of a large rstd is ill-conditioned (the reference's fp32 LayerNorm has the same property)
+    cond = 10.0 if C == 2 else 1.0
+    assert rel_err(out, ref) < 1e-5 * cond
+    for name, a, r in zip(("planes", "gamma", "beta", "z"), ins, ref_in):
+        if a is not None:
+            tol = 2e-4 if name in ("gamma", "beta") else 2e-5 * cond   # gamma / beta: sums over B * L terms in fp32
+            assert rel_err(a.grad, r.grad) < tol, (name, rel_err(a.grad, r.grad))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("Bsz,C,H,W", [(2, 32, 16, 16), (1, 16, 32, 48), (2, 2, 64, 64)])
+def test_merge_norm_gate_half(Bsz, C, H, W, dtype, tol):
+    """AMP: z and the result are half tensors (y.to(x.dtype), act(z) rounded to half, half product), the LayerNorm is fp32;
+    against the same statements in torch on the GPU at the same dtypes"""
+    from vm_asr_b200 import ss2d
+    g = torch.Generator().manual_seed(41)
+    planes = torch.randn(2, Bsz, C, H * W, generator=g).cuda()
+    gamma, beta = (1.0 + 0.3 * torch.randn(C, generator=g)).cuda(), (0.3 * torch.randn(C, generator=g)).cuda()
+    z = torch.randn(Bsz, H, W, C, generator=g).cuda().to(dtype)
+    gout = torch.randn(Bsz, H, W, C, generator=g).cuda().to(dtype)
+    ins = [planes.clone().requires_grad_(), gamma.clone().requires_grad_(), beta.clone().requires_grad_(), z.clone().requires_grad_()]
+    out = ss2d.MergeNormGate.apply(*ins, H, W, 1e-5, True, dtype)
+    out.backward(gout)
+    ref_in = [planes.clone().requires_grad_(), gamma.clone().requires_grad_(), beta.clone().requires_grad_(), z.clone().requires_grad_()]
+    ref = _tail_oracle(*ref_in, H, W, True, dtype)
+    ref.backward(gout)
+    assert out.dtype == dtype and rel_err(out, ref) < tol
+    for name, a, r in zip(("planes", "gamma", "beta", "z"), ins, ref_in):
+        assert rel_err(a.grad, r.grad) < 2 * tol, (name, rel_err(a.grad, r.grad))
+
+
+@pytest.mark.parametrize("Bsz,C,H,W,R", [(2, 8, 72, 64, 2), (2, 4, 16, 16, 1), (1, 16, 64, 80, 1), (4, 16, 256, 256, 1)])
+def test_ss2d_core_out_matches_core_plus_tail(Bsz, C, H, W, R):
+    """ss2d_core_out (planes of the fused core -> MergeNormGate) against ss2d_core followed by the oracle's tail in torch on the
+    GPU: output and the gradients of the map, the gate, the LayerNorm and every parameter of the core"""
+    from vm_asr_b200 import ss2d
+    g = torch.Generator().manual_seed(42)
+    vals = (torch.randn(Bsz, C, H, W, generator=g),) + _core_params(C, R, seed=43)
+    gamma, beta = 1.0 + 0.3 * torch.randn(C, generator=g), 0.3 * torch.randn(C, generator=g)
+    z = torch.randn(Bsz, H, W, C, generator=g)
+    gout = torch.randn(Bsz, H, W, C, generator=g).cuda()
+    a_in = [v.cuda().requires_grad_() for v in vals + (gamma, beta, z)]
+    out = ss2d.ss2d_core_out(*a_in[:6], a_in[6], a_in[7], z=a_in[8])
+    out.backward(gout)
+    b_in = [v.cuda().requires_grad_() for v in vals + (gamma, beta, z)]
+    y = ss2d.ss2d_core(*b_in[:6], fused=True)
+    ref = ss2d_ref.out_norm_gate(y, b_in[6], b_in[7], b_in[8], H, W)
+    ref.backward(gout)
+    assert rel_err(out, ref) < 2e-5
+    for n, a, r in zip(("x", "xw", "dw", "db", "A_logs", "Ds", "gamma", "beta", "z"), a_in, b_in):
+        assert rel_err(a.grad, r.grad) < 2e-4, (n, rel_err(a.grad, r.grad))
+
+
+def test_merge_norm_gate_inference_keeps_nothing():
+    """without autograd the merged map and the statistics are not written: the tail allocates its output only"""
+    from vm_asr_b200 import ss2d
+    Bsz, C, H, W = 2, 32, 64, 64
+    planes = torch.randn(2, Bsz, C, H * W, device="cuda")
+    gamma, beta = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+    z = torch.randn(Bsz, H, W, C, device="cuda")
+    torch.cuda.synchronize()
+    base = torch.cuda.memory_allocated()
+    torch.cuda.reset_peak_memory_stats()
+    with torch.no_grad():
+        out = ss2d.MergeNormGate.apply(planes, gamma, beta, z, H, W, 1e-5, True, torch.float32)
+    torch.cuda.synchronize()
+    assert torch.cuda.max_memory_allocated() - base <= out.numel() * 4 + (1 << 20)
+    ref = _tail_oracle(planes, gamma, beta, z, H, W, True, None, dtype=torch.float32)
+    assert rel_err(out, ref) < 1e-5

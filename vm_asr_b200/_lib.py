@@ -21,7 +21,8 @@ _lock = threading.Lock()
 VMASR_F32, VMASR_F16, VMASR_BF16 = 0, 1, 2
 SCAN_REVERSE, SCAN_ACCUMULATE = 1, 2
 SCAN_MAX_GROUP = 8
-ABI_VERSION = 3
+SS2D_DYT_GIVEN = 1
+ABI_VERSION = 4
 SCAN_CHUNK = 2048
 DTYPE_CODE = {torch.float32: VMASR_F32, torch.float16: VMASR_F16, torch.bfloat16: VMASR_BF16}
 
@@ -68,8 +69,19 @@ class SS2DParams(ctypes.Structure):
         ("stream", _vp),
         ("x_dbl", _vp * 4), ("x_dbl_batch_stride", _i64 * 4), ("x_dbl_row_stride", _i64 * 4),
         ("dt_weight", _vp), ("d_x_dbl", _vp * 4), ("d_dt_weight", _vp),
-        ("dt_rank", _i32), ("reserved0", _i32),
+        ("dt_rank", _i32), ("flags", _i32),
     ]
+
+
+class OutNormParams(ctypes.Structure):
+    """Mirror of ``vmasr_outnorm_params`` (include/vmasr_b200.h)."""
+
+    _fields_ = (
+        [(n, _vp) for n in ("p_rm", "p_cm", "gamma", "beta", "z", "out", "y", "stats", "dout", "dy", "dz", "dgb_partial")]
+        + [("eps", ctypes.c_float)]
+        + [(n, _i32) for n in ("batch", "channels", "H", "W", "io_dtype", "z_silu", "device")]
+        + [("stream", _vp)]
+    )
 
 
 EXPORTS = {
@@ -86,6 +98,9 @@ EXPORTS = {
     "vmasr_ss2d_core_bwd": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(SS2DParams)]),
     "vmasr_map_transpose": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "vmasr_map_merge2": (ctypes.c_int, [_vp, _vp, _vp, _i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+    "vmasr_outnorm_patches": (_i64, [ctypes.c_int] * 4),
+    "vmasr_outnorm_gate_fwd": (ctypes.c_int, [ctypes.POINTER(OutNormParams)]),
+    "vmasr_outnorm_gate_bwd": (ctypes.c_int, [ctypes.POINTER(OutNormParams)]),
     "vmasr_cross_scan": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
     "vmasr_cross_merge": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
     "vmasr_cross_scan_1b1": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),

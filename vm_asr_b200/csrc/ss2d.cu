@@ -27,7 +27,7 @@ static int ss2d_check(const vmasr_ss2d_params *p, bool bwd, const char *who) {
         for (int k = 0; k < 4; ++k)
             if (!p->delta[k] || !p->B[k] || !p->C[k]) return fail("%s: delta / B / C of direction %d missing", who, k);
     }
-    if (!bwd && !p->y) return fail("%s: y must be non-null", who);
+    // (forward: y may be NULL -- the caller merges the two planes itself, e.g. with vmasr_outnorm_gate_fwd)
     if (bwd) {
         if (!p->dy || !p->dyT || !p->dA) return fail("%s: dy, dyT, dA must be non-null", who);
         if (proj) {
@@ -165,7 +165,7 @@ static int ss2d_run(int n, const vmasr_ss2d_params *ps, bool bwd) {
         const vmasr_ss2d_params *p = &ps[i];
         const long long planes = (long long)p->batch * p->channels, L = (long long)p->H * p->W;
         (void)L;
-        if (bwd)
+        if (bwd && !(p->flags & VMASR_SS2D_DYT_GIVEN))
             if (int rc = map_transpose_launch(p->dy, p->dyT, planes, p->H, p->W, stream)) return rc;
         if (one_pass)
             if (int rc = check_cuda(cudaMemsetAsync(p->planes, 0, sizeof(float) * 2 * planes * L, stream), "ss2d planes memset")) return rc;

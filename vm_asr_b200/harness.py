@@ -78,6 +78,15 @@ class HotPathNet(nn.Module):
             self.glue.append(convs)
             c_prev = call.d_inner
         self.head = nn.ModuleList([nn.Conv2d(c_prev, 1, 1), nn.Conv2d(c_prev, 1, 1)])
+        # the glue is initialised from the same generator as the cores (not from the global RNG: two harnesses built in one
+        # process are identical), the heads small: the net starts close to the identity STFT -> iSTFT, as a residual generator does
+        with torch.no_grad():
+            for conv in [c for convs in self.glue for c in convs] + list(self.head):
+                bound = 1.0 / math.sqrt(conv.in_channels)
+                conv.weight.copy_((torch.rand(conv.weight.shape, generator=gen) * 2 - 1) * bound)
+                conv.bias.zero_()
+            for conv in self.head:
+                conv.weight.mul_(0.05)
 
     @staticmethod
     def _rms(y):
@@ -120,9 +129,12 @@ class HotPathNet(nn.Module):
             outs = []
             for s in range(2):
                 y = ys[s].view(Bsz, call.d_inner, call.H, call.W)
-                outs.append(xs[s] + self._rms(y))
-            m = outs[0] + outs[1]                                                # model.py:1129-1131
-            streams = [m, outs[1] + m]
+                outs.append((xs[s] + self._rms(y)) * 0.7071067811865476)
+            # the streams interact after every pair as in model.py:1129-1131 (mag = mag + phase; phase = phase + mag); AVERAGED
+            # here: the reference's blocks renormalise what they add, this glue does not, and 17 plain sums grow like 3^17 --
+            # log2-magnitudes of that size overflow exp2 in spectro2wav (or underflow it to an all-zero wave with zero gradient)
+            m = 0.5 * (outs[0] + outs[1])
+            streams = [m, 0.5 * (outs[1] + m)]
         full_h, full_w = residual_mag.shape[-2:]
         out = [self.head[s](self._resample(streams[s], full_h, full_w)) for s in range(2)]
         mag_out = torch.cat([dc[0], out[0] + residual_mag], dim=-2)              # model.py:1205-1215

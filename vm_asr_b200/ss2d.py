@@ -72,6 +72,11 @@ class MapTranspose(torch.autograd.Function):
 
 
 _PER_MAP = 11  # tensors per map of _SS2DScan
+# first argument of the two scan Functions: bit 0 = delta_softplus (so plain True / False keep their meaning), bit 1 = return the
+# core's two PLANES (2, B, C, L) -- y0 + y2 with w fastest, y1 + y3 with h fastest -- instead of the merged map: the caller
+# merges them itself (MergeNormGate below fuses that merge with the block's LayerNorm / gate tail), and the backward then
+# receives (dy, dy^T) stacked the same way
+_SOFTPLUS, _PLANES = 1, 2
 
 
 def _fill(p: SS2DParams, x, xT, dts_rm, dts_cm, Bs_rm, Bs_cm, Cs_rm, Cs_cm, As, Ds, bias, softplus):
@@ -115,6 +120,7 @@ class _SS2DScan(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, softplus, n_maps, *tensors):
         lib = _lib.load_library()
+        want_planes, softplus = bool(int(softplus) & _PLANES), bool(int(softplus) & _SOFTPLUS)
         arr = (SS2DParams * n_maps)()
         keep, ys = [], []
         dev = tensors[0].device
@@ -128,20 +134,20 @@ class _SS2DScan(torch.autograd.Function):
             Bsz, C, H, W = x.shape
             L = H * W
             n_chunks = (L + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
-            y = torch.empty((Bsz, C, L), dtype=torch.float32, device=dev)
+            y = None if want_planes else torch.empty((Bsz, C, L), dtype=torch.float32, device=dev)
             planes = torch.empty((2, Bsz, C, L), dtype=torch.float32, device=dev)
             states = torch.empty((4, Bsz, C, n_chunks, 2), dtype=torch.float32, device=dev)
             p = arr[m]
             _fill(p, *t, softplus)
-            p.y, p.planes, p.states = y.data_ptr(), planes.data_ptr(), states.data_ptr()
+            p.y, p.planes, p.states = (None if want_planes else y.data_ptr()), planes.data_ptr(), states.data_ptr()
             if wbytes[m]:
                 p.workspace, p.workspace_bytes = ws.data_ptr() + off, wbytes[m]
                 off += wbytes[m]
             keep.append((planes, states))
-            ys.append(y)
+            ys.append(planes if want_planes else y)
         with torch.cuda.device(dev):
             _lib.check(lib.vmasr_ss2d_core_fwd(n_maps, arr))
-        ctx.softplus, ctx.n_maps = softplus, n_maps
+        ctx.softplus, ctx.n_maps, ctx.want_planes = softplus, n_maps, want_planes
         ctx.save_for_backward(*tensors, *[k[1] for k in keep])
         return tuple(ys) if n_maps > 1 else ys[0]
 
@@ -163,9 +169,13 @@ class _SS2DScan(torch.autograd.Function):
             x = t[0]
             Bsz, C, H, W = x.shape
             L = H * W
-            dy = dys[m].to(torch.float32).contiguous()
+            if ctx.want_planes:   # the gradient of the planes IS (dy, dy^T)
+                g = dys[m].to(torch.float32).contiguous()
+                dy, dyT = g[0], g[1]
+            else:
+                dy = dys[m].to(torch.float32).contiguous()
+                dyT = torch.empty((Bsz, C, L), dtype=torch.float32, device=dev)
             planes = torch.empty((2, Bsz, C, L), dtype=torch.float32, device=dev)
-            dyT = torch.empty((Bsz, C, L), dtype=torch.float32, device=dev)
             ddts = torch.empty((2, Bsz, 2, C, L), dtype=torch.float32, device=dev)   # [rm | cm]
             dBC = torch.zeros((2, 4, Bsz, L), dtype=torch.float32, device=dev)       # [dB | dC], direction-major
             small = torch.zeros((3, 4 * C), dtype=torch.float32, device=dev)         # dA, dD, ddelta_bias
@@ -173,6 +183,7 @@ class _SS2DScan(torch.autograd.Function):
             _fill(p, *t, ctx.softplus)
             p.planes, p.states = planes.data_ptr(), states_all[m].data_ptr()
             p.dy, p.dyT, p.dx = dy.data_ptr(), dyT.data_ptr(), None
+            p.flags = _lib.SS2D_DYT_GIVEN if ctx.want_planes else 0
             for k in range(4):
                 d = ddts[k % 2][:, k // 2]
                 p.ddelta[k], p.ddelta_batch_stride[k], p.ddelta_d_stride[k] = d.data_ptr(), d.stride(0), d.stride(1)
@@ -238,6 +249,7 @@ class _SS2DScanProj(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, softplus, n_maps, *tensors):
         lib = _lib.load_library()
+        want_planes, softplus = bool(int(softplus) & _PLANES), bool(int(softplus) & _SOFTPLUS)
         arr = (SS2DParams * n_maps)()
         keep, ys = [], []
         dev = tensors[0].device
@@ -250,19 +262,19 @@ class _SS2DScanProj(torch.autograd.Function):
             Bsz, C, H, W = t[0].shape
             L = H * W
             n_chunks = (L + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
-            y = torch.empty((Bsz, C, L), dtype=torch.float32, device=dev)
+            y = None if want_planes else torch.empty((Bsz, C, L), dtype=torch.float32, device=dev)
             planes = torch.empty((2, Bsz, C, L), dtype=torch.float32, device=dev)
             states = torch.empty((4, Bsz, C, n_chunks, 2), dtype=torch.float32, device=dev)
             p = arr[m]
             _fill_proj(p, *t, softplus)
-            p.y, p.planes, p.states = y.data_ptr(), planes.data_ptr(), states.data_ptr()
+            p.y, p.planes, p.states = (None if want_planes else y.data_ptr()), planes.data_ptr(), states.data_ptr()
             p.workspace, p.workspace_bytes = ws.data_ptr() + off, wbytes[m]
             off += wbytes[m]
             keep.append((planes, states))
-            ys.append(y)
+            ys.append(planes if want_planes else y)
         with torch.cuda.device(dev):
             _lib.check(lib.vmasr_ss2d_core_fwd(n_maps, arr))
-        ctx.softplus, ctx.n_maps = softplus, n_maps
+        ctx.softplus, ctx.n_maps, ctx.want_planes = softplus, n_maps, want_planes
         ctx.save_for_backward(*tensors, *[k[1] for k in keep])
         return tuple(ys) if n_maps > 1 else ys[0]
 
@@ -283,15 +295,20 @@ class _SS2DScanProj(torch.autograd.Function):
             t = tensors[m * _PER_MAP_PROJ:(m + 1) * _PER_MAP_PROJ]
             Bsz, C, H, W = t[0].shape
             L = H * W
-            dy = dys[m].to(torch.float32).contiguous()
+            if ctx.want_planes:   # the gradient of the planes IS (dy, dy^T)
+                g = dys[m].to(torch.float32).contiguous()
+                dy, dyT = g[0], g[1]
+            else:
+                dy = dys[m].to(torch.float32).contiguous()
+                dyT = torch.empty((Bsz, C, L), dtype=torch.float32, device=dev)
             planes = torch.empty((2, Bsz, C, L), dtype=torch.float32, device=dev)
-            dyT = torch.empty((Bsz, C, L), dtype=torch.float32, device=dev)
             dxdbl = torch.zeros((2, Bsz, 2, 3, L), dtype=torch.float32, device=dev)   # [rm | cm], accumulated into
             small = torch.zeros((4, 4 * C), dtype=torch.float32, device=dev)          # dA, dD, ddelta_bias, d dt_weight
             p = arr[m]
             _fill_proj(p, *t, ctx.softplus)
             p.planes, p.states = planes.data_ptr(), states_all[m].data_ptr()
             p.dy, p.dyT, p.dx = dy.data_ptr(), dyT.data_ptr(), None
+            p.flags = _lib.SS2D_DYT_GIVEN if ctx.want_planes else 0
             for k in range(4):
                 p.d_x_dbl[k] = dxdbl[k % 2][:, k // 2].data_ptr()
             p.dA, p.dD, p.ddelta_bias, p.d_dt_weight = (small[i].data_ptr() for i in range(4))
@@ -303,6 +320,98 @@ class _SS2DScanProj(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.vmasr_ss2d_core_bwd(n_maps, arr))
         return (None, None, *grads)
+
+
+class MergeNormGate(torch.autograd.Function):
+    """The block's tail fused into the merge of the core's planes (``vmasr_outnorm_gate_fwd`` / ``_bwd``):
+    ``y = P_rm + transpose(P_cm)`` (vmamba.py:57-60) -> ``out_norm = LayerNorm(C)`` on (B, L, C) (:1527-1529) -> ``.to(dtype)``
+    (:1531) -> ``* act(z)`` (forwardv2 :1536-1550).  planes (2, B, C, L) float32, gamma / beta (C), z (B, H, W, C) or None
+    (dtype of z = dtype of the result; without z: ``out_dtype``).  Returns (B, H, W, C)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, planes, gamma, beta, z, H, W, eps, z_silu, out_dtype):
+        lib = _lib.load_library()
+        _, Bsz, C, L = planes.shape
+        dev = planes.device
+        io = z.dtype if z is not None else out_dtype
+        if planes.dtype != torch.float32 or not planes.is_contiguous() or L != H * W or io not in _lib.DTYPE_CODE:
+            raise RuntimeError("MergeNormGate: planes must be contiguous float32 (2, B, C, H*W); io dtype float32 / float16 / bfloat16")
+        if z is not None:
+            z = z.contiguous()
+            if tuple(z.shape) != (Bsz, H, W, C):
+                raise RuntimeError("MergeNormGate: z must be (B, H, W, C)")
+        need = any(ctx.needs_input_grad[:4])
+        out = torch.empty((Bsz, H, W, C), dtype=io, device=dev)
+        y = torch.empty((Bsz, C, L), dtype=torch.float32, device=dev) if need else None
+        stats = torch.empty((Bsz, L, 2), dtype=torch.float32, device=dev) if need else None
+        g32 = None if gamma is None else gamma.detach().to(torch.float32).contiguous()
+        b32 = None if beta is None else beta.detach().to(torch.float32).contiguous()
+        p = _lib.OutNormParams()
+        p.p_rm, p.p_cm = planes[0].data_ptr(), planes[1].data_ptr()
+        p.gamma, p.beta = (None if g32 is None else g32.data_ptr()), (None if b32 is None else b32.data_ptr())
+        p.z, p.out = (None if z is None else z.data_ptr()), out.data_ptr()
+        p.y, p.stats = (None if y is None else y.data_ptr()), (None if stats is None else stats.data_ptr())
+        p.eps, p.batch, p.channels, p.H, p.W = float(eps), Bsz, C, H, W
+        p.io_dtype, p.z_silu, p.device = _lib.DTYPE_CODE[io], int(bool(z_silu)), _dev(planes)
+        p.stream = _lib.current_stream_ptr(dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.vmasr_outnorm_gate_fwd(ctypes.byref(p)))
+        ctx.save_for_backward(y, stats, z, g32, b32)
+        ctx.dims = (Bsz, C, H, W, float(eps), bool(z_silu), io, gamma is not None, beta is not None)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        lib = _lib.load_library()
+        y, stats, z, g32, b32 = ctx.saved_tensors
+        Bsz, C, H, W, eps, z_silu, io, has_g, has_b = ctx.dims
+        dev, L = y.device, H * W
+        dout = dout.to(io).contiguous()
+        g = torch.empty((2, Bsz, C, L), dtype=torch.float32, device=dev)     # (dy, dy^T): the gradient of the planes
+        dz = torch.empty_like(z) if z is not None else None
+        patches = int(lib.vmasr_outnorm_patches(Bsz, C, H, W))
+        part = torch.empty((patches, 2, C), dtype=torch.float32, device=dev)
+        p = _lib.OutNormParams()
+        p.gamma, p.beta = (None if g32 is None else g32.data_ptr()), (None if b32 is None else b32.data_ptr())
+        p.z, p.dz = (None if z is None else z.data_ptr()), (None if dz is None else dz.data_ptr())
+        p.y, p.stats, p.dout, p.dy, p.dgb_partial = y.data_ptr(), stats.data_ptr(), dout.data_ptr(), g[0].data_ptr(), part.data_ptr()
+        p.eps, p.batch, p.channels, p.H, p.W = eps, Bsz, C, H, W
+        p.io_dtype, p.z_silu, p.device = _lib.DTYPE_CODE[io], int(z_silu), _dev(y)
+        p.stream = _lib.current_stream_ptr(dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.vmasr_outnorm_gate_bwd(ctypes.byref(p)))
+            _lib.check(lib.vmasr_map_transpose(g[0].data_ptr(), g[1].data_ptr(), Bsz * C, H, W, _dev(y), p.stream))
+        sums = part.sum(0)
+        return g, (sums[0] if has_g else None), (sums[1] if has_b else None), dz, None, None, None, None, None
+
+
+def outnorm_fusable(x: torch.Tensor, N: int) -> bool:
+    """the fused tail applies: fused core + W a multiple of 8 + a patch of all channels fits shared memory"""
+    if not _fusable(x, N) or x.shape[3] % 8:
+        return False
+    return int(_lib.load_library().vmasr_outnorm_patches(x.shape[0], x.shape[1], x.shape[2], x.shape[3])) > 0
+
+
+def ss2d_core_out(x: torch.Tensor, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm_weight, out_norm_bias,
+                  z: torch.Tensor | None = None, z_silu: bool = True, eps: float = 1e-5, delta_softplus: bool = True,
+                  x_proj_bias=None, projected: bool | None = None) -> torch.Tensor:
+    """``forward_corev2`` INCLUDING its tail and the gate of ``forwardv2`` (vmamba.py:1472-1531, 1536-1550) for the configs'
+    layout (channel_first False, out_norm = nn.LayerNorm): x (B, C, H, W) -> (B, H, W, C) in the dtype of z (of x without a
+    gate).  The core's planes go straight into ``MergeNormGate``: the merged map is written once (for the backward) and never
+    read back in the forward; transpose, LayerNorm, cast, SiLU and the product are not separate passes."""
+    N = A_logs.shape[1]
+    if not outnorm_fusable(x, N):
+        raise RuntimeError("ss2d_core_out: needs a CUDA map with H % 4 == 0, W % 8 == 0, d_state 1 and channels that fit a patch")
+    if projected is None:
+        projected = _projectable(x, dt_projs_weight, N)
+    mode = (_SOFTPLUS if delta_softplus else 0) | _PLANES
+    if projected:
+        planes = _SS2DScanProj.apply(mode, 1, *_prepare_proj(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias))
+    else:
+        planes = _SS2DScan.apply(mode, 1, *_prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias))
+    return MergeNormGate.apply(planes, out_norm_weight, out_norm_bias, z, x.shape[2], x.shape[3], eps, z_silu, x.dtype)
 
 
 def _projections(x, xT, x_proj_weight, x_proj_bias, dt_projs_weight, R, N):
