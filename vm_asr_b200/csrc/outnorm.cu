@@ -9,7 +9,7 @@
 // takes), dz and per-tile partial sums of d gamma / d beta.
 //
 // Three memory orders meet: P_rm has w fastest, P_cm has h fastest, z / out have c fastest.  A CTA owns a patch of PH x TW
-// positions (PH = 8 or 4 rows, TW a multiple of 8 columns chosen so that a patch holds 4-16 K elements) of ALL channels in
+// positions (PH = 8 or 4 rows, TW = 8 * 2^k columns chosen so that a patch holds about 4 K elements) of ALL channels in
 // shared memory, pitch P + 1 floats per channel: column accesses (lanes along positions) and row accesses (lanes along
 // channels) are both conflict-free.  Global accesses: 128-bit along h for P_cm, 32-byte row pieces for P_rm / y / dy, fully
 // coalesced runs of TW * C elements for z / out / dout / dz.  LayerNorm statistics are two-pass (mean, then squared
@@ -67,22 +67,38 @@ __global__ void __launch_bounds__(256) outnorm_fwd_kernel(const OutNormArgs a) {
     {
         const int HQ = PH / 4, TPC = HQ * TW;  // items per channel: h-quads x columns
         const int items = C * TPC;
-        for (int i = t; i < items; i += 256) {
-            const int c = i / TPC, r = i - c * TPC;
-            const int q = r / TW, w = r - q * TW;
-            const long long plane = ((long long)b * C + c) * L;
-            float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (a.p_cm) {
-                const float4 cm = __ldg(reinterpret_cast<const float4 *>(a.p_cm + plane + (long long)(w0 + w) * H + h0 + 4 * q));
-                v[0] = cm.x; v[1] = cm.y; v[2] = cm.z; v[3] = cm.w;
+        constexpr int U = 4;  // items in flight per thread: every load of a batch is issued before the first use
+        for (int i0 = t; i0 < items; i0 += 256 * U) {
+            float4 cm[U];
+            float rm[U][4];
+            long long off0[U];
+            int sidx[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + 256 * u;
+                if (i < items) {
+                    const int c = i / TPC, r = i - c * TPC;
+                    const int q = r / TW, w = r - q * TW;
+                    const long long plane = ((long long)b * C + c) * L;
+                    cm[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (a.p_cm) cm[u] = __ldg(reinterpret_cast<const float4 *>(a.p_cm + plane + (long long)(w0 + w) * H + h0 + 4 * q));
+                    off0[u] = plane + (long long)(h0 + 4 * q) * W + w0 + w;
+                    sidx[u] = c * PITCH + 4 * q * TW + w;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) rm[u][k] = __ldg(a.p_rm + off0[u] + (long long)k * W);
+                }
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const long long off = plane + (long long)(h0 + 4 * q + k) * W + w0 + w;
-                const float rm = __ldg(a.p_rm + off);
-                const float yv = a.p_cm ? __fadd_rn(rm, v[k]) : rm;
-                sy[(size_t)c * PITCH + (4 * q + k) * TW + w] = yv;
-                if (a.y) a.y[off] = yv;
+            for (int u = 0; u < U; ++u) {
+                if (i0 + 256 * u < items) {
+                    const float v[4] = {cm[u].x, cm[u].y, cm[u].z, cm[u].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float yv = a.p_cm ? __fadd_rn(rm[u][k], v[k]) : rm[u][k];
+                        sy[sidx[u] + k * TW] = yv;
+                        if (a.y) a.y[off0[u] + (long long)k * W] = yv;
+                    }
+                }
             }
         }
     }
@@ -205,9 +221,16 @@ __global__ void __launch_bounds__(256) outnorm_bwd_kernel(const OutNormArgs a) {
     const T *dout = static_cast<const T *>(a.dout);
     T *dz = static_cast<T *>(a.dz);
     const int row_elems = TW * C;
+    // a thread walks elements t, t + 256, ...: its channel repeats with period K = C / gcd(C, 256) steps.  For the channel
+    // counts of the configs (powers of two) K is 1 (C <= 256) or C / 256, and the thread's sums for d gamma / d beta stay in
+    // registers, one shared-memory atomic per thread and channel at the end; any other C adds per element.
+    const int K = (256 % C == 0) ? 1 : (C % 256 == 0 && C <= 1024 ? C / 256 : 0);
+    for (int kk = 0; kk < (K ? K : 1); ++kk) {
+    float acc_g = 0.0f, acc_b = 0.0f;
+    const int step = K ? 256 * K : 256;
     for (int ph = 0; ph < PH; ++ph) {
         const long long base = ((long long)b * L + (long long)(h0 + ph) * W + w0) * C;
-        for (int e = t; e < row_elems; e += 256) {
+        for (int e = t + 256 * kk; e < row_elems; e += step) {
             int pw, c;
             split_pc(e, C, a.c_shift, pw, c);
             const int p = ph * TW + pw;
@@ -228,9 +251,20 @@ __global__ void __launch_bounds__(256) outnorm_bwd_kernel(const OutNormArgs a) {
                 if (dz) dz[base + e] = from_f32<T>(go * ln * dgate);
             }
             sd[(size_t)c * PITCH + p] = dln * g;
-            atomicAdd(&sgb[c], dln * xh);
-            atomicAdd(&sgb[C + c], dln);
+            if (K) {
+                acc_g = fmaf(dln, xh, acc_g);
+                acc_b += dln;
+            } else {
+                atomicAdd(&sgb[c], dln * xh);
+                atomicAdd(&sgb[C + c], dln);
+            }
         }
+    }
+    if (K && t + 256 * kk < row_elems) {
+        const int c = (t + 256 * kk) % C;
+        atomicAdd(&sgb[c], acc_g);
+        atomicAdd(&sgb[C + c], acc_b);
+    }
     }
     __syncthreads();
     if (a.dgb) {
@@ -286,9 +320,10 @@ __global__ void __launch_bounds__(256) outnorm_bwd_kernel(const OutNormArgs a) {
     }
 }
 
-// patch shape: PH rows x TW columns of all channels; TW the largest multiple-of-8 divisor of W that keeps the patch at
-// <= 8192 elements (and P a power of two <= 256 or a multiple of 256, which the statistics pass relies on)
-static int plan_patch(int C, int H, int W, bool bwd, int &PH, int &TW, size_t &smem) {
+// patch shape: PH rows x TW columns of all channels; TW the largest 8 * 2^k divisor of W that keeps the patch at <= 4096
+// elements (P is then a power of two <= 256 or a multiple of 256, which the statistics pass relies on), halved while the grid
+// would leave SMs without a CTA
+static int plan_patch(int batch, int C, int H, int W, bool bwd, int &PH, int &TW, size_t &smem) {
     if (H % 4 || W % 8) return fail("outnorm: H must be a multiple of 4 and W a multiple of 8 (got %d x %d)", H, W);
     const size_t limit = 200 * 1024;
     const int arrays = bwd ? 2 : 1;
@@ -301,10 +336,12 @@ static int plan_patch(int C, int H, int W, bool bwd, int &PH, int &TW, size_t &s
             if (P > 256 && P % 256) continue;
             const size_t bytes = sizeof(float) * ((size_t)arrays * C * (P + 1) + 512 + 3 * (size_t)P + 2 * (size_t)C);
             if (bytes > limit) break;
-            if ((long long)P * C > 8192 && best) break;
+            if ((long long)P * C > 4096 && best) break;
             best = tw;
         }
         if (best) {
+            while (best > 8 && (long long)batch * (H / ph) * (W / best) < 2 * 148) best /= 2;
+            if (ph == 8 && best == 8 && H % 4 == 0 && (long long)batch * (H / 8) * (W / 8) < 2 * 148) ph = 4;
             PH = ph;
             TW = best;
             smem = sizeof(float) * ((size_t)arrays * C * (PH * TW + 1) + 512 + 3 * (size_t)PH * TW + 2 * (size_t)C);
@@ -340,7 +377,7 @@ static int outnorm_run(const vmasr_outnorm_params *p, bool bwd) {
     }
     int PH = 0, TW = 0;
     size_t smem = 0;
-    if (int rc = plan_patch(p->channels, p->H, p->W, bwd, PH, TW, smem)) return rc;
+    if (int rc = plan_patch(p->batch, p->channels, p->H, p->W, bwd, PH, TW, smem)) return rc;
     const long long grid = (long long)p->batch * (p->H / PH) * (p->W / TW);
     if (grid > 0x7fffffffLL) return fail("%s: too many patches", who);
     a.p_rm = p->p_rm; a.p_cm = p->p_cm; a.gamma = p->gamma; a.beta = p->beta;
@@ -368,7 +405,7 @@ extern "C" int64_t vmasr_outnorm_patches(int batch, int channels, int H, int W) 
     int PH = 0, TW = 0;
     size_t smem = 0;
     if (batch <= 0 || channels <= 0 || H <= 0 || W <= 0) return -1;
-    if (vmasr::plan_patch(channels, H, W, true, PH, TW, smem)) return -1;
+    if (vmasr::plan_patch(batch, channels, H, W, true, PH, TW, smem)) return -1;
     return (int64_t)batch * (H / PH) * (W / TW);
 }
 extern "C" int vmasr_outnorm_gate_fwd(const vmasr_outnorm_params *p) { return vmasr::outnorm_run(p, false); }
