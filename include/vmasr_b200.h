@@ -285,6 +285,36 @@ VMASR_API int vmasr_outnorm_gate_fwd(const vmasr_outnorm_params *p);
 VMASR_API int vmasr_outnorm_gate_bwd(const vmasr_outnorm_params *p);
 
 /* ------------------------------------------------------------------------------------------------
+ * Head of the SS2D block fused into the core's load.  Replaces, in one kernel, SS2D.forwardv2's
+ *   x.permute(0, 3, 1, 2).contiguous() -> conv2d (depthwise 3x3, padding 1, bias; model/vmamba.py:860-868) -> SiLU
+ *   (vmamba.py:1541-1546) and the float32 cast / transpose the fused core needs in front of it.
+ *   xin    : (B, H, W, C) of io_dtype, channel-last, xin_pos_stride elements between positions (0 = C; in_proj's (B, H, W, 2C)
+ *            output is read in place with stride 2C)
+ *   weight : (C, 1, 3, 3) float32 contiguous;  bias: (C) float32 or NULL
+ *   x, xT  : (B, C, H, W) and (B, C, W, H) float32 -- what vmasr_ss2d_core_fwd takes (xT may be NULL).  The convolution and
+ *            the activation are rounded to io_dtype where the reference holds tensors of that dtype.
+ *   backward: dx (B, C, H, W), dxT (B, C, W, H) float32 (the `planes` vmasr_ss2d_core_bwd leaves; dxT may be NULL) ->
+ *            dxin (B, H, W, C) of io_dtype, contiguous, and dwb_partial (patches, C, 10) float32: per-patch sums of d weight (9)
+ *            and d bias, every entry written; the caller sums over patches (vmasr_dwconv_patches()); NULL = not wanted.
+ * H % 4 == 0, W % 8 == 0.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vmasr_dwconv_params {
+    const void *xin;
+    const float *weight, *bias;
+    float *x, *xT;
+    const float *dx, *dxT;
+    void *dxin;
+    float *dwb_partial;
+    int64_t xin_pos_stride;
+    int32_t batch, channels, H, W;
+    int32_t io_dtype, device;
+    void *stream;
+} vmasr_dwconv_params;
+VMASR_API int64_t vmasr_dwconv_patches(int batch, int channels, int H, int W);
+VMASR_API int vmasr_dwconv_silu_fwd(const vmasr_dwconv_params *p);
+VMASR_API int vmasr_dwconv_silu_bwd(const vmasr_dwconv_params *p);
+
+/* ------------------------------------------------------------------------------------------------
  * Magnitude/phase STFT and inverse.  Replace wav2spectro / spectro2wav (utils/stft.py:22-68, 71-115),
  * i.e. torch.stft / torch.istft(normalized=True, center=True, reflect pad, periodic Hann of win_length
  * zero-padded to n_fft, onesided) fused with log2(|X|+1e-8)/angle and exp2/polar.  float32 only.

@@ -204,6 +204,14 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, dtyp
     return cross_merge(ys.reshape(Bsz, K, C, H, W))
 
 
+def dwconv_silu(x_cl, weight, bias):
+    """Head of the block for the configs' layout (forwardv2, vmamba.py:1541-1546): channel-last (B, H, W, C) ->
+    permute -> depthwise conv 3x3 (padding 1, vmamba.py:860-868) -> SiLU -> (B, C, H, W)."""
+    x = x_cl.permute(0, 3, 1, 2).contiguous()                                      # :1541-1542
+    x = F.conv2d(x, weight, bias, padding=1, groups=x.shape[1])                    # :1543-1544
+    return F.silu(x)                                                               # :1545
+
+
 def out_norm_gate(y, gamma, beta, z, H, W, eps=1e-5, z_silu=True, out_dtype=None):
     """Tail of the block for the configs' layout: forward_corev2's out_norm branch (vmamba.py:1525-1531; channel_first False,
     out_norm_shape "v0", out_norm = nn.LayerNorm(d_inner)) followed by the gate of forwardv2 (:1536-1550).

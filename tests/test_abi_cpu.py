@@ -44,19 +44,21 @@ def test_workspace_sizing():
     assert lib.vmasr_scan_workspace_bytes(0, 8, 4096, 1) == 0
 
 
-def test_struct_layout_matches_header():
-    """ctypes mirror of vmasr_scan_params has the fields of the header, in order."""
+@pytest.mark.parametrize("struct,mirror", [("vmasr_scan_params", "ScanParams"), ("vmasr_ss2d_params", "SS2DParams"),
+                                           ("vmasr_outnorm_params", "OutNormParams"), ("vmasr_dwconv_params", "DwConvParams")])
+def test_struct_layout_matches_header(struct, mirror):
+    """every ctypes mirror has the fields of its struct in the header, in order (array members by name)"""
     from vm_asr_b200 import _lib
     text = open(os.path.join(ROOT, "include", "vmasr_b200.h")).read()
-    body = text[text.index("typedef struct vmasr_scan_params {") + len("typedef struct vmasr_scan_params {"):
-                text.index("} vmasr_scan_params;")]
+    start = text.index("typedef struct %s {" % struct) + len("typedef struct %s {" % struct)
+    body = text[start:text.index("} %s;" % struct)]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     quals = {"const", "void", "float", "int32_t", "int64_t", "uint64_t"}
     names = []
     for decl in body.split(";"):
-        parts = decl.replace("*", " ").replace(",", " ").split()
+        parts = re.sub(r"\[\d+\]", "", decl).replace("*", " ").replace(",", " ").split()
         names += [p for p in parts if p not in quals]
-    assert names == [f[0] for f in _lib.ScanParams._fields_]
+    assert names == [f[0] for f in getattr(_lib, mirror)._fields_]
 
 
 def test_operators_refuse_cpu_tensors():

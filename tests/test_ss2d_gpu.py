@@ -444,3 +444,82 @@ def test_merge_norm_gate_inference_keeps_nothing():
     assert torch.cuda.max_memory_allocated() - base <= out.numel() * 4 + (1 << 20)
     ref = _tail_oracle(planes, gamma, beta, z, H, W, True, None, dtype=torch.float32)
     assert rel_err(out, ref) < 1e-5
+
+
+# ---- permute + depthwise conv 3x3 + SiLU + transpose in one kernel (vmamba.py:1541-1546) ------------------------
+HEAD_CASES = [(2, 16, 16, 8), (1, 32, 48, 16), (2, 64, 64, 2), (1, 12, 24, 6), (1, 16, 16, 256), (1, 8, 16, 70), (2, 128, 128, 32),
+              (4, 512, 512, 2)]
+
+
+@pytest.mark.parametrize("Bsz,H,W,C", HEAD_CASES)
+@pytest.mark.parametrize("strided", [False, True])
+def test_conv_silu_input_fp32(Bsz, H, W, C, strided):
+    """x and x^T against the float64 oracle (x^T bit-identical to transpose(x)); d input, d weight, d bias with gradients arriving
+    through BOTH outputs; `strided`: the input is the first half of a (B, H, W, 2C) tensor, read in place"""
+    from vm_asr_b200 import ss2d
+    if strided and Bsz * H * W * C > 1 << 20:
+        pytest.skip("large maps once")
+    g = torch.Generator().manual_seed(50)
+    full = torch.randn(Bsz, H, W, 2 * C if strided else C, generator=g)
+    wt, bs = 0.4 * torch.randn(C, 1, 3, 3, generator=g), 0.3 * torch.randn(C, generator=g)
+    gx, gxT = torch.randn(Bsz, C, H, W, generator=g), torch.randn(Bsz, C, W, H, generator=g)
+    leaf = full.cuda().requires_grad_()
+    w_, b_ = wt.cuda().requires_grad_(), bs.cuda().requires_grad_()
+    x, xT = ss2d.ConvSiluInput.apply(leaf[..., :C], w_, b_)
+    assert torch.equal(xT, x.transpose(2, 3).contiguous())
+    ((x * gx.cuda()).sum() + (xT * gxT.cuda()).sum()).backward()
+    rleaf, rw, rb = full.double().requires_grad_(), wt.double().requires_grad_(), bs.double().requires_grad_()
+    rx = ss2d_ref.dwconv_silu(rleaf[..., :C], rw, rb)
+    ((rx * gx.double()).sum() + (rx.transpose(2, 3) * gxT.double()).sum()).backward()
+    assert rel_err(x, rx) < 1e-5
+    assert rel_err(leaf.grad, rleaf.grad) < 2e-5
+    assert rel_err(w_.grad, rw.grad) < 2e-4 and rel_err(b_.grad, rb.grad) < 2e-4   # sums over B * H * W terms in fp32
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+def test_conv_silu_input_half(dtype, tol):
+    """AMP: the input is a half tensor; conv and activation are rounded to half as the reference's tensors are, x / x^T come out
+    in float32 (the scan is forced to fp32, vmamba.py:1487-1491); against the same statements in torch on the GPU"""
+    from vm_asr_b200 import ss2d
+    Bsz, H, W, C = 2, 32, 32, 24
+    g = torch.Generator().manual_seed(51)
+    xin = torch.randn(Bsz, H, W, C, generator=g).cuda().to(dtype)
+    wt, bs = (0.4 * torch.randn(C, 1, 3, 3, generator=g)).cuda(), (0.3 * torch.randn(C, generator=g)).cuda()
+    gx = torch.randn(Bsz, C, H, W, generator=g).cuda()
+    a = [xin.clone().requires_grad_(), wt.clone().requires_grad_(), bs.clone().requires_grad_()]
+    x, xT = ss2d.ConvSiluInput.apply(*a)
+    (x * gx).sum().backward()
+    r = [xin.clone().requires_grad_(), wt.clone().requires_grad_(), bs.clone().requires_grad_()]
+    rx = ss2d_ref.dwconv_silu(r[0], r[1].to(dtype), r[2].to(dtype)).float()
+    (rx * gx).sum().backward()
+    assert x.dtype == torch.float32 and rel_err(x, rx) < tol
+    assert a[0].grad.dtype == dtype
+    for n, u, v in zip(("xin", "weight", "bias"), a, r):
+        assert rel_err(u.grad, v.grad) < 2 * tol, (n, rel_err(u.grad, v.grad))
+
+
+@pytest.mark.parametrize("Bsz,C,H,W,R", [(2, 8, 72, 64, 2), (1, 16, 64, 80, 1), (2, 32, 16, 16, 2)])
+def test_ss2d_block_core_matches_separate_statements(Bsz, C, H, W, R):
+    """ss2d_block_core (head kernel -> fused core -> tail kernel) against oracle head -> ss2d_core -> oracle tail in torch on the GPU:
+    output and the gradients of the input, the gate and every parameter (conv, core, LayerNorm)"""
+    from vm_asr_b200 import ss2d
+    g = torch.Generator().manual_seed(52)
+    xz = torch.randn(Bsz, H, W, 2 * C, generator=g)                      # in_proj's output: x half and z half side by side
+    wt, bs = 0.4 * torch.randn(C, 1, 3, 3, generator=g), 0.3 * torch.randn(C, generator=g)
+    core = _core_params(C, R, seed=53)
+    gamma, beta = 1.0 + 0.3 * torch.randn(C, generator=g), 0.3 * torch.randn(C, generator=g)
+    gout = torch.randn(Bsz, H, W, C, generator=g).cuda()
+    names = ("xz", "conv_w", "conv_b", "xw", "dw", "db", "A_logs", "Ds", "gamma", "beta")
+    vals = (xz, wt, bs) + core + (gamma, beta)
+    a = [v.cuda().requires_grad_() for v in vals]
+    xa, za = a[0].chunk(2, dim=-1)
+    out = ss2d.ss2d_block_core(xa, a[1], a[2], *a[3:8], a[8], a[9], z=za)
+    out.backward(gout)
+    b = [v.cuda().requires_grad_() for v in vals]
+    xb, zb = b[0].chunk(2, dim=-1)
+    y = ss2d.ss2d_core(ss2d_ref.dwconv_silu(xb, b[1], b[2]), *b[3:8], fused=True)
+    ref = ss2d_ref.out_norm_gate(y, b[8], b[9], zb, H, W)
+    ref.backward(gout)
+    assert rel_err(out, ref) < 2e-5
+    for n, u, v in zip(names, a, b):
+        assert rel_err(u.grad, v.grad) < 2e-4, (n, rel_err(u.grad, v.grad))

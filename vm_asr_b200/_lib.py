@@ -84,6 +84,17 @@ class OutNormParams(ctypes.Structure):
     )
 
 
+class DwConvParams(ctypes.Structure):
+    """Mirror of ``vmasr_dwconv_params`` (include/vmasr_b200.h)."""
+
+    _fields_ = (
+        [(n, _vp) for n in ("xin", "weight", "bias", "x", "xT", "dx", "dxT", "dxin", "dwb_partial")]
+        + [("xin_pos_stride", _i64)]
+        + [(n, _i32) for n in ("batch", "channels", "H", "W", "io_dtype", "device")]
+        + [("stream", _vp)]
+    )
+
+
 EXPORTS = {
     "vmasr_abi_version": (ctypes.c_int, []),
     "vmasr_last_error": (ctypes.c_char_p, []),
@@ -101,6 +112,9 @@ EXPORTS = {
     "vmasr_outnorm_patches": (_i64, [ctypes.c_int] * 4),
     "vmasr_outnorm_gate_fwd": (ctypes.c_int, [ctypes.POINTER(OutNormParams)]),
     "vmasr_outnorm_gate_bwd": (ctypes.c_int, [ctypes.POINTER(OutNormParams)]),
+    "vmasr_dwconv_patches": (_i64, [ctypes.c_int] * 4),
+    "vmasr_dwconv_silu_fwd": (ctypes.c_int, [ctypes.POINTER(DwConvParams)]),
+    "vmasr_dwconv_silu_bwd": (ctypes.c_int, [ctypes.POINTER(DwConvParams)]),
     "vmasr_cross_scan": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
     "vmasr_cross_merge": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
     "vmasr_cross_scan_1b1": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),

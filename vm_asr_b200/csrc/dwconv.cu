@@ -1,0 +1,275 @@
+// Head of the SS2D block fused into the core's load (second half).  SS2D.forwardv2 (model/vmamba.py:1541-1546):
+//     x = x.permute(0, 3, 1, 2).contiguous()     channel-last (B, H, W, C) -> channel-first
+//     x = self.conv2d(x)                         depthwise 3x3, padding 1, bias (vmamba.py:860-868)
+//     x = self.act(x)                            SiLU
+// and forward_corev2 then needs the map in float32 and (the fused core) its transpose.  The reference runs a permute copy, a
+// cuDNN depthwise convolution, an elementwise SiLU, a cast and (here) a transpose: five kernels, ten passes.  One kernel reads the
+// channel-last input once -- straight out of in_proj's (B, H, W, 2C) output: a position stride is taken, no chunk copy -- and
+// writes x (B, C, H, W) and x^T (B, C, W, H) in float32.  Its backward takes the two map gradients the core's backward leaves
+// (d x row-major, d x^T column-major), recomputes the convolution on a halo, and writes d input (channel-last) and per-patch
+// partial sums of d weight / d bias.
+//
+// The convolution is depthwise, so a CTA owns a patch of PH x TW positions of a BLOCK of CB channels (no reduction over
+// channels): input patch + halo in shared memory at an odd pitch per channel, so that loads from the channel-last input (lanes
+// along channels) and the stencil / stores (lanes along w) are both conflict-free.  Global accesses: runs of CB elements per
+// position for the channel-last tensors, 32-byte row pieces for x / d x, 128-bit pieces along h for x^T.  Bound: HBM.
+#include "common.cuh"
+
+namespace vmasr {
+
+struct DwArgs {
+    const void *xin;   // (B, H, W, C) at position stride `ps` elements
+    const float *w9;   // (C, 9)
+    const float *bias; // (C) or null
+    float *x, *xT;     // forward outputs
+    const float *dx, *dxT;
+    void *dxin;        // (B, H, W, C) contiguous
+    float *dwb;        // (patches, C, 10): d weight (9) and d bias per patch
+    long long ps;
+    int B, C, H, W, PH, TW, CB;
+};
+
+__device__ __forceinline__ float silu_val(float v) { return v / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu_grad(float v) {
+    const float s = 1.0f / (1.0f + __expf(-v));
+    return s * (1.0f + v * (1.0f - s));
+}
+
+// patch coordinates of this CTA
+struct DwJob {
+    int b, h0, w0, c0, nc, patch;
+    __device__ __forceinline__ DwJob(const DwArgs &a) {
+        const int tiles_w = a.W / a.TW, tiles_h = a.H / a.PH, cblocks = (a.C + a.CB - 1) / a.CB;
+        int t = blockIdx.x;
+        const int cb = t % cblocks;
+        t /= cblocks;
+        patch = t;
+        const int tw = t % tiles_w;
+        t /= tiles_w;
+        const int th = t % tiles_h;
+        b = t / tiles_h;
+        h0 = th * a.PH;
+        w0 = tw * a.TW;
+        c0 = cb * a.CB;
+        nc = min(a.CB, a.C - c0);
+    }
+};
+
+// input patch with a halo of HALO positions (zeros outside the map) -> s[c][(PH + 2 HALO) x (TW + 2 HALO)], lanes along channels
+template <typename T, int HALO>
+__device__ __forceinline__ void load_patch(const DwArgs &a, const DwJob &j, float *s, int pitch) {
+    const T *xin = static_cast<const T *>(a.xin);
+    const int RW = a.TW + 2 * HALO, RH = a.PH + 2 * HALO;
+    const int total = RH * RW * j.nc;
+    for (int i = threadIdx.x; i < total; i += 256) {
+        const int pos = i / j.nc, c = i - pos * j.nc;
+        const int r = pos / RW, q = pos - r * RW;
+        const int h = j.h0 - HALO + r, w = j.w0 - HALO + q;
+        float v = 0.0f;
+        if (h >= 0 && h < a.H && w >= 0 && w < a.W) v = to_f32<T>(xin[(((long long)j.b * a.H + h) * a.W + w) * a.ps + j.c0 + c]);
+        s[c * pitch + pos] = v;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv_silu_fwd_kernel(const DwArgs a) {
+    extern __shared__ float smem_dw[];
+    const DwJob j(a);
+    const int PH = a.PH, TW = a.TW, RW = TW + 2;
+    const int pitch = ((PH + 2) * RW) | 1;
+    float *s = smem_dw;                       // [CB][pitch]
+    float *sw = s + (size_t)a.CB * pitch;     // [CB][10] weights and bias
+    for (int i = threadIdx.x; i < j.nc * 10; i += 256) {
+        const int c = i / 10, k = i - c * 10;
+        sw[i] = k < 9 ? __ldg(a.w9 + (long long)(j.c0 + c) * 9 + k) : (a.bias ? __ldg(a.bias + j.c0 + c) : 0.0f);
+    }
+    load_patch<T, 1>(a, j, s, pitch);
+    __syncthreads();
+    // item = (channel, quad of rows, column): four outputs down a column -> 32-byte row pieces of x, 128-bit pieces of x^T
+    const long long L = (long long)a.H * a.W;
+    const int HQ = PH / 4, items = j.nc * HQ * TW;
+    for (int i = threadIdx.x; i < items; i += 256) {
+        const int c = i / (HQ * TW), r = i - c * HQ * TW;
+        const int q = r / TW, w = r - q * TW;
+        const float *wt = sw + c * 10;
+        const float *src = s + c * pitch + (4 * q) * RW + w;  // top-left of the 6 x 3 window
+        float acc[4] = {wt[9], wt[9], wt[9], wt[9]};
+#pragma unroll
+        for (int rr = 0; rr < 6; ++rr) {
+            const float v0 = src[rr * RW], v1 = src[rr * RW + 1], v2 = src[rr * RW + 2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int kh = rr - k;  // output row k uses window rows k .. k + 2
+                if (kh >= 0 && kh < 3) acc[k] = fmaf(wt[kh * 3 + 2], v2, fmaf(wt[kh * 3 + 1], v1, fmaf(wt[kh * 3], v0, acc[k])));
+            }
+        }
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = to_f32<T>(from_f32<T>(silu_val(to_f32<T>(from_f32<T>(acc[k])))));  // conv and act are tensors of the input's dtype
+        const long long plane = ((long long)j.b * a.C + j.c0 + c) * L;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a.x[plane + (long long)(j.h0 + 4 * q + k) * a.W + j.w0 + w] = o[k];
+        if (a.xT) *reinterpret_cast<float4 *>(a.xT + plane + (long long)(j.w0 + w) * a.H + j.h0 + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// Backward.  pre = conv(xin) + bias (recomputed on the patch + 1), g = d x + transpose(d x^T), d pre = g * silu'(pre);
+//   d xin[h, w] = sum_k w[kh, kw] d pre[h - kh + 1, w - kw + 1];  d w[kh, kw] = sum d pre[h, w] xin[h + kh - 1, w + kw - 1];  d bias = sum d pre
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv_silu_bwd_kernel(const DwArgs a) {
+    extern __shared__ float smem_dw[];
+    const DwJob j(a);
+    const int PH = a.PH, TW = a.TW;
+    const int XW = TW + 4, XH = PH + 4, DW = TW + 2, DH = PH + 2;
+    const int xpitch = (XH * XW) | 1, dpitch = (DH * DW) | 1;
+    float *sx = smem_dw;                        // [CB][xpitch]  input patch, halo 2
+    float *sd = sx + (size_t)a.CB * xpitch;     // [CB][dpitch]  d pre, halo 1
+    float *sw = sd + (size_t)a.CB * dpitch;     // [CB][10]
+    float *sacc = sw + (size_t)a.CB * 10;       // [CB][10] d weight / d bias of this patch
+    for (int i = threadIdx.x; i < j.nc * 10; i += 256) {
+        const int c = i / 10, k = i - c * 10;
+        sw[i] = k < 9 ? __ldg(a.w9 + (long long)(j.c0 + c) * 9 + k) : (a.bias ? __ldg(a.bias + j.c0 + c) : 0.0f);
+        sacc[i] = 0.0f;
+    }
+    load_patch<T, 2>(a, j, sx, xpitch);
+    __syncthreads();
+    // d pre on the patch + 1 (zero outside the map): lanes along w
+    const long long L = (long long)a.H * a.W;
+    for (int i = threadIdx.x; i < j.nc * DH * DW; i += 256) {
+        const int c = i / (DH * DW), r = i - c * DH * DW;
+        const int dr = r / DW, dq = r - dr * DW;
+        const int h = j.h0 - 1 + dr, w = j.w0 - 1 + dq;
+        float dp = 0.0f;
+        if (h >= 0 && h < a.H && w >= 0 && w < a.W) {
+            const float *wt = sw + c * 10;
+            const float *src = sx + c * xpitch + dr * XW + dq;  // window of (h, w): rows dr .. dr + 2 of the halo-2 patch
+            float pre = wt[9];
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) pre = fmaf(wt[kh * 3 + kw], src[kh * XW + kw], pre);
+            pre = to_f32<T>(from_f32<T>(pre));
+            const long long plane = ((long long)j.b * a.C + j.c0 + c) * L;
+            float g = __ldg(a.dx + plane + (long long)h * a.W + w);
+            if (a.dxT) g += __ldg(a.dxT + plane + (long long)w * a.H + h);
+            dp = g * silu_grad(pre);
+        }
+        sd[c * dpitch + r] = dp;
+    }
+    __syncthreads();
+    // d weight / d bias over the positions this patch OWNS: a warp takes a channel, lanes the positions
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int c = warp; c < j.nc; c += 8) {
+            float acc[10];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) acc[k] = 0.0f;
+            for (int p = lane; p < PH * TW; p += 32) {
+                const int ph = p / TW, pw = p - ph * TW;
+                const float dp = sd[c * dpitch + (ph + 1) * DW + pw + 1];
+                const float *src = sx + c * xpitch + (ph + 1) * XW + pw + 1;  // window of the owned position
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) acc[kh * 3 + kw] = fmaf(dp, src[kh * XW + kw], acc[kh * 3 + kw]);
+                acc[9] += dp;
+            }
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                float v = acc[k];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if (lane == 0) sacc[c * 10 + k] = v;
+            }
+        }
+    }
+    // d input, channel-last: lanes along channels
+    T *dxin = static_cast<T *>(a.dxin);
+    for (int i = threadIdx.x; i < PH * TW * j.nc; i += 256) {
+        const int pos = i / j.nc, c = i - pos * j.nc;
+        const int ph = pos / TW, pw = pos - ph * TW;
+        const float *wt = sw + c * 10;
+        const float *src = sd + c * dpitch + ph * DW + pw;  // d pre rows ph .. ph + 2 (halo 1) = positions h - 1 .. h + 1
+        float acc = 0.0f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) acc = fmaf(wt[kh * 3 + kw], src[(2 - kh) * DW + (2 - kw)], acc);
+        dxin[(((long long)j.b * a.H + j.h0 + ph) * a.W + j.w0 + pw) * a.C + j.c0 + c] = from_f32<T>(acc);
+    }
+    __syncthreads();
+    if (a.dwb) {
+        float *dst = a.dwb + ((long long)j.patch * a.C + j.c0) * 10;
+        for (int i = threadIdx.x; i < j.nc * 10; i += 256) dst[i] = sacc[i];
+    }
+}
+
+// patch (PH x TW positions) x channel block: about 4 K outputs per CTA, shared memory under 100 KB, grid large enough
+static int plan_dw(int batch, int C, int H, int W, bool bwd, int &PH, int &TW, int &CB, size_t &smem) {
+    if (H % 4 || W % 8) return fail("dwconv_silu: H must be a multiple of 4 and W a multiple of 8 (got %d x %d)", H, W);
+    PH = (H % 8 == 0) ? 8 : 4;
+    CB = C < 64 ? C : 64;
+    TW = 8;
+    while (TW * 2 <= W && W % (TW * 2) == 0 && (long long)PH * TW * 2 * CB <= 4096) TW *= 2;
+    auto grid = [&]() { return (long long)batch * (H / PH) * (W / TW) * ((C + CB - 1) / CB); };
+    while (TW > 8 && grid() < 2 * 148) TW /= 2;
+    while (CB > 16 && grid() < 2 * 148) CB /= 2;
+    const int halo = bwd ? 2 : 1;
+    const size_t xp = (size_t)((PH + 2 * halo) * (TW + 2 * halo)) | 1, dp = (size_t)((PH + 2) * (TW + 2)) | 1;
+    smem = sizeof(float) * ((size_t)CB * (xp + (bwd ? dp : 0)) + (size_t)CB * 20);
+    if (smem > 200 * 1024) return fail("dwconv_silu: patch does not fit shared memory");
+    return 0;
+}
+
+template <typename T>
+static int launch_dw(const DwArgs &a, bool bwd, size_t smem, long long grid, cudaStream_t stream) {
+    auto kernel = bwd ? dwconv_silu_bwd_kernel<T> : dwconv_silu_fwd_kernel<T>;
+    if (smem > 48 * 1024)
+        if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "dwconv_silu smem attribute")) return rc;
+    kernel<<<(unsigned)grid, 256, smem, stream>>>(a);
+    return check_cuda(cudaGetLastError(), bwd ? "dwconv_silu_bwd launch" : "dwconv_silu_fwd launch");
+}
+
+static int dw_run(const vmasr_dwconv_params *p, bool bwd) {
+    const char *who = bwd ? "dwconv_silu_bwd" : "dwconv_silu_fwd";
+    if (!p) return fail("%s: null params", who);
+    if (p->batch <= 0 || p->channels <= 0 || p->H <= 0 || p->W <= 0) return fail("%s: sizes must be positive", who);
+    if (p->io_dtype != VMASR_F32 && p->io_dtype != VMASR_F16 && p->io_dtype != VMASR_BF16) return fail("%s: unknown io_dtype %d", who, p->io_dtype);
+    if (!p->xin || !p->weight) return fail("%s: xin and weight must be non-null", who);
+    if (p->xin_pos_stride != 0 && p->xin_pos_stride < p->channels) return fail("%s: xin_pos_stride must be 0 (contiguous) or >= channels", who);
+    if (!bwd) {
+        if (!p->x) return fail("%s: x must be non-null", who);
+        if (reinterpret_cast<uintptr_t>(p->xT) & 15u) return fail("%s: xT must be 16-byte aligned", who);
+    } else {
+        if (!p->dx || !p->dxin) return fail("%s: dx and dxin must be non-null", who);
+    }
+    DwArgs a{};
+    size_t smem = 0;
+    if (int rc = plan_dw(p->batch, p->channels, p->H, p->W, bwd, a.PH, a.TW, a.CB, smem)) return rc;
+    const long long grid = (long long)p->batch * (p->H / a.PH) * (p->W / a.TW) * ((p->channels + a.CB - 1) / a.CB);
+    if (grid > 0x7fffffffLL) return fail("%s: too many patches", who);
+    a.xin = p->xin; a.w9 = p->weight; a.bias = p->bias; a.x = p->x; a.xT = p->xT;
+    a.dx = p->dx; a.dxT = p->dxT; a.dxin = p->dxin; a.dwb = p->dwb_partial;
+    a.ps = p->xin_pos_stride ? p->xin_pos_stride : p->channels;
+    a.B = p->batch; a.C = p->channels; a.H = p->H; a.W = p->W;
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail("%s: cannot select CUDA device %d", who, p->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(p->stream);
+    switch (p->io_dtype) {
+        case VMASR_F32: return launch_dw<float>(a, bwd, smem, grid, stream);
+        case VMASR_F16: return launch_dw<__half>(a, bwd, smem, grid, stream);
+        default: return launch_dw<__nv_bfloat16>(a, bwd, smem, grid, stream);
+    }
+}
+
+}  // namespace vmasr
+
+extern "C" int64_t vmasr_dwconv_patches(int batch, int channels, int H, int W) {
+    int PH = 0, TW = 0, CB = 0;
+    size_t smem = 0;
+    if (batch <= 0 || channels <= 0 || H <= 0 || W <= 0) return -1;
+    if (vmasr::plan_dw(batch, channels, H, W, true, PH, TW, CB, smem)) return -1;
+    return (int64_t)batch * (H / PH) * (W / TW);
+}
+extern "C" int vmasr_dwconv_silu_fwd(const vmasr_dwconv_params *p) { return vmasr::dw_run(p, false); }
+extern "C" int vmasr_dwconv_silu_bwd(const vmasr_dwconv_params *p) { return vmasr::dw_run(p, true); }

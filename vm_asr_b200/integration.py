@@ -52,14 +52,21 @@ def _fused_forwardv2(self, x, **kwargs):
     z = None
     if not self.disable_z:
         x, z = x.chunk(2, dim=(1 if self.channel_first else -1))
+    core_is_v2 = getattr(self.forward_core, "func", None) is not None and self.forward_core.func.__name__ in ("forward_corev2", "_fused_forward_corev2")
+    tail_ok = core_is_v2 and not self.channel_first and isinstance(self.out_norm, nn.LayerNorm) and self.out_norm.elementwise_affine
+    # head too: depthwise 3x3 + SiLU read from the channel-last in_proj output in place, writing x and x^T for the core
+    if (tail_ok and with_dconv and self.d_conv == 3 and isinstance(self.act, nn.SiLU) and x.is_cuda
+            and ss2d.outnorm_fusable(x.permute(0, 3, 1, 2), self.A_logs.shape[1])):
+        y = ss2d.ss2d_block_core(x, self.conv2d.weight, self.conv2d.bias, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias,
+                                 self.A_logs, self.Ds, self.out_norm.weight, self.out_norm.bias, z=z, z_silu=not self.disable_z_act,
+                                 eps=self.out_norm.eps, x_proj_bias=getattr(self, "x_proj_bias", None))
+        return self.dropout(self.out_proj(y))
     if not self.channel_first:
         x = x.permute(0, 3, 1, 2).contiguous()
     if with_dconv:
         x = self.conv2d(x)
     x = self.act(x)
-    core_is_v2 = getattr(self.forward_core, "func", None) is not None and self.forward_core.func.__name__ in ("forward_corev2", "_fused_forward_corev2")
-    fuse_tail = (core_is_v2 and not self.channel_first and isinstance(self.out_norm, nn.LayerNorm) and self.out_norm.elementwise_affine
-                 and ss2d.outnorm_fusable(x, self.A_logs.shape[1]))
+    fuse_tail = tail_ok and ss2d.outnorm_fusable(x, self.A_logs.shape[1])
     if fuse_tail:
         y = ss2d.ss2d_core_out(x, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds,
                                self.out_norm.weight, self.out_norm.bias, z=z, z_silu=not self.disable_z_act,

@@ -387,6 +387,62 @@ class MergeNormGate(torch.autograd.Function):
         return g, (sums[0] if has_g else None), (sums[1] if has_b else None), dz, None, None, None, None, None
 
 
+class ConvSiluInput(torch.autograd.Function):
+    """The block's head fused into the core's load (``vmasr_dwconv_silu_fwd`` / ``_bwd``): channel-last
+    ``xin (B, H, W, C)`` -- e.g. the x half of in_proj's output, read in place through its position stride -- ->
+    ``permute -> conv2d (depthwise 3x3, padding 1) -> SiLU`` (vmamba.py:1541-1546) -> ``(x (B, C, H, W), x^T (B, C, W, H))`` in
+    float32, the two tensors the fused core reads.  weight (C, 1, 3, 3), bias (C) or None."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, xin, weight, bias):
+        lib = _lib.load_library()
+        _lib.require_cuda(xin, "xin")
+        if xin.dim() != 4 or xin.dtype not in _lib.DTYPE_CODE or tuple(weight.shape[1:]) != (1, 3, 3) or weight.shape[0] != xin.shape[3]:
+            raise RuntimeError("ConvSiluInput: xin (B, H, W, C) float32 / float16 / bfloat16, weight (C, 1, 3, 3)")
+        Bsz, H, W, C = xin.shape
+        ps = xin.stride(2)
+        if not (xin.stride(3) == 1 and ps >= C and xin.stride(1) == W * ps and xin.stride(0) == H * W * ps):
+            xin = xin.contiguous()
+            ps = C
+        dev = xin.device
+        w32 = weight.detach().to(torch.float32).contiguous()
+        b32 = None if bias is None else bias.detach().to(torch.float32).contiguous()
+        x = torch.empty((Bsz, C, H, W), dtype=torch.float32, device=dev)
+        xT = torch.empty((Bsz, C, W, H), dtype=torch.float32, device=dev)
+        p = _lib.DwConvParams()
+        p.xin, p.weight, p.bias = xin.data_ptr(), w32.data_ptr(), (None if b32 is None else b32.data_ptr())
+        p.x, p.xT, p.xin_pos_stride = x.data_ptr(), xT.data_ptr(), ps
+        p.batch, p.channels, p.H, p.W = Bsz, C, H, W
+        p.io_dtype, p.device, p.stream = _lib.DTYPE_CODE[xin.dtype], _dev(xin), _lib.current_stream_ptr(dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.vmasr_dwconv_silu_fwd(ctypes.byref(p)))
+        ctx.save_for_backward(xin, w32, b32)
+        ctx.ps, ctx.has_bias = ps, bias is not None
+        return x, xT
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dx, dxT):
+        lib = _lib.load_library()
+        xin, w32, b32 = ctx.saved_tensors
+        Bsz, H, W, C = xin.shape
+        dev = xin.device
+        dx, dxT = dx.to(torch.float32).contiguous(), dxT.to(torch.float32).contiguous()
+        dxin = torch.empty((Bsz, H, W, C), dtype=xin.dtype, device=dev)
+        patches = int(lib.vmasr_dwconv_patches(Bsz, C, H, W))
+        part = torch.empty((patches, C, 10), dtype=torch.float32, device=dev)
+        p = _lib.DwConvParams()
+        p.xin, p.weight, p.bias = xin.data_ptr(), w32.data_ptr(), (None if b32 is None else b32.data_ptr())
+        p.dx, p.dxT, p.dxin, p.dwb_partial, p.xin_pos_stride = dx.data_ptr(), dxT.data_ptr(), dxin.data_ptr(), part.data_ptr(), ctx.ps
+        p.batch, p.channels, p.H, p.W = Bsz, C, H, W
+        p.io_dtype, p.device, p.stream = _lib.DTYPE_CODE[xin.dtype], _dev(xin), _lib.current_stream_ptr(dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.vmasr_dwconv_silu_bwd(ctypes.byref(p)))
+        sums = part.sum(0)
+        return dxin, sums[:, :9].reshape(C, 1, 3, 3), (sums[:, 9] if ctx.has_bias else None)
+
+
 def outnorm_fusable(x: torch.Tensor, N: int) -> bool:
     """the fused tail applies: fused core + W a multiple of 8 + a patch of all channels fits shared memory"""
     if not _fusable(x, N) or x.shape[3] % 8:
@@ -396,7 +452,7 @@ def outnorm_fusable(x: torch.Tensor, N: int) -> bool:
 
 def ss2d_core_out(x: torch.Tensor, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm_weight, out_norm_bias,
                   z: torch.Tensor | None = None, z_silu: bool = True, eps: float = 1e-5, delta_softplus: bool = True,
-                  x_proj_bias=None, projected: bool | None = None) -> torch.Tensor:
+                  x_proj_bias=None, projected: bool | None = None, xT: torch.Tensor | None = None, out_dtype=None) -> torch.Tensor:
     """``forward_corev2`` INCLUDING its tail and the gate of ``forwardv2`` (vmamba.py:1472-1531, 1536-1550) for the configs'
     layout (channel_first False, out_norm = nn.LayerNorm): x (B, C, H, W) -> (B, H, W, C) in the dtype of z (of x without a
     gate).  The core's planes go straight into ``MergeNormGate``: the merged map is written once (for the backward) and never
@@ -408,10 +464,24 @@ def ss2d_core_out(x: torch.Tensor, x_proj_weight, dt_projs_weight, dt_projs_bias
         projected = _projectable(x, dt_projs_weight, N)
     mode = (_SOFTPLUS if delta_softplus else 0) | _PLANES
     if projected:
-        planes = _SS2DScanProj.apply(mode, 1, *_prepare_proj(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias))
+        planes = _SS2DScanProj.apply(mode, 1, *_prepare_proj(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias, xT))
     else:
-        planes = _SS2DScan.apply(mode, 1, *_prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias))
-    return MergeNormGate.apply(planes, out_norm_weight, out_norm_bias, z, x.shape[2], x.shape[3], eps, z_silu, x.dtype)
+        planes = _SS2DScan.apply(mode, 1, *_prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias, xT))
+    return MergeNormGate.apply(planes, out_norm_weight, out_norm_bias, z, x.shape[2], x.shape[3], eps, z_silu, out_dtype or x.dtype)
+
+
+def ss2d_block_core(x_cl: torch.Tensor, conv_weight, conv_bias, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds,
+                    out_norm_weight, out_norm_bias, z: torch.Tensor | None = None, z_silu: bool = True, eps: float = 1e-5,
+                    delta_softplus: bool = True, x_proj_bias=None, projected: bool | None = None) -> torch.Tensor:
+    """Everything of ``SS2D.forwardv2`` between in_proj and out_proj (vmamba.py:1536-1550 with forward_corev2 inside) for the
+    configs' layout: channel-last x_cl (B, H, W, C) -- a strided view of in_proj's output is read in place -- -> depthwise
+    conv 3x3 + SiLU + permute + transpose (``ConvSiluInput``) -> fused core -> merge + LayerNorm + cast + gate
+    (``MergeNormGate``) -> (B, H, W, C).  Four kernels of this library and the two small einsums; no ``xs`` / ``ys`` / ``dts``
+    copies, no separate permute, activation, transpose, normalisation or gate passes."""
+    x, xT = ConvSiluInput.apply(x_cl, conv_weight, conv_bias)
+    return ss2d_core_out(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm_weight, out_norm_bias, z=z,
+                         z_silu=z_silu, eps=eps, delta_softplus=delta_softplus, x_proj_bias=x_proj_bias, projected=projected,
+                         xT=xT, out_dtype=x_cl.dtype)
 
 
 def _projections(x, xT, x_proj_weight, x_proj_bias, dt_projs_weight, R, N):
@@ -440,13 +510,13 @@ def _projectable(x, dt_projs_weight, N):
     return _fusable(x, N) and dt_projs_weight.shape[2] == 1 and L > _lib.SCAN_CHUNK and L % 16 == 0
 
 
-def _prepare_proj(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias):
+def _prepare_proj(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias, xT=None):
     """inputs of _SS2DScanProj: x_dbl (vmamba.py:1473-1475) of the two pairs in memory order; the dt projection (:1477) is
     left to the kernels"""
     Bsz, C, H, W = x.shape
     L = H * W
     x32 = x.to(torch.float32).contiguous()
-    xT = MapTranspose.apply(x32)
+    xT = MapTranspose.apply(x32) if xT is None else xT
     xd = []
     for par, src in ((0, x32.view(Bsz, C, L)), (1, xT.view(Bsz, C, L))):
         x_dbl = torch.einsum("bdl,kcd->bkcl", src, x_proj_weight[par::2].to(torch.float32))
@@ -458,11 +528,11 @@ def _prepare_proj(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, 
             dt_projs_bias.reshape(-1).to(torch.float).contiguous())
 
 
-def _prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias):
+def _prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias, xT=None):
     K, _, R = dt_projs_weight.shape
     N = A_logs.shape[1]
     x32 = x.to(torch.float32).contiguous()
-    xT = MapTranspose.apply(x32)
+    xT = MapTranspose.apply(x32) if xT is None else xT
     (dts_rm, Bs_rm, Cs_rm), (dts_cm, Bs_cm, Cs_cm) = _projections(x32, xT, x_proj_weight, x_proj_bias, dt_projs_weight, R, N)
     # force_fp32 (vmamba.py:1487-1491; a no-op outside autocast); einsum is free to return any strides: the kernels need
     # unit stride along L only (the reference makes Bs / Cs / dts contiguous unconditionally, vmamba.py:1480-1483)
