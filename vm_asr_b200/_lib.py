@@ -92,6 +92,8 @@ class DwConvParams(ctypes.Structure):
         + [("xin_pos_stride", _i64)]
         + [(n, _i32) for n in ("batch", "channels", "H", "W", "io_dtype", "device")]
         + [("stream", _vp)]
+        + [(n, _vp) for n in ("x_proj_weight", "x_proj_bias", "x_dbl_rm", "x_dbl_cm", "d_x_dbl_rm", "d_x_dbl_cm", "d_x_proj_weight_partial")]
+        + [("x_proj_rows", _i32), ("reserved0", _i32)]
     )
 
 

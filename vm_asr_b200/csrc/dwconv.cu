@@ -13,6 +13,13 @@
 // channels): input patch + halo in shared memory at an odd pitch per channel, so that loads from the channel-last input (lanes
 // along channels) and the stencil / stores (lanes along w) are both conflict-free.  Global accesses: runs of CB elements per
 // position for the channel-last tensors, 32-byte row pieces for x / d x, 128-bit pieces along h for x^T.  Bound: HBM.
+//
+// x_proj too (optional; SURVEY.md 8f-1: `x_dbl = einsum(xs, x_proj_weight)`, vmamba.py:1473-1475).  The projection commutes with
+// the permutation of positions, so x_dbl of the row-major pair (directions 0, 2) and of the column-major pair (1, 3) are the
+// same per-position contraction over channels stored in two position orders.  The CTA keeps its activations in shared memory,
+// contracts them with its channel block's slice of the weight, and adds the 4 (R + 2) partial rows into x_dbl_rm / x_dbl_cm
+// (plain stores when one block holds all channels).  The backward adds W^T d x_dbl to the map gradient before SiLU' and writes
+// per-patch partial sums of d x_proj_weight.  The einsum's two cuBLAS launches and their passes over x and x^T are gone.
 #include "common.cuh"
 
 namespace vmasr {
@@ -25,8 +32,12 @@ struct DwArgs {
     const float *dx, *dxT;
     void *dxin;        // (B, H, W, C) contiguous
     float *dwb;        // (patches, C, 10): d weight (9) and d bias per patch
+    const float *xpw, *xpb;        // x_proj weight (4, RP, C) and bias (4, RP) or null; RP = dt_rank + 2 d_state rows per direction
+    float *xd_rm, *xd_cm;          // (B, 2, RP, L): x_dbl of directions (0, 2) in row-major and (1, 3) in column-major position order
+    const float *dxd_rm, *dxd_cm;  // their gradients (backward)
+    float *dxpw;                   // (patches, 4 RP, C): d x_proj weight per patch
     long long ps;
-    int B, C, H, W, PH, TW, CB;
+    int B, C, H, W, PH, TW, CB, RP;
 };
 
 __device__ __forceinline__ float silu_val(float v) { return v / (1.0f + __expf(-v)); }
@@ -79,10 +90,18 @@ __global__ void __launch_bounds__(256) dwconv_silu_fwd_kernel(const DwArgs a) {
     const int pitch = ((PH + 2) * RW) | 1;
     float *s = smem_dw;                       // [CB][pitch]
     float *sw = s + (size_t)a.CB * pitch;     // [CB][10] weights and bias
+    const int P = PH * TW, opitch = P | 1, KR = 4 * a.RP;
+    float *so = sw + (size_t)a.CB * 10;       // [CB][opitch] activations of the patch (x_proj only)
+    float *sxw = so + (size_t)a.CB * opitch;  // [KR][CB] x_proj weight slice (x_proj only)
     for (int i = threadIdx.x; i < j.nc * 10; i += 256) {
         const int c = i / 10, k = i - c * 10;
         sw[i] = k < 9 ? __ldg(a.w9 + (long long)(j.c0 + c) * 9 + k) : (a.bias ? __ldg(a.bias + j.c0 + c) : 0.0f);
     }
+    if (a.xpw)
+        for (int i = threadIdx.x; i < KR * j.nc; i += 256) {
+            const int kr = i / j.nc, c = i - kr * j.nc;
+            sxw[kr * a.CB + c] = __ldg(a.xpw + (long long)kr * a.C + j.c0 + c);
+        }
     load_patch<T, 1>(a, j, s, pitch);
     __syncthreads();
     // item = (channel, quad of rows, column): four outputs down a column -> 32-byte row pieces of x, 128-bit pieces of x^T
@@ -110,6 +129,35 @@ __global__ void __launch_bounds__(256) dwconv_silu_fwd_kernel(const DwArgs a) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) a.x[plane + (long long)(j.h0 + 4 * q + k) * a.W + j.w0 + w] = o[k];
         if (a.xT) *reinterpret_cast<float4 *>(a.xT + plane + (long long)(j.w0 + w) * a.H + j.h0 + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+        if (a.xpw) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) so[c * opitch + (4 * q + k) * TW + w] = o[k];
+        }
+    }
+    if (!a.xpw) return;
+    __syncthreads();
+    // x_dbl rows of this channel block: (direction k, row r) x position; even directions leave in row-major position order (lanes
+    // along w), odd ones in column-major order (lanes along h)
+    const bool single = a.C <= a.CB;
+    for (int i = threadIdx.x; i < KR * P; i += 256) {
+        const int kr = i / P, qpos = i - kr * P;
+        const int k = kr / a.RP, r = kr - k * a.RP;
+        int ph, pw;
+        if (k & 1) {
+            pw = qpos / PH;
+            ph = qpos - pw * PH;
+        } else {
+            ph = qpos / TW;
+            pw = qpos - ph * TW;
+        }
+        const float *act = so + ph * TW + pw;
+        const float *wk = sxw + kr * a.CB;
+        float acc = (j.c0 == 0 && a.xpb) ? __ldg(a.xpb + kr) : 0.0f;
+        for (int c = 0; c < j.nc; ++c) acc = fmaf(wk[c], act[c * opitch], acc);
+        const long long row = (((long long)j.b * 2 + (k >> 1)) * a.RP + r) * L;
+        float *dst = (k & 1) ? a.xd_cm + row + (long long)(j.w0 + pw) * a.H + j.h0 + ph : a.xd_rm + row + (long long)(j.h0 + ph) * a.W + j.w0 + pw;
+        if (single) *dst = acc;
+        else atomicAdd(dst, acc);
     }
 }
 
@@ -126,15 +174,43 @@ __global__ void __launch_bounds__(256) dwconv_silu_bwd_kernel(const DwArgs a) {
     float *sd = sx + (size_t)a.CB * xpitch;     // [CB][dpitch]  d pre, halo 1
     float *sw = sd + (size_t)a.CB * dpitch;     // [CB][10]
     float *sacc = sw + (size_t)a.CB * 10;       // [CB][10] d weight / d bias of this patch
+    const int KR = 4 * a.RP;
+    float *sxw = sacc + (size_t)a.CB * 10;      // [KR][CB] x_proj weight slice (x_proj only)
+    float *sdx = sxw + (size_t)KR * a.CB;       // [KR][dpitch] d x_dbl on the patch + 1 (x_proj only)
     for (int i = threadIdx.x; i < j.nc * 10; i += 256) {
         const int c = i / 10, k = i - c * 10;
         sw[i] = k < 9 ? __ldg(a.w9 + (long long)(j.c0 + c) * 9 + k) : (a.bias ? __ldg(a.bias + j.c0 + c) : 0.0f);
         sacc[i] = 0.0f;
     }
+    const long long L = (long long)a.H * a.W;
+    if (a.xpw) {
+        for (int i = threadIdx.x; i < KR * j.nc; i += 256) {
+            const int kr = i / j.nc, c = i - kr * j.nc;
+            sxw[kr * a.CB + c] = __ldg(a.xpw + (long long)kr * a.C + j.c0 + c);
+        }
+        for (int i = threadIdx.x; i < KR * DH * DW; i += 256) {
+            const int kr = i / (DH * DW), qpos = i - kr * DH * DW;
+            const int k = kr / a.RP, r = kr - k * a.RP;
+            int dr, dq;
+            if (k & 1) {  // column-major source: lanes along h
+                dq = qpos / DH;
+                dr = qpos - dq * DH;
+            } else {
+                dr = qpos / DW;
+                dq = qpos - dr * DW;
+            }
+            const int h = j.h0 - 1 + dr, w = j.w0 - 1 + dq;
+            float v = 0.0f;
+            if (h >= 0 && h < a.H && w >= 0 && w < a.W) {
+                const long long row = (((long long)j.b * 2 + (k >> 1)) * a.RP + r) * L;
+                v = (k & 1) ? __ldg(a.dxd_cm + row + (long long)w * a.H + h) : __ldg(a.dxd_rm + row + (long long)h * a.W + w);
+            }
+            sdx[kr * dpitch + dr * DW + dq] = v;
+        }
+    }
     load_patch<T, 2>(a, j, sx, xpitch);
     __syncthreads();
     // d pre on the patch + 1 (zero outside the map): lanes along w
-    const long long L = (long long)a.H * a.W;
     for (int i = threadIdx.x; i < j.nc * DH * DW; i += 256) {
         const int c = i / (DH * DW), r = i - c * DH * DW;
         const int dr = r / DW, dq = r - dr * DW;
@@ -152,6 +228,8 @@ __global__ void __launch_bounds__(256) dwconv_silu_bwd_kernel(const DwArgs a) {
             const long long plane = ((long long)j.b * a.C + j.c0 + c) * L;
             float g = __ldg(a.dx + plane + (long long)h * a.W + w);
             if (a.dxT) g += __ldg(a.dxT + plane + (long long)w * a.H + h);
+            if (a.xpw)  // x_dbl = W x: its gradient reaches the map through W^T
+                for (int kr = 0; kr < KR; ++kr) g = fmaf(sxw[kr * a.CB + c], sdx[kr * dpitch + r], g);
             dp = g * silu_grad(pre);
         }
         sd[c * dpitch + r] = dp;
@@ -181,6 +259,32 @@ __global__ void __launch_bounds__(256) dwconv_silu_bwd_kernel(const DwArgs a) {
                 for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
                 if (lane == 0) sacc[c * 10 + k] = v;
             }
+            if (a.xpw) {  // d x_proj weight[kr][c] = sum over owned positions of d x_dbl[kr] * act(c), act recomputed from the input patch
+                const float *wt = sw + c * 10;
+                for (int kr0 = 0; kr0 < KR; kr0 += 4) {
+                    float aw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    for (int p = lane; p < PH * TW; p += 32) {
+                        const int ph = p / TW, pw = p - ph * TW;
+                        const float *src = sx + c * xpitch + (ph + 1) * XW + pw + 1;
+                        float pre = wt[9];
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                            for (int kw = 0; kw < 3; ++kw) pre = fmaf(wt[kh * 3 + kw], src[kh * XW + kw], pre);
+                        const float act = to_f32<T>(from_f32<T>(silu_val(to_f32<T>(from_f32<T>(pre)))));
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (kr0 + u < KR) aw[u] = fmaf(sdx[(kr0 + u) * dpitch + (ph + 1) * DW + pw + 1], act, aw[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float v = aw[u];
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                        if (lane == 0 && kr0 + u < KR) a.dxpw[((long long)j.patch * KR + kr0 + u) * a.C + j.c0 + c] = v;
+                    }
+                }
+            }
         }
     }
     // d input, channel-last: lanes along channels
@@ -205,7 +309,7 @@ __global__ void __launch_bounds__(256) dwconv_silu_bwd_kernel(const DwArgs a) {
 }
 
 // patch (PH x TW positions) x channel block: about 4 K outputs per CTA, shared memory under 100 KB, grid large enough
-static int plan_dw(int batch, int C, int H, int W, bool bwd, int &PH, int &TW, int &CB, size_t &smem) {
+static int plan_dw(int batch, int C, int H, int W, bool bwd, int RP, int &PH, int &TW, int &CB, size_t &smem) {
     if (H % 4 || W % 8) return fail("dwconv_silu: H must be a multiple of 4 and W a multiple of 8 (got %d x %d)", H, W);
     PH = (H % 8 == 0) ? 8 : 4;
     CB = C < 64 ? C : 64;
@@ -217,6 +321,7 @@ static int plan_dw(int batch, int C, int H, int W, bool bwd, int &PH, int &TW, i
     const int halo = bwd ? 2 : 1;
     const size_t xp = (size_t)((PH + 2 * halo) * (TW + 2 * halo)) | 1, dp = (size_t)((PH + 2) * (TW + 2)) | 1;
     smem = sizeof(float) * ((size_t)CB * (xp + (bwd ? dp : 0)) + (size_t)CB * 20);
+    if (RP > 0) smem += sizeof(float) * ((size_t)4 * RP * CB + (bwd ? (size_t)4 * RP * dp : (size_t)CB * (((size_t)PH * TW) | 1)));
     if (smem > 200 * 1024) return fail("dwconv_silu: patch does not fit shared memory");
     return 0;
 }
@@ -245,11 +350,20 @@ static int dw_run(const vmasr_dwconv_params *p, bool bwd) {
     }
     DwArgs a{};
     size_t smem = 0;
-    if (int rc = plan_dw(p->batch, p->channels, p->H, p->W, bwd, a.PH, a.TW, a.CB, smem)) return rc;
+    const int RP = p->x_proj_weight ? p->x_proj_rows : 0;
+    if (p->x_proj_weight) {
+        if (RP < 1 || RP > 64) return fail("%s: x_proj_rows must be in [1, 64]", who);
+        if (!bwd && (!p->x_dbl_rm || !p->x_dbl_cm)) return fail("%s: x_dbl_rm and x_dbl_cm must be given with x_proj_weight", who);
+        if (bwd && (!p->d_x_dbl_rm || !p->d_x_dbl_cm || !p->d_x_proj_weight_partial))
+            return fail("%s: d_x_dbl_rm, d_x_dbl_cm and d_x_proj_weight_partial must be given with x_proj_weight", who);
+    }
+    if (int rc = plan_dw(p->batch, p->channels, p->H, p->W, bwd, RP, a.PH, a.TW, a.CB, smem)) return rc;
     const long long grid = (long long)p->batch * (p->H / a.PH) * (p->W / a.TW) * ((p->channels + a.CB - 1) / a.CB);
     if (grid > 0x7fffffffLL) return fail("%s: too many patches", who);
     a.xin = p->xin; a.w9 = p->weight; a.bias = p->bias; a.x = p->x; a.xT = p->xT;
     a.dx = p->dx; a.dxT = p->dxT; a.dxin = p->dxin; a.dwb = p->dwb_partial;
+    a.xpw = p->x_proj_weight; a.xpb = p->x_proj_bias; a.xd_rm = p->x_dbl_rm; a.xd_cm = p->x_dbl_cm;
+    a.dxd_rm = p->d_x_dbl_rm; a.dxd_cm = p->d_x_dbl_cm; a.dxpw = p->d_x_proj_weight_partial; a.RP = RP;
     a.ps = p->xin_pos_stride ? p->xin_pos_stride : p->channels;
     a.B = p->batch; a.C = p->channels; a.H = p->H; a.W = p->W;
     DeviceGuard guard(p->device);
@@ -268,7 +382,7 @@ extern "C" int64_t vmasr_dwconv_patches(int batch, int channels, int H, int W) {
     int PH = 0, TW = 0, CB = 0;
     size_t smem = 0;
     if (batch <= 0 || channels <= 0 || H <= 0 || W <= 0) return -1;
-    if (vmasr::plan_dw(batch, channels, H, W, true, PH, TW, CB, smem)) return -1;
+    if (vmasr::plan_dw(batch, channels, H, W, true, 0, PH, TW, CB, smem)) return -1;
     return (int64_t)batch * (H / PH) * (W / TW);
 }
 extern "C" int vmasr_dwconv_silu_fwd(const vmasr_dwconv_params *p) { return vmasr::dw_run(p, false); }

@@ -391,11 +391,16 @@ class ConvSiluInput(torch.autograd.Function):
     """The block's head fused into the core's load (``vmasr_dwconv_silu_fwd`` / ``_bwd``): channel-last
     ``xin (B, H, W, C)`` -- e.g. the x half of in_proj's output, read in place through its position stride -- ->
     ``permute -> conv2d (depthwise 3x3, padding 1) -> SiLU`` (vmamba.py:1541-1546) -> ``(x (B, C, H, W), x^T (B, C, W, H))`` in
-    float32, the two tensors the fused core reads.  weight (C, 1, 3, 3), bias (C) or None."""
+    float32, the two tensors the fused core reads.  weight (C, 1, 3, 3), bias (C) or None.
+
+    With ``x_proj_weight`` (4, R + 2, C) [and ``x_proj_bias`` (4, R + 2)] the same kernel also forms
+    ``x_dbl = einsum(xs, x_proj_weight)`` (vmamba.py:1473-1475) -- the rows of directions (0, 2) in row-major and of (1, 3) in
+    column-major position order, ``(B, 2, R + 2, L)`` each, what ``_SS2DScanProj`` takes -- and returns
+    ``(x, x^T, x_dbl_rm, x_dbl_cm)``: the einsum's cuBLAS launches and their passes over x and x^T disappear."""
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
-    def forward(ctx, xin, weight, bias):
+    def forward(ctx, xin, weight, bias, x_proj_weight=None, x_proj_bias=None):
         lib = _lib.load_library()
         _lib.require_cuda(xin, "xin")
         if xin.dim() != 4 or xin.dtype not in _lib.DTYPE_CODE or tuple(weight.shape[1:]) != (1, 3, 3) or weight.shape[0] != xin.shape[3]:
@@ -415,17 +420,29 @@ class ConvSiluInput(torch.autograd.Function):
         p.x, p.xT, p.xin_pos_stride = x.data_ptr(), xT.data_ptr(), ps
         p.batch, p.channels, p.H, p.W = Bsz, C, H, W
         p.io_dtype, p.device, p.stream = _lib.DTYPE_CODE[xin.dtype], _dev(xin), _lib.current_stream_ptr(dev)
+        xw32 = xb32 = xd = None
+        if x_proj_weight is not None:
+            if x_proj_weight.dim() != 3 or x_proj_weight.shape[0] != 4 or x_proj_weight.shape[2] != C:
+                raise RuntimeError("ConvSiluInput: x_proj_weight must be (4, R + 2, C)")
+            RP = x_proj_weight.shape[1]
+            xw32 = x_proj_weight.detach().to(torch.float32).contiguous()
+            xb32 = None if x_proj_bias is None else x_proj_bias.detach().to(torch.float32).contiguous()
+            xd = torch.zeros((2, Bsz, 2, RP, H * W), dtype=torch.float32, device=dev)   # [rm | cm], accumulated into
+            p.x_proj_weight, p.x_proj_bias = xw32.data_ptr(), (None if xb32 is None else xb32.data_ptr())
+            p.x_dbl_rm, p.x_dbl_cm, p.x_proj_rows = xd[0].data_ptr(), xd[1].data_ptr(), RP
         with torch.cuda.device(dev):
             _lib.check(lib.vmasr_dwconv_silu_fwd(ctypes.byref(p)))
-        ctx.save_for_backward(xin, w32, b32)
-        ctx.ps, ctx.has_bias = ps, bias is not None
+        ctx.save_for_backward(xin, w32, b32, xw32)
+        ctx.ps, ctx.has_bias, ctx.has_xb = ps, bias is not None, x_proj_bias is not None
+        if xd is not None:
+            return x, xT, xd[0], xd[1]
         return x, xT
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
-    def backward(ctx, dx, dxT):
+    def backward(ctx, dx, dxT, dxd_rm=None, dxd_cm=None):
         lib = _lib.load_library()
-        xin, w32, b32 = ctx.saved_tensors
+        xin, w32, b32, xw32 = ctx.saved_tensors
         Bsz, H, W, C = xin.shape
         dev = xin.device
         dx, dxT = dx.to(torch.float32).contiguous(), dxT.to(torch.float32).contiguous()
@@ -437,10 +454,21 @@ class ConvSiluInput(torch.autograd.Function):
         p.dx, p.dxT, p.dxin, p.dwb_partial, p.xin_pos_stride = dx.data_ptr(), dxT.data_ptr(), dxin.data_ptr(), part.data_ptr(), ctx.ps
         p.batch, p.channels, p.H, p.W = Bsz, C, H, W
         p.io_dtype, p.device, p.stream = _lib.DTYPE_CODE[xin.dtype], _dev(xin), _lib.current_stream_ptr(dev)
+        d_xw = d_xb = xpart = None
+        if xw32 is not None:
+            RP = xw32.shape[1]
+            dxd_rm, dxd_cm = dxd_rm.to(torch.float32).contiguous(), dxd_cm.to(torch.float32).contiguous()
+            xpart = torch.empty((patches, 4 * RP, C), dtype=torch.float32, device=dev)
+            p.x_proj_weight, p.x_proj_rows = xw32.data_ptr(), RP
+            p.d_x_dbl_rm, p.d_x_dbl_cm, p.d_x_proj_weight_partial = dxd_rm.data_ptr(), dxd_cm.data_ptr(), xpart.data_ptr()
         with torch.cuda.device(dev):
             _lib.check(lib.vmasr_dwconv_silu_bwd(ctypes.byref(p)))
         sums = part.sum(0)
-        return dxin, sums[:, :9].reshape(C, 1, 3, 3), (sums[:, 9] if ctx.has_bias else None)
+        if xw32 is not None:
+            d_xw = xpart.sum(0).view(4, RP, C)
+            if ctx.has_xb:   # rows k = 2 j + parity: d x_proj_bias[k, r] = sum over batch and positions of d x_dbl
+                d_xb = torch.stack([dxd_rm.sum((0, 3)), dxd_cm.sum((0, 3))], dim=1).reshape(4, RP)
+        return dxin, sums[:, :9].reshape(C, 1, 3, 3), (sums[:, 9] if ctx.has_bias else None), d_xw, d_xb
 
 
 def outnorm_fusable(x: torch.Tensor, N: int) -> bool:
