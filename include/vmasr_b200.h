@@ -312,7 +312,8 @@ typedef struct vmasr_dwconv_params {
     /* ---- x_proj in the same pass (optional; SURVEY.md 8f-1: x_dbl = einsum(xs, x_proj_weight) [+ x_proj_bias], vmamba.py:1473-1475).
      * x_proj_weight (4, x_proj_rows, C) float32 contiguous, x_proj_rows = dt_rank + 2 d_state; x_proj_bias (4, x_proj_rows) or NULL.
      * x_dbl_rm / x_dbl_cm: (B, 2, x_proj_rows, H*W) float32, the rows of directions (0, 2) in row-major and of (1, 3) in column-major
-     * position order -- exactly vmasr_ss2d_params.x_dbl[] -- ACCUMULATED INTO when the channels span several CTAs: caller zero-fills.
+     * position order -- exactly vmasr_ss2d_params.x_dbl[] -- ACCUMULATED INTO when the channels span several CTAs
+     * (vmasr_dwconv_channel_blocks() > 1): the caller zero-fills them then.
      * backward: d_x_dbl_rm / d_x_dbl_cm in, their contribution is added to the map gradient; d_x_proj_weight_partial
      * (patches, 4 * x_proj_rows, C) float32, every entry written, the caller sums over patches (d x_proj_bias is the plain sum of
      * d x_dbl over batch and positions: left to the caller). */
@@ -323,6 +324,8 @@ typedef struct vmasr_dwconv_params {
     int32_t x_proj_rows, reserved0;
 } vmasr_dwconv_params;
 VMASR_API int64_t vmasr_dwconv_patches(int batch, int channels, int H, int W);
+/* CTAs the channels of one patch are spread over: 1 = x_dbl_rm / x_dbl_cm are plainly stored (no zero-fill needed) */
+VMASR_API int vmasr_dwconv_channel_blocks(int batch, int channels, int H, int W);
 VMASR_API int vmasr_dwconv_silu_fwd(const vmasr_dwconv_params *p);
 VMASR_API int vmasr_dwconv_silu_bwd(const vmasr_dwconv_params *p);
 

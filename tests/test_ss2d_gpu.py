@@ -498,6 +498,34 @@ def test_conv_silu_input_half(dtype, tol):
         assert rel_err(u.grad, v.grad) < 2 * tol, (n, rel_err(u.grad, v.grad))
 
 
+@pytest.mark.parametrize("Bsz,H,W,C,R", [(2, 16, 16, 8, 1), (1, 32, 48, 16, 2), (2, 64, 64, 2, 1), (1, 8, 16, 70, 3), (1, 16, 16, 256, 8),
+                                         (2, 128, 128, 32, 1)])
+def test_conv_silu_input_forms_x_dbl(Bsz, H, W, C, R):
+    """the head kernel with x_proj inside (vmamba.py:1473-1475): x_dbl of the row-major and of the column-major pair against the
+    einsums on the oracle's activations in float64 (70 and 256 channels span several CTAs: atomic partial sums), and the
+    gradients of input, conv, x_proj_weight and x_proj_bias with gradients arriving through all four outputs"""
+    from vm_asr_b200 import ss2d
+    g = torch.Generator().manual_seed(54)
+    L = H * W
+    xin = torch.randn(Bsz, H, W, C, generator=g)
+    wt, bs = 0.4 * torch.randn(C, 1, 3, 3, generator=g), 0.3 * torch.randn(C, generator=g)
+    xw, xb = 0.3 * torch.randn(4, R + 2, C, generator=g), 0.2 * torch.randn(4, R + 2, generator=g)
+    ups = [torch.randn(Bsz, C, H, W, generator=g), torch.randn(Bsz, C, W, H, generator=g),
+           torch.randn(Bsz, 2, R + 2, L, generator=g), torch.randn(Bsz, 2, R + 2, L, generator=g)]
+    a = [t.cuda().requires_grad_() for t in (xin, wt, bs, xw, xb)]
+    outs = ss2d.ConvSiluInput.apply(*a)
+    sum((o * u.cuda()).sum() for o, u in zip(outs, ups)).backward()
+    r = [t.double().requires_grad_() for t in (xin, wt, bs, xw, xb)]
+    rx = ss2d_ref.dwconv_silu(r[0], r[1], r[2])
+    rxT = rx.transpose(2, 3)
+    rd_rm = torch.einsum("bdl,kcd->bkcl", rx.reshape(Bsz, C, L), r[3][0::2]) + r[4][0::2].view(1, 2, -1, 1)
+    rd_cm = torch.einsum("bdl,kcd->bkcl", rxT.reshape(Bsz, C, L), r[3][1::2]) + r[4][1::2].view(1, 2, -1, 1)
+    sum((o * u.double()).sum() for o, u in zip((rx, rxT, rd_rm, rd_cm), ups)).backward()
+    assert rel_err(outs[0], rx) < 1e-5 and rel_err(outs[2], rd_rm) < 2e-5 and rel_err(outs[3], rd_cm) < 2e-5
+    for n, u, v in zip(("xin", "conv_w", "conv_b", "x_proj_w", "x_proj_b"), a, r):
+        assert rel_err(u.grad, v.grad) < 2e-4, (n, rel_err(u.grad, v.grad))
+
+
 @pytest.mark.parametrize("Bsz,C,H,W,R", [(2, 8, 72, 64, 2), (1, 16, 64, 80, 1), (2, 32, 16, 16, 2)])
 def test_ss2d_block_core_matches_separate_statements(Bsz, C, H, W, R):
     """ss2d_block_core (head kernel -> fused core -> tail kernel) against oracle head -> ss2d_core -> oracle tail in torch on the GPU:

@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="vm_asr_48k_MPD")
 ap.add_argument("--dtype", default="float32")
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--xproj", action="store_true", help="with the x_proj contraction inside the kernel, against the chain + the two einsums")
 args = ap.parse_args()
 wl = W.WORKLOADS[args.workload]
 dt = getattr(torch, args.dtype)
@@ -32,10 +33,16 @@ for call, count in W.distinct_shapes(wl):
     sets = [dict(xz=torch.randn(B, H, Wd, 2 * C, device=dev, generator=gen).to(dt), gx=torch.randn(B, C, H, Wd, device=dev, generator=gen),
                  gxT=torch.randn(B, C, Wd, H, device=dev, generator=gen)) for _ in range(n_sets)]
     wt, bs = 0.3 * torch.randn(C, 1, 3, 3, device=dev), torch.zeros(C, device=dev)
+    R = max(1, -(-(C // 2) // 16))
+    xw = 0.3 * torch.randn(4, R + 2, C, device=dev)
+    gxd = [torch.randn(B, 2, R + 2, L, device=dev) for _ in range(2)]
 
     def fused(i, grad=False):
         d = sets[i]
         ins = [d["xz"].requires_grad_(grad), wt.requires_grad_(grad), bs.requires_grad_(grad)]
+        if args.xproj:
+            ins.append(xw.requires_grad_(grad))
+            return ss2d.ConvSiluInput.apply(ins[0][..., :C], ins[1], ins[2], ins[3]), ins, (d["gx"], d["gxT"], gxd[0], gxd[1])
         x, xT = ss2d.ConvSiluInput.apply(ins[0][..., :C], ins[1], ins[2])
         return (x, xT), ins, (d["gx"], d["gxT"])
 
@@ -44,7 +51,12 @@ for call, count in W.distinct_shapes(wl):
         ins = [d["xz"].requires_grad_(grad), wt.requires_grad_(grad), bs.requires_grad_(grad)]
         x = ins[0][..., :C].permute(0, 3, 1, 2).contiguous()
         x = F.silu(F.conv2d(x, ins[1].to(dt), ins[2].to(dt), padding=1, groups=C)).float()
-        return (x, ss2d.MapTranspose.apply(x)), ins, (d["gx"], d["gxT"])
+        xT = ss2d.MapTranspose.apply(x)
+        if args.xproj:
+            ins.append(xw.requires_grad_(grad))
+            xd = [torch.einsum("bdl,kcd->bkcl", src.view(B, C, L), ins[3][par::2]) for par, src in ((0, x), (1, xT))]
+            return (x, xT, xd[0], xd[1]), ins, (d["gx"], d["gxT"], gxd[0], gxd[1])
+        return (x, xT), ins, (d["gx"], d["gxT"])
 
     def fwd_of(f):
         def run(i):
@@ -59,7 +71,7 @@ for call, count in W.distinct_shapes(wl):
         return run
 
     fwd_bytes, bwd_bytes = n * (es + 8), n * (es + 8 + es)
-    row = dict(B=B, C=C, H=H, W=Wd, dtype=args.dtype, calls=count)
+    row = dict(B=B, C=C, H=H, W=Wd, dtype=args.dtype, calls=count, x_proj=bool(args.xproj), R=R)
     for name, fn, by in (("fused_fwd", fwd_of(fused), fwd_bytes), ("chain_fwd", fwd_of(chain), None),
                          ("fused_fwd_bwd", both_of(fused), fwd_bytes + bwd_bytes), ("chain_fwd_bwd", both_of(chain), None)):
         ms = timeit(fn, args.reps, n_sets)

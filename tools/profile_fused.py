@@ -23,6 +23,12 @@ if W % 8 == 0:
         z = torch.randn(B, H, W, C, device=dev).to(dt).requires_grad_()
         o = ss2d.ss2d_core_out(x, *prm, gam, bet, z=z)
         o.float().square().mean().backward()
+    # the whole block between in_proj and out_proj: head (conv + SiLU + x_proj) -> core -> tail
+    xz = torch.randn(B, H, W, 2 * C, device=dev, requires_grad=True)
+    cw, cb = (0.3 * torch.randn(C, 1, 3, 3, device=dev)).requires_grad_(), torch.zeros(C, device=dev, requires_grad=True)
+    xa, za = xz.chunk(2, dim=-1)
+    ob = ss2d.ss2d_block_core(xa, cw, cb, *prm, gam, bet, z=za)
+    ob.square().mean().backward()
 ya, yb = ss2d.ss2d_core_pair(x.detach(), [p.detach() for p in prm], x.detach() * 0.5, [p.detach() for p in prm])
 w = (0.1 * torch.randn(2, 1, 240 * 20, device=dev)).requires_grad_()
 m, p = stft.wav2spectro(w, 1024, 240, 1024, "log2")

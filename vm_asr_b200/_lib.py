@@ -115,6 +115,7 @@ EXPORTS = {
     "vmasr_outnorm_gate_fwd": (ctypes.c_int, [ctypes.POINTER(OutNormParams)]),
     "vmasr_outnorm_gate_bwd": (ctypes.c_int, [ctypes.POINTER(OutNormParams)]),
     "vmasr_dwconv_patches": (_i64, [ctypes.c_int] * 4),
+    "vmasr_dwconv_channel_blocks": (ctypes.c_int, [ctypes.c_int] * 4),
     "vmasr_dwconv_silu_fwd": (ctypes.c_int, [ctypes.POINTER(DwConvParams)]),
     "vmasr_dwconv_silu_bwd": (ctypes.c_int, [ctypes.POINTER(DwConvParams)]),
     "vmasr_cross_scan": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 6 + [_vp]),

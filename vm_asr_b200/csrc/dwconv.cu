@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(256) dwconv_silu_bwd_kernel(const DwArgs a) {
     const int KR = 4 * a.RP;
     float *sxw = sacc + (size_t)a.CB * 10;      // [KR][CB] x_proj weight slice (x_proj only)
     float *sdx = sxw + (size_t)KR * a.CB;       // [KR][dpitch] d x_dbl on the patch + 1 (x_proj only)
+    float *sxacc = sdx + (size_t)KR * dpitch;   // [KR][CB] d x_proj weight of this patch (x_proj only)
     for (int i = threadIdx.x; i < j.nc * 10; i += 256) {
         const int c = i / 10, k = i - c * 10;
         sw[i] = k < 9 ? __ldg(a.w9 + (long long)(j.c0 + c) * 9 + k) : (a.bias ? __ldg(a.bias + j.c0 + c) : 0.0f);
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(256) dwconv_silu_bwd_kernel(const DwArgs a) {
         for (int i = threadIdx.x; i < KR * j.nc; i += 256) {
             const int kr = i / j.nc, c = i - kr * j.nc;
             sxw[kr * a.CB + c] = __ldg(a.xpw + (long long)kr * a.C + j.c0 + c);
+            sxacc[kr * a.CB + c] = 0.0f;
         }
         for (int i = threadIdx.x; i < KR * DH * DW; i += 256) {
             const int kr = i / (DH * DW), qpos = i - kr * DH * DW;
@@ -235,14 +237,17 @@ __global__ void __launch_bounds__(256) dwconv_silu_bwd_kernel(const DwArgs a) {
         sd[c * dpitch + r] = dp;
     }
     __syncthreads();
-    // d weight / d bias over the positions this patch OWNS: a warp takes a channel, lanes the positions
+    // d weight / d bias over the positions this patch OWNS: a warp takes a channel (a slice of its positions when the block has
+    // fewer than 8 channels, so that every warp has work), lanes the positions; slices meet in shared memory
     {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int c = warp; c < j.nc; c += 8) {
+        const int S = j.nc >= 8 ? 1 : 8 / j.nc;
+        for (int unit = warp; unit < j.nc * S; unit += 8) {
+            const int c = unit / S, sl = unit - c * S;
             float acc[10];
 #pragma unroll
             for (int k = 0; k < 10; ++k) acc[k] = 0.0f;
-            for (int p = lane; p < PH * TW; p += 32) {
+            for (int p = sl * 32 + lane; p < PH * TW; p += 32 * S) {
                 const int ph = p / TW, pw = p - ph * TW;
                 const float dp = sd[c * dpitch + (ph + 1) * DW + pw + 1];
                 const float *src = sx + c * xpitch + (ph + 1) * XW + pw + 1;  // window of the owned position
@@ -257,13 +262,13 @@ __global__ void __launch_bounds__(256) dwconv_silu_bwd_kernel(const DwArgs a) {
                 float v = acc[k];
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                if (lane == 0) sacc[c * 10 + k] = v;
+                if (lane == 0) atomicAdd(&sacc[c * 10 + k], v);
             }
             if (a.xpw) {  // d x_proj weight[kr][c] = sum over owned positions of d x_dbl[kr] * act(c), act recomputed from the input patch
                 const float *wt = sw + c * 10;
                 for (int kr0 = 0; kr0 < KR; kr0 += 4) {
                     float aw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                    for (int p = lane; p < PH * TW; p += 32) {
+                    for (int p = sl * 32 + lane; p < PH * TW; p += 32 * S) {
                         const int ph = p / TW, pw = p - ph * TW;
                         const float *src = sx + c * xpitch + (ph + 1) * XW + pw + 1;
                         float pre = wt[9];
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(256) dwconv_silu_bwd_kernel(const DwArgs a) {
                         float v = aw[u];
 #pragma unroll
                         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                        if (lane == 0 && kr0 + u < KR) a.dxpw[((long long)j.patch * KR + kr0 + u) * a.C + j.c0 + c] = v;
+                        if (lane == 0 && kr0 + u < KR) atomicAdd(&sxacc[(kr0 + u) * a.CB + c], v);
                     }
                 }
             }
@@ -306,6 +311,11 @@ __global__ void __launch_bounds__(256) dwconv_silu_bwd_kernel(const DwArgs a) {
         float *dst = a.dwb + ((long long)j.patch * a.C + j.c0) * 10;
         for (int i = threadIdx.x; i < j.nc * 10; i += 256) dst[i] = sacc[i];
     }
+    if (a.xpw)
+        for (int i = threadIdx.x; i < KR * j.nc; i += 256) {
+            const int kr = i / j.nc, c = i - kr * j.nc;
+            a.dxpw[((long long)j.patch * KR + kr) * a.C + j.c0 + c] = sxacc[kr * a.CB + c];
+        }
 }
 
 // patch (PH x TW positions) x channel block: about 4 K outputs per CTA, shared memory under 100 KB, grid large enough
@@ -321,7 +331,7 @@ static int plan_dw(int batch, int C, int H, int W, bool bwd, int RP, int &PH, in
     const int halo = bwd ? 2 : 1;
     const size_t xp = (size_t)((PH + 2 * halo) * (TW + 2 * halo)) | 1, dp = (size_t)((PH + 2) * (TW + 2)) | 1;
     smem = sizeof(float) * ((size_t)CB * (xp + (bwd ? dp : 0)) + (size_t)CB * 20);
-    if (RP > 0) smem += sizeof(float) * ((size_t)4 * RP * CB + (bwd ? (size_t)4 * RP * dp : (size_t)CB * (((size_t)PH * TW) | 1)));
+    if (RP > 0) smem += sizeof(float) * ((size_t)4 * RP * CB + (bwd ? (size_t)4 * RP * (dp + CB) : (size_t)CB * (((size_t)PH * TW) | 1)));
     if (smem > 200 * 1024) return fail("dwconv_silu: patch does not fit shared memory");
     return 0;
 }
@@ -384,6 +394,13 @@ extern "C" int64_t vmasr_dwconv_patches(int batch, int channels, int H, int W) {
     if (batch <= 0 || channels <= 0 || H <= 0 || W <= 0) return -1;
     if (vmasr::plan_dw(batch, channels, H, W, true, 0, PH, TW, CB, smem)) return -1;
     return (int64_t)batch * (H / PH) * (W / TW);
+}
+extern "C" int vmasr_dwconv_channel_blocks(int batch, int channels, int H, int W) {
+    int PH = 0, TW = 0, CB = 0;
+    size_t smem = 0;
+    if (batch <= 0 || channels <= 0 || H <= 0 || W <= 0) return -1;
+    if (vmasr::plan_dw(batch, channels, H, W, false, 0, PH, TW, CB, smem)) return -1;
+    return (channels + CB - 1) / CB;
 }
 extern "C" int vmasr_dwconv_silu_fwd(const vmasr_dwconv_params *p) { return vmasr::dw_run(p, false); }
 extern "C" int vmasr_dwconv_silu_bwd(const vmasr_dwconv_params *p) { return vmasr::dw_run(p, true); }

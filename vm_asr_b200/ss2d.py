@@ -427,7 +427,9 @@ class ConvSiluInput(torch.autograd.Function):
             RP = x_proj_weight.shape[1]
             xw32 = x_proj_weight.detach().to(torch.float32).contiguous()
             xb32 = None if x_proj_bias is None else x_proj_bias.detach().to(torch.float32).contiguous()
-            xd = torch.zeros((2, Bsz, 2, RP, H * W), dtype=torch.float32, device=dev)   # [rm | cm], accumulated into
+            # [rm | cm]; partial sums are added into them when the channels of a patch span several CTAs
+            alloc = torch.zeros if int(lib.vmasr_dwconv_channel_blocks(Bsz, C, H, W)) > 1 else torch.empty
+            xd = alloc((2, Bsz, 2, RP, H * W), dtype=torch.float32, device=dev)
             p.x_proj_weight, p.x_proj_bias = xw32.data_ptr(), (None if xb32 is None else xb32.data_ptr())
             p.x_dbl_rm, p.x_dbl_cm, p.x_proj_rows = xd[0].data_ptr(), xd[1].data_ptr(), RP
         with torch.cuda.device(dev):
@@ -480,7 +482,7 @@ def outnorm_fusable(x: torch.Tensor, N: int) -> bool:
 
 def ss2d_core_out(x: torch.Tensor, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm_weight, out_norm_bias,
                   z: torch.Tensor | None = None, z_silu: bool = True, eps: float = 1e-5, delta_softplus: bool = True,
-                  x_proj_bias=None, projected: bool | None = None, xT: torch.Tensor | None = None, out_dtype=None) -> torch.Tensor:
+                  x_proj_bias=None, projected: bool | None = None, xT: torch.Tensor | None = None, out_dtype=None, xd=None) -> torch.Tensor:
     """``forward_corev2`` INCLUDING its tail and the gate of ``forwardv2`` (vmamba.py:1472-1531, 1536-1550) for the configs'
     layout (channel_first False, out_norm = nn.LayerNorm): x (B, C, H, W) -> (B, H, W, C) in the dtype of z (of x without a
     gate).  The core's planes go straight into ``MergeNormGate``: the merged map is written once (for the backward) and never
@@ -492,36 +494,47 @@ def ss2d_core_out(x: torch.Tensor, x_proj_weight, dt_projs_weight, dt_projs_bias
         projected = _projectable(x, dt_projs_weight, N)
     mode = (_SOFTPLUS if delta_softplus else 0) | _PLANES
     if projected:
-        planes = _SS2DScanProj.apply(mode, 1, *_prepare_proj(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias, xT))
+        planes = _SS2DScanProj.apply(mode, 1, *_prepare_proj(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias, xT, xd))
     else:
-        planes = _SS2DScan.apply(mode, 1, *_prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias, xT))
+        planes = _SS2DScan.apply(mode, 1, *_prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias, xT, xd))
     return MergeNormGate.apply(planes, out_norm_weight, out_norm_bias, z, x.shape[2], x.shape[3], eps, z_silu, out_dtype or x.dtype)
 
 
 def ss2d_block_core(x_cl: torch.Tensor, conv_weight, conv_bias, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds,
                     out_norm_weight, out_norm_bias, z: torch.Tensor | None = None, z_silu: bool = True, eps: float = 1e-5,
-                    delta_softplus: bool = True, x_proj_bias=None, projected: bool | None = None) -> torch.Tensor:
+                    delta_softplus: bool = True, x_proj_bias=None, projected: bool | None = None, fuse_x_proj: bool = True) -> torch.Tensor:
     """Everything of ``SS2D.forwardv2`` between in_proj and out_proj (vmamba.py:1536-1550 with forward_corev2 inside) for the
     configs' layout: channel-last x_cl (B, H, W, C) -- a strided view of in_proj's output is read in place -- -> depthwise
     conv 3x3 + SiLU + permute + transpose (``ConvSiluInput``) -> fused core -> merge + LayerNorm + cast + gate
-    (``MergeNormGate``) -> (B, H, W, C).  Four kernels of this library and the two small einsums; no ``xs`` / ``ys`` / ``dts``
-    copies, no separate permute, activation, transpose, normalisation or gate passes."""
-    x, xT = ConvSiluInput.apply(x_cl, conv_weight, conv_bias)
+    (``MergeNormGate``) -> (B, H, W, C).  With ``fuse_x_proj`` the head kernel also forms ``x_dbl`` (the x_proj einsum of
+    vmamba.py:1473-1475), and where ``dt_rank`` is 1 the scan kernels form ``delta`` themselves: the block then runs on four
+    kernels of this library and nothing else -- no ``xs`` / ``ys`` / ``dts`` copies, no einsum, no separate permute, activation,
+    transpose, normalisation or gate passes."""
+    xd = None
+    if fuse_x_proj:
+        x, xT, xd_rm, xd_cm = ConvSiluInput.apply(x_cl, conv_weight, conv_bias, x_proj_weight, x_proj_bias)
+        xd = (xd_rm, xd_cm)
+    else:
+        x, xT = ConvSiluInput.apply(x_cl, conv_weight, conv_bias)
     return ss2d_core_out(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm_weight, out_norm_bias, z=z,
                          z_silu=z_silu, eps=eps, delta_softplus=delta_softplus, x_proj_bias=x_proj_bias, projected=projected,
-                         xT=xT, out_dtype=x_cl.dtype)
+                         xT=xT, out_dtype=x_cl.dtype, xd=xd)
 
 
-def _projections(x, xT, x_proj_weight, x_proj_bias, dt_projs_weight, R, N):
+def _projections(x, xT, x_proj_weight, x_proj_bias, dt_projs_weight, R, N, xd=None):
     """x_dbl and dts of vmamba.py:1473-1477 in memory order: the row-major pair from the map, the column-major pair from
-    its transpose.  Returns dts (B,2,C,L), Bs, Cs (B,2,N,L) per pair; Bs / Cs are VIEWS of x_dbl (no contiguous copies)."""
+    its transpose.  Returns dts (B,2,C,L), Bs, Cs (B,2,N,L) per pair; Bs / Cs are VIEWS of x_dbl (no contiguous copies).
+    ``xd`` = (x_dbl_rm, x_dbl_cm) when the head kernel has formed them already."""
     Bsz, C, H, W = x.shape
     L = H * W
     out = []
     for par, src in ((0, x.view(Bsz, C, L)), (1, xT.view(Bsz, C, L))):
-        x_dbl = torch.einsum("bdl,kcd->bkcl", src, x_proj_weight[par::2])
-        if x_proj_bias is not None:
-            x_dbl = x_dbl + x_proj_bias[par::2].view(1, 2, -1, 1)
+        if xd is not None:
+            x_dbl = xd[par]
+        else:
+            x_dbl = torch.einsum("bdl,kcd->bkcl", src, x_proj_weight[par::2])
+            if x_proj_bias is not None:
+                x_dbl = x_dbl + x_proj_bias[par::2].view(1, 2, -1, 1)
         dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
         dts = torch.einsum("bkrl,kdr->bkdl", dts, dt_projs_weight[par::2])
         out.append((dts, Bs, Cs))
@@ -538,30 +551,31 @@ def _projectable(x, dt_projs_weight, N):
     return _fusable(x, N) and dt_projs_weight.shape[2] == 1 and L > _lib.SCAN_CHUNK and L % 16 == 0
 
 
-def _prepare_proj(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias, xT=None):
+def _prepare_proj(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias, xT=None, xd=None):
     """inputs of _SS2DScanProj: x_dbl (vmamba.py:1473-1475) of the two pairs in memory order; the dt projection (:1477) is
     left to the kernels"""
     Bsz, C, H, W = x.shape
     L = H * W
     x32 = x.to(torch.float32).contiguous()
     xT = MapTranspose.apply(x32) if xT is None else xT
-    xd = []
-    for par, src in ((0, x32.view(Bsz, C, L)), (1, xT.view(Bsz, C, L))):
-        x_dbl = torch.einsum("bdl,kcd->bkcl", src, x_proj_weight[par::2].to(torch.float32))
-        if x_proj_bias is not None:
-            x_dbl = x_dbl + x_proj_bias[par::2].view(1, 2, -1, 1)
-        xd.append(x_dbl.to(torch.float32).contiguous())
+    if xd is None:
+        xd = []
+        for par, src in ((0, x32.view(Bsz, C, L)), (1, xT.view(Bsz, C, L))):
+            x_dbl = torch.einsum("bdl,kcd->bkcl", src, x_proj_weight[par::2].to(torch.float32))
+            if x_proj_bias is not None:
+                x_dbl = x_dbl + x_proj_bias[par::2].view(1, 2, -1, 1)
+            xd.append(x_dbl.to(torch.float32).contiguous())
     As = -torch.exp(A_logs.to(torch.float))
     return (x32, xT, xd[0], xd[1], dt_projs_weight.to(torch.float).contiguous(), As.contiguous(), Ds.to(torch.float).contiguous(),
             dt_projs_bias.reshape(-1).to(torch.float).contiguous())
 
 
-def _prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias, xT=None):
+def _prepare(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, x_proj_bias, xT=None, xd=None):
     K, _, R = dt_projs_weight.shape
     N = A_logs.shape[1]
     x32 = x.to(torch.float32).contiguous()
     xT = MapTranspose.apply(x32) if xT is None else xT
-    (dts_rm, Bs_rm, Cs_rm), (dts_cm, Bs_cm, Cs_cm) = _projections(x32, xT, x_proj_weight, x_proj_bias, dt_projs_weight, R, N)
+    (dts_rm, Bs_rm, Cs_rm), (dts_cm, Bs_cm, Cs_cm) = _projections(x32, xT, x_proj_weight, x_proj_bias, dt_projs_weight, R, N, xd)
     # force_fp32 (vmamba.py:1487-1491; a no-op outside autocast); einsum is free to return any strides: the kernels need
     # unit stride along L only (the reference makes Bs / Cs / dts contiguous unconditionally, vmamba.py:1480-1483)
     f = lambda t: t.to(torch.float32) if t.stride(-1) == 1 else t.to(torch.float32).contiguous()
