@@ -725,7 +725,7 @@ def main():
                  "what": "torch.no_grad forward of the harness (STFT -> 34 fused cores -> iSTFT), eager, inputs on the device"}
         e2e = {"value": round(world * step_bytes / t_train / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": 2 * host_in.numel() * 4,
                "d2h_bytes_per_step": 4, "ms_per_step": round(t_train * 1e3, 2), "steps": n_train,
-               "api": "vm_asr_b200.harness.TrainStep: pinned host waveforms -> device, wav2spectro, 34 x ss2d_core (fused, paired) forward + "
+               "api": "vm_asr_b200.harness.TrainStep: pinned host waveforms -> device, wav2spectro, 34 x SS2D body (in_proj -> conv+SiLU+x_proj head kernel -> fused core -> merge+LayerNorm+gate tail kernel -> out_proj; paired) forward + "
                       "backward, spectro2wav (+ backward), L1 + multi-resolution STFT loss read back to the host, gradient all-reduce, AdamW; the step's "
                       "algorithmic scan bytes over its wall time"}
 

@@ -551,3 +551,36 @@ def test_ss2d_block_core_matches_separate_statements(Bsz, C, H, W, R):
     assert rel_err(out, ref) < 2e-5
     for n, u, v in zip(names, a, b):
         assert rel_err(u.grad, v.grad) < 2e-4, (n, rel_err(u.grad, v.grad))
+
+
+@pytest.mark.parametrize("R", [1, 2])
+def test_block_core_pair_equals_two_single_calls(R):
+    """ss2d_block_core_pair (the generator's two streams: heads and tails one after the other, the two cores' scans in ONE grid)
+    against two ss2d_block_core calls: same output bits, same gradients of inputs, gates and every parameter"""
+    from vm_asr_b200 import ss2d
+    Bsz, C, H, W = 2, 8, 64, 80
+    res = {}
+    for mode in ("single", "pair"):
+        ins, blks = [], []
+        for s in (61, 62):
+            g = torch.Generator().manual_seed(s)
+            xz = torch.randn(Bsz, H, W, 2 * C, generator=g).cuda().requires_grad_()
+            wt, bs = 0.4 * torch.randn(C, 1, 3, 3, generator=g), 0.3 * torch.randn(C, generator=g)
+            gamma, beta = 1.0 + 0.3 * torch.randn(C, generator=g), 0.3 * torch.randn(C, generator=g)
+            blk = [t.cuda().requires_grad_() for t in (wt, bs) + _core_params(C, R, seed=s) + (gamma, beta)]
+            ins.append(xz)
+            blks.append(blk)
+        halves = [t.chunk(2, dim=-1) for t in ins]
+        if mode == "single":
+            ys = [ss2d.ss2d_block_core(h[0], *blk, z=h[1]) for h, blk in zip(halves, blks)]
+        else:
+            ys = ss2d.ss2d_block_core_pair(halves[0][0], blks[0], halves[1][0], blks[1], z_a=halves[0][1], z_b=halves[1][1])
+        (ys[0].sum() + (ys[1] * ys[1]).sum()).backward()
+        res[mode] = (ys, ins, blks)
+    for a, b in zip(res["single"][0], res["pair"][0]):
+        assert torch.equal(a, b)
+    for a, b in zip(res["single"][1], res["pair"][1]):
+        assert rel_err(b.grad, a.grad) < 1e-6
+    for pa, pb in zip(res["single"][2], res["pair"][2]):
+        for u, v in zip(pa, pb):
+            assert rel_err(v.grad, u.grad) < 1e-5

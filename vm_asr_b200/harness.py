@@ -57,12 +57,39 @@ class SS2DCoreParams(nn.Module):
         return (self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds)
 
 
+class VSSBlockParams(nn.Module):
+    """What SS2D holds around its core (vmamba.py:853-890): in_proj (d -> 2 d_inner: the x half and the gate z), the depthwise
+    conv 3x3, out_norm (LayerNorm) and out_proj; here d = d_inner (the harness keeps its streams at d_inner channels)."""
+
+    def __init__(self, d_inner: int, generator: torch.Generator):
+        super().__init__()
+        self.core = SS2DCoreParams(d_inner, generator)
+        self.in_proj = nn.Linear(d_inner, 2 * d_inner, bias=False)
+        self.out_proj = nn.Linear(d_inner, d_inner, bias=False)
+        self.conv_weight = nn.Parameter((torch.rand(d_inner, 1, 3, 3, generator=generator) * 2 - 1) / 3.0)
+        self.conv_bias = nn.Parameter(torch.zeros(d_inner))
+        self.norm_weight = nn.Parameter(torch.ones(d_inner))
+        self.norm_bias = nn.Parameter(torch.zeros(d_inner))
+        with torch.no_grad():
+            for lin in (self.in_proj, self.out_proj):
+                bound = 1.0 / math.sqrt(lin.in_features)
+                lin.weight.copy_((torch.rand(lin.weight.shape, generator=generator) * 2 - 1) * bound)
+
+    def block_tensors(self):
+        c = self.core
+        return (self.conv_weight, self.conv_bias, c.x_proj_weight, c.dt_projs_weight, c.dt_projs_bias, c.A_logs, c.Ds,
+                self.norm_weight, self.norm_bias)
+
+
 class HotPathNet(nn.Module):
     """STFT -> 17 pairs of SS2D cores (magnitude stream, phase stream) -> iSTFT, see the module docstring."""
 
-    def __init__(self, wl: Workload, seed: int = 123, pair: bool = True):
+    def __init__(self, wl: Workload, seed: int = 123, pair: bool = True, block: bool = True):
+        """``block``: every core call is a whole SS2D module body -- in_proj, then head (conv + SiLU + x_proj) -> core -> tail
+        (LayerNorm + gate) on this library's four kernels (``ss2d.ss2d_block_core``), then out_proj -- instead of the bare core
+        between normalisations."""
         super().__init__()
-        self.wl, self.pair = wl, pair
+        self.wl, self.pair, self.block = wl, pair, block
         gen = torch.Generator().manual_seed(seed)
         assert len(wl.calls) % 2 == 0
         self.steps = [wl.calls[i] for i in range(0, len(wl.calls), 2)]   # calls 2j, 2j + 1: the two streams' same-shape pair
@@ -70,7 +97,8 @@ class HotPathNet(nn.Module):
         self.glue = nn.ModuleList()
         c_prev = 1
         for call in self.steps:
-            self.cores.append(nn.ModuleList([SS2DCoreParams(call.d_inner, gen), SS2DCoreParams(call.d_inner, gen)]))
+            make = VSSBlockParams if block else SS2DCoreParams
+            self.cores.append(nn.ModuleList([make(call.d_inner, gen), make(call.d_inner, gen)]))
             if call.d_inner != c_prev:
                 convs = nn.ModuleList([nn.Conv2d(c_prev, call.d_inner, 1), nn.Conv2d(c_prev, call.d_inner, 1)])
             else:
@@ -122,6 +150,21 @@ class HotPathNet(nn.Module):
             # core is cubic in the scale of its input (B, C and u are all linear in it), so the pre-normalisation is what keeps
             # the activations (and the fp16 gradients under autocast) in range, exactly as in the reference.
             xn = [self._rms(x) for x in xs]
+            if self.block and call.H % 4 == 0 and call.W % 8 == 0:
+                # SS2D.forwardv2 (vmamba.py:1533-1552): in_proj -> [head -> core -> tail on this library] -> out_proj
+                xz = [cores[s].in_proj(xn[s].permute(0, 2, 3, 1)) for s in range(2)]          # (B, H, W, 2 d_inner), channel-last
+                halves = [t.chunk(2, dim=-1) for t in xz]
+                if self.pair:
+                    ys = ss2d.ss2d_block_core_pair(halves[0][0], cores[0].block_tensors(), halves[1][0], cores[1].block_tensors(),
+                                                   z_a=halves[0][1], z_b=halves[1][1])
+                else:
+                    ys = [ss2d.ss2d_block_core(halves[s][0], *cores[s].block_tensors(), z=halves[s][1]) for s in range(2)]
+                outs = [(xs[s] + cores[s].out_proj(ys[s]).permute(0, 3, 1, 2)) * 0.7071067811865476 for s in range(2)]
+                m = 0.5 * (outs[0] + outs[1])
+                streams = [m, 0.5 * (outs[1] + m)]
+                continue
+            if self.block:
+                cores = [c.core for c in cores]
             if self.pair and call.H % 4 == 0 and call.W % 4 == 0:
                 ys = ss2d.ss2d_core_pair(xn[0], cores[0].tensors(), xn[1], cores[1].tensors())
             else:

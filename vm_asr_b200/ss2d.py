@@ -521,6 +521,29 @@ def ss2d_block_core(x_cl: torch.Tensor, conv_weight, conv_bias, x_proj_weight, d
                          xT=xT, out_dtype=x_cl.dtype, xd=xd)
 
 
+def ss2d_block_core_pair(x_cl_a, blk_a, x_cl_b, blk_b, z_a=None, z_b=None, z_silu: bool = True, eps: float = 1e-5,
+                         delta_softplus: bool = True):
+    """``ss2d_block_core`` for the generator's two streams (same shapes, independent until their interaction point,
+    model/model.py:1124-1131): the two heads and the two tails are launched one after the other, the two cores' scans as ONE
+    grid.  ``blk_*`` = (conv_weight, conv_bias, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm_weight,
+    out_norm_bias[, x_proj_bias]).  Returns (out_a, out_b), each (B, H, W, C)."""
+    Bsz, H, W, C = x_cl_a.shape
+    proj = all(_projectable(x.permute(0, 3, 1, 2), blk[3], blk[5].shape[1]) for x, blk in ((x_cl_a, blk_a), (x_cl_b, blk_b)))
+    args = []
+    for x_cl, blk in ((x_cl_a, blk_a), (x_cl_b, blk_b)):
+        xpb = blk[9] if len(blk) > 9 else None
+        if not outnorm_fusable(x_cl.permute(0, 3, 1, 2), blk[5].shape[1]):
+            raise RuntimeError("ss2d_block_core_pair: needs CUDA maps with H % 4 == 0, W % 8 == 0, d_state 1")
+        x, xT, xd_rm, xd_cm = ConvSiluInput.apply(x_cl, blk[0], blk[1], blk[2], xpb)
+        args += list((_prepare_proj if proj else _prepare)(x, blk[2], blk[3], blk[4], blk[5], blk[6], xpb, xT, (xd_rm, xd_cm)))
+    mode = (_SOFTPLUS if delta_softplus else 0) | _PLANES
+    planes = (_SS2DScanProj if proj else _SS2DScan).apply(mode, 2, *args)
+    outs = []
+    for pl, blk, z, x_cl in ((planes[0], blk_a, z_a, x_cl_a), (planes[1], blk_b, z_b, x_cl_b)):
+        outs.append(MergeNormGate.apply(pl, blk[7], blk[8], z, H, W, eps, z_silu, x_cl.dtype))
+    return tuple(outs)
+
+
 def _projections(x, xT, x_proj_weight, x_proj_bias, dt_projs_weight, R, N, xd=None):
     """x_dbl and dts of vmamba.py:1473-1477 in memory order: the row-major pair from the map, the column-major pair from
     its transpose.  Returns dts (B,2,C,L), Bs, Cs (B,2,N,L) per pair; Bs / Cs are VIEWS of x_dbl (no contiguous copies).
