@@ -38,6 +38,7 @@ struct DwArgs {
     float *dxpw;                   // (patches, 4 RP, C): d x_proj weight per patch
     long long ps;
     int B, C, H, W, PH, TW, CB, RP;
+    unsigned m_xw, m_dw, m_dh, m_dp, m_rp;  // multiply-high reciprocals of TW + 4, TW + 2, PH + 2, (PH + 2)(TW + 2), RP (backward; FastDiv)
 };
 
 __device__ __forceinline__ float silu_val(float v) { return v / (1.0f + __expf(-v)); }
@@ -161,160 +162,333 @@ __global__ void __launch_bounds__(256) dwconv_silu_fwd_kernel(const DwArgs a) {
     }
 }
 
-// Backward.  pre = conv(xin) + bias (recomputed on the patch + 1), g = d x + transpose(d x^T), d pre = g * silu'(pre);
+// i / d for i * d < 2^32 (every index of a patch is far below that): one multiply-high instead of the ~20-instruction
+// division sequence; the loops below decode several flat indices per item.
+static inline __host__ __device__ unsigned fastdiv_magic(unsigned d) { return d > 1 ? 0xFFFFFFFFu / d + 1u : 0u; }
+struct FastDiv {
+    unsigned d, m;
+    __device__ __forceinline__ explicit FastDiv(unsigned d_) : d(d_), m(fastdiv_magic(d_)) {}
+    __device__ __forceinline__ FastDiv(unsigned d_, unsigned m_) : d(d_), m(m_) {}  // reciprocal computed on the host
+    __device__ __forceinline__ unsigned div(unsigned i) const { return d > 1 ? __umulhi(i, m) : i; }
+};
+
+// shared-memory carve-up of the backward (floats); host and device agree through this one function
+struct DwBwdLayout {
+    int xpitch, dpitch, apitch;
+    size_t sx, sd, sw, sacc, sxw, sdx, sxacc, sa, total;
+    __host__ __device__ DwBwdLayout(int CB, int PH, int TW, int RP) {
+        xpitch = ((PH + 4) * (TW + 4)) | 1;
+        dpitch = ((PH + 2) * (TW + 2)) | 1;
+        apitch = (PH * TW) | 1;
+        const int KR = 4 * RP;
+        auto up = [](size_t v) { return (v + 3) & ~(size_t)3; };
+        size_t o = 0;
+        sx = o; o = up(o + (size_t)CB * xpitch);
+        sd = o; o = up(o + (size_t)CB * dpitch);
+        sw = o; o = up(o + (size_t)CB * 10);
+        sacc = o; o = up(o + (size_t)CB * 10);
+        sxw = o; o = up(o + (size_t)KR * CB);
+        sdx = o; o = up(o + (size_t)KR * dpitch);
+        sxacc = o; o = up(o + (size_t)KR * CB);
+        sa = o; o = up(o + (RP > 0 ? (size_t)CB * apitch : 0));
+        total = o;
+    }
+};
+
+// Backward.  pre = conv(xin) + bias (recomputed on the patch + 1), g = d x + transpose(d x^T) + W^T d x_dbl, d pre = g * silu'(pre);
 //   d xin[h, w] = sum_k w[kh, kw] d pre[h - kh + 1, w - kw + 1];  d w[kh, kw] = sum d pre[h, w] xin[h + kh - 1, w + kw - 1];  d bias = sum d pre
+// Four phases between three barriers; every phase hands each thread SEVERAL independent items per trip (loads first, then the
+// stores), flat indices are decoded with multiply-high, and each global tensor is read with lanes along ITS fast axis:
+//   A  xin patch (halo 2; lanes along channels), d x^T (halo 1; lanes along h), d x_dbl rows (even directions lanes along w, odd
+//      ones along h) -> shared memory
+//   B  two channels per thread: pre, g (d x read here, lanes along w), d pre -> sd; the activation of owned positions -> sa
+//   C  reductions over the positions the patch OWNS: a unit is one channel's 9 + 1 stencil sums or four rows of d x_proj_weight
+//      for one channel (one load of d pre / the activation feeds 10 / 4 FMAs), positions split over S slices so that every
+//      thread has a unit; slices meet through shared-memory atomics
+//   D  d xin (lanes along channels)
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv_silu_bwd_kernel(const DwArgs a) {
     extern __shared__ float smem_dw[];
     const DwJob j(a);
-    const int PH = a.PH, TW = a.TW;
-    const int XW = TW + 4, XH = PH + 4, DW = TW + 2, DH = PH + 2;
-    const int xpitch = (XH * XW) | 1, dpitch = (DH * DW) | 1;
-    float *sx = smem_dw;                        // [CB][xpitch]  input patch, halo 2
-    float *sd = sx + (size_t)a.CB * xpitch;     // [CB][dpitch]  d pre, halo 1
-    float *sw = sd + (size_t)a.CB * dpitch;     // [CB][10]
-    float *sacc = sw + (size_t)a.CB * 10;       // [CB][10] d weight / d bias of this patch
+    const int PH = a.PH, TW = a.TW, P = PH * TW, CB = a.CB, nc = j.nc;
+    const int XW = TW + 4, XH = PH + 4, DW = TW + 2, DH = PH + 2, DP = DH * DW;
+    const DwBwdLayout lay(CB, PH, TW, a.RP);
+    const int xpitch = lay.xpitch, dpitch = lay.dpitch, apitch = lay.apitch;
+    float *sx = smem_dw + lay.sx;        // [CB][xpitch]  input patch, halo 2
+    float *sd = smem_dw + lay.sd;        // [CB][dpitch]  d x^T, then d pre, halo 1
+    float *sw = smem_dw + lay.sw;        // [CB][10]
+    float *sacc = smem_dw + lay.sacc;    // [CB][10] d weight / d bias of this patch
     const int KR = 4 * a.RP;
-    float *sxw = sacc + (size_t)a.CB * 10;      // [KR][CB] x_proj weight slice (x_proj only)
-    float *sdx = sxw + (size_t)KR * a.CB;       // [KR][dpitch] d x_dbl on the patch + 1 (x_proj only)
-    float *sxacc = sdx + (size_t)KR * dpitch;   // [KR][CB] d x_proj weight of this patch (x_proj only)
-    for (int i = threadIdx.x; i < j.nc * 10; i += 256) {
+    float *sxw = smem_dw + lay.sxw;      // [KR][CB] x_proj weight slice (x_proj only)
+    float *sdx = smem_dw + lay.sdx;      // [KR][dpitch] d x_dbl on the patch + 1 (x_proj only)
+    float *sxacc = smem_dw + lay.sxacc;  // [KR][CB] d x_proj weight of this patch (x_proj only)
+    float *sa = smem_dw + lay.sa;        // [CB][apitch] activation on the owned positions (x_proj only)
+    const FastDiv dn(nc), dxw(XW, a.m_xw), ddw(DW, a.m_dw), ddh(DH, a.m_dh), ddp(DP, a.m_dp);
+    const int tid = threadIdx.x;
+    const int twsh = 31 - __clz(TW);     // TW is a power of two (plan_dw)
+    const long long L = (long long)a.H * a.W;
+    const bool xp = a.xpw != nullptr;
+
+    // ---- A ----
+    for (int i = tid; i < nc * 10; i += 256) {
         const int c = i / 10, k = i - c * 10;
         sw[i] = k < 9 ? __ldg(a.w9 + (long long)(j.c0 + c) * 9 + k) : (a.bias ? __ldg(a.bias + j.c0 + c) : 0.0f);
         sacc[i] = 0.0f;
     }
-    const long long L = (long long)a.H * a.W;
-    if (a.xpw) {
-        for (int i = threadIdx.x; i < KR * j.nc; i += 256) {
-            const int kr = i / j.nc, c = i - kr * j.nc;
-            sxw[kr * a.CB + c] = __ldg(a.xpw + (long long)kr * a.C + j.c0 + c);
-            sxacc[kr * a.CB + c] = 0.0f;
+    if (xp) {
+        for (int i = tid; i < KR * nc; i += 256) {
+            const int kr = dn.div(i), c = i - kr * nc;
+            sxw[kr * CB + c] = __ldg(a.xpw + (long long)kr * a.C + j.c0 + c);
+            sxacc[kr * CB + c] = 0.0f;
         }
-        for (int i = threadIdx.x; i < KR * DH * DW; i += 256) {
-            const int kr = i / (DH * DW), qpos = i - kr * DH * DW;
-            const int k = kr / a.RP, r = kr - k * a.RP;
-            int dr, dq;
-            if (k & 1) {  // column-major source: lanes along h
-                dq = qpos / DH;
-                dr = qpos - dq * DH;
-            } else {
-                dr = qpos / DW;
-                dq = qpos - dr * DW;
-            }
-            const int h = j.h0 - 1 + dr, w = j.w0 - 1 + dq;
-            float v = 0.0f;
-            if (h >= 0 && h < a.H && w >= 0 && w < a.W) {
-                const long long row = (((long long)j.b * 2 + (k >> 1)) * a.RP + r) * L;
-                v = (k & 1) ? __ldg(a.dxd_cm + row + (long long)w * a.H + h) : __ldg(a.dxd_rm + row + (long long)h * a.W + w);
-            }
-            sdx[kr * dpitch + dr * DW + dq] = v;
-        }
+        if (nc & 1)
+            for (int kr = tid; kr < KR; kr += 256) sxw[kr * CB + nc] = 0.0f;  // phase B reads channel pairs
     }
-    load_patch<T, 2>(a, j, sx, xpitch);
-    __syncthreads();
-    // d pre on the patch + 1 (zero outside the map): lanes along w
-    for (int i = threadIdx.x; i < j.nc * DH * DW; i += 256) {
-        const int c = i / (DH * DW), r = i - c * DH * DW;
-        const int dr = r / DW, dq = r - dr * DW;
-        const int h = j.h0 - 1 + dr, w = j.w0 - 1 + dq;
-        float dp = 0.0f;
-        if (h >= 0 && h < a.H && w >= 0 && w < a.W) {
-            const float *wt = sw + c * 10;
-            const float *src = sx + c * xpitch + dr * XW + dq;  // window of (h, w): rows dr .. dr + 2 of the halo-2 patch
-            float pre = wt[9];
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) pre = fmaf(wt[kh * 3 + kw], src[kh * XW + kw], pre);
-            pre = to_f32<T>(from_f32<T>(pre));
-            const long long plane = ((long long)j.b * a.C + j.c0 + c) * L;
-            float g = __ldg(a.dx + plane + (long long)h * a.W + w);
-            if (a.dxT) g += __ldg(a.dxT + plane + (long long)w * a.H + h);
-            if (a.xpw)  // x_dbl = W x: its gradient reaches the map through W^T
-                for (int kr = 0; kr < KR; ++kr) g = fmaf(sxw[kr * a.CB + c], sdx[kr * dpitch + r], g);
-            dp = g * silu_grad(pre);
-        }
-        sd[c * dpitch + r] = dp;
-    }
-    __syncthreads();
-    // d weight / d bias over the positions this patch OWNS: a warp takes a channel (a slice of its positions when the block has
-    // fewer than 8 channels, so that every warp has work), lanes the positions; slices meet in shared memory
     {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int S = j.nc >= 8 ? 1 : 8 / j.nc;
-        for (int unit = warp; unit < j.nc * S; unit += 8) {
-            const int c = unit / S, sl = unit - c * S;
-            float acc[10];
+        constexpr int U = 8;
+        const T *xin = static_cast<const T *>(a.xin);
+        const int total = XH * XW * nc;
+        for (int i0 = tid; i0 < total; i0 += 256 * U) {
+            float v[U];
+            int at[U];
 #pragma unroll
-            for (int k = 0; k < 10; ++k) acc[k] = 0.0f;
-            for (int p = sl * 32 + lane; p < PH * TW; p += 32 * S) {
-                const int ph = p / TW, pw = p - ph * TW;
-                const float dp = sd[c * dpitch + (ph + 1) * DW + pw + 1];
-                const float *src = sx + c * xpitch + (ph + 1) * XW + pw + 1;  // window of the owned position
-#pragma unroll
-                for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) acc[kh * 3 + kw] = fmaf(dp, src[kh * XW + kw], acc[kh * 3 + kw]);
-                acc[9] += dp;
+            for (int k = 0; k < U; ++k) {
+                const int i = i0 + 256 * k;
+                v[k] = 0.0f;
+                at[k] = -1;
+                if (i < total) {
+                    const int pos = dn.div(i), c = i - pos * nc;
+                    const int r = dxw.div(pos), q = pos - r * XW;
+                    const int h = j.h0 - 2 + r, w = j.w0 - 2 + q;
+                    at[k] = c * xpitch + pos;
+                    if (h >= 0 && h < a.H && w >= 0 && w < a.W) v[k] = to_f32<T>(xin[(((long long)j.b * a.H + h) * a.W + w) * a.ps + j.c0 + c]);
+                }
             }
 #pragma unroll
-            for (int k = 0; k < 10; ++k) {
-                float v = acc[k];
+            for (int k = 0; k < U; ++k)
+                if (at[k] >= 0) sx[at[k]] = v[k];
+        }
+    }
+    {   // d x^T on the patch + 1, lanes along h (its fast axis); zeros outside the map or when there is no d x^T
+        constexpr int U = 6;
+        const int total = nc * DP;
+        for (int i0 = tid; i0 < total; i0 += 256 * U) {
+            float v[U];
+            int at[U];
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                if (lane == 0) atomicAdd(&sacc[c * 10 + k], v);
+            for (int k = 0; k < U; ++k) {
+                const int i = i0 + 256 * k;
+                v[k] = 0.0f;
+                at[k] = -1;
+                if (i < total) {
+                    const int c = ddp.div(i), rem = i - c * DP;
+                    const int dq = ddh.div(rem), dr = rem - dq * DH;
+                    const int h = j.h0 - 1 + dr, w = j.w0 - 1 + dq;
+                    at[k] = c * dpitch + dr * DW + dq;
+                    if (a.dxT && h >= 0 && h < a.H && w >= 0 && w < a.W) v[k] = __ldg(a.dxT + ((long long)j.b * a.C + j.c0 + c) * L + (long long)w * a.H + h);
+                }
             }
-            if (a.xpw) {  // d x_proj weight[kr][c] = sum over owned positions of d x_dbl[kr] * act(c), act recomputed from the input patch
-                const float *wt = sw + c * 10;
-                for (int kr0 = 0; kr0 < KR; kr0 += 4) {
-                    float aw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                    for (int p = sl * 32 + lane; p < PH * TW; p += 32 * S) {
-                        const int ph = p / TW, pw = p - ph * TW;
-                        const float *src = sx + c * xpitch + (ph + 1) * XW + pw + 1;
-                        float pre = wt[9];
 #pragma unroll
-                        for (int kh = 0; kh < 3; ++kh)
+            for (int k = 0; k < U; ++k)
+                if (at[k] >= 0) sd[at[k]] = v[k];
+        }
+    }
+    if (xp) {
+        constexpr int U = 4;
+        const int total = KR * DP;
+        const FastDiv drp(a.RP, a.m_rp);
+        for (int i0 = tid; i0 < total; i0 += 256 * U) {
+            float v[U];
+            int at[U];
 #pragma unroll
-                            for (int kw = 0; kw < 3; ++kw) pre = fmaf(wt[kh * 3 + kw], src[kh * XW + kw], pre);
-                        const float act = to_f32<T>(from_f32<T>(silu_val(to_f32<T>(from_f32<T>(pre)))));
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (kr0 + u < KR) aw[u] = fmaf(sdx[(kr0 + u) * dpitch + (ph + 1) * DW + pw + 1], act, aw[u]);
+            for (int k = 0; k < U; ++k) {
+                const int i = i0 + 256 * k;
+                v[k] = 0.0f;
+                at[k] = -1;
+                if (i < total) {
+                    const int kr = ddp.div(i), qpos = i - kr * DP;
+                    const int kd = drp.div(kr), r = kr - kd * a.RP;
+                    int dr, dq;
+                    if (kd & 1) {  // column-major source: lanes along h
+                        dq = ddh.div(qpos);
+                        dr = qpos - dq * DH;
+                    } else {
+                        dr = ddw.div(qpos);
+                        dq = qpos - dr * DW;
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float v = aw[u];
-#pragma unroll
-                        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                        if (lane == 0 && kr0 + u < KR) atomicAdd(&sxacc[(kr0 + u) * a.CB + c], v);
+                    const int h = j.h0 - 1 + dr, w = j.w0 - 1 + dq;
+                    at[k] = kr * dpitch + dr * DW + dq;
+                    if (h >= 0 && h < a.H && w >= 0 && w < a.W) {
+                        const long long row = (((long long)j.b * 2 + (kd >> 1)) * a.RP + r) * L;
+                        v[k] = (kd & 1) ? __ldg(a.dxd_cm + row + (long long)w * a.H + h) : __ldg(a.dxd_rm + row + (long long)h * a.W + w);
                     }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k)
+                if (at[k] >= 0) sdx[at[k]] = v[k];
+        }
+    }
+    __syncthreads();
+
+    // ---- B ----  item = (channel pair, position of the patch + 1), lanes along w
+    {
+        constexpr int U = 2;
+        const int npairs = (nc + 1) >> 1, total = npairs * DP;
+        for (int i0 = tid; i0 < total; i0 += 256 * U) {
+            float gx[U][2];
+            int cp[U], rr[U];
+            bool in[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int i = i0 + 256 * k;
+                gx[k][0] = gx[k][1] = 0.0f;
+                in[k] = false;
+                cp[k] = -1;
+                rr[k] = 0;
+                if (i < total) {
+                    cp[k] = ddp.div(i);
+                    rr[k] = i - cp[k] * DP;
+                    const int dr = ddw.div(rr[k]), dq = rr[k] - dr * DW;
+                    const int h = j.h0 - 1 + dr, w = j.w0 - 1 + dq;
+                    in[k] = h >= 0 && h < a.H && w >= 0 && w < a.W;
+                    if (in[k]) {
+                        const long long plane = ((long long)j.b * a.C + j.c0 + 2 * cp[k]) * L + (long long)h * a.W + w;
+                        gx[k][0] = __ldg(a.dx + plane);
+                        if (2 * cp[k] + 1 < nc) gx[k][1] = __ldg(a.dx + plane + L);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                if (cp[k] < 0) continue;
+                const int r = rr[k], c = 2 * cp[k];
+                const bool two = c + 1 < nc;
+                const int dr = ddw.div(r), dq = r - dr * DW;
+                float dp0 = 0.0f, dp1 = 0.0f;
+                if (in[k]) {
+                    const float *w0 = sw + c * 10, *w1 = w0 + (two ? 10 : 0);
+                    const float *s0 = sx + c * xpitch + dr * XW + dq, *s1 = s0 + (two ? xpitch : 0);  // window of (h, w) in the halo-2 patch
+                    float pre0 = w0[9], pre1 = w1[9];
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            pre0 = fmaf(w0[kh * 3 + kw], s0[kh * XW + kw], pre0);
+                            pre1 = fmaf(w1[kh * 3 + kw], s1[kh * XW + kw], pre1);
+                        }
+                    pre0 = to_f32<T>(from_f32<T>(pre0));
+                    pre1 = to_f32<T>(from_f32<T>(pre1));
+                    float g0 = gx[k][0] + sd[c * dpitch + r], g1 = gx[k][1] + (two ? sd[(c + 1) * dpitch + r] : 0.0f);
+                    if (xp) {  // x_dbl = W x: its gradient reaches the map through W^T
+                        const float *wk = sxw + c, *dk = sdx + r;
+                        for (int kr = 0; kr < KR; ++kr) {
+                            const float d = dk[kr * dpitch];
+                            g0 = fmaf(wk[kr * CB], d, g0);
+                            g1 = fmaf(wk[kr * CB + 1], d, g1);
+                        }
+                    }
+                    const float sg0 = 1.0f / (1.0f + __expf(-pre0)), sg1 = 1.0f / (1.0f + __expf(-pre1));
+                    dp0 = g0 * sg0 * (1.0f + pre0 * (1.0f - sg0));
+                    dp1 = g1 * sg1 * (1.0f + pre1 * (1.0f - sg1));
+                    if (xp && dr >= 1 && dr <= PH && dq >= 1 && dq <= TW) {  // owned: keep the activation for d x_proj_weight
+                        const int p = (dr - 1) * TW + dq - 1;
+                        sa[c * apitch + p] = to_f32<T>(from_f32<T>(silu_val(pre0)));
+                        if (two) sa[(c + 1) * apitch + p] = to_f32<T>(from_f32<T>(silu_val(pre1)));
+                    }
+                }
+                sd[c * dpitch + r] = dp0;
+                if (two) sd[(c + 1) * dpitch + r] = dp1;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- C ----  unit = (slice of the owned positions, kind, channel), channel fastest (odd pitches: conflict-free)
+    {
+        const int kinds = 1 + (xp ? (KR + 3) / 4 : 0);
+        const int per = kinds * nc;
+        int S = 1;
+        while (S < 32 && per * S < 256 && (P >> 1) >= S * 8) S <<= 1;
+        const FastDiv dper(per);
+        for (int unit = tid; unit < per * S; unit += 256) {
+            const int sl = dper.div(unit), rest = unit - sl * per;
+            const int kind = dn.div(rest), c = rest - kind * nc;
+            if (kind == 0) {
+                float acc[10];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) acc[k] = 0.0f;
+                for (int p = sl; p < P; p += S) {
+                    const int ph = p >> twsh, pw = p & (TW - 1);
+                    const float dp = sd[c * dpitch + (ph + 1) * DW + pw + 1];
+                    const float *src = sx + c * xpitch + (ph + 1) * XW + pw + 1;  // window of the owned position
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) acc[kh * 3 + kw] = fmaf(dp, src[kh * XW + kw], acc[kh * 3 + kw]);
+                    acc[9] += dp;
+                }
+#pragma unroll
+                for (int k = 0; k < 10; ++k) atomicAdd(&sacc[c * 10 + k], acc[k]);
+            } else {
+                const int kr0 = (kind - 1) * 4;
+                float aw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                for (int p = sl; p < P; p += S) {
+                    const int ph = p >> twsh, pw = p & (TW - 1);
+                    const float act = sa[c * apitch + p];
+                    const float *dk = sdx + (ph + 1) * DW + pw + 1;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (kr0 + u < KR) aw[u] = fmaf(dk[(kr0 + u) * dpitch], act, aw[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (kr0 + u < KR) atomicAdd(&sxacc[(kr0 + u) * CB + c], aw[u]);
+            }
+        }
+    }
+    // ---- D ----  d input, channel-last: lanes along channels
+    {
+        constexpr int U = 4;
+        T *dxin = static_cast<T *>(a.dxin);
+        const int total = P * nc;
+        for (int i0 = tid; i0 < total; i0 += 256 * U) {
+            float acc[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int i = i0 + 256 * k;
+                acc[k] = 0.0f;
+                if (i < total) {
+                    const int pos = dn.div(i), c = i - pos * nc;
+                    const int ph = pos >> twsh, pw = pos & (TW - 1);
+                    const float *wt = sw + c * 10;
+                    const float *src = sd + c * dpitch + ph * DW + pw;  // d pre rows ph .. ph + 2 (halo 1) = positions h - 1 .. h + 1
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) acc[k] = fmaf(wt[kh * 3 + kw], src[(2 - kh) * DW + (2 - kw)], acc[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int i = i0 + 256 * k;
+                if (i < total) {
+                    const int pos = dn.div(i), c = i - pos * nc;
+                    const int ph = pos >> twsh, pw = pos & (TW - 1);
+                    dxin[(((long long)j.b * a.H + j.h0 + ph) * a.W + j.w0 + pw) * a.C + j.c0 + c] = from_f32<T>(acc[k]);
                 }
             }
         }
     }
-    // d input, channel-last: lanes along channels
-    T *dxin = static_cast<T *>(a.dxin);
-    for (int i = threadIdx.x; i < PH * TW * j.nc; i += 256) {
-        const int pos = i / j.nc, c = i - pos * j.nc;
-        const int ph = pos / TW, pw = pos - ph * TW;
-        const float *wt = sw + c * 10;
-        const float *src = sd + c * dpitch + ph * DW + pw;  // d pre rows ph .. ph + 2 (halo 1) = positions h - 1 .. h + 1
-        float acc = 0.0f;
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) acc = fmaf(wt[kh * 3 + kw], src[(2 - kh) * DW + (2 - kw)], acc);
-        dxin[(((long long)j.b * a.H + j.h0 + ph) * a.W + j.w0 + pw) * a.C + j.c0 + c] = from_f32<T>(acc);
-    }
     __syncthreads();
     if (a.dwb) {
         float *dst = a.dwb + ((long long)j.patch * a.C + j.c0) * 10;
-        for (int i = threadIdx.x; i < j.nc * 10; i += 256) dst[i] = sacc[i];
+        for (int i = tid; i < nc * 10; i += 256) dst[i] = sacc[i];
     }
-    if (a.xpw)
-        for (int i = threadIdx.x; i < KR * j.nc; i += 256) {
-            const int kr = i / j.nc, c = i - kr * j.nc;
-            a.dxpw[((long long)j.patch * KR + kr) * a.C + j.c0 + c] = sxacc[kr * a.CB + c];
+    if (xp)
+        for (int i = tid; i < KR * nc; i += 256) {
+            const int kr = dn.div(i), c = i - kr * nc;
+            a.dxpw[((long long)j.patch * KR + kr) * a.C + j.c0 + c] = sxacc[kr * CB + c];
         }
 }
 
@@ -328,10 +502,19 @@ static int plan_dw(int batch, int C, int H, int W, bool bwd, int RP, int &PH, in
     auto grid = [&]() { return (long long)batch * (H / PH) * (W / TW) * ((C + CB - 1) / CB); };
     while (TW > 8 && grid() < 2 * 148) TW /= 2;
     while (CB > 16 && grid() < 2 * 148) CB /= 2;
+    if (bwd) {  // the backward keeps four planes per channel: stay under ~56 KB so that four CTAs share an SM
+        auto fits = [&](int cb, int tw, int rp) { return sizeof(float) * DwBwdLayout(cb, PH, tw, rp).total <= 56 * 1024; };
+        // TW fixes the patch count, which vmasr_dwconv_patches reports without knowing RP: sized for dt_rank 1 whatever RP is
+        while (CB > 16 && !fits(CB, TW, 3)) CB /= 2;
+        while (TW > 8 && !fits(CB, TW, 3)) TW /= 2;
+        while (CB > 16 && !fits(CB, TW, RP)) CB /= 2;  // more x_dbl rows
+    }
     const int halo = bwd ? 2 : 1;
     const size_t xp = (size_t)((PH + 2 * halo) * (TW + 2 * halo)) | 1, dp = (size_t)((PH + 2) * (TW + 2)) | 1;
-    smem = sizeof(float) * ((size_t)CB * (xp + (bwd ? dp : 0)) + (size_t)CB * 20);
-    if (RP > 0) smem += sizeof(float) * ((size_t)4 * RP * CB + (bwd ? (size_t)4 * RP * (dp + CB) : (size_t)CB * (((size_t)PH * TW) | 1)));
+    smem = sizeof(float) * ((size_t)CB * xp + (size_t)CB * 20);
+    if (RP > 0) smem += sizeof(float) * ((size_t)4 * RP * CB + (size_t)CB * (((size_t)PH * TW) | 1));
+    if (bwd) smem = sizeof(float) * DwBwdLayout(CB, PH, TW, RP).total;
+    (void)dp;
     if (smem > 200 * 1024) return fail("dwconv_silu: patch does not fit shared memory");
     return 0;
 }
@@ -341,6 +524,11 @@ static int launch_dw(const DwArgs &a, bool bwd, size_t smem, long long grid, cud
     auto kernel = bwd ? dwconv_silu_bwd_kernel<T> : dwconv_silu_fwd_kernel<T>;
     if (smem > 48 * 1024)
         if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "dwconv_silu smem attribute")) return rc;
+    static PerDeviceOnce carved[2];  // the driver otherwise picks the smallest carve-out that holds ONE CTA
+    if (!carved[bwd]()) {
+        if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "dwconv_silu carve-out")) return rc;
+        carved[bwd]() = true;
+    }
     kernel<<<(unsigned)grid, 256, smem, stream>>>(a);
     return check_cuda(cudaGetLastError(), bwd ? "dwconv_silu_bwd launch" : "dwconv_silu_fwd launch");
 }
@@ -376,6 +564,8 @@ static int dw_run(const vmasr_dwconv_params *p, bool bwd) {
     a.dxd_rm = p->d_x_dbl_rm; a.dxd_cm = p->d_x_dbl_cm; a.dxpw = p->d_x_proj_weight_partial; a.RP = RP;
     a.ps = p->xin_pos_stride ? p->xin_pos_stride : p->channels;
     a.B = p->batch; a.C = p->channels; a.H = p->H; a.W = p->W;
+    a.m_xw = fastdiv_magic(a.TW + 4); a.m_dw = fastdiv_magic(a.TW + 2); a.m_dh = fastdiv_magic(a.PH + 2);
+    a.m_dp = fastdiv_magic((a.PH + 2) * (a.TW + 2)); a.m_rp = fastdiv_magic(RP);
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail("%s: cannot select CUDA device %d", who, p->device);
     cudaStream_t stream = static_cast<cudaStream_t>(p->stream);
