@@ -67,19 +67,43 @@ struct DwJob {
     }
 };
 
+// i / d for i * d < 2^32 (every index of a patch is far below that): one multiply-high instead of the ~20-instruction
+// division sequence; the loops below decode several flat indices per item.
+static inline __host__ __device__ unsigned fastdiv_magic(unsigned d) { return d > 1 ? 0xFFFFFFFFu / d + 1u : 0u; }
+struct FastDiv {
+    unsigned d, m;
+    __device__ __forceinline__ explicit FastDiv(unsigned d_) : d(d_), m(fastdiv_magic(d_)) {}
+    __device__ __forceinline__ FastDiv(unsigned d_, unsigned m_) : d(d_), m(m_) {}  // reciprocal computed on the host
+    __device__ __forceinline__ unsigned div(unsigned i) const { return d > 1 ? __umulhi(i, m) : i; }
+};
+
 // input patch with a halo of HALO positions (zeros outside the map) -> s[c][(PH + 2 HALO) x (TW + 2 HALO)], lanes along channels
 template <typename T, int HALO>
 __device__ __forceinline__ void load_patch(const DwArgs &a, const DwJob &j, float *s, int pitch) {
     const T *xin = static_cast<const T *>(a.xin);
     const int RW = a.TW + 2 * HALO, RH = a.PH + 2 * HALO;
     const int total = RH * RW * j.nc;
-    for (int i = threadIdx.x; i < total; i += 256) {
-        const int pos = i / j.nc, c = i - pos * j.nc;
-        const int r = pos / RW, q = pos - r * RW;
-        const int h = j.h0 - HALO + r, w = j.w0 - HALO + q;
-        float v = 0.0f;
-        if (h >= 0 && h < a.H && w >= 0 && w < a.W) v = to_f32<T>(xin[(((long long)j.b * a.H + h) * a.W + w) * a.ps + j.c0 + c]);
-        s[c * pitch + pos] = v;
+    const FastDiv dn(j.nc), drw(RW);
+    constexpr int U = 8;  // loads of a batch are issued before the first store
+    for (int i0 = threadIdx.x; i0 < total; i0 += 256 * U) {
+        float v[U];
+        int at[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = i0 + 256 * k;
+            v[k] = 0.0f;
+            at[k] = -1;
+            if (i < total) {
+                const int pos = dn.div(i), c = i - pos * j.nc;
+                const int r = drw.div(pos), q = pos - r * RW;
+                const int h = j.h0 - HALO + r, w = j.w0 - HALO + q;
+                at[k] = c * pitch + pos;
+                if (h >= 0 && h < a.H && w >= 0 && w < a.W) v[k] = to_f32<T>(xin[(((long long)j.b * a.H + h) * a.W + w) * a.ps + j.c0 + c]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+            if (at[k] >= 0) s[at[k]] = v[k];
     }
 }
 
@@ -87,40 +111,51 @@ template <typename T>
 __global__ void __launch_bounds__(256) dwconv_silu_fwd_kernel(const DwArgs a) {
     extern __shared__ float smem_dw[];
     const DwJob j(a);
-    const int PH = a.PH, TW = a.TW, RW = TW + 2;
+    const int PH = a.PH, TW = a.TW, RW = TW + 2, CB = a.CB, nc = j.nc;
     const int pitch = ((PH + 2) * RW) | 1;
-    float *s = smem_dw;                       // [CB][pitch]
-    float *sw = s + (size_t)a.CB * pitch;     // [CB][10] weights and bias
     const int P = PH * TW, opitch = P | 1, KR = 4 * a.RP;
-    float *so = sw + (size_t)a.CB * 10;       // [CB][opitch] activations of the patch (x_proj only)
-    float *sxw = so + (size_t)a.CB * opitch;  // [KR][CB] x_proj weight slice (x_proj only)
-    for (int i = threadIdx.x; i < j.nc * 10; i += 256) {
+    const int RQ = (2 * a.RP + 7) & ~7;       // x_dbl rows of one position order (two directions), padded to eights
+    auto up4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
+    float *s = smem_dw;                                   // [CB][pitch]
+    float *sw = s + up4((size_t)CB * pitch);              // [CB][10] weights and bias
+    float *so = sw + up4((size_t)CB * 10);                // [CB][opitch] activations of the patch (x_proj only)
+    float *sxw = so + up4((size_t)CB * opitch);           // [2][CB][RQ] x_proj weight slice, rows of a position order contiguous (x_proj only)
+    const FastDiv dn(nc);
+    for (int i = threadIdx.x; i < nc * 10; i += 256) {
         const int c = i / 10, k = i - c * 10;
         sw[i] = k < 9 ? __ldg(a.w9 + (long long)(j.c0 + c) * 9 + k) : (a.bias ? __ldg(a.bias + j.c0 + c) : 0.0f);
     }
-    if (a.xpw)
-        for (int i = threadIdx.x; i < KR * j.nc; i += 256) {
-            const int kr = i / j.nc, c = i - kr * j.nc;
-            sxw[kr * a.CB + c] = __ldg(a.xpw + (long long)kr * a.C + j.c0 + c);
+    if (a.xpw) {
+        for (int i = threadIdx.x; i < 2 * nc * RQ; i += 256) sxw[(i / (nc * RQ)) * CB * RQ + i % (nc * RQ)] = 0.0f;  // the padding rows
+        __syncthreads();
+        for (int i = threadIdx.x; i < KR * nc; i += 256) {
+            const int kr = dn.div(i), c = i - kr * nc;
+            const int k = kr / a.RP, r = kr - k * a.RP;
+            sxw[((k & 1) * CB + c) * RQ + (k >> 1) * a.RP + r] = __ldg(a.xpw + (long long)kr * a.C + j.c0 + c);
         }
+    }
     load_patch<T, 1>(a, j, s, pitch);
     __syncthreads();
     // item = (channel, quad of rows, column): four outputs down a column -> 32-byte row pieces of x, 128-bit pieces of x^T
     const long long L = (long long)a.H * a.W;
-    const int HQ = PH / 4, items = j.nc * HQ * TW;
+    const int twsh = 31 - __clz(TW), hqsh = PH == 8 ? 1 : 0;  // TW is a power of two, PH is 8 or 4 (plan_dw)
+    const int items = nc << (hqsh + twsh);
     for (int i = threadIdx.x; i < items; i += 256) {
-        const int c = i / (HQ * TW), r = i - c * HQ * TW;
-        const int q = r / TW, w = r - q * TW;
+        const int c = i >> (hqsh + twsh), r = i & ((1 << (hqsh + twsh)) - 1);
+        const int q = r >> twsh, w = r & (TW - 1);
         const float *wt = sw + c * 10;
         const float *src = s + c * pitch + (4 * q) * RW + w;  // top-left of the 6 x 3 window
-        float acc[4] = {wt[9], wt[9], wt[9], wt[9]};
+        float wv[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) wv[k] = wt[k];
+        float acc[4] = {wv[9], wv[9], wv[9], wv[9]};
 #pragma unroll
         for (int rr = 0; rr < 6; ++rr) {
             const float v0 = src[rr * RW], v1 = src[rr * RW + 1], v2 = src[rr * RW + 2];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int kh = rr - k;  // output row k uses window rows k .. k + 2
-                if (kh >= 0 && kh < 3) acc[k] = fmaf(wt[kh * 3 + 2], v2, fmaf(wt[kh * 3 + 1], v1, fmaf(wt[kh * 3], v0, acc[k])));
+                if (kh >= 0 && kh < 3) acc[k] = fmaf(wv[kh * 3 + 2], v2, fmaf(wv[kh * 3 + 1], v1, fmaf(wv[kh * 3], v0, acc[k])));
             }
         }
         float o[4];
@@ -137,40 +172,50 @@ __global__ void __launch_bounds__(256) dwconv_silu_fwd_kernel(const DwArgs a) {
     }
     if (!a.xpw) return;
     __syncthreads();
-    // x_dbl rows of this channel block: (direction k, row r) x position; even directions leave in row-major position order (lanes
-    // along w), odd ones in column-major order (lanes along h)
-    const bool single = a.C <= a.CB;
-    for (int i = threadIdx.x; i < KR * P; i += 256) {
-        const int kr = i / P, qpos = i - kr * P;
-        const int k = kr / a.RP, r = kr - k * a.RP;
+    // x_dbl rows of this channel block.  item = (position order, eight rows, position): one load of the activation and two
+    // 128-bit broadcast loads of the weights feed eight FMAs per channel; even directions leave in row-major position order
+    // (lanes along w), odd ones in column-major order (lanes along h)
+    const bool single = a.C <= CB;
+    const int chunks = RQ >> 3, phsh = PH == 8 ? 3 : 2;
+    const int psh = twsh + phsh;  // P = PH * TW
+    for (int i = threadIdx.x; i < 2 * chunks * P; i += 256) {
+        const int qpos = i & (P - 1), pc = i >> psh;
+        const int par = pc / chunks, ch = pc - par * chunks;
         int ph, pw;
-        if (k & 1) {
-            pw = qpos / PH;
-            ph = qpos - pw * PH;
+        if (par) {
+            pw = qpos >> phsh;
+            ph = qpos & (PH - 1);
         } else {
-            ph = qpos / TW;
-            pw = qpos - ph * TW;
+            ph = qpos >> twsh;
+            pw = qpos & (TW - 1);
         }
         const float *act = so + ph * TW + pw;
-        const float *wk = sxw + kr * a.CB;
-        float acc = (j.c0 == 0 && a.xpb) ? __ldg(a.xpb + kr) : 0.0f;
-        for (int c = 0; c < j.nc; ++c) acc = fmaf(wk[c], act[c * opitch], acc);
-        const long long row = (((long long)j.b * 2 + (k >> 1)) * a.RP + r) * L;
-        float *dst = (k & 1) ? a.xd_cm + row + (long long)(j.w0 + pw) * a.H + j.h0 + ph : a.xd_rm + row + (long long)(j.h0 + ph) * a.W + j.w0 + pw;
-        if (single) *dst = acc;
-        else atomicAdd(dst, acc);
+        const float4 *wk = reinterpret_cast<const float4 *>(sxw + (size_t)par * CB * RQ + ch * 8);
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0.0f;
+        for (int c = 0; c < nc; ++c) {
+            const float v = act[c * opitch];
+            const float4 w0 = wk[c * (RQ >> 2)], w1 = wk[c * (RQ >> 2) + 1];
+            acc[0] = fmaf(w0.x, v, acc[0]); acc[1] = fmaf(w0.y, v, acc[1]); acc[2] = fmaf(w0.z, v, acc[2]); acc[3] = fmaf(w0.w, v, acc[3]);
+            acc[4] = fmaf(w1.x, v, acc[4]); acc[5] = fmaf(w1.y, v, acc[5]); acc[6] = fmaf(w1.z, v, acc[6]); acc[7] = fmaf(w1.w, v, acc[7]);
+        }
+        const long long pofs = par ? (long long)(j.w0 + pw) * a.H + j.h0 + ph : (long long)(j.h0 + ph) * a.W + j.w0 + pw;
+        float *base = par ? a.xd_cm : a.xd_rm;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int jr = ch * 8 + u;  // (direction of this order, row)
+            if (jr < 2 * a.RP) {
+                const int kd = jr / a.RP, r = jr - kd * a.RP;
+                float v = acc[u];
+                if (j.c0 == 0 && a.xpb) v += __ldg(a.xpb + (2 * kd + par) * a.RP + r);
+                float *dst = base + (((long long)j.b * 2 + kd) * a.RP + r) * L + pofs;
+                if (single) *dst = v;
+                else atomicAdd(dst, v);
+            }
+        }
     }
 }
-
-// i / d for i * d < 2^32 (every index of a patch is far below that): one multiply-high instead of the ~20-instruction
-// division sequence; the loops below decode several flat indices per item.
-static inline __host__ __device__ unsigned fastdiv_magic(unsigned d) { return d > 1 ? 0xFFFFFFFFu / d + 1u : 0u; }
-struct FastDiv {
-    unsigned d, m;
-    __device__ __forceinline__ explicit FastDiv(unsigned d_) : d(d_), m(fastdiv_magic(d_)) {}
-    __device__ __forceinline__ FastDiv(unsigned d_, unsigned m_) : d(d_), m(m_) {}  // reciprocal computed on the host
-    __device__ __forceinline__ unsigned div(unsigned i) const { return d > 1 ? __umulhi(i, m) : i; }
-};
 
 // shared-memory carve-up of the backward (floats); host and device agree through this one function
 struct DwBwdLayout {
@@ -512,7 +557,8 @@ static int plan_dw(int batch, int C, int H, int W, bool bwd, int RP, int &PH, in
     const int halo = bwd ? 2 : 1;
     const size_t xp = (size_t)((PH + 2 * halo) * (TW + 2 * halo)) | 1, dp = (size_t)((PH + 2) * (TW + 2)) | 1;
     smem = sizeof(float) * ((size_t)CB * xp + (size_t)CB * 20);
-    if (RP > 0) smem += sizeof(float) * ((size_t)4 * RP * CB + (size_t)CB * (((size_t)PH * TW) | 1));
+    if (RP > 0) smem += sizeof(float) * ((size_t)2 * CB * ((2 * RP + 7) & ~7) + (size_t)CB * (((size_t)PH * TW) | 1));
+    smem += 64;  // the regions start at multiples of 16 bytes
     if (bwd) smem = sizeof(float) * DwBwdLayout(CB, PH, TW, RP).total;
     (void)dp;
     if (smem > 200 * 1024) return fail("dwconv_silu: patch does not fit shared memory");

@@ -143,24 +143,37 @@ __global__ void __launch_bounds__(256) outnorm_fwd_kernel(const OutNormArgs a) {
     const T *z = static_cast<const T *>(a.z);
     T *out = static_cast<T *>(a.out);
     const int row_elems = TW * C;
+    constexpr int U3 = 4;  // elements in flight per thread: the z loads of a batch are issued before the first use
     for (int ph = 0; ph < PH; ++ph) {
         const long long base = ((long long)b * L + (long long)(h0 + ph) * W + w0) * C;
-        for (int e = t; e < row_elems; e += 256) {
-            int pw, c;
-            split_pc(e, C, a.c_shift, pw, c);
-            const int p = ph * TW + pw;
-            const float g = a.gamma ? __ldg(a.gamma + c) : 1.0f, be = a.beta ? __ldg(a.beta + c) : 0.0f;
-            const float ln = fmaf((sy[(size_t)c * PITCH + p] - smean[p]) * srstd[p], g, be);
-            float o = to_f32<T>(from_f32<T>(ln));  // y.to(x.dtype)
-            if (z) {
-                float zv = to_f32<T>(z[base + e]);
-                if (a.z_silu) {
-                    float sig;
-                    zv = to_f32<T>(from_f32<T>(silu_f(zv, sig)));  // act(z) is a tensor of z's dtype in the reference
-                }
-                o *= zv;
+        for (int e0 = t; e0 < row_elems; e0 += 256 * U3) {
+            float zv[U3];
+#pragma unroll
+            for (int u = 0; u < U3; ++u) {
+                const int e = e0 + 256 * u;
+                zv[u] = 1.0f;
+                if (z && e < row_elems) zv[u] = to_f32<T>(z[base + e]);
             }
-            out[base + e] = from_f32<T>(o);
+#pragma unroll
+            for (int u = 0; u < U3; ++u) {
+                const int e = e0 + 256 * u;
+                if (e >= row_elems) break;
+                int pw, c;
+                split_pc(e, C, a.c_shift, pw, c);
+                const int p = ph * TW + pw;
+                const float g = a.gamma ? __ldg(a.gamma + c) : 1.0f, be = a.beta ? __ldg(a.beta + c) : 0.0f;
+                const float ln = fmaf((sy[(size_t)c * PITCH + p] - smean[p]) * srstd[p], g, be);
+                float o = to_f32<T>(from_f32<T>(ln));  // y.to(x.dtype)
+                if (z) {
+                    float gate = zv[u];
+                    if (a.z_silu) {
+                        float sig;
+                        gate = to_f32<T>(from_f32<T>(silu_f(gate, sig)));  // act(z) is a tensor of z's dtype in the reference
+                    }
+                    o *= gate;
+                }
+                out[base + e] = from_f32<T>(o);
+            }
         }
     }
 }
@@ -203,16 +216,33 @@ __global__ void __launch_bounds__(256) outnorm_bwd_kernel(const OutNormArgs a) {
     // ---- phase 1: xhat of the patch from the saved merged map (rows of TW floats, 128-bit) ----
     {
         const int V = TW / 4, items = C * PH * V;
-        for (int i = t; i < items; i += 256) {
-            const int c = i / (PH * V), r = i - c * PH * V;
-            const int ph = r / V, wv = (r - ph * V) * 4;
-            const float4 yv = __ldg(reinterpret_cast<const float4 *>(a.y_in + ((long long)b * C + c) * L + (long long)(h0 + ph) * W + w0 + wv));
-            const int p = ph * TW + wv;
-            float *dst = sx + (size_t)c * PITCH + p;
-            dst[0] = (yv.x - smean[p]) * srstd[p];
-            dst[1] = (yv.y - smean[p + 1]) * srstd[p + 1];
-            dst[2] = (yv.z - smean[p + 2]) * srstd[p + 2];
-            dst[3] = (yv.w - smean[p + 3]) * srstd[p + 3];
+        constexpr int U = 4;
+        for (int i0 = t; i0 < items; i0 += 256 * U) {
+            float4 yv[U];
+            int at[U], pp[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + 256 * u;
+                at[u] = -1;
+                pp[u] = 0;
+                if (i < items) {
+                    const int c = i / (PH * V), r = i - c * PH * V;
+                    const int ph = r / V, wv = (r - ph * V) * 4;
+                    yv[u] = __ldg(reinterpret_cast<const float4 *>(a.y_in + ((long long)b * C + c) * L + (long long)(h0 + ph) * W + w0 + wv));
+                    pp[u] = ph * TW + wv;
+                    at[u] = c * PITCH + pp[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (at[u] < 0) continue;
+                const int p = pp[u];
+                float *dst = sx + at[u];
+                dst[0] = (yv[u].x - smean[p]) * srstd[p];
+                dst[1] = (yv[u].y - smean[p + 1]) * srstd[p + 1];
+                dst[2] = (yv[u].z - smean[p + 2]) * srstd[p + 2];
+                dst[3] = (yv[u].w - smean[p + 3]) * srstd[p + 3];
+            }
         }
     }
     __syncthreads();
@@ -230,33 +260,50 @@ __global__ void __launch_bounds__(256) outnorm_bwd_kernel(const OutNormArgs a) {
     const int step = K ? 256 * K : 256;
     for (int ph = 0; ph < PH; ++ph) {
         const long long base = ((long long)b * L + (long long)(h0 + ph) * W + w0) * C;
-        for (int e = t + 256 * kk; e < row_elems; e += step) {
-            int pw, c;
-            split_pc(e, C, a.c_shift, pw, c);
-            const int p = ph * TW + pw;
-            const float g = a.gamma ? __ldg(a.gamma + c) : 1.0f, be = a.beta ? __ldg(a.beta + c) : 0.0f;
-            const float xh = sx[(size_t)c * PITCH + p];
-            const float ln = to_f32<T>(from_f32<T>(fmaf(xh, g, be)));
-            const float go = to_f32<T>(dout[base + e]);
-            float dln = go;
-            if (z) {
-                const float zv = to_f32<T>(z[base + e]);
-                float gate = zv, dgate = 1.0f;
-                if (a.z_silu) {
-                    float sig;
-                    gate = to_f32<T>(from_f32<T>(silu_f(zv, sig)));
-                    dgate = sig * (1.0f + zv * (1.0f - sig));
+        constexpr int U2 = 4;  // elements in flight per thread
+        for (int e0 = t + 256 * kk; e0 < row_elems; e0 += step * U2) {
+            float gov[U2], zvv[U2];
+#pragma unroll
+            for (int u = 0; u < U2; ++u) {
+                const int e = e0 + step * u;
+                gov[u] = 0.0f;
+                zvv[u] = 0.0f;
+                if (e < row_elems) {
+                    gov[u] = to_f32<T>(dout[base + e]);
+                    if (z) zvv[u] = to_f32<T>(z[base + e]);
                 }
-                dln = go * gate;
-                if (dz) dz[base + e] = from_f32<T>(go * ln * dgate);
             }
-            sd[(size_t)c * PITCH + p] = dln * g;
-            if (K) {
-                acc_g = fmaf(dln, xh, acc_g);
-                acc_b += dln;
-            } else {
-                atomicAdd(&sgb[c], dln * xh);
-                atomicAdd(&sgb[C + c], dln);
+#pragma unroll
+            for (int u = 0; u < U2; ++u) {
+                const int e = e0 + step * u;
+                if (e >= row_elems) break;
+                int pw, c;
+                split_pc(e, C, a.c_shift, pw, c);
+                const int p = ph * TW + pw;
+                const float g = a.gamma ? __ldg(a.gamma + c) : 1.0f, be = a.beta ? __ldg(a.beta + c) : 0.0f;
+                const float xh = sx[(size_t)c * PITCH + p];
+                const float ln = to_f32<T>(from_f32<T>(fmaf(xh, g, be)));
+                const float go = gov[u];
+                float dln = go;
+                if (z) {
+                    const float zv = zvv[u];
+                    float gate = zv, dgate = 1.0f;
+                    if (a.z_silu) {
+                        float sig;
+                        gate = to_f32<T>(from_f32<T>(silu_f(zv, sig)));
+                        dgate = sig * (1.0f + zv * (1.0f - sig));
+                    }
+                    dln = go * gate;
+                    if (dz) dz[base + e] = from_f32<T>(go * ln * dgate);
+                }
+                sd[(size_t)c * PITCH + p] = dln * g;
+                if (K) {
+                    acc_g = fmaf(dln, xh, acc_g);
+                    acc_b += dln;
+                } else {
+                    atomicAdd(&sgb[c], dln * xh);
+                    atomicAdd(&sgb[C + c], dln);
+                }
             }
         }
     }
