@@ -29,7 +29,7 @@ def main():
         for _ in range(args.steps):
             ts(x, y)
         torch.cuda.synchronize()
-    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=90))
+    print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=60, max_name_column_width=90))
 
 
 if __name__ == "__main__":

@@ -11,8 +11,11 @@
 //     P1(j), j = 0..n-1   u / delta / dout of channel j arrive by TMA (all issued at kernel start); softplus, decay, the
 //                thread's aggregates of BOTH recurrences (forward state h left to right, adjoint g right to left), two
 //                interleaved warp scans, warp aggregates to shared memory, ARRIVE on mbarrier tot[j].  The only
-//                per-position value kept is dt (log2 domain), parked in delta's slot; four registers per channel hold
-//                the thread's warp-exclusive prefixes.
+//                per-position value kept is dt (log2 domain), parked in delta's slot; the thread's warp-exclusive
+//                prefixes of both scans (16 bytes per channel) wait in a thread-private shared-memory slot.  (They used
+//                to be four registers per channel selected by `if (i == j)` chains: ptxas kept all sixteen in local
+//                memory and moved every one of them in and out in every iteration of both loops.)  B and C live in
+//                registers for the whole tile; their landing slots are the last stage's.
 //     P2(j), j = 0..n-1   waits on mbarrier in[j]; re-reads u, dt, dout, recomputes the decay (one ex2) and the sigmoid
 //                (1 - 2^-dt, one ex2) instead of carrying them in registers across the exchange, walks both recurrences,
 //                forms the gradients; 128-bit stores of du / ddelta; dB / dC accumulate in registers over the channels.
@@ -42,7 +45,8 @@ template <bool TAIL, bool SP, int STAGES, bool REV, bool F1>
 __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const TileMaps &tm, unsigned char *smem, const int chunk, const int rg) {
     constexpr int NC = 256, ITEMS = 8, WPR = 8, SEG = NC * ITEMS;
 
-    // shared memory carve-up (header 2048 bytes)
+    // shared memory carve-up (header 1024 bytes; 1024 + STAGES * (24576 + 4096) bytes in all: with 4 stages exactly the
+    // 113 KB a CTA may take when two share an SM)
     unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(smem);  // [STAGES] TMA completion
     unsigned long long *bar_bc = bar_full + STAGES;                               // B / C segment
     unsigned long long *bar_tot = bar_bc + 1;                                     // [STAGES] 8 arrivals
@@ -52,11 +56,12 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
     float2 *s_in = reinterpret_cast<float2 *>(smem + 640);                        // [STAGES][8] {h, g} entering each warp
     float *s_red = reinterpret_cast<float *>(smem + 896);                         // [STAGES][4] channel sums dA, dD, dbias
     float *s_par = reinterpret_cast<float *>(smem + 960);                         // [4][4]  A, D, bias * log2 e, (F1) dt weight
-    float *s_c = reinterpret_cast<float *>(smem + 2048);                          // [SEG]   C
-    float *s_stage = s_c + SEG;                                                   // [STAGES][3][SEG]  u, delta -> dt, dout
-    float *s_b = s_stage + (size_t)(STAGES - 1) * 3 * SEG;                        // B: borrowed from the last stage
+    float *s_stage = reinterpret_cast<float *>(smem + 1024);                      // [STAGES][3][SEG]  u, delta -> dt, dout
+    float4 *s_exc = reinterpret_cast<float4 *>(s_stage + (size_t)STAGES * 3 * SEG);  // [STAGES][NC] thread-private: warp-exclusive prefixes of both scans
+    float *s_b = s_stage + (size_t)(STAGES - 1) * 3 * SEG;                        // B and C land in the last stage and move to registers
     float *s_row = s_b + SEG;                                                     // F1: the dt row (the last stage stays free)
     float *s_drow = s_b + 2 * SEG;                                                // F1: its gradient, summed over the tile's channels
+    float *s_c = F1 ? s_drow : s_b + SEG;                                         // (F1: the gradient slot is zeroed after C has been read)
     static_assert(!F1 || STAGES == 4, "delta on the fly keeps the dt row in the fourth stage");
 
     const int ctile = rg % a.n_ctiles;
@@ -126,7 +131,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
     const long long seq0 = (long long)b * a.dim + d0;
     if (exchange) {
         // ================= exchange warp =================
-        __syncthreads();  // the compute warps hold B in registers: the last stage is free for data now
+        __syncthreads();  // the compute warps hold B and C in registers: the last stage is free for data now
         if (lane == 0 && STAGES - 1 < n_iter) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue_stage(STAGES - 1);
@@ -204,41 +209,28 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
         const bool accum = a.accum == 1, addm = a.accum == 2;  // red.add / load-add-store (scan.cuh)
         int nvalid = ITEMS;
         if (TAIL) nvalid = max(0, min(ITEMS, L - pos));
-        float *du_ptr = reinterpret_cast<float *>(a.du) + b * a.du_bs + (long long)d0 * a.du_ds + pos;
-        float *dd_ptr = F1 ? nullptr : reinterpret_cast<float *>(a.ddelta) + b * a.ddelta_bs + (long long)d0 * a.ddelta_ds + pos;
+        // CTA-uniform parts of the output addresses (the thread's own part, tseg * ITEMS, is added at the stores)
+        const long long du_tile = b * a.du_bs + (long long)d0 * a.du_ds + seg0;
+        const long long dd_tile = F1 ? 0 : b * a.ddelta_bs + (long long)d0 * a.ddelta_ds + seg0;
 
-        float2 Bv[4], dBacc[4], dCacc[4];
-        float *sC = s_c + slot;  // this thread's C values (only this thread touches them)
+        float2 Bv[4], Cv[4];  // this thread's B and C values: registers for the whole tile
         mbar_wait(bar_bc, 0);
         if (threadIdx.x == 0) VMASR_TL(a, 2);
         lds8_priv(s_b + slot, sel, Bv);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            dBacc[k] = f2(0.0f);
-            dCacc[k] = f2(0.0f);
-        }
+        lds8_priv(s_c + slot, sel, Cv);
         if (TAIL) {  // positions past the end contribute nothing and stay finite
-            float2 Cv[4];
-            lds8_priv(sC, sel, Cv);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (2 * k >= nvalid) { Bv[k].x = 0.0f; Cv[k].x = 0.0f; }
                 if (2 * k + 1 >= nvalid) { Bv[k].y = 0.0f; Cv[k].y = 0.0f; }
             }
-            sts8_priv(sC, sel, Cv);
         }
-        __syncthreads();  // (also keeps the register allocation of the sweeps below in check: without it ptxas spills 3x more)
+        __syncthreads();  // B and C are in registers: the last stage is free (the exchange warp refills it)
         if (F1) {
             const float2 zero[4] = {f2(0.0f), f2(0.0f), f2(0.0f), f2(0.0f)};
             sts8_priv(s_drow + slot, sel, zero);  // thread-private accumulator of d_dt_rows
         }
-
-        Aff excf[STAGES], excr[STAGES];  // registers: only constant indices below
-#pragma unroll
-        for (int i = 0; i < STAGES; ++i) {
-            excf[i] = Aff{1.0f, 0.0f};
-            excr[i] = Aff{1.0f, 0.0f};
-        }
+        float4 *my_exc = s_exc + threadIdx.x;  // + j * NC: the prefixes of channel j wait here between P1(j) and P2(j)
 #pragma unroll 1
         for (int j = 0; j < n_iter; ++j) {
             {
@@ -248,11 +240,10 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
                 float *su = s_stage + (size_t)j * 3 * SEG + slot;
                 mbar_wait(&bar_full[j], 0);
                 if (threadIdx.x == 0 && j == 0) VMASR_TL(a, 3);
-                float2 uv[4], dl[4], dy[4], Cv[4], dts[4];
+                float2 uv[4], dl[4], dy[4], dts[4];
                 lds8_priv(su, sel, uv);
                 lds8_priv(F1 ? s_row + slot : su + SEG, sel, dl);  // delta, or (F1) the dt row
                 lds8_priv(su + 2 * SEG, sel, dy);
-                lds8_priv(sC, sel, Cv);
                 const float wdt = F1 ? s_par[3 * 4 + j] * kLog2e : kLog2e;
                 if (TAIL) {
 #pragma unroll
@@ -290,12 +281,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
                     scan_step_down(inc_r.p, inc_r.q, off);
                 }
                 const Aff exf = shift_up1(inc_f, lane), exr = shift_down1(inc_r, lane);
-#pragma unroll
-                for (int i = 0; i < STAGES; ++i)
-                    if (i == j) {
-                        excf[i] = exf;
-                        excr[i] = exr;
-                    }
+                my_exc[j * NC] = make_float4(exf.p, exf.q, exr.p, exr.q);
                 const float qr0 = __shfl_sync(0xffffffffu, inc_r.q, 0);
                 if (lane == 31) s_tot[j * WPR + warp] = make_float4(inc_f.p, inc_f.q, qr0, 0.0f);
                 __syncwarp();
@@ -303,30 +289,28 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
             }
         }
         if (threadIdx.x == 0) VMASR_TL(a, 4);
+        float2 dBacc[4], dCacc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            dBacc[k] = f2(0.0f);
+            dCacc[k] = f2(0.0f);
+        }
 #pragma unroll 1
         for (int j = 0; j < n_iter; ++j) {
             {
                 // ---- P2(j) ----
-                Aff exf = excf[0], exr = excr[0];
-#pragma unroll
-                for (int i = 1; i < STAGES; ++i)
-                    if (i == j) {
-                        exf = excf[i];
-                        exr = excr[i];
-                    }
+                const float4 exc = my_exc[j * NC];
+                const Aff exf = {exc.x, exc.y}, exr = {exc.z, exc.w};
                 const float Av = s_par[j];
                 const float Dv = s_par[4 + j];
-                float *o_du = du_ptr + (long long)j * a.du_ds;
-                float *o_dd = F1 ? nullptr : dd_ptr + (long long)j * a.ddelta_ds;
                 mbar_wait(&bar_in[j], 0);
                 if (threadIdx.x == 0) VMASR_TL(a, j == 0 ? 5 : 6);
                 const float2 in = s_in[j * WPR + warp];
                 const float *su = s_stage + (size_t)j * 3 * SEG + slot;
-                float2 uv[4], dts[4], dy[4], Cv[4];
+                float2 uv[4], dts[4], dy[4];
                 lds8_priv(su, sel, uv);
                 lds8_priv(su + SEG, sel, dts);
                 lds8_priv(su + 2 * SEG, sel, dy);
-                lds8_priv(sC, sel, Cv);
                 float2 av[4], bu[4], dtn[4], hs[4], gl[4];
                 // forward states of this thread's positions
                 {
@@ -360,8 +344,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
                     const float2 carried = fma2(mul2(dtn[k], bu[k]), f2(-1.0f), hs[k]);  // a_l h_{l-1}
                     const float2 w = mul2(gl[k], dtn[k]);
                     du[k] = fma2(w, Bv[k], mul2(dy[k], f2(Dv)));
-                    const float2 gc = mul2(gl[k], carried);
-                    const float2 ddt = fma2(gl[k], bu[k], mul2(gc, f2(Av)));
+                    const float2 ddt = mul2(gl[k], fma2(carried, f2(Av), bu[k]));  // g (B u + A a h_prev)
                     if (SP) {
                         // sigmoid(delta + bias) = 1 - exp(-softplus) = 1 - 2^(-dt2); exactly 1 above the reference's threshold.
                         // Below softplus = 1/16 the subtraction would cancel (the Mamba-style dt range 1e-3 .. 1e-1 lives there):
@@ -374,8 +357,7 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
                         float2 sig = make_float2(1.0f - ex2_approx(-dts[k].x), 1.0f - ex2_approx(-dts[k].y));
                         if (sn.x < 0.0625f) sig.x = ser.x;
                         if (sn.y < 0.0625f) sig.y = ser.y;
-                        if (dts[k].x > kSoftplusThr2) sig.x = 1.0f;
-                        if (dts[k].y > kSoftplusThr2) sig.y = 1.0f;
+                        // (above the threshold 2^(-dt2) < 2^-28 and the subtraction already returns exactly 1)
                         ddl[k] = mul2(ddt, sig);
                     } else {
                         ddl[k] = ddt;
@@ -399,6 +381,8 @@ __device__ __forceinline__ void scan_bwd_pipe_body(const ScanArgs &a, const Tile
                     sts8_priv(s_drow + slot, sel, dr);
                 }
                 {
+                    float *o_du = reinterpret_cast<float *>(a.du) + (du_tile + (long long)j * a.du_ds) + tseg * ITEMS;
+                    float *o_dd = F1 ? nullptr : reinterpret_cast<float *>(a.ddelta) + (dd_tile + (long long)j * a.ddelta_ds) + tseg * ITEMS;
                     if (!TAIL || nvalid == ITEMS) {
                         if (accum) {
                             red8(o_du, du);
@@ -490,7 +474,7 @@ __global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const _
 
 template <bool SP, int STAGES, bool F1>
 static int launch_bwd_pipe(const GroupArgs &ga, int grid, cudaStream_t stream) {
-    const size_t smem = 2048 + sizeof(float) * (2048 + (size_t)STAGES * 3 * 2048);
+    const size_t smem = 1024 + (size_t)STAGES * (3 * 2048 * sizeof(float) + 256 * sizeof(float4));
     static PerDeviceOnce configured;  // the attribute is per function and per device
     if (!configured()) {
         if (int rc = check_cuda(cudaFuncSetAttribute(scan_bwd_pipe_kernel<SP, STAGES, F1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),

@@ -126,7 +126,11 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, const TileM
     }
 
     const int n_groups16 = (a.n_chunks + 15) >> 4;
-    const bool multi = a.n_chunks > 1;  // then ROWS == 1
+#ifdef VMASR_TUNING
+    const bool multi = a.n_chunks > 1;  // then ROWS == 1 (VMASR_SCAN_BWD=tma sends longer sequences here)
+#else
+    constexpr bool multi = false;  // the product library sends single-chunk sequences only (scan_host.cu::decide)
+#endif
     const bool leader = warp_in_row == 0;
     const int jrev = a.n_chunks - 1 - chunk;  // position of this chunk in the adjoint's scan order
 
@@ -294,8 +298,7 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, const TileM
             const float2 carried = fma2(bx[j], f2(-1.0f), hs[j]);  // a_l h_{l-1}
             const float2 w = mul2(gl[j], dtn[j]);
             du[j] = fma2(w, Bv[j], mul2(dy[j], f2(Dv)));
-            const float2 gc = mul2(gl[j], carried);
-            const float2 ddt = fma2(gl[j], mul2(Bv[j], uv[j]), mul2(gc, f2(Av)));
+            const float2 ddt = mul2(gl[j], fma2(carried, f2(Av), mul2(Bv[j], uv[j])));  // g (B u + A a h_prev)
             ddl[j] = mul2(ddt, sig[j]);
             sA = fma2(w, carried, sA);
             dBacc[j] = fma2(w, uv[j], dBacc[j]);
