@@ -35,7 +35,7 @@ def bwd():
                  b["du"], b["ddelta"], b["dA"], b["dB"], b["dC"], b["dD"], b["dbias"])
 
 
-names = {(0, 1): "entry -> parameters staged", (1, 2): "-> B/C arrived", (2, 3): "-> channel 0 arrived", (3, 4): "P1 sweep",
+names = {(0, 1): "entry -> parameters staged", (1, 2): "-> B/C arrived", (0, 2): "tile start -> B/C arrived (persistent)", (2, 3): "-> channel 0 arrived", (3, 4): "P1 sweep",
          (4, 5): "wait entering state ch 0", (5, 6): "P2 up to the last channel's wait", (6, 7): "P2 last channel",
          (0, 8): "[x] entry -> totals of ch 0", (8, 9): "[x] -> totals of last ch", (9, 10): "[x] -> look-back finished",
          (0, 7): "TOTAL compute warp 0", (0, 10): "TOTAL exchange warp"}
@@ -60,6 +60,8 @@ for name, fn in (("fwd", fwd), ("bwd", bwd)):
     for (a, c), label in names.items():
         ok = (t[:, a] > 0) & (t[:, c] > 0)
         d = (t[ok, c] - t[ok, a]) / 1e3
+        if len(d) == 0:  # (the persistent kernels do not stamp slot 1)
+            continue
         print(f"   {label:40s} mean {d.mean():7.2f} us   p10 {sorted(d)[len(d) // 10]:7.2f}   p90 {sorted(d)[9 * len(d) // 10]:7.2f}")
     # residency: tiles per SM over time
     import numpy as np

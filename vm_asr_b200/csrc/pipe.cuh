@@ -160,7 +160,7 @@ __device__ __forceinline__ unsigned launch_epoch(const ScanArgs &a, int lane) {
     if (lane == 0) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(raw) : "l"(a.ws_header + 2) : "memory");
         const unsigned prev = atomicAdd(a.ws_header + 1, 1u);
-        if (prev == (unsigned)(a.n_chunks * a.n_rowgroups) - 1u) {
+        if (prev == (unsigned)a.n_tiles - 1u) {
             a.ws_header[0] = 0u;
             a.ws_header[1] = 0u;
             a.ws_header[2] = raw + 1u;

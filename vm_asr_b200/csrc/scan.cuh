@@ -34,6 +34,9 @@ struct ScanArgs {
     int chan_per_tile;    // channels one CTA walks (multiple of ROWS)
     int n_ctiles;         // ceil(chan_per_group / chan_per_tile)
     int n_rowgroups;      // batch * ngroups * n_ctiles
+    int n_tiles;          // tiles of this problem in the launch: n_chunks * n_rowgroups + the tiles split_from adds
+    int split_from;       // multi-chunk fast kernels: tiles from this index on are HALF tiles (two per planned tile, chan_per_tile / 2
+                          // channels each): the launch's last, partly filled round of resident CTAs then takes half as long (scan_host.cu)
     int softplus;
     int rev;              // fast kernels only: the scan runs over the row back to front (time index l <-> seqlen - 1 - l); every positional
                           // tensor (u, delta, B, C, out, dout, du, ddelta, dB, dC) keeps its memory order.  Directions 2 and 3 of SS2D.

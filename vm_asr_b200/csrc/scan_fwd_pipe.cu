@@ -40,7 +40,8 @@ constexpr int kPipeThreads = 288;     // 8 compute warps + the exchange warp
 // stage j, forms delta = w_j * row in registers, and before its own Y1 overwrites the row hands it down to stage j + 1 (a
 // thread only ever touches its own 32 bytes of a row, so the hand-down needs no synchronisation).
 template <bool TAIL, bool SP, bool REV, bool F1>
-__device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const TileMaps &tm, unsigned char *smem, const int chunk, const int rg) {
+__device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const TileMaps &tm, unsigned char *smem, const int chunk, const int rg,
+                                                   const int half) {
     constexpr int NC = 256, ITEMS = 8, WPR = 8, SEG = NC * ITEMS, STAGES = kPipeStages;
 
     // shared memory carve-up (header 2048 bytes)
@@ -70,8 +71,9 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
     const int line0 = seg0 / kTileLine;                             // ... and its first line in the tensor maps
     constexpr unsigned seg_bytes = SEG * 4u;                        // a box always counts in full (lines past the end arrive as zeros)
 
-    const int c_begin = ctile * a.chan_per_tile;
-    const int n_iter = min(a.chan_per_group, c_begin + a.chan_per_tile) - c_begin;  // channels of this tile (<= STAGES)
+    // half >= 0: one half of a planned tile (the launch's last round, scan_host.cu::split_last_round)
+    const int c_begin = ctile * a.chan_per_tile + (half > 0 ? a.chan_per_tile >> 1 : 0);
+    const int n_iter = half >= 0 ? a.chan_per_tile >> 1 : min(a.chan_per_group, c_begin + a.chan_per_tile) - c_begin;  // channels of this tile (<= STAGES)
     const int d0 = g * a.chan_per_group + c_begin;
 
     auto issue_stage = [&](int it) {  // lane 0 of the exchange warp only
@@ -324,16 +326,21 @@ __global__ void __launch_bounds__(kPipeThreads, 3) scan_fwd_pipe_kernel(const __
     const int prob = group_problem(ga, tile);
     const ScanArgs &a = ga.a[prob];
     const TileMaps &tm = ga.tm[prob];
+    int half = -1;
+    if (tile >= a.split_from) {
+        half = (tile - a.split_from) & 1;
+        tile = a.split_from + ((tile - a.split_from) >> 1);
+    }
     const int chunk = tile / a.n_rowgroups;  // chunk-major in TIME order: a tile only waits on tiles dispatched before it
     const int rg = tile - chunk * a.n_rowgroups;
     const int mchunk = a.rev ? a.n_chunks - 1 - chunk : chunk;
     const bool tail = (mchunk + 1) * 2048 > a.seqlen;
     if (a.rev) {
-        if (tail) scan_fwd_pipe_body<true, SP, true, F1>(a, tm, smem_fwd_pipe, chunk, rg);
-        else scan_fwd_pipe_body<false, SP, true, F1>(a, tm, smem_fwd_pipe, chunk, rg);
+        if (tail) scan_fwd_pipe_body<true, SP, true, F1>(a, tm, smem_fwd_pipe, chunk, rg, half);
+        else scan_fwd_pipe_body<false, SP, true, F1>(a, tm, smem_fwd_pipe, chunk, rg, half);
     } else {
-        if (tail) scan_fwd_pipe_body<true, SP, false, F1>(a, tm, smem_fwd_pipe, chunk, rg);
-        else scan_fwd_pipe_body<false, SP, false, F1>(a, tm, smem_fwd_pipe, chunk, rg);
+        if (tail) scan_fwd_pipe_body<true, SP, false, F1>(a, tm, smem_fwd_pipe, chunk, rg, half);
+        else scan_fwd_pipe_body<false, SP, false, F1>(a, tm, smem_fwd_pipe, chunk, rg, half);
     }
 }
 

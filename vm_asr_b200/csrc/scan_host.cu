@@ -192,6 +192,8 @@ static ScanArgs make_args(const vmasr_scan_params *p, int n_chunks, int chan_per
     a.chan_per_tile = chan_per_tile;
     a.n_ctiles = n_ctiles;
     a.n_rowgroups = p->batch * p->ngroups * n_ctiles;
+    a.n_tiles = n_chunks * a.n_rowgroups;
+    a.split_from = 0x7fffffff;
     a.softplus = p->delta_softplus;
     a.rev = (p->flags & VMASR_SCAN_REVERSE) ? 1 : 0;
     a.accum = (p->flags & VMASR_SCAN_ACCUMULATE) ? 1 : (p->flags & VMASR_SCAN_ADD) ? 2 : 0;
@@ -218,6 +220,25 @@ static ScanArgs make_args(const vmasr_scan_params *p, int n_chunks, int chan_per
 }
 
 enum ScanVariant { kGeneric = 0, kSingleChunk = 1, kMultiChunk = 2 };
+
+// Multi-chunk launches run in rounds of `slots` resident CTAs (2 per SM backward, 3 forward) and a tile takes 8 - 12 us, so
+// a launch of 3.46 rounds costs as much as one of 4.  When the last round is at most half full, its tiles -- the LAST tiles of
+// the launch's last problem -- are cut in two (half the channels each): twice as many CTAs, still one round, about half as
+// long.  Returns the number of tiles this adds; the kernels decode the halves from ScanArgs::split_from.
+static int split_last_round(GroupArgs &ga, int tiles, bool bwd, int device) {
+    if (const char *e = tuning_env("VMASR_SCAN_SPLIT"))
+        if (!atoi(e)) return 0;
+    const int slots = sm_count(device) * (bwd ? 2 : 3);
+    if (tiles <= slots) return 0;
+    const int rest = tiles % slots;
+    ScanArgs &a = ga.a[ga.n - 1];
+    const int cpt = a.chan_per_tile;
+    if (rest == 0 || 2 * rest > slots || (cpt & 1) || a.chan_per_group % cpt != 0 || rest > a.n_tiles) return 0;
+    a.split_from = a.n_tiles - rest;
+    a.n_tiles += rest;
+    ga.tile_end[ga.n - 1] += rest;
+    return rest;
+}
 
 // Everything the launch needs, decided on the host without touching the device (also behind vmasr_scan_plan).
 static int decide(const vmasr_scan_params *p, bool bwd, int peers, ScanPlan &pl, ScanArgs &a, int &variant) {
@@ -308,6 +329,7 @@ int scan_run_group(int n, const vmasr_scan_params *ps, bool bwd) {
             ga.tile_end[ga.n] = grid;
             ++ga.n;
         }
+        if (variant[i] == kMultiChunk) grid += split_last_round(ga, grid, bwd, ps[0].device);
         for (int j = ga.n; j < kMaxGroup; ++j) ga.tile_end[j] = grid;
         int rc;
         if (variant[i] == kMultiChunk) rc = bwd ? scan_bwd_pipe_dispatch(ga, grid, stream) : scan_fwd_pipe_dispatch(ga, grid, stream);
