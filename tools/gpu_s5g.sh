@@ -1,0 +1,19 @@
+#!/bin/bash
+# session 5: epoch read once per problem in the persistent backward -- parity, bench line, per-shape rows, timeline
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+for shape in "2 8 4096" "4 8 262144" "4 256 4096" "4 64 65536"; do
+  timeout -k 5 60 python tools/profile_one.py $shape 3 > gpurun_out/quick_$(echo $shape | tr ' ' '_').log 2>&1
+  rc=$?; echo "quick $shape rc=$rc"
+  if [ $rc -ne 0 ]; then tail -3 gpurun_out/quick_$(echo $shape | tr ' ' '_').log; echo "abort: quick shape failed"; exit 1; fi
+done
+timeout -k 10 900 python -m pytest ${PYTEST_FILES:-tests/test_scan_gpu.py} -m gpu -q -x --timeout 120 --timeout-method=thread > gpurun_out/pytest_s5g.log 2>&1
+echo "pytest rc=$?"; tail -3 gpurun_out/pytest_s5g.log
+timeout -k 10 600 python bench.py --no-e2e --no-core --no-stft --no-cpu-baseline > gpurun_out/bench_s5g.log 2>&1; echo "bench (product) rc=$?"; tail -1 gpurun_out/bench_s5g.log | cut -c1-200
+timeout -k 10 300 python tools/shape_bench.py --what scan > gpurun_out/shape_bench_s5g.log 2>&1; grep "scan_bwd" gpurun_out/shape_bench_s5g.log | cut -c1-120
+export VMASR_B200_LIBRARY=vm_asr_b200/lib_tuning/libvmasr_b200.so
+rm -f gpurun_out/timeline_s5g.txt
+for shape in "4 64 65536"; do
+  timeout -k 5 120 python tools/timeline.py $shape >> gpurun_out/timeline_s5g.txt 2>&1
+done
+grep -A18 "== bwd" gpurun_out/timeline_s5g.txt | cut -c1-150

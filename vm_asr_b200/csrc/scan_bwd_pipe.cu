@@ -219,12 +219,28 @@ __device__ __forceinline__ void bpipe_exchange(const GroupArgs &ga, const BPipeS
     constexpr int WPR = kBPipeWPR;
     unsigned totpar = 0;  // bit j: parity of the next phase of tot[j]
     int n = 0;
+    int epoch_prob = -1;   // the problem whose epoch this warp holds
+    unsigned epoch_raw = 0, epoch = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++n) {
         const BPipeTile c = bpipe_tile(ga, t);
         const ScanArgs &a = ga.a[c.prob];
         const int chunk = c.chunk, n_iter = c.n_iter;
         const long long seq0 = (long long)c.b * a.dim + c.d0;
-        const unsigned epoch = launch_epoch(a, lane);  // (also recycles the carry workspace for the next launch: pipe.cuh)
+        // Epoch tag of the launch (pipe.cuh::launch_epoch): read once per problem, not once per tile -- with the tile's rows
+        // already in shared memory the round trip of that load was the first thing every tile waited for.  Every tile still
+        // counts itself in (after the read: the acquire orders the two); what the count returns is only looked at when the
+        // tile is done, and the tile that completes the count recycles the workspace there (pipe.cuh explains why that is
+        // safe at any time after the count is complete).
+        unsigned counted = 0;
+        if (lane == 0) {
+            if (c.prob != epoch_prob) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(epoch_raw) : "l"(a.ws_header + 2) : "memory");
+            counted = atomicAdd(a.ws_header + 1, 1u);
+        }
+        if (c.prob != epoch_prob) {
+            epoch_raw = __shfl_sync(0xffffffffu, epoch_raw, 0);
+            epoch = epoch_raw % 0xfffffffeu + 1u;
+            epoch_prob = c.prob;
+        }
         const int n_groups16 = (a.n_chunks + 15) >> 4;
         const int jrev = a.n_chunks - 1 - chunk;  // position of this chunk in the adjoint's scan order
         // per channel: publish the chunk's adjoint aggregate as soon as it exists and start its look-back; finish the
@@ -294,6 +310,11 @@ __device__ __forceinline__ void bpipe_exchange(const GroupArgs &ga, const BPipeS
                 else if (which == 2) { if (a.ddelta_bias) atomicAdd(a.ddelta_bias + d, v); }
                 else atomicAdd(a.d_dt_w + d * a.dtw_ds, v);
             }
+        }
+        if (lane == 0 && counted == (unsigned)a.n_tiles - 1u) {  // every tile of the problem holds the current epoch: next launch, next tag
+            a.ws_header[0] = 0u;
+            a.ws_header[1] = 0u;
+            a.ws_header[2] = epoch_raw + 1u;
         }
         __syncwarp();
     }
