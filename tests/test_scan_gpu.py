@@ -481,6 +481,9 @@ def test_flags_need_fast_path():
     [(4, 32, 16384)] * 2,                   # two multi-chunk calls
     [(2, 16, 4096), (2, 16, 256), (2, 8, 40976), (1, 16, 1024), (2, 16, 4100), (2, 16, 4096)],  # mixed families (one generic): launched family by family
     [(1, 8, 8208)] * 8,                     # the most one launch takes
+    [(4, 256, 4096)] * 2,                   # 1024 tiles: persistent backward CTAs of 3 - 4 tiles, last round on half tiles in both directions
+    [(4, 128, 16384)] * 2,                  # 2048 tiles: seven tiles per persistent backward CTA, look-back over 8 chunks
+    [(2, 8, 65536), (2, 8, 65536)],         # tiles of two channels (three-stage backward variant, one-tile CTAs), 32 chunks
 ])
 def test_grouped_launch_equals_separate_calls(shapes):
     """vmasr_scan_fwd_grouped / _bwd_grouped: one grid over several calls, bit-identical to the calls made one by one

@@ -194,9 +194,10 @@ __device__ __forceinline__ void bpipe_producer(const GroupArgs &ga, const BPipeS
             tensor_load(st + (F1 ? 2 : 1) * SEG, &tm.C, c.line0, c.g, c.b, &sm.bar_full[R]);   // (F1: the gradient slot, zeroed after C has been read)
             if (F1) tensor_load(st + SEG, &tm.delta, c.line0, c.g, c.b, &sm.bar_full[R]);      // dt_rank 1: row index = group
         }
-        if (lane < 16) sm.s_par[(n & 1) * 16 + lane] = par_v;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sm.bar_par);  // (release: the stores above are visible to whoever sees the phase complete)
+        if (lane < 16) {  // every writer releases its own store (16 arrivals complete the phase)
+            sm.s_par[(n & 1) * 16 + lane] = par_v;
+            mbar_arrive(sm.bar_par);
+        }
         for (int j = 0; j < c.n_iter; ++j) {
             const int s = bpipe_stage<STAGES>(R, j);
             acquire(s);  // j = STAGES - 1: B and C have moved to registers
@@ -259,6 +260,9 @@ __device__ __forceinline__ void bpipe_exchange(const GroupArgs &ga, const BPipeS
                 publish_entry(l2_row + (jrev >> 4), epoch, g16.p, g16.q);
             }
             if (lane < WPR) {  // every writer releases its own store
+                // channel 0: the per-channel sums start from zero again (the tile before has been flushed by this warp, and the
+                // compute warps add to them only after in[0]); the lanes that arrive are the lanes that write
+                if (j == 0) reinterpret_cast<float2 *>(sm.s_red)[lane] = make_float2(0.0f, 0.0f);
                 sm.s_in[j * WPR + lane] = make_float2(fmaf(before_f.p, hc, before_f.q), fmaf(before_r.p, acc.q, before_r.q));
                 mbar_arrive(&sm.bar_in[j]);
             }
@@ -303,7 +307,6 @@ __device__ __forceinline__ void bpipe_exchange(const GroupArgs &ga, const BPipeS
             const int cc = lane >> 2, which = lane & 3;
             if (cc < n_iter && which < (F1 ? 4 : 3)) {
                 const float v = sm.s_red[cc * 4 + which];
-                sm.s_red[cc * 4 + which] = 0.0f;  // for the next tile (its first addition comes after this warp's in[0] of that tile)
                 const int d = c.d0 + cc;
                 if (which == 0) atomicAdd(a.dA + d * a.A_ds, v);
                 else if (which == 1) { if (a.dD) atomicAdd(a.dD + d, v); }
@@ -616,7 +619,7 @@ __global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const _
             mbar_init(&sm.bar_in[i], kBPipeWPR);
         }
         mbar_init(sm.bar_done, kBPipeWPR);
-        mbar_init(sm.bar_par, 1);
+        mbar_init(sm.bar_par, 16);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < STAGES * 4) sm.s_red[threadIdx.x] = 0.0f;
