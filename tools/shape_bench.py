@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--what", default="scan,cross,stft")
     ap.add_argument("--dtype", default="float32")
+    ap.add_argument("--pairs", action="store_true", help="scan only: the grouped launch of two same-shape calls, as the bench step issues them")
     args = ap.parse_args()
     wl = W.WORKLOADS[args.workload]
     peak, _ = load_peaks()
@@ -61,6 +62,8 @@ def main():
         fwd_bytes = es * (3 * B * D * L + 2 * B * 4 * L)
         bwd_bytes = es * (5 * B * D * L + 4 * B * 4 * L)
         n_sets = max(2, min(8, int(400e6 // max(fwd_bytes, 1)) + 1))  # rotate > 126 MB of distinct data
+        if args.pairs:
+            n_sets = 2 * max(2, n_sets // 2 + 1)
         if "scan" in args.what:
             sets = []
             for _ in range(n_sets):
@@ -83,6 +86,26 @@ def main():
                 scan.bwd_out(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], inp["dout"], b["x"],
                              True, b["du"], b["ddelta"], b["dA"], b["dB"], b["dC"], b["dD"], b["dbias"])
 
+            def fp(i):
+                a, b = sets[2 * i], sets[2 * i + 1]
+                scan.fwd_grouped([(s_[0]["u"], s_[0]["delta"], s_[0]["A"], s_[0]["B"], s_[0]["C"], s_[0]["D"], s_[0]["bias"], True) for s_ in (a, b)],
+                                 [(s_[1]["out"], s_[1]["x"]) for s_ in (a, b)])
+
+            def gp(i):
+                a, b = sets[2 * i], sets[2 * i + 1]
+                scan.bwd_grouped([(s_[0]["u"], s_[0]["delta"], s_[0]["A"], s_[0]["B"], s_[0]["C"], s_[0]["D"], s_[0]["bias"], s_[0]["dout"],
+                                   s_[1]["x"], True) for s_ in (a, b)],
+                                 [(s_[1]["du"], s_[1]["ddelta"], s_[1]["dA"], s_[1]["dB"], s_[1]["dC"], s_[1]["dD"], s_[1]["dbias"]) for s_ in (a, b)])
+
+            if args.pairs:
+                for name, fn, nbytes in (("scan_fwd_pair", fp, 2 * fwd_bytes), ("scan_bwd_pair", gp, 2 * bwd_bytes)):
+                    ms = timeit(fn, args.reps, n_sets // 2)
+                    rows.append(dict(kernel=name, B=B, D=D, L=L, launches_per_step=count // 2, ms=round(ms, 5),
+                                     GBps=round(nbytes / ms / 1e6, 1), frac=round(nbytes / ms / 1e6 / peak, 3)))
+                    print(json.dumps(rows[-1]), flush=True)
+                del sets
+                torch.cuda.empty_cache()
+                continue
             for name, fn, nbytes in (("scan_fwd", f, fwd_bytes), ("scan_bwd", g, bwd_bytes)):
                 ms = timeit(fn, args.reps, n_sets)
                 rows.append(dict(kernel=name, B=B, D=D, L=L, calls=count, ms=round(ms, 5), GBps=round(nbytes / ms / 1e6, 1),

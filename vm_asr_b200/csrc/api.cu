@@ -24,7 +24,7 @@ int check_cuda(cudaError_t e, const char *what) {
 }
 
 bool pdl_enabled() {
-    static const bool on = [] { const char *e = tuning_env("VMASR_PDL"); return e ? atoi(e) != 0 : false; }();
+    static const bool on = [] { const char *e = tuning_env("VMASR_PDL"); return e ? atoi(e) != 0 : true; }();
     return on;
 }
 
