@@ -8,6 +8,11 @@
  * forward from the Python main thread and its backward from an autograd worker thread
  * (model/vmamba.py:325-356), each on torch's current stream.
  *
+ * The fast scan kernels are launched with the programmatic-stream-serialization attribute (their CTAs may be scheduled while
+ * the previous kernel of the stream drains); each of them executes griddepcontrol.wait before its first access to global
+ * memory, so stream order holds behind any predecessor.  The multi-chunk backward runs a grid of persistent CTAs sized to
+ * what the device keeps resident at once (cudaOccupancyMaxActiveBlocksPerMultiprocessor x SM count).
+ *
  * Each entry point names the reference interface it replaces (paths relative to the VM-ASR tree).
  */
 #ifndef VMASR_B200_H

@@ -74,9 +74,11 @@ unsigned long long *debug_timeline();
 // The scan kernels of a model run back to back on one stream.  Launched with the programmatic-stream-serialization
 // attribute, the CTAs of kernel N + 1 are scheduled while the last wave of kernel N drains; they park on
 // `griddepcontrol.wait` (first statement that touches global memory) until kernel N has completed and flushed.
-// What overlaps is the launch latency and the CTA start-up.  Measured on the bench step (68 launches in one CUDA graph):
-// +0.7 % on the B = 4 config, -0.4 % on a B = 8 config, i.e. nothing -- graph launches already leave no gap worth hiding.
-// Off by default; VMASR_PDL=1 turns it on (for eager, un-graphed callers).
+// What overlaps is the launch latency and the CTA start-up.  Measured on the bench step (34 launches in one CUDA graph): nothing
+// while every kernel ran one-tile CTAs (+0.7 % / -0.4 %, rounds 1 and 2); 0.6 % (same box, four alternating runs) to 1 % now
+// that the backward's persistent CTAs have a longer start-up (barriers, producer warp, first copies).  ON in the product
+// library; measurement builds turn it off with VMASR_PDL=0.  Every kernel launched this way executes griddepcontrol.wait
+// before its first global access, so it is correct behind any predecessor, PDL-aware or not.
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 int launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, const char *what, Args &&...args) {
