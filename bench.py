@@ -176,11 +176,17 @@ class DeviceStep:
         self.side = None
         gen = torch.Generator(device=device).manual_seed(1234)
         self.calls = []
+        # calls whose backward STORES dB / dC (VMASR_SCAN_DBDC_STORE: one tile spans a whole B / C group -- the C = 2 maps) need
+        # no zero-fill of the two; the same rule vm_asr_b200.scan.bwd applies for the tensors it allocates itself
+        self.store = [c.L > 2048 and c.L % 16 == 0 and c.D // 4 <= 4 and not os.environ.get("VMASR_BENCH_NO_DBDC_STORE")
+                      for c in wl.calls]
         acc_floats = 0
-        for c in wl.calls:
-            acc_floats += c.D * 3 + 2 * wl.batch * 4 * c.L
-        # one arena for every accumulated gradient (dA, dD, ddelta_bias, dB, dC of all calls): zeroed by ONE memset
+        for c, st in zip(wl.calls, self.store):
+            acc_floats += c.D * 3 + (0 if st else 2 * wl.batch * 4 * c.L)
+        # one arena for every accumulated gradient (dA, dD, ddelta_bias of all calls, dB / dC where they are summed over channel
+        # tiles): zeroed by ONE memset
         self.arena = torch.zeros(acc_floats, dtype=torch.float32, device=device)
+        self.zero_fill_bytes = 4 * acc_floats
         off = 0
 
         def take(n, shape):
@@ -189,14 +195,15 @@ class DeviceStep:
             off += n
             return t
 
-        for c in wl.calls:
+        for c, st in zip(wl.calls, self.store):
             inp = make_call_inputs(c, wl.batch, device, gen)
             n_chunks = (c.L + 2047) // 2048
+            bc = (lambda: torch.empty(wl.batch, 4, 1, c.L, device=device)) if st else (lambda: take(wl.batch * 4 * c.L, (wl.batch, 4, 1, c.L)))
             bufs = dict(
                 out=torch.empty_like(inp["u"]), x=torch.empty(wl.batch, c.D, n_chunks, 2, device=device),
                 du=torch.empty_like(inp["u"]), ddelta=torch.empty_like(inp["u"]),
                 dA=take(c.D, (c.D, 1)), dD=take(c.D, (c.D,)), dbias=take(c.D, (c.D,)),
-                dB=take(wl.batch * 4 * c.L, (wl.batch, 4, 1, c.L)), dC=take(wl.batch * 4 * c.L, (wl.batch, 4, 1, c.L)),
+                dB=bc(), dC=bc(), flags=self.scan.SCAN_DBDC_STORE if st else 0,
             )
             self.calls.append((c, inp, bufs))
         self.graph = None
@@ -208,7 +215,7 @@ class DeviceStep:
     def bwd_call(self, i):
         c, inp, b = self.calls[i]
         self.scan.bwd_out(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], inp["dout"], b["x"],
-                          True, b["du"], b["ddelta"], b["dA"], b["dB"], b["dC"], b["dD"], b["dbias"])
+                          True, b["du"], b["ddelta"], b["dA"], b["dB"], b["dC"], b["dD"], b["dbias"], flags=b["flags"])
 
     # The generator's two streams (magnitude, phase) issue the same-shape SS2D call independently between their interaction
     # points (model/model.py:1124-1127, 1167-1176): calls 2j and 2j + 1 of the workload are such a pair.
@@ -224,7 +231,7 @@ class DeviceStep:
         args, outs = [], []
         for k in (i, i + 1):
             c, inp, b = self.calls[k]
-            args.append((inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], inp["dout"], b["x"], True))
+            args.append((inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], inp["dout"], b["x"], True, b["flags"]))
             outs.append((b["du"], b["ddelta"], b["dA"], b["dB"], b["dC"], b["dD"], b["dbias"]))
         self.scan.bwd_grouped(args, outs)
 
@@ -645,6 +652,7 @@ def main():
     k_ms, k_bytes, k_per_step = time_dominant_kernel(ds, max(2, min(args.steps, 5)))
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
     eager = time_eager(ds, 5) if rank == 0 else None
+    zero_fill_bytes = ds.zero_fill_bytes
     del ds
     torch.cuda.empty_cache()
 
@@ -756,6 +764,7 @@ def main():
                 "algorithmic_bytes_per_step": step_bytes, "scan_elements_per_step": wl.scan_elements(),
                 "l2": "inputs larger than L2: every call has its own buffers, ~5.4 GB touched per step vs 126 MB L2",
                 "launch": "eager launches" if args.no_graph else "one CUDA graph per step", "pairing": args.pairing,
+                "zero_fill_bytes_per_step": zero_fill_bytes,  # accumulated gradients (dA, dD, ddelta_bias; dB / dC unless stored)
                 "parallelism": f"dp{world}: one rank per GPU on its own batch shard, no data-path collective" if world > 1 else "single",
             },
             "frac_of_hbm_peak": round(value / world / peak, 4), "hbm_peak_gbs": peak, "hbm_peak_source": peak_src,

@@ -139,10 +139,17 @@ typedef struct vmasr_scan_params {
  *   VMASR_SCAN_ACCUMULATE : `out` (forward) and `du` (backward) are ADDED INTO with 128-bit reductions (red.global.add)
  *                           instead of stored: any number of calls may add into one buffer concurrently.
  *   VMASR_SCAN_ADD        : the same sum as a plain load / add / store: cheaper, but the call must be the ONLY writer of the
- *                           buffer while it runs (stream order after whatever wrote it before).  Exclusive with ACCUMULATE. */
+ *                           buffer while it runs (stream order after whatever wrote it before).  Exclusive with ACCUMULATE.
+ *   VMASR_SCAN_DBDC_STORE : backward only: dB and dC are STORED, not accumulated into -- the caller need not zero-fill them
+ *                           (the reference zero-fills and accumulates with atomics, selective_scan.cpp:321-323,
+ *                           bwd_kernel.cuh:216-221).  Possible when one tile covers all channels of a B / C group, i.e. when
+ *                           vmasr_scan_plan(p, 1, out) reports variant 2 (multi-chunk fast path) and out[3] (channel tiles per
+ *                           group) == 1: every dB / dC element then has exactly one writer.  The call FAILS otherwise
+ *                           (nothing is launched), so a caller can never end up with sums on top of unset memory. */
 #define VMASR_SCAN_REVERSE 1
 #define VMASR_SCAN_ACCUMULATE 2
 #define VMASR_SCAN_ADD 4
+#define VMASR_SCAN_DBDC_STORE 8
 /* most problems one grouped launch takes */
 #define VMASR_SCAN_MAX_GROUP 8
 

@@ -468,6 +468,54 @@ def test_accumulate_flag(L):
     assert torch.equal(z, out0 + out_r)
 
 
+@pytest.mark.parametrize("Bsz,Dm,L", [(2, 8, 6144), (1, 16, 4112), (3, 4, 2064), (2, 8, 65536), (1, 12, 8208)])
+def test_dbdc_store_flag(Bsz, Dm, L):
+    """VMASR_SCAN_DBDC_STORE: when one multi-chunk tile spans a whole B / C group the backward stores dB / dC -- bit-identical to
+    accumulating into zeros (one writer per element either way), on buffers the caller never cleared; scan.bwd uses it by
+    itself for such shapes; a launch that cannot honour it fails instead of summing onto unset memory."""
+    scan = _ops()
+    _, g = make_inputs(Bsz, Dm, L, 4, 1, torch.float32, seed=3)
+    args = (g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], g["bias"])
+    assert scan.dbdc_store_candidate(g["u"], g["A"], g["B"])
+    out, x = scan.fwd(*args, True, 1)
+    du0, dd0 = torch.empty_like(out), torch.empty_like(out)
+    acc = scan._grad_buffers(g["u"], g["A"], g["D"], g["bias"], (Bsz, Dm, L, 1, 4))
+    scan.bwd_out(*args, g["dout"], x, True, du0, dd0, *acc)
+    du1, dd1 = torch.empty_like(out), torch.empty_like(out)
+    sto = scan._grad_buffers(g["u"], g["A"], g["D"], g["bias"], (Bsz, Dm, L, 1, 4))
+    sto[1].fill_(float("nan"))
+    sto[2].fill_(float("nan"))
+    scan.bwd_out(*args, g["dout"], x, True, du1, dd1, *sto, flags=scan.SCAN_DBDC_STORE)
+    assert torch.equal(du0, du1) and torch.equal(dd0, dd1)
+    assert torch.equal(acc[1], sto[1]) and torch.equal(acc[2], sto[2])
+    auto = scan.bwd(*args, g["dout"], x, True, 1)
+    assert torch.equal(auto[3], acc[1]) and torch.equal(auto[4], acc[2])
+    grouped = scan.bwd_grouped([(*args, g["dout"], x, True)] * 2)
+    for r in grouped:
+        assert torch.equal(r[3], acc[1]) and torch.equal(r[4], acc[2])
+
+
+def test_dbdc_store_refused():
+    scan = _ops()
+    # eight channels per group: two channel tiles write every dB / dC element
+    _, g = make_inputs(1, 32, 4096, 4, 1, torch.float32)
+    args = (g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], g["bias"])
+    assert not scan.dbdc_store_candidate(g["u"], g["A"], g["B"])
+    out, x = scan.fwd(*args, True, 1)
+    bufs = scan._grad_buffers(g["u"], g["A"], g["D"], g["bias"], (1, 32, 4096, 1, 4))
+    with pytest.raises(RuntimeError, match="one channel tile"):
+        scan.bwd_out(*args, g["dout"], x, True, torch.empty_like(out), torch.empty_like(out), *bufs, flags=scan.SCAN_DBDC_STORE)
+    with pytest.raises(RuntimeError, match="backward flag"):
+        scan.fwd_out(*args, True, out, x, flags=scan.SCAN_DBDC_STORE)
+    # a single-chunk call has no multi-chunk tile at all
+    _, g = make_inputs(1, 8, 1024, 4, 1, torch.float32)
+    args = (g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], g["bias"])
+    out, x = scan.fwd(*args, True, 1)
+    bufs = scan._grad_buffers(g["u"], g["A"], g["D"], g["bias"], (1, 8, 1024, 1, 4))
+    with pytest.raises(RuntimeError):
+        scan.bwd_out(*args, g["dout"], x, True, torch.empty_like(out), torch.empty_like(out), *bufs, flags=scan.SCAN_DBDC_STORE)
+
+
 def test_flags_need_fast_path():
     scan = _ops()
     _, g = make_inputs(1, 8, 132, 4, 1, torch.float32)  # length not a multiple of 16: generic kernels

@@ -19,7 +19,7 @@ _lib = None
 _lock = threading.Lock()
 
 VMASR_F32, VMASR_F16, VMASR_BF16 = 0, 1, 2
-SCAN_REVERSE, SCAN_ACCUMULATE = 1, 2
+SCAN_REVERSE, SCAN_ACCUMULATE, SCAN_ADD, SCAN_DBDC_STORE = 1, 2, 4, 8
 SCAN_MAX_GROUP = 8
 SS2D_DYT_GIVEN = 1
 ABI_VERSION = 4

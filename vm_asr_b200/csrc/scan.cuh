@@ -42,6 +42,7 @@ struct ScanArgs {
                           // tensor (u, delta, B, C, out, dout, du, ddelta, dB, dC) keeps its memory order.  Directions 2 and 3 of SS2D.
     int accum;            // fast kernels only: `out` (forward) / `du` (backward) are added into instead of stored:
                           // 1 = 128-bit red.global.add (concurrent writers), 2 = load / add / store (this launch is the only writer)
+    int dbdc_store;       // multi-chunk backward, one channel tile per group: dB / dC are stored, not added into (VMASR_SCAN_DBDC_STORE)
     int debug_nowait;     // VMASR_TUNING builds only, timing experiment: do not wait for neighbours' aggregates -> WRONG results
     unsigned long long *timeline;  // VMASR_TUNING builds only: 16 timestamps per CTA (common.cuh), else null
     long long u_bs, u_ds, delta_bs, delta_ds, A_ds, A_ns, B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;

@@ -590,7 +590,18 @@ __device__ __forceinline__ void bpipe_compute_tile(const ScanArgs &a, const BPip
             }
         }
     }
-    if (!TAIL || nvalid == ITEMS) {
+    if (a.dbdc_store) {  // this tile holds every channel of its group: the only writer of these positions (VMASR_SCAN_DBDC_STORE)
+        if (!TAIL || nvalid == ITEMS) {
+            stg8(dBg + pos, dBacc);
+            stg8(dCg + pos, dCacc);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (2 * k < nvalid) { dBg[pos + 2 * k] = dBacc[k].x; dCg[pos + 2 * k] = dCacc[k].x; }
+                if (2 * k + 1 < nvalid) { dBg[pos + 2 * k + 1] = dBacc[k].y; dCg[pos + 2 * k + 1] = dCacc[k].y; }
+            }
+        }
+    } else if (!TAIL || nvalid == ITEMS) {
         red8(dBg + pos, dBacc);
         red8(dCg + pos, dCacc);
     } else {

@@ -78,7 +78,8 @@ static int validate(const vmasr_scan_params *p, bool bwd) {
                     p->dim, p->seqlen, p->dstate, p->ngroups);
     if (p->dim % p->ngroups != 0) return fail("dims should be dividable by n_groups");
     if (p->dstate > 256) return fail("selective_scan only supports state dimension <= 256");
-    if (p->flags & ~(VMASR_SCAN_REVERSE | VMASR_SCAN_ACCUMULATE | VMASR_SCAN_ADD)) return fail("selective_scan: unknown flag bits 0x%x", p->flags);
+    if (p->flags & ~(VMASR_SCAN_REVERSE | VMASR_SCAN_ACCUMULATE | VMASR_SCAN_ADD | VMASR_SCAN_DBDC_STORE)) return fail("selective_scan: unknown flag bits 0x%x", p->flags);
+    if ((p->flags & VMASR_SCAN_DBDC_STORE) && !bwd) return fail("selective_scan_fwd: VMASR_SCAN_DBDC_STORE is a backward flag");
     if ((p->flags & VMASR_SCAN_ACCUMULATE) && (p->flags & VMASR_SCAN_ADD)) return fail("selective_scan: VMASR_SCAN_ACCUMULATE and VMASR_SCAN_ADD exclude each other");
     if (p->dt_rank < 0) return fail("selective_scan: dt_rank must not be negative");
     if (!p->u || (!p->delta && p->dt_rank == 0) || !p->A || !p->B || !p->C) return fail("selective_scan: u, delta, A, B, C must be non-null");
@@ -197,6 +198,7 @@ static ScanArgs make_args(const vmasr_scan_params *p, int n_chunks, int chan_per
     a.softplus = p->delta_softplus;
     a.rev = (p->flags & VMASR_SCAN_REVERSE) ? 1 : 0;
     a.accum = (p->flags & VMASR_SCAN_ACCUMULATE) ? 1 : (p->flags & VMASR_SCAN_ADD) ? 2 : 0;
+    a.dbdc_store = (p->flags & VMASR_SCAN_DBDC_STORE) ? 1 : 0;
     const char *nowait = tuning_env("VMASR_DEBUG_NOWAIT");
     a.debug_nowait = nowait ? atoi(nowait) : 0;
 #ifdef VMASR_TUNING
@@ -234,6 +236,7 @@ static int split_last_round(GroupArgs &ga, int tiles, bool bwd, int device) {
     ScanArgs &a = ga.a[ga.n - 1];
     const int cpt = a.chan_per_tile;
     if (rest == 0 || 2 * rest > slots || (cpt & 1) || a.chan_per_group % cpt != 0 || rest > a.n_tiles) return 0;
+    if (a.dbdc_store) return 0;  // (half tiles would be two writers per dB / dC element)
     a.split_from = a.n_tiles - rest;
     a.n_tiles += rest;
     ga.tile_end[ga.n - 1] += rest;
@@ -272,6 +275,9 @@ static int decide(const vmasr_scan_params *p, bool bwd, int peers, ScanPlan &pl,
         return fail("selective_scan: delta on the fly (dt_rank %d) needs dt_rank 1 on the multi-chunk fast path (float32, d_state 1, seqlen > %d and a "
                     "multiple of 16, 16-byte aligned rows and strides)", p->dt_rank, VMASR_SCAN_CHUNK);
     if (p->dB_batch_stride != 0 && variant == kGeneric) return fail("selective_scan: dB / dC batch strides need the fast path");
+    if ((p->flags & VMASR_SCAN_DBDC_STORE) && (variant != kMultiChunk || a.n_ctiles != 1))
+        return fail("selective_scan_bwd: VMASR_SCAN_DBDC_STORE needs the multi-chunk fast path with one channel tile per B / C group "
+                    "(vmasr_scan_plan: variant 2, out[3] == 1); this call has variant %d and %d channel tiles per group", variant, a.n_ctiles);
     if (variant == kGeneric && p->flags != 0)
         return fail("selective_scan: VMASR_SCAN_REVERSE / _ACCUMULATE / _ADD need the fast path (float32, d_state 1, seqlen a multiple of 16, "
                     "16-byte aligned rows and strides)");

@@ -27,7 +27,7 @@ import threading
 import torch
 
 from . import _lib
-from ._lib import SCAN_ACCUMULATE, SCAN_REVERSE, ScanParams  # noqa: F401
+from ._lib import SCAN_ACCUMULATE, SCAN_ADD, SCAN_DBDC_STORE, SCAN_REVERSE, ScanParams  # noqa: F401
 
 
 def _check(cond: bool, msg: str):
@@ -213,14 +213,14 @@ def _bwd_launch(s, u, delta, A, B, C, D, delta_bias, dout, x, du, ddelta, dA, dB
         _lib.check(lib.vmasr_scan_bwd(ctypes.byref(s.p)))
 
 
-def _grad_buffers(u, A, D, delta_bias, dims):
+def _grad_buffers(u, A, D, delta_bias, dims, zero_bc=True):
     """The five accumulated gradients (selective_scan.cpp:319-327 allocates five zero tensors): dB and dC share one
-    zero-filled buffer, the three small parameter gradients another, so that a parameter's ``.grad`` never keeps the
-    large buffer alive; two memsets per call instead of five."""
+    buffer, the three small parameter gradients another, so that a parameter's ``.grad`` never keeps the large buffer
+    alive; two memsets per call instead of five -- one when the launch stores dB / dC (``zero_bc`` False: SCAN_DBDC_STORE)."""
     batch, dim, seqlen, dstate, ngroups = dims
     n_bc = batch * ngroups * dstate * seqlen
     n_bc_pad = (n_bc + 3) // 4 * 4
-    big = torch.zeros(2 * n_bc_pad, dtype=torch.float32, device=u.device)
+    big = (torch.zeros if zero_bc else torch.empty)(2 * n_bc_pad, dtype=torch.float32, device=u.device)
     dB = big[:n_bc].view(batch, ngroups, dstate, seqlen)
     dC = big[n_bc_pad:n_bc_pad + n_bc].view(batch, ngroups, dstate, seqlen)
     n_a = dim * dstate
@@ -237,14 +237,54 @@ def _grad_buffers(u, A, D, delta_bias, dims):
     return dA, dB, dC, dD, dbias
 
 
-def bwd(u, delta, A, B, C, D, delta_bias, dout, x=None, delta_softplus=False, nrows=1):
-    """``selective_scan_cuda_core.bwd``: returns ``[du, ddelta, dA, dB, dC, dD, ddelta_bias]``."""
-    s = _site(u, delta, A, B, C, D, delta_bias, delta_softplus, 0)
+def dbdc_store_candidate(u, A, B, flags=0) -> bool:
+    """Necessary conditions of VMASR_SCAN_DBDC_STORE (include/vmasr_b200.h): float32, d_state 1, more than one chunk, and a
+    B / C group narrow enough for ONE multi-chunk tile (4 channels), so that every dB / dC element has a single writer.
+    The library has the last word (alignment, strides): ``_store_plan_ok`` asks it before a launch relies on the flag."""
+    if flags & SCAN_DBDC_STORE:
+        return True
+    return (u.dtype == torch.float32 and A.shape[1] == 1 and u.shape[2] > _lib.SCAN_CHUNK and u.shape[2] % 16 == 0
+            and u.shape[1] // B.shape[1] <= 4)
+
+
+def _store_plan_ok(s: _Site) -> bool:
+    """``vmasr_scan_plan`` on the FILLED parameter block of a site that carries SCAN_DBDC_STORE: 0 = the launch will store."""
+    out = (ctypes.c_int32 * 8)()
+    return _lib.load_library().vmasr_scan_plan(ctypes.byref(s.p), 1, out) == 0
+
+
+def _bwd_prepare(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, flags, workspace=None):
+    """Allocate the gradients of one backward call and fill its parameter block.  Where the plan allows it dB / dC are left
+    unset and the launch stores them (no zero-fill pass over the two largest accumulated gradients)."""
     du = torch.empty_like(u)
     ddelta = torch.empty_like(delta)
-    dA, dB, dC, dD, dbias = _grad_buffers(u, A, D, delta_bias, s.dims)
-    _bwd_launch(s, u, delta, A, B, C, D, delta_bias, dout, x, du, ddelta, dA, dB, dC, dD, dbias)
-    return [du, ddelta, dA, dB.to(B.dtype), dC.to(C.dtype), dD, dbias]
+    if dbdc_store_candidate(u, A, B):
+        s = _site(u, delta, A, B, C, D, delta_bias, delta_softplus, flags | SCAN_DBDC_STORE)
+        dA, dB, dC, dD, dbias = _grad_buffers(u, A, D, delta_bias, s.dims, zero_bc=False)
+        with _device_of(u):
+            _fill_inputs(s, u, delta, A, B, C, D, delta_bias, workspace)
+            _fill_bwd(s, A, dout, x, du, ddelta, dA, dB, dC, dD, dbias)
+        if _store_plan_ok(s):
+            return s, [du, ddelta, dA, dB, dC, dD, dbias]
+        dB.zero_()  # the library would refuse the flag for this call (alignment, strides): accumulate into zeros instead
+        dC.zero_()
+        s = _site(u, delta, A, B, C, D, delta_bias, delta_softplus, flags)
+    else:
+        s = _site(u, delta, A, B, C, D, delta_bias, delta_softplus, flags)
+        dA, dB, dC, dD, dbias = _grad_buffers(u, A, D, delta_bias, s.dims)
+    with _device_of(u):
+        _fill_inputs(s, u, delta, A, B, C, D, delta_bias, workspace)
+        _fill_bwd(s, A, dout, x, du, ddelta, dA, dB, dC, dD, dbias)
+    return s, [du, ddelta, dA, dB, dC, dD, dbias]
+
+
+def bwd(u, delta, A, B, C, D, delta_bias, dout, x=None, delta_softplus=False, nrows=1):
+    """``selective_scan_cuda_core.bwd``: returns ``[du, ddelta, dA, dB, dC, dD, ddelta_bias]``."""
+    s, res = _bwd_prepare(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, 0)
+    with _device_of(u):
+        _lib.check(_lib.load_library().vmasr_scan_bwd(ctypes.byref(s.p)))
+    res[3], res[4] = res[3].to(B.dtype), res[4].to(C.dtype)
+    return res
 
 
 # ---- delta generated inside the kernels (SURVEY.md 8f-1; include/vmasr_b200.h, dt_rank > 0) -------------------------------
@@ -381,14 +421,14 @@ def bwd_grouped(calls, outs=None):
         for i, (s, c) in enumerate(zip(sites, calls)):
             u, delta, A, B, C, D, bias, dout, x, sp = c[:10]
             if outs is not None:
-                du, ddelta, dA, dB, dC, dD, dbias = outs[i]
-            else:
-                du, ddelta = torch.empty_like(u), torch.empty_like(delta)
-                dA, dB, dC, dD, dbias = _grad_buffers(u, A, D, bias, s.dims)
-            _fill_inputs(s, u, delta, A, B, C, D, bias, workspace=wss[i])
-            _fill_bwd(s, A, dout, x, du, ddelta, dA, dB, dC, dD, dbias)
+                res = list(outs[i])
+                du, ddelta, dA, dB, dC, dD, dbias = res
+                _fill_inputs(s, u, delta, A, B, C, D, bias, workspace=wss[i])
+                _fill_bwd(s, A, dout, x, du, ddelta, dA, dB, dC, dD, dbias)
+            else:  # (dB / dC stored instead of zero-filled and accumulated where the plan allows it)
+                s, res = _bwd_prepare(u, delta, A, B, C, D, bias, dout, x, sp, s.p.flags, workspace=wss[i])
             ctypes.memmove(ctypes.addressof(arr[i]), ctypes.addressof(s.p), size)
-            results.append([du, ddelta, dA, dB, dC, dD, dbias])
+            results.append(res)
         _lib.check(_lib.load_library().vmasr_scan_bwd_grouped(n, arr))
     return results
 
