@@ -180,11 +180,13 @@ class DeviceStep:
         # no zero-fill of the two; the same rule vm_asr_b200.scan.bwd applies for the tensors it allocates itself
         self.store = [c.L > 2048 and c.L % 16 == 0 and c.D // 4 <= 4 and not os.environ.get("VMASR_BENCH_NO_DBDC_STORE")
                       for c in wl.calls]
+        # every other call's dB / dC buffer is cleared by the call's own FORWARD launch (vmasr_scan_params.zero_ptr: the tiles
+        # spread the stores over the time they wait for their first bytes), as vm_asr_b200.scan.SelectiveScanCore does
+        self.fwd_zero = not os.environ.get("VMASR_BENCH_NO_FWD_ZERO")
         acc_floats = 0
         for c, st in zip(wl.calls, self.store):
-            acc_floats += c.D * 3 + (0 if st else 2 * wl.batch * 4 * c.L)
-        # one arena for every accumulated gradient (dA, dD, ddelta_bias of all calls, dB / dC where they are summed over channel
-        # tiles): zeroed by ONE memset
+            acc_floats += c.D * 3 + (0 if st or self.fwd_zero else 2 * wl.batch * 4 * c.L)
+        # one arena for what is left of the accumulated gradients (dA, dD, ddelta_bias of all calls): zeroed by ONE memset
         self.arena = torch.zeros(acc_floats, dtype=torch.float32, device=device)
         self.zero_fill_bytes = 4 * acc_floats
         off = 0
@@ -198,19 +200,27 @@ class DeviceStep:
         for c, st in zip(wl.calls, self.store):
             inp = make_call_inputs(c, wl.batch, device, gen)
             n_chunks = (c.L + 2047) // 2048
-            bc = (lambda: torch.empty(wl.batch, 4, 1, c.L, device=device)) if st else (lambda: take(wl.batch * 4 * c.L, (wl.batch, 4, 1, c.L)))
+            n_bc = wl.batch * 4 * c.L
+            bc = None
+            if st:
+                dB, dC = (torch.empty(wl.batch, 4, 1, c.L, device=device) for _ in range(2))
+            elif self.fwd_zero:
+                bc = torch.empty(2 * n_bc, device=device)
+                dB, dC = bc[:n_bc].view(wl.batch, 4, 1, c.L), bc[n_bc:].view(wl.batch, 4, 1, c.L)
+            else:
+                dB, dC = take(n_bc, (wl.batch, 4, 1, c.L)), take(n_bc, (wl.batch, 4, 1, c.L))
             bufs = dict(
                 out=torch.empty_like(inp["u"]), x=torch.empty(wl.batch, c.D, n_chunks, 2, device=device),
                 du=torch.empty_like(inp["u"]), ddelta=torch.empty_like(inp["u"]),
                 dA=take(c.D, (c.D, 1)), dD=take(c.D, (c.D,)), dbias=take(c.D, (c.D,)),
-                dB=bc(), dC=bc(), flags=self.scan.SCAN_DBDC_STORE if st else 0,
+                dB=dB, dC=dC, bc=bc, flags=self.scan.SCAN_DBDC_STORE if st else 0,
             )
             self.calls.append((c, inp, bufs))
         self.graph = None
 
     def fwd_call(self, i):
         c, inp, b = self.calls[i]
-        self.scan.fwd_out(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], True, b["out"], b["x"])
+        self.scan.fwd_out(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], True, b["out"], b["x"], zero=b["bc"])
 
     def bwd_call(self, i):
         c, inp, b = self.calls[i]
@@ -220,12 +230,13 @@ class DeviceStep:
     # The generator's two streams (magnitude, phase) issue the same-shape SS2D call independently between their interaction
     # points (model/model.py:1124-1127, 1167-1176): calls 2j and 2j + 1 of the workload are such a pair.
     def fwd_pair(self, i):
-        args, outs = [], []
+        args, outs, zero = [], [], []
         for k in (i, i + 1):
             c, inp, b = self.calls[k]
             args.append((inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], True))
             outs.append((b["out"], b["x"]))
-        self.scan.fwd_grouped(args, outs)
+            zero.append(b["bc"])
+        self.scan.fwd_grouped(args, outs, zero=zero)
 
     def bwd_pair(self, i):
         args, outs = [], []
@@ -335,17 +346,18 @@ def time_eager(ds: DeviceStep, steps: int):
         plans = []
         n = len(ds.calls)
         for i in range(0, n, 2):
-            args, outs = [], []
+            args, outs, zero = [], [], []
             for k in (i, i + 1):
                 c, inp, b = ds.calls[k]
                 args.append((inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], True))
                 outs.append((b["out"], b["x"]))
-            plans.append(ds.scan.prepare_fwd(args, outs))
+                zero.append(b["bc"])
+            plans.append(ds.scan.prepare_fwd(args, outs, zero))
         for i in reversed(range(0, n, 2)):
             args, outs = [], []
             for k in (i, i + 1):
                 c, inp, b = ds.calls[k]
-                args.append((inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], inp["dout"], b["x"], True))
+                args.append((inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], inp["dout"], b["x"], True, b["flags"]))
                 outs.append((b["du"], b["ddelta"], b["dA"], b["dB"], b["dC"], b["dD"], b["dbias"]))
             plans.append(ds.scan.prepare_bwd(args, outs))
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VMASR_ABI_VERSION 4
+#define VMASR_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define VMASR_API __attribute__((visibility("default")))
@@ -128,6 +128,16 @@ typedef struct vmasr_scan_params {
     int64_t dB_batch_stride, dC_batch_stride;
     int32_t dt_rank;
     int32_t reserved0;
+    /* ---- side job: a region the launch ZERO-FILLS while it runs (ABI 5) ----
+     * zero_ptr (16-byte aligned) / zero_bytes (a multiple of 16; 0 = none): cleared by the time the launch completes, in
+     * stream order after whatever precedes the launch.  Meant for the accumulated gradients of the backward call that
+     * belongs to this forward call (dB / dC, and dA / dD / ddelta_bias if they sit in the same buffer): the reference
+     * zero-fills them with five memsets in front of its backward kernel (selective_scan.cpp:319-327); here the forward's
+     * fast kernels spread the stores over their tiles, where they cost nothing measurable (the tiles wait for their first
+     * bytes then), and every other kernel family falls back to one cudaMemsetAsync in front of its launch -- the caller
+     * never needs to know which.  The region must not overlap anything the launch reads or writes. */
+    void *zero_ptr;
+    uint64_t zero_bytes;
 } vmasr_scan_params;
 
 /* flags (fast path only: float32, d_state 1, seqlen a multiple of 16, 16-byte aligned rows and strides; otherwise the call

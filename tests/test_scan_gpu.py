@@ -516,6 +516,60 @@ def test_dbdc_store_refused():
         scan.bwd_out(*args, g["dout"], x, True, torch.empty_like(out), torch.empty_like(out), *bufs, flags=scan.SCAN_DBDC_STORE)
 
 
+@pytest.mark.parametrize("Bsz,Dm,L,itype,units", [
+    (2, 32, 6144, torch.float32, 1237),      # multi-chunk fast path, region not a multiple of the tile count
+    (2, 32, 1024, torch.float32, 40000),     # single-chunk fast path, many units per tile
+    (1, 16, 4112, torch.float32, 1),         # one 16-byte unit: most tiles have nothing to clear
+    (4, 256, 4096, torch.float32, 262144),   # last round on half tiles: the tile count the region is cut by includes them
+    (1, 8, 132, torch.float32, 77),          # generic kernels: one memset in front of the launch
+    (2, 8, 2500, torch.float16, 1000),       # generic kernels, half precision
+])
+def test_zero_region_side_job(Bsz, Dm, L, itype, units):
+    """vmasr_scan_params.zero_ptr / zero_bytes: the launch clears the region (whatever the kernel family) and computes what it
+    computes without it."""
+    scan = _ops()
+    _, g = make_inputs(Bsz, Dm, L, 4, 1, itype, seed=5)
+    args = (g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], g["bias"])
+    out0, x0 = scan.fwd(*args, True, 1)
+    guard = torch.full((4 * units + 8,), float("nan"), device="cuda")
+    region = guard[4:4 + 4 * units]
+    out1, x1 = scan.fwd(*args, True, 1, zero=region)
+    assert torch.equal(out0, out1) and torch.equal(x0, x1)
+    assert torch.count_nonzero(region).item() == 0 and not torch.isnan(region).any()
+    assert torch.isnan(guard[:4]).all() and torch.isnan(guard[4 + 4 * units:]).all()   # nothing outside the region is touched
+    # grouped: every problem clears its own region
+    regions = [torch.full((4 * units,), float("nan"), device="cuda") for _ in range(2)]
+    res = scan.fwd_grouped([(*args, True)] * 2, zero=regions)
+    for (o, xx), r in zip(res, regions):
+        assert torch.equal(o, out0) and torch.equal(xx, x0) and torch.count_nonzero(r).item() == 0 and not torch.isnan(r).any()
+    # a region that is not 16-byte aligned is refused
+    with pytest.raises(RuntimeError):
+        scan.fwd(*args, True, 1, zero=guard[1:5])
+
+
+@pytest.mark.parametrize("Bsz,Dm,L", [(2, 32, 6144), (2, 32, 1024), (2, 8, 6144), (1, 8, 132)])
+def test_autograd_forward_clears_bc_accumulator(Bsz, Dm, L):
+    """SelectiveScanCore: the forward launch clears the buffer its backward sums dB / dC into (or the backward stores them):
+    same gradients as the explicit fwd / bwd pair; a second backward over the retained graph starts from zeros again."""
+    scan = _ops()
+    _, g = make_inputs(Bsz, Dm, L, 4, 1, torch.float32, seed=9)
+    leaves = [g[k].clone().requires_grad_(True) for k in ("u", "delta", "A", "B", "C", "D", "bias")]
+    out = scan.SelectiveScanCore.apply(*leaves, True)
+    out.backward(g["dout"], retain_graph=True)
+    first = [t.grad.clone() for t in leaves]
+    for t in leaves:
+        t.grad = None
+    out.backward(g["dout"])
+    second = [t.grad for t in leaves]
+    o, x = scan.fwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], g["bias"], True, 1)
+    ref = scan.bwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], g["bias"], g["dout"], x, True, 1)
+    assert torch.equal(out, o)
+    for got in (first, second):
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+        for a, b in zip(got[2:], ref[2:]):
+            assert rel_err(a, b.double().cpu().numpy()) < 1e-5
+
+
 def test_flags_need_fast_path():
     scan = _ops()
     _, g = make_inputs(1, 8, 132, 4, 1, torch.float32)  # length not a multiple of 16: generic kernels

@@ -22,7 +22,7 @@ VMASR_F32, VMASR_F16, VMASR_BF16 = 0, 1, 2
 SCAN_REVERSE, SCAN_ACCUMULATE, SCAN_ADD, SCAN_DBDC_STORE = 1, 2, 4, 8
 SCAN_MAX_GROUP = 8
 SS2D_DYT_GIVEN = 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 SCAN_CHUNK = 2048
 DTYPE_CODE = {torch.float32: VMASR_F32, torch.float16: VMASR_F16, torch.bfloat16: VMASR_BF16}
 
@@ -48,6 +48,7 @@ class ScanParams(ctypes.Structure):
         + [(n, _i64) for n in ("dt_rows_batch_stride", "dt_rows_row_stride", "dt_weight_d_stride", "dB_batch_stride",
                                "dC_batch_stride")]
         + [("dt_rank", _i32), ("reserved0", _i32)]
+        + [("zero_ptr", _vp), ("zero_bytes", _u64)]
     )
 
 

@@ -54,6 +54,10 @@ struct ScanArgs {
     long long dtr_bs, dtr_rs, dtw_ds;
     long long dB_bs, dC_bs;  // batch strides of dB / dC (default ngroups * seqlen)
     int dt_rank;
+    // side job (vmasr_scan_params.zero_ptr): tile t of this problem clears 16-byte units [t * zero_per_tile, (t + 1) * zero_per_tile)
+    // of the region, cut at zero_n.  zero_n == 0: nothing to do (or the host has queued a memset instead).
+    float4 *zero_ptr;
+    long long zero_n, zero_per_tile;
 };
 
 // (P, Q) represents the affine map  s -> P*s + Q  of a run of positions on the recurrence state.
@@ -178,6 +182,17 @@ __device__ __forceinline__ int group_problem(const GroupArgs &ga, int &tile) {
     while (prob + 1 < ga.n && (int)blockIdx.x >= ga.tile_end[prob]) start = ga.tile_end[prob++];
     tile = (int)blockIdx.x - start;
     return prob;
+}
+
+// side job of a forward launch (vmasr_scan_params.zero_ptr): this tile's share of the region, 128-bit stores by every thread.
+// Issued at the top of the CTA: the stores drain while the tile waits for its first bytes.
+__device__ __forceinline__ void zero_side_region(const ScanArgs &a, int tile) {
+    if (a.zero_n == 0) return;
+    const long long i0 = (long long)tile * a.zero_per_tile;
+    const long long left = a.zero_n - i0;
+    const int n = (int)(left < a.zero_per_tile ? (left < 0 ? 0 : left) : a.zero_per_tile);
+    float4 *dst = a.zero_ptr + i0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 // host side (scan_host.cu)

@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) scan_fwd_pipe_kernel(const __
     const int prob = group_problem(ga, tile);
     const ScanArgs &a = ga.a[prob];
     const TileMaps &tm = ga.tm[prob];
+    zero_side_region(a, tile);
     int half = -1;
     if (tile >= a.split_from) {
         half = (tile - a.split_from) & 1;

@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(256, 3) scan_fwd_tma_kernel(const __grid_const
     const int prob = group_problem(ga, tile);
     const ScanArgs &a = ga.a[prob];
     const TileMaps &tm = ga.tm[prob];
+    zero_side_region(a, tile);
     const int chunk = tile / a.n_rowgroups;
     const int rg = tile - chunk * a.n_rowgroups;
     const bool tail = (chunk + 1) * SEG > a.seqlen;

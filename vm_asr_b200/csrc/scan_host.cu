@@ -81,6 +81,8 @@ static int validate(const vmasr_scan_params *p, bool bwd) {
     if (p->flags & ~(VMASR_SCAN_REVERSE | VMASR_SCAN_ACCUMULATE | VMASR_SCAN_ADD | VMASR_SCAN_DBDC_STORE)) return fail("selective_scan: unknown flag bits 0x%x", p->flags);
     if ((p->flags & VMASR_SCAN_DBDC_STORE) && !bwd) return fail("selective_scan_fwd: VMASR_SCAN_DBDC_STORE is a backward flag");
     if ((p->flags & VMASR_SCAN_ACCUMULATE) && (p->flags & VMASR_SCAN_ADD)) return fail("selective_scan: VMASR_SCAN_ACCUMULATE and VMASR_SCAN_ADD exclude each other");
+    if (p->zero_bytes != 0 && (!p->zero_ptr || !aligned16(p->zero_ptr) || (p->zero_bytes & 15)))
+        return fail("selective_scan: zero_ptr must be non-null and 16-byte aligned, zero_bytes a multiple of 16");
     if (p->dt_rank < 0) return fail("selective_scan: dt_rank must not be negative");
     if (!p->u || (!p->delta && p->dt_rank == 0) || !p->A || !p->B || !p->C) return fail("selective_scan: u, delta, A, B, C must be non-null");
     if (p->dt_rank > 0) {
@@ -199,6 +201,9 @@ static ScanArgs make_args(const vmasr_scan_params *p, int n_chunks, int chan_per
     a.rev = (p->flags & VMASR_SCAN_REVERSE) ? 1 : 0;
     a.accum = (p->flags & VMASR_SCAN_ACCUMULATE) ? 1 : (p->flags & VMASR_SCAN_ADD) ? 2 : 0;
     a.dbdc_store = (p->flags & VMASR_SCAN_DBDC_STORE) ? 1 : 0;
+    a.zero_ptr = static_cast<float4 *>(p->zero_ptr);
+    a.zero_n = (long long)(p->zero_bytes / 16);
+    a.zero_per_tile = 0;
     const char *nowait = tuning_env("VMASR_DEBUG_NOWAIT");
     a.debug_nowait = nowait ? atoi(nowait) : 0;
 #ifdef VMASR_TUNING
@@ -313,6 +318,14 @@ int scan_run_group(int n, const vmasr_scan_params *ps, bool bwd) {
     DeviceGuard guard(ps[0].device);
     if (!guard.ok) return fail("selective_scan: cannot select CUDA device %d", ps[0].device);
     cudaStream_t stream = static_cast<cudaStream_t>(ps[0].stream);
+    // side job (vmasr_scan_params.zero_ptr): the forward's fast kernels clear the region themselves, tile by tile; every
+    // other family gets one memset in front of its launch
+    for (int i = 0; i < n; ++i) {
+        if (a[i].zero_n == 0 || (!bwd && variant[i] != kGeneric)) continue;
+        if (int rc = check_cuda(cudaMemsetAsync(a[i].zero_ptr, 0, (size_t)a[i].zero_n * 16, stream), "selective_scan: zero-fill of the side region"))
+            return rc;
+        a[i].zero_n = 0;
+    }
     bool done[kMaxGroup] = {};
     for (int i = 0; i < n; ++i) {
         if (done[i]) continue;
@@ -336,6 +349,10 @@ int scan_run_group(int n, const vmasr_scan_params *ps, bool bwd) {
             ++ga.n;
         }
         if (variant[i] == kMultiChunk) grid += split_last_round(ga, grid, bwd, ps[0].device);
+        for (int j = 0; j < ga.n; ++j) {  // (tile counts are final now: the split above may have added half tiles)
+            const long long tiles = ga.tile_end[j] - (j ? ga.tile_end[j - 1] : 0);
+            if (ga.a[j].zero_n) ga.a[j].zero_per_tile = (ga.a[j].zero_n + tiles - 1) / tiles;
+        }
         for (int j = ga.n; j < kMaxGroup; ++j) ga.tile_end[j] = grid;
         int rc;
         if (variant[i] == kMultiChunk) rc = bwd ? scan_bwd_pipe_dispatch(ga, grid, stream) : scan_fwd_pipe_dispatch(ga, grid, stream);

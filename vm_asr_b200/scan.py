@@ -134,7 +134,20 @@ def _fill_inputs(s: _Site, u, delta, A, B, C, D, delta_bias, workspace=None):
     return p
 
 
-def _fill_fwd(s: _Site, out, x):
+def _set_zero_region(p, zero):
+    """``vmasr_scan_params.zero_ptr / zero_bytes``: a float32 / 16-byte aligned contiguous tensor the launch clears as a side
+    job (the accumulated gradients of the backward call to come), or None.  Always set: parameter blocks are reused."""
+    if zero is None:
+        p.zero_ptr, p.zero_bytes = None, 0
+        return
+    nbytes = zero.numel() * zero.element_size()
+    _check(zero.is_cuda and zero.is_contiguous() and nbytes % 16 == 0 and zero.data_ptr() % 16 == 0,
+           "selective_scan: the zero region must be a contiguous CUDA tensor, 16-byte aligned, a multiple of 16 bytes long")
+    p.zero_ptr, p.zero_bytes = zero.data_ptr(), nbytes
+
+
+def _fill_fwd(s: _Site, out, x, zero=None):
+    _set_zero_region(s.p, zero)
     batch, dim, seqlen, dstate, _ = s.dims
     _check(out.dtype == _DTYPE_OF[s.p.io_dtype] and tuple(out.shape) == (batch, dim, seqlen) and (out.stride(-1) == 1 or seqlen == 1),
            "selective_scan: out must look like delta")
@@ -161,6 +174,7 @@ def _fill_bwd(s: _Site, A, dout, x, du, ddelta, dA, dB, dC, dD, ddelta_bias):
                f"selective_scan: {name} must be contiguous float32 (batch, n_groups, dstate, seqlen)")
     _check(dA.dtype == torch.float32 and dA.stride() == A.stride(), "selective_scan: dA must look like A")
     p = s.p
+    p.zero_ptr, p.zero_bytes = None, 0
     p.dout, p.x = dout.data_ptr(), _ptr(x)
     p.du, p.ddelta, p.dA, p.dB, p.dC = du.data_ptr(), ddelta.data_ptr(), dA.data_ptr(), dB.data_ptr(), dC.data_ptr()
     p.dD, p.ddelta_bias = _ptr(dD), _ptr(ddelta_bias)
@@ -172,29 +186,40 @@ def _fill_bwd(s: _Site, A, dout, x, du, ddelta, dA, dB, dC, dD, ddelta_bias):
 _DTYPE_OF = {v: k for k, v in _lib.DTYPE_CODE.items()}
 
 
-def fwd_out(u, delta, A, B, C, D, delta_bias, delta_softplus, out, x, flags=0, workspace=None):
+def fwd_out(u, delta, A, B, C, D, delta_bias, delta_softplus, out, x, flags=0, workspace=None, zero=None):
     """Launch the forward into caller-provided ``out`` (like delta) and ``x`` (batch, dim, n_chunks, 2*dstate)
-    float32.  No allocation when the stream's carry workspace exists already (or ``workspace`` is given)."""
-    _fwd_launch(_site(u, delta, A, B, C, D, delta_bias, delta_softplus, flags), u, delta, A, B, C, D, delta_bias, out, x, workspace)
+    float32.  No allocation when the stream's carry workspace exists already (or ``workspace`` is given).
+    ``zero``: a tensor the launch clears as a side job (see ``bc_accumulator``)."""
+    _fwd_launch(_site(u, delta, A, B, C, D, delta_bias, delta_softplus, flags), u, delta, A, B, C, D, delta_bias, out, x, workspace, zero)
 
 
-def _fwd_launch(s, u, delta, A, B, C, D, delta_bias, out, x, workspace=None):
+def _fwd_launch(s, u, delta, A, B, C, D, delta_bias, out, x, workspace=None, zero=None):
     lib = _lib.load_library()
     with _device_of(u):
         _fill_inputs(s, u, delta, A, B, C, D, delta_bias, workspace)
-        _fill_fwd(s, out, x)
+        _fill_fwd(s, out, x, zero)
         _lib.check(lib.vmasr_scan_fwd(ctypes.byref(s.p)))
 
 
-def fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1):
+def fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1, zero=None):
     """``selective_scan_cuda_core.fwd``: returns ``[out, x]``.  ``nrows`` is accepted and ignored, like the
     reference's core kernel does (selective_scan.cpp:163)."""
     s = _site(u, delta, A, B, C, D, delta_bias, delta_softplus, 0)
     batch, dim, seqlen, dstate, _ = s.dims
     out = torch.empty_like(delta)
     x = torch.empty((batch, dim, s.n_chunks, 2 * dstate), dtype=torch.float32, device=u.device)
-    _fwd_launch(s, u, delta, A, B, C, D, delta_bias, out, x)
+    _fwd_launch(s, u, delta, A, B, C, D, delta_bias, out, x, zero=zero)
     return [out, x]
+
+
+def bc_accumulator(u, A, B):
+    """The buffer the backward of this call will sum dB and dC into, NOT cleared: hand it to the forward as ``zero=`` (the
+    forward's kernels clear it while they wait for their first bytes: no memset pass in front of the backward) and to ``bwd``
+    as ``bc=``.  None when the backward stores dB / dC anyway (``dbdc_store_candidate``)."""
+    if dbdc_store_candidate(u, A, B):
+        return None
+    n_bc = u.shape[0] * B.shape[1] * A.shape[1] * u.shape[2]
+    return torch.empty(2 * ((n_bc + 3) // 4 * 4), dtype=torch.float32, device=u.device)
 
 
 def bwd_out(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, du, ddelta, dA, dB, dC, dD, ddelta_bias, flags=0,
@@ -213,14 +238,18 @@ def _bwd_launch(s, u, delta, A, B, C, D, delta_bias, dout, x, du, ddelta, dA, dB
         _lib.check(lib.vmasr_scan_bwd(ctypes.byref(s.p)))
 
 
-def _grad_buffers(u, A, D, delta_bias, dims, zero_bc=True):
+def _grad_buffers(u, A, D, delta_bias, dims, zero_bc=True, bc=None):
     """The five accumulated gradients (selective_scan.cpp:319-327 allocates five zero tensors): dB and dC share one
     buffer, the three small parameter gradients another, so that a parameter's ``.grad`` never keeps the large buffer
     alive; two memsets per call instead of five -- one when the launch stores dB / dC (``zero_bc`` False: SCAN_DBDC_STORE)."""
     batch, dim, seqlen, dstate, ngroups = dims
     n_bc = batch * ngroups * dstate * seqlen
     n_bc_pad = (n_bc + 3) // 4 * 4
-    big = (torch.zeros if zero_bc else torch.empty)(2 * n_bc_pad, dtype=torch.float32, device=u.device)
+    if bc is not None:  # cleared by the forward launch (bc_accumulator)
+        _check(bc.dtype == torch.float32 and bc.numel() == 2 * n_bc_pad and bc.device == u.device, "selective_scan: bc has the wrong size")
+        big = bc
+    else:
+        big = (torch.zeros if zero_bc else torch.empty)(2 * n_bc_pad, dtype=torch.float32, device=u.device)
     dB = big[:n_bc].view(batch, ngroups, dstate, seqlen)
     dC = big[n_bc_pad:n_bc_pad + n_bc].view(batch, ngroups, dstate, seqlen)
     n_a = dim * dstate
@@ -253,12 +282,12 @@ def _store_plan_ok(s: _Site) -> bool:
     return _lib.load_library().vmasr_scan_plan(ctypes.byref(s.p), 1, out) == 0
 
 
-def _bwd_prepare(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, flags, workspace=None):
+def _bwd_prepare(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, flags, workspace=None, bc=None):
     """Allocate the gradients of one backward call and fill its parameter block.  Where the plan allows it dB / dC are left
     unset and the launch stores them (no zero-fill pass over the two largest accumulated gradients)."""
     du = torch.empty_like(u)
     ddelta = torch.empty_like(delta)
-    if dbdc_store_candidate(u, A, B):
+    if bc is None and dbdc_store_candidate(u, A, B):
         s = _site(u, delta, A, B, C, D, delta_bias, delta_softplus, flags | SCAN_DBDC_STORE)
         dA, dB, dC, dD, dbias = _grad_buffers(u, A, D, delta_bias, s.dims, zero_bc=False)
         with _device_of(u):
@@ -271,16 +300,17 @@ def _bwd_prepare(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, flag
         s = _site(u, delta, A, B, C, D, delta_bias, delta_softplus, flags)
     else:
         s = _site(u, delta, A, B, C, D, delta_bias, delta_softplus, flags)
-        dA, dB, dC, dD, dbias = _grad_buffers(u, A, D, delta_bias, s.dims)
+        dA, dB, dC, dD, dbias = _grad_buffers(u, A, D, delta_bias, s.dims, bc=bc)
     with _device_of(u):
         _fill_inputs(s, u, delta, A, B, C, D, delta_bias, workspace)
         _fill_bwd(s, A, dout, x, du, ddelta, dA, dB, dC, dD, dbias)
     return s, [du, ddelta, dA, dB, dC, dD, dbias]
 
 
-def bwd(u, delta, A, B, C, D, delta_bias, dout, x=None, delta_softplus=False, nrows=1):
-    """``selective_scan_cuda_core.bwd``: returns ``[du, ddelta, dA, dB, dC, dD, ddelta_bias]``."""
-    s, res = _bwd_prepare(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, 0)
+def bwd(u, delta, A, B, C, D, delta_bias, dout, x=None, delta_softplus=False, nrows=1, bc=None):
+    """``selective_scan_cuda_core.bwd``: returns ``[du, ddelta, dA, dB, dC, dD, ddelta_bias]``.  ``bc``: the buffer of
+    ``bc_accumulator`` that the forward call cleared (used up by this call: never pass it twice)."""
+    s, res = _bwd_prepare(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, 0, bc=bc)
     with _device_of(u):
         _lib.check(_lib.load_library().vmasr_scan_bwd(ctypes.byref(s.p)))
     res[3], res[4] = res[3].to(B.dtype), res[4].to(C.dtype)
@@ -366,10 +396,11 @@ def _group_workspaces(sites, device):
     return out
 
 
-def fwd_grouped(calls, outs=None):
+def fwd_grouped(calls, outs=None, zero=None):
     """``calls``: list of ``(u, delta, A, B, C, D, delta_bias, delta_softplus[, flags])`` tuples, at most
     ``SCAN_MAX_GROUP`` of them, all on one device.  One launch per kernel family (normally one).  Returns a list of
-    ``[out, x]``; ``outs`` may give pre-allocated ``(out, x)`` pairs."""
+    ``[out, x]``; ``outs`` may give pre-allocated ``(out, x)`` pairs, ``zero`` one tensor (or None) per call that the call's
+    tiles clear as a side job (``bc_accumulator``)."""
     _check(0 < len(calls) <= _lib.SCAN_MAX_GROUP, f"fwd_grouped: 1..{_lib.SCAN_MAX_GROUP} calls")
     sites, args = [], []
     for c in calls:
@@ -394,7 +425,7 @@ def fwd_grouped(calls, outs=None):
                 out = torch.empty_like(a[1])
                 x = torch.empty((batch, dim, s.n_chunks, 2 * dstate), dtype=torch.float32, device=device)
             _fill_inputs(s, *a, workspace=wss[i])
-            _fill_fwd(s, out, x)
+            _fill_fwd(s, out, x, None if zero is None else zero[i])
             ctypes.memmove(ctypes.addressof(arr[i]), ctypes.addressof(s.p), size)
             results.append([out, x])
         _lib.check(_lib.load_library().vmasr_scan_fwd_grouped(n, arr))
@@ -440,12 +471,12 @@ class PreparedCalls:
     allocation, no per-tensor work.  ``prepare_fwd`` / ``prepare_bwd`` build it from the arguments of ``fwd_grouped`` /
     ``bwd_grouped`` with pre-allocated outputs."""
 
-    def __init__(self, kind, calls, outs):
+    def __init__(self, kind, calls, outs, zero=None):
         _check(outs is not None and len(outs) == len(calls), "prepare: pre-allocated outputs are required")
         _check(0 < len(calls) <= _lib.SCAN_MAX_GROUP, f"prepare: 1..{_lib.SCAN_MAX_GROUP} calls")
         lib = _lib.load_library()
         self._fn = lib.vmasr_scan_fwd_grouped if kind == "fwd" else lib.vmasr_scan_bwd_grouped
-        self._keep = (calls, outs)
+        self._keep = (calls, outs, zero)
         self.device = calls[0][0].device
         self._dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
         n = self.n = len(calls)
@@ -458,7 +489,7 @@ class PreparedCalls:
                 flags = c[8] if len(c) > 8 else 0
                 s = _site(u, delta, A, B, C, D, bias, sp, flags)
                 _fill_inputs(s, u, delta, A, B, C, D, bias, workspace=torch.empty(0) if s.ws_bytes else None)
-                _fill_fwd(s, o[0], o[1])
+                _fill_fwd(s, o[0], o[1], None if zero is None else zero[i])
             else:
                 u, delta, A, B, C, D, bias, dout, x, sp = c[:10]
                 flags = c[10] if len(c) > 10 else 0
@@ -489,8 +520,8 @@ class PreparedCalls:
             _lib.check(rc)
 
 
-def prepare_fwd(calls, outs) -> PreparedCalls:
-    return PreparedCalls("fwd", calls, outs)
+def prepare_fwd(calls, outs, zero=None) -> PreparedCalls:
+    return PreparedCalls("fwd", calls, outs, zero)
 
 
 def prepare_bwd(calls, outs) -> PreparedCalls:
@@ -505,7 +536,9 @@ class SelectiveScanCore(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1, backnrows=1, oflex=True):
         ctx.delta_softplus = delta_softplus
-        out, x = fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, 1)
+        _site(u, delta, A, B, C, D, delta_bias, delta_softplus, 0)  # (validates: reference-style errors before anything else)
+        ctx.bc = bc_accumulator(u, A, B) if any(ctx.needs_input_grad) else None
+        out, x = fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, 1, zero=ctx.bc)
         ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, x)
         return out
 
@@ -515,7 +548,8 @@ class SelectiveScanCore(torch.autograd.Function):
         u, delta, A, B, C, D, delta_bias, x = ctx.saved_tensors
         if dout.stride(-1) != 1:
             dout = dout.contiguous()
-        du, ddelta, dA, dB, dC, dD, ddelta_bias = bwd(u, delta, A, B, C, D, delta_bias, dout, x, ctx.delta_softplus, 1)
+        bc, ctx.bc = ctx.bc, None  # (a second backward over a retained graph gets fresh zeros)
+        du, ddelta, dA, dB, dC, dD, ddelta_bias = bwd(u, delta, A, B, C, D, delta_bias, dout, x, ctx.delta_softplus, 1, bc=bc)
         return (du, ddelta, dA, dB, dC, dD, ddelta_bias, None, None, None, None)
 
 
@@ -545,7 +579,9 @@ class _SelectiveScanFn(torch.autograd.Function):
         if delta_bias is not None:
             delta_bias = delta_bias.float().contiguous()
         ctx.delta_softplus = delta_softplus
-        out, x = fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, 1)
+        _site(u, delta, A, B, C, D, delta_bias, delta_softplus, 0)  # (validates: reference-style errors before anything else)
+        ctx.bc = bc_accumulator(u, A, B) if any(ctx.needs_input_grad) else None
+        out, x = fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, 1, zero=ctx.bc)
         ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, x)
         if return_last_state:
             last_state = x[:, :, -1, 1::2]
@@ -558,7 +594,8 @@ class _SelectiveScanFn(torch.autograd.Function):
         u, delta, A, B, C, D, delta_bias, x = ctx.saved_tensors
         if dout.stride(-1) != 1:
             dout = dout.contiguous()
-        du, ddelta, dA, dB, dC, dD, dbias = bwd(u, delta, A, B, C, D, delta_bias, dout, x, ctx.delta_softplus, 1)
+        bc, ctx.bc = ctx.bc, None
+        du, ddelta, dA, dB, dC, dD, dbias = bwd(u, delta, A, B, C, D, delta_bias, dout, x, ctx.delta_softplus, 1, bc=bc)
         if ctx.squeeze_B:
             dB = dB.squeeze(1)
         if ctx.squeeze_C:
