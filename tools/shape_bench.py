@@ -71,30 +71,36 @@ def main():
                 for k in ("u", "delta", "B", "C", "dout"):
                     inp[k] = inp[k].to(dt)
                 n_chunks = (L + 2047) // 2048
+                # as the step issues them: dB / dC stored where one tile spans the group (VMASR_SCAN_DBDC_STORE), otherwise summed
+                # into a buffer that the forward launch clears as its side job (fp32 fast path; zeros allocated once otherwise)
+                store = dt == torch.float32 and scan.dbdc_store_candidate(inp["u"], inp["A"], inp["B"])
+                bc = torch.zeros(2 * B * 4 * L, device=dev) if not store else None
+                dB, dC = ((torch.empty(B, 4, 1, L, device=dev) for _ in range(2)) if store
+                          else (bc[:B * 4 * L].view(B, 4, 1, L), bc[B * 4 * L:].view(B, 4, 1, L)))
                 bufs = dict(out=torch.empty_like(inp["u"]), x=torch.empty(B, D, n_chunks, 2, device=dev),
                             du=torch.empty_like(inp["u"]), ddelta=torch.empty_like(inp["u"]),
                             dA=torch.zeros(D, 1, device=dev), dD=torch.zeros(D, device=dev), dbias=torch.zeros(D, device=dev),
-                            dB=torch.zeros(B, 4, 1, L, device=dev), dC=torch.zeros(B, 4, 1, L, device=dev))
+                            dB=dB, dC=dC, bc=bc, flags=scan.SCAN_DBDC_STORE if store else 0)
                 sets.append((inp, bufs))
 
             def f(i):
                 inp, b = sets[i]
-                scan.fwd_out(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], True, b["out"], b["x"])
+                scan.fwd_out(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], True, b["out"], b["x"], zero=b["bc"])
 
             def g(i):
                 inp, b = sets[i]
                 scan.bwd_out(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["bias"], inp["dout"], b["x"],
-                             True, b["du"], b["ddelta"], b["dA"], b["dB"], b["dC"], b["dD"], b["dbias"])
+                             True, b["du"], b["ddelta"], b["dA"], b["dB"], b["dC"], b["dD"], b["dbias"], flags=b["flags"])
 
             def fp(i):
                 a, b = sets[2 * i], sets[2 * i + 1]
                 scan.fwd_grouped([(s_[0]["u"], s_[0]["delta"], s_[0]["A"], s_[0]["B"], s_[0]["C"], s_[0]["D"], s_[0]["bias"], True) for s_ in (a, b)],
-                                 [(s_[1]["out"], s_[1]["x"]) for s_ in (a, b)])
+                                 [(s_[1]["out"], s_[1]["x"]) for s_ in (a, b)], zero=[s_[1]["bc"] for s_ in (a, b)])
 
             def gp(i):
                 a, b = sets[2 * i], sets[2 * i + 1]
                 scan.bwd_grouped([(s_[0]["u"], s_[0]["delta"], s_[0]["A"], s_[0]["B"], s_[0]["C"], s_[0]["D"], s_[0]["bias"], s_[0]["dout"],
-                                   s_[1]["x"], True) for s_ in (a, b)],
+                                   s_[1]["x"], True, s_[1]["flags"]) for s_ in (a, b)],
                                  [(s_[1]["du"], s_[1]["ddelta"], s_[1]["dA"], s_[1]["dB"], s_[1]["dC"], s_[1]["dD"], s_[1]["dbias"]) for s_ in (a, b)])
 
             if args.pairs:

@@ -618,9 +618,14 @@ __global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const _
     extern __shared__ __align__(1024) unsigned char smem_bwd_pipe[];  // swizzled tiles need 512-byte aligned slots
     static_assert(!F1 || STAGES == 4, "delta on the fly keeps the dt row in the tile's fourth stage");
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
     const BPipeSmem<STAGES> sm(smem_bwd_pipe);
     const int total = ga.tile_end[ga.n - 1];
+    {
+        int t0;
+        const int p0 = group_problem(ga, t0);  // (problem of this CTA's first tile)
+        prefetch_tile_maps(ga.a[p0], ga.tm[p0], true);
+        if (ga.a[p0].pdl_mode & 1) pdl_wait();
+    }
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < STAGES; ++i) {
@@ -635,6 +640,7 @@ __global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const _
     }
     if (threadIdx.x < STAGES * 4) sm.s_red[threadIdx.x] = 0.0f;
     __syncthreads();  // the only CTA-wide barrier: from here on the three roles meet on mbarriers
+    pdl_wait();       // ... and this one touches global memory only after its predecessor has completed
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == kBPipeWPR + 1) {
         bpipe_producer<STAGES, F1>(ga, sm, total, lane);

@@ -72,6 +72,7 @@ __device__ __forceinline__ void scan_bwd_tma_body(const ScanArgs &a, const TileM
         for (int i = 0; i < STAGES * ROWS + 1; ++i) mbar_init(&bars[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_wait();  // every thread, in front of its first access to global memory
     if (threadIdx.x < 64) s_red[threadIdx.x] = 0.0f;
     // the parameter loads start first, but nothing waits for them until the bulk copies below are on their way
     float par_v = 0.0f;
@@ -397,12 +398,15 @@ template <int TPR, bool SP>
 __global__ void __launch_bounds__(256, 2) scan_bwd_tma_kernel(const __grid_constant__ GroupArgs ga) {
     extern __shared__ __align__(1024) unsigned char smem_bwd_tma[];  // swizzled tiles need 512-byte aligned slots
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
     constexpr int SEG = TPR * 8;
     int gtile;
     const int prob = group_problem(ga, gtile);
     const ScanArgs &a = ga.a[prob];
     const TileMaps &tm = ga.tm[prob];
+    prefetch_tile_maps(a, tm, true);
+    // ... and this one touches global memory only after its predecessor has completed: the wait is in the body, behind the index
+    // arithmetic and the mbarrier initialisation (here already when the tile is claimed by ticket, which is a global atomic)
+    if ((a.pdl_mode & 1) || a.n_chunks > 1) pdl_wait();
     unsigned tile = (unsigned)gtile, epoch = 0;
     if (a.n_chunks > 1) claim_tile(a, reinterpret_cast<unsigned *>(smem_bwd_tma + 384), tile, epoch);  // VMASR_TUNING builds only
     const int chunk = a.n_chunks - 1 - (int)(tile / a.n_rowgroups);  // adjoint: late chunks first

@@ -41,7 +41,7 @@ constexpr int kPipeThreads = 288;     // 8 compute warps + the exchange warp
 // thread only ever touches its own 32 bytes of a row, so the hand-down needs no synchronisation).
 template <bool TAIL, bool SP, bool REV, bool F1>
 __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const TileMaps &tm, unsigned char *smem, const int chunk, const int rg,
-                                                   const int half) {
+                                                   const int half, const int ztile) {
     constexpr int NC = 256, ITEMS = 8, WPR = 8, SEG = NC * ITEMS, STAGES = kPipeStages;
 
     // shared memory carve-up (header 2048 bytes)
@@ -99,6 +99,10 @@ __device__ __forceinline__ void scan_fwd_pipe_body(const ScanArgs &a, const Tile
         }
         mbar_init(bar_free, WPR);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_wait();  // every thread, in front of its first access to global memory
+    zero_side_region(a, ztile);
+    if (threadIdx.x == NC) {
         if (F1) {
             mbar_expect_tx(bar_bc, 3u * seg_bytes);
             tensor_load(y1_slot(0), &tm.delta, line0, g, b, bar_bc);  // dt row of this group (dt_rank 1: row index = group)
@@ -321,12 +325,14 @@ template <bool SP, bool F1>
 __global__ void __launch_bounds__(kPipeThreads, 3) scan_fwd_pipe_kernel(const __grid_constant__ GroupArgs ga) {
     extern __shared__ __align__(1024) unsigned char smem_fwd_pipe[];  // swizzled tiles need 512-byte aligned slots
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
     int tile;
     const int prob = group_problem(ga, tile);
     const ScanArgs &a = ga.a[prob];
     const TileMaps &tm = ga.tm[prob];
-    zero_side_region(a, tile);
+    prefetch_tile_maps(a, tm, false);
+    if (a.pdl_mode & 1) pdl_wait();
+    const int ztile = tile;   // ... and this one touches global memory only after its predecessor has completed: the wait is in the body,
+                              // behind the CTA's own set-up (index arithmetic, mbarrier initialisation), which needs nothing from memory
     int half = -1;
     if (tile >= a.split_from) {
         half = (tile - a.split_from) & 1;
@@ -337,11 +343,11 @@ __global__ void __launch_bounds__(kPipeThreads, 3) scan_fwd_pipe_kernel(const __
     const int mchunk = a.rev ? a.n_chunks - 1 - chunk : chunk;
     const bool tail = (mchunk + 1) * 2048 > a.seqlen;
     if (a.rev) {
-        if (tail) scan_fwd_pipe_body<true, SP, true, F1>(a, tm, smem_fwd_pipe, chunk, rg, half);
-        else scan_fwd_pipe_body<false, SP, true, F1>(a, tm, smem_fwd_pipe, chunk, rg, half);
+        if (tail) scan_fwd_pipe_body<true, SP, true, F1>(a, tm, smem_fwd_pipe, chunk, rg, half, ztile);
+        else scan_fwd_pipe_body<false, SP, true, F1>(a, tm, smem_fwd_pipe, chunk, rg, half, ztile);
     } else {
-        if (tail) scan_fwd_pipe_body<true, SP, false, F1>(a, tm, smem_fwd_pipe, chunk, rg, half);
-        else scan_fwd_pipe_body<false, SP, false, F1>(a, tm, smem_fwd_pipe, chunk, rg, half);
+        if (tail) scan_fwd_pipe_body<true, SP, false, F1>(a, tm, smem_fwd_pipe, chunk, rg, half, ztile);
+        else scan_fwd_pipe_body<false, SP, false, F1>(a, tm, smem_fwd_pipe, chunk, rg, half, ztile);
     }
 }
 

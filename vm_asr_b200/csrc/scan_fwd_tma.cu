@@ -22,7 +22,8 @@ constexpr int kMaxTileChannels = 64;
 
 // REV (time runs against memory order) is supported for single-chunk sequences, which is all the host sends here.
 template <int TPR, bool TAIL, bool SP, int STAGES, bool REV>
-__device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, const TileMaps &tm, unsigned char *smem, const int chunk, const int rg) {
+__device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, const TileMaps &tm, unsigned char *smem, const int chunk, const int rg,
+                                                  const int ztile) {
     constexpr int NT = 256, ITEMS = 8;
     constexpr int ROWS = NT / TPR;
     constexpr int WPR = TPR / 32;
@@ -72,6 +73,8 @@ __device__ __forceinline__ void scan_fwd_tma_body(const ScanArgs &a, const TileM
         for (int i = 0; i < STAGES * ROWS + 1; ++i) mbar_init(&bars[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_wait();  // every thread, in front of its first access to global memory
+    zero_side_region(a, ztile);
     if (a.n_chunks > 1) epoch = *reinterpret_cast<volatile unsigned *>(a.ws_header + 2) % 0xfffffffeu + 1u;
     // per-channel parameters of the tile
     // the parameter loads start first, but nothing waits for them until the bulk copies below are on their way
@@ -279,22 +282,24 @@ template <int TPR, bool SP, int STAGES>
 __global__ void __launch_bounds__(256, 3) scan_fwd_tma_kernel(const __grid_constant__ GroupArgs ga) {
     extern __shared__ __align__(1024) unsigned char smem_fwd_tma[];  // swizzled tiles need 512-byte aligned slots
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
-    pdl_wait();               // ... and this one touches global memory only after its predecessor has completed
     constexpr int SEG = TPR * 8;
     int tile;
     const int prob = group_problem(ga, tile);
     const ScanArgs &a = ga.a[prob];
     const TileMaps &tm = ga.tm[prob];
-    zero_side_region(a, tile);
+    prefetch_tile_maps(a, tm, false);
+    if (a.pdl_mode & 1) pdl_wait();
+    const int ztile = tile;   // ... and this one touches global memory only after its predecessor has completed (wait in the body,
+                              // behind the index arithmetic and the mbarrier initialisation)
     const int chunk = tile / a.n_rowgroups;
     const int rg = tile - chunk * a.n_rowgroups;
     const bool tail = (chunk + 1) * SEG > a.seqlen;
     if (a.rev) {  // single chunk only (host-checked)
-        if (tail) scan_fwd_tma_body<TPR, true, SP, STAGES, true>(a, tm, smem_fwd_tma, chunk, rg);
-        else scan_fwd_tma_body<TPR, false, SP, STAGES, true>(a, tm, smem_fwd_tma, chunk, rg);
+        if (tail) scan_fwd_tma_body<TPR, true, SP, STAGES, true>(a, tm, smem_fwd_tma, chunk, rg, ztile);
+        else scan_fwd_tma_body<TPR, false, SP, STAGES, true>(a, tm, smem_fwd_tma, chunk, rg, ztile);
     } else {
-        if (tail) scan_fwd_tma_body<TPR, true, SP, STAGES, false>(a, tm, smem_fwd_tma, chunk, rg);
-        else scan_fwd_tma_body<TPR, false, SP, STAGES, false>(a, tm, smem_fwd_tma, chunk, rg);
+        if (tail) scan_fwd_tma_body<TPR, true, SP, STAGES, false>(a, tm, smem_fwd_tma, chunk, rg, ztile);
+        else scan_fwd_tma_body<TPR, false, SP, STAGES, false>(a, tm, smem_fwd_tma, chunk, rg, ztile);
     }
 }
 

@@ -204,6 +204,8 @@ static ScanArgs make_args(const vmasr_scan_params *p, int n_chunks, int chan_per
     a.zero_ptr = static_cast<float4 *>(p->zero_ptr);
     a.zero_n = (long long)(p->zero_bytes / 16);
     a.zero_per_tile = 0;
+    const char *pdlx = tuning_env("VMASR_PDL_X");
+    a.pdl_mode = pdlx ? atoi(pdlx) : 0;
     const char *nowait = tuning_env("VMASR_DEBUG_NOWAIT");
     a.debug_nowait = nowait ? atoi(nowait) : 0;
 #ifdef VMASR_TUNING
