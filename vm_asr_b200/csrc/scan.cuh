@@ -43,8 +43,8 @@ struct ScanArgs {
     int accum;            // fast kernels only: `out` (forward) / `du` (backward) are added into instead of stored:
                           // 1 = 128-bit red.global.add (concurrent writers), 2 = load / add / store (this launch is the only writer)
     int dbdc_store;       // multi-chunk backward, one channel tile per group: dB / dC are stored, not added into (VMASR_SCAN_DBDC_STORE)
-    int pdl_mode;         // VMASR_TUNING builds only (VMASR_PDL_X): bit 0 = griddepcontrol.wait at the very top of the kernel as before
-                          // (0: after the CTA's own set-up), bit 1 = no tensor-map prefetch in front of the wait
+    int pdl_mode;         // VMASR_TUNING builds only (VMASR_PDL_X): 1 = griddepcontrol.wait at the very top of the kernel (0: behind
+                          // the CTA's own set-up).  A prefetch.tensormap of the tile's maps in front of the wait was measured 0.5 % SLOWER.
     int debug_nowait;     // VMASR_TUNING builds only, timing experiment: do not wait for neighbours' aggregates -> WRONG results
     unsigned long long *timeline;  // VMASR_TUNING builds only: 16 timestamps per CTA (common.cuh), else null
     long long u_bs, u_ds, delta_bs, delta_ds, A_ds, A_ns, B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;
@@ -184,22 +184,6 @@ __device__ __forceinline__ int group_problem(const GroupArgs &ga, int &tile) {
     while (prob + 1 < ga.n && (int)blockIdx.x >= ga.tile_end[prob]) start = ga.tile_end[prob++];
     tile = (int)blockIdx.x - start;
     return prob;
-}
-
-// In front of griddepcontrol.wait (the predecessor on the stream may still be running): one lane per tensor map asks for the
-// descriptor, which sits in kernel-parameter memory and is not anybody's output, so the first bulk copy after the wait finds it cached.
-__device__ __forceinline__ void prefetch_tile_maps(const ScanArgs &a, const TileMaps &tm, bool bwd) {
-    if (a.pdl_mode & 2) return;
-    const CUtensorMap *m = nullptr;
-    switch (threadIdx.x) {
-        case 0: m = &tm.u; break;
-        case 1: m = &tm.delta; break;
-        case 2: m = &tm.B; break;
-        case 3: m = &tm.C; break;
-        case 4: m = bwd ? &tm.dout : nullptr; break;
-        default: break;
-    }
-    if (m) asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }
 
 // side job of a forward launch (vmasr_scan_params.zero_ptr): this tile's share of the region, 128-bit stores by every thread.

@@ -620,12 +620,9 @@ __global__ void __launch_bounds__(kBPipeThreads, 2) scan_bwd_pipe_kernel(const _
     pdl_launch_dependents();  // the next kernel on the stream may be scheduled while this one drains ...
     const BPipeSmem<STAGES> sm(smem_bwd_pipe);
     const int total = ga.tile_end[ga.n - 1];
-    {
-        int t0;
-        const int p0 = group_problem(ga, t0);  // (problem of this CTA's first tile)
-        prefetch_tile_maps(ga.a[p0], ga.tm[p0], true);
-        if (ga.a[p0].pdl_mode & 1) pdl_wait();
-    }
+#ifdef VMASR_TUNING
+    if (ga.a[0].pdl_mode & 1) pdl_wait();  // (VMASR_PDL_X bit 0: the wait at the very top, as before)
+#endif
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < STAGES; ++i) {

@@ -403,7 +403,6 @@ __global__ void __launch_bounds__(256, 2) scan_bwd_tma_kernel(const __grid_const
     const int prob = group_problem(ga, gtile);
     const ScanArgs &a = ga.a[prob];
     const TileMaps &tm = ga.tm[prob];
-    prefetch_tile_maps(a, tm, true);
     // ... and this one touches global memory only after its predecessor has completed: the wait is in the body, behind the index
     // arithmetic and the mbarrier initialisation (here already when the tile is claimed by ticket, which is a global atomic)
     if ((a.pdl_mode & 1) || a.n_chunks > 1) pdl_wait();

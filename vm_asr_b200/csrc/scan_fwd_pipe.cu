@@ -329,7 +329,6 @@ __global__ void __launch_bounds__(kPipeThreads, 3) scan_fwd_pipe_kernel(const __
     const int prob = group_problem(ga, tile);
     const ScanArgs &a = ga.a[prob];
     const TileMaps &tm = ga.tm[prob];
-    prefetch_tile_maps(a, tm, false);
     if (a.pdl_mode & 1) pdl_wait();
     const int ztile = tile;   // ... and this one touches global memory only after its predecessor has completed: the wait is in the body,
                               // behind the CTA's own set-up (index arithmetic, mbarrier initialisation), which needs nothing from memory

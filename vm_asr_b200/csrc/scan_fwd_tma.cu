@@ -287,7 +287,6 @@ __global__ void __launch_bounds__(256, 3) scan_fwd_tma_kernel(const __grid_const
     const int prob = group_problem(ga, tile);
     const ScanArgs &a = ga.a[prob];
     const TileMaps &tm = ga.tm[prob];
-    prefetch_tile_maps(a, tm, false);
     if (a.pdl_mode & 1) pdl_wait();
     const int ztile = tile;   // ... and this one touches global memory only after its predecessor has completed (wait in the body,
                               // behind the index arithmetic and the mbarrier initialisation)
