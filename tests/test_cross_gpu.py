@@ -41,6 +41,7 @@ SHAPES = [
     (8, 32, 256, 256), (8, 64, 128, 128), (8, 128, 64, 64), (8, 256, 32, 32), (8, 512, 16, 16), (4, 128, 32, 32),
     (3, 7, 24, 32), (2, 5, 8, 16),   # vector path with a partial plane group / tile
     (70000, 1, 4, 4),                # more planes than the old gridDim.z limit (65535)
+    (1, 889, 8, 8), (1, 1779, 4, 4),  # small maps, two / four planes per CTA (enough CTAs for three per SM) with a partial last group
 ]
 
 

@@ -126,15 +126,28 @@ __global__ void __launch_bounds__(256) cross_merge_vec(const T *__restrict__ ys,
 #pragma unroll
         for (int k = 0; k < VE; ++k) s[pl][(hl + k) * PAD + wl] = t.v[k];
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < job.n_planes * job.hv * vpr; i += 256) {
-        const int pl = i / (job.hv * vpr), r = i - pl * job.hv * vpr;
-        const int hl = r / vpr, wl = (r - hl * vpr) * VE;
-        const long long bc = job.plane0 + pl, b = bc / C, c = bc - b * C;
-        const long long l = (long long)(job.h0 + hl) * W + job.w0 + wl;
+    // the row-major pair (ys0 + flip ys2) does not depend on the transposed tile: a thread's first pair of loads goes out BEFORE the
+    // barrier, so the two round trips to memory overlap (small maps are one item per thread: the whole kernel is those two trips)
+    const int n_row = job.n_planes * job.hv * vpr;
+    auto row_pair = [&](int i, int &pl, int &hl, int &wl, long long &bc, long long &l) {
+        pl = i / (job.hv * vpr);
+        const int r = i - pl * job.hv * vpr;
+        hl = r / vpr;
+        wl = (r - hl * vpr) * VE;
+        bc = job.plane0 + pl;
+        const long long b = bc / C, c = bc - b * C;
+        l = (long long)(job.h0 + hl) * W + job.w0 + wl;
         const Pack<T> a = ld16(ys + ((b * 4 + 0) * C + c) * L + l);
         const Pack<T> bb = rev16(ld16(ys + ((b * 4 + 2) * C + c) * L + (L - VE - l)));
-        const Pack<T> rowp = add16(a, bb);
+        return add16(a, bb);
+    };
+    int pl = 0, hl = 0, wl = 0;
+    long long bc = 0, l = 0;
+    Pack<T> rowp;
+    if ((int)threadIdx.x < n_row) rowp = row_pair(threadIdx.x, pl, hl, wl, bc, l);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_row; i += 256) {
+        if (i != (int)threadIdx.x) rowp = row_pair(i, pl, hl, wl, bc, l);
         Pack<T> colp;
 #pragma unroll
         for (int k = 0; k < VE; ++k) colp.v[k] = s[pl][hl * PAD + wl + k];
@@ -357,11 +370,35 @@ static int run_cross_t(const void *in_, void *out_, int B, int C, int H, int W, 
     constexpr int VE = Vec16<T>::N;
     const long long planes = (long long)B * C;
     const bool vec = (H % VE == 0) && (W % VE == 0) && ((reinterpret_cast<uintptr_t>(in_) | reinterpret_cast<uintptr_t>(out_)) & 15u) == 0;
-    if (vec && H <= 32 && W <= 32) {  // small maps: several channels per CTA
-        const long long g = tile_grid<32, 4>(planes, H, W);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const long long sms = sm_count(dev);
+    // maps larger than 32 x 32: tiles of 32 x 32 instead of 64 x 64 for the fp32 merge (its two dependent trips to memory want many
+    // small CTAs: 7.2 vs 9.9 us on 64 x 64 maps, 11.2 vs 12.0 on 128 x 128, 19.4 vs 20.7 on 256 x 256) and for an fp32 scan of fewer than
+    // three 64 x 64 tiles per SM; half precision keeps 64 x 64 (a 32-wide row is only 64 bytes).  profiles/r2_s6_cross_tiles.txt
+    bool t32 = sizeof(T) == 4 && (MERGE || tile_grid<64, 1>(planes, H, W) < 3 * sms);
+    if (const char *e = tuning_env("VMASR_CROSS_T32")) t32 = atoi(e) != 0;
+    if (vec && H <= 32 && W <= 32) {
+        // small maps: four planes per CTA when that still leaves three CTAs per SM; otherwise as many planes as give every thread
+        // one 16-byte item (a 32 x 32 fp32 plane is 256 items, a 16 x 16 one 64)
+        const long long items = (long long)H * W / VE;
+        const long long g4 = tile_grid<32, 4>(planes, H, W), g2 = tile_grid<32, 2>(planes, H, W), g1 = tile_grid<32, 1>(planes, H, W);
+        if (int rc = grid_ok(g1, who)) return rc;
+        if (g4 >= 3 * sms || items <= 64) {
+            if (MERGE) cross_merge_vec<T, 32, 4><<<(unsigned)g4, 256, 0, stream>>>(in, out, planes, C, H, W);
+            else cross_scan_vec<T, 32, 4><<<(unsigned)g4, 256, 0, stream>>>(in, out, planes, C, H, W);
+        } else if (items <= 128) {
+            if (MERGE) cross_merge_vec<T, 32, 2><<<(unsigned)g2, 256, 0, stream>>>(in, out, planes, C, H, W);
+            else cross_scan_vec<T, 32, 2><<<(unsigned)g2, 256, 0, stream>>>(in, out, planes, C, H, W);
+        } else {
+            if (MERGE) cross_merge_vec<T, 32, 1><<<(unsigned)g1, 256, 0, stream>>>(in, out, planes, C, H, W);
+            else cross_scan_vec<T, 32, 1><<<(unsigned)g1, 256, 0, stream>>>(in, out, planes, C, H, W);
+        }
+    } else if (vec && t32) {
+        const long long g = tile_grid<32, 1>(planes, H, W);
         if (int rc = grid_ok(g, who)) return rc;
-        if (MERGE) cross_merge_vec<T, 32, 4><<<(unsigned)g, 256, 0, stream>>>(in, out, planes, C, H, W);
-        else cross_scan_vec<T, 32, 4><<<(unsigned)g, 256, 0, stream>>>(in, out, planes, C, H, W);
+        if (MERGE) cross_merge_vec<T, 32, 1><<<(unsigned)g, 256, 0, stream>>>(in, out, planes, C, H, W);
+        else cross_scan_vec<T, 32, 1><<<(unsigned)g, 256, 0, stream>>>(in, out, planes, C, H, W);
     } else if (vec) {
         const long long g = tile_grid<64, 1>(planes, H, W);
         if (int rc = grid_ok(g, who)) return rc;
