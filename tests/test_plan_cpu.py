@@ -110,3 +110,56 @@ def test_argument_checks_mirror_the_reference():
     p.dD = 0
     rc, _, err = _plan(p, True)
     assert rc != 0 and "dD must be given exactly when D is" in err
+
+
+# ---- session 6: stored dB / dC and the zero-fill side job (host rules only; the kernels are tested in test_scan_gpu.py) -------------
+DBDC_STORE = 8
+
+
+@pytest.mark.parametrize("B,D,L,ok", [
+    (4, 8, 262144, True),     # the C = 2 maps: one tile of two channels spans the group
+    (2, 16, 4112, True),      # four channels per group, ragged last chunk
+    (4, 64, 65536, False),    # sixteen channels per group: four channel tiles write every dB / dC element
+    (4, 8, 1024, False),      # single chunk: no multi-chunk tile
+    (1, 8, 4100, False),      # length not a multiple of 16: generic kernels
+])
+def test_dbdc_store_needs_one_channel_tile_per_group(B, D, L, ok):
+    """VMASR_SCAN_DBDC_STORE is honoured exactly where every dB / dC element has one writer, and refused (nothing launched)
+    otherwise -- the Python rule that decides whether to ASK agrees with the library on the config shapes."""
+    import torch
+    from vm_asr_b200 import scan
+    p = _params(B, D, L, bwd=True)
+    p.flags = DBDC_STORE
+    rc, pl, err = _plan(p, True)
+    assert (rc == 0) == ok, err
+    if ok:
+        assert pl["variant"] == MULTI and pl["n_ctiles"] == 1
+    else:
+        assert "VMASR_SCAN_DBDC_STORE" in err or "fast path" in err
+    meta = lambda *s: torch.empty(*s, device="meta")
+    cand = scan.dbdc_store_candidate(meta(B, D, L), meta(D, 1), meta(B, 4, 1, L))
+    assert cand or not ok            # the candidate rule is necessary ...
+    if L % 16 == 0:
+        assert cand == ok            # ... and exact on aligned float32 calls
+
+
+def test_dbdc_store_is_a_backward_flag():
+    p = _params(4, 8, 8192)
+    p.flags = DBDC_STORE
+    rc, _, err = _plan(p, False)
+    assert rc != 0 and "backward flag" in err
+
+
+@pytest.mark.parametrize("ptr,nbytes,ok", [(0x20000000, 4096, True), (0x20000000, 16, True), (0, 0, True),
+                                           (0x20000004, 4096, False), (0x20000000, 4100, False), (0, 64, False)])
+@pytest.mark.parametrize("bwd", [False, True])
+def test_zero_region_arguments(ptr, nbytes, ok, bwd):
+    """zero_ptr / zero_bytes: 16-byte aligned, a multiple of 16 bytes, non-null when non-empty -- for every kernel family
+    (the fast forward kernels clear it themselves, the others get a memset in front)."""
+    for shape in ((4, 64, 16384), (4, 512, 1024), (1, 8, 132)):
+        p = _params(*shape, bwd=bwd)
+        p.zero_ptr, p.zero_bytes = ptr, nbytes
+        rc, _, err = _plan(p, bwd)
+        assert (rc == 0) == ok, err
+        if not ok:
+            assert "zero_ptr" in err

@@ -15,6 +15,11 @@ Beyond the reference surface: ``fwd_grouped`` / ``bwd_grouped`` launch several i
 (``vmasr_scan_fwd_grouped``), and ``flags`` (``SCAN_REVERSE``, ``SCAN_ACCUMULATE``) select the time-reversed /
 accumulating variants the fused SS2D core is built from (``vm_asr_b200.ss2d``).
 
+No zero-fill pass in front of the backward (the reference allocates five zero tensors, selective_scan.cpp:319-327): where one
+tile spans a whole B / C group the backward STORES dB / dC (``SCAN_DBDC_STORE``; ``bwd`` asks ``vmasr_scan_plan`` and sets it by
+itself), elsewhere the buffer the backward sums them into is cleared by the FORWARD launch as a side job of its tiles
+(``bc_accumulator``, ``fwd(..., zero=)``, ``bwd(..., bc=)``); the autograd functions below do both.
+
 Host cost.  A call site (same shapes, strides, dtypes, device) is validated ONCE; its filled-in parameter block is cached
 per thread and later calls only refresh pointers, stream and workspace (the reference's pybind entry re-checks every call).
 """
@@ -266,12 +271,10 @@ def _grad_buffers(u, A, D, delta_bias, dims, zero_bc=True, bc=None):
     return dA, dB, dC, dD, dbias
 
 
-def dbdc_store_candidate(u, A, B, flags=0) -> bool:
+def dbdc_store_candidate(u, A, B) -> bool:
     """Necessary conditions of VMASR_SCAN_DBDC_STORE (include/vmasr_b200.h): float32, d_state 1, more than one chunk, and a
     B / C group narrow enough for ONE multi-chunk tile (4 channels), so that every dB / dC element has a single writer.
     The library has the last word (alignment, strides): ``_store_plan_ok`` asks it before a launch relies on the flag."""
-    if flags & SCAN_DBDC_STORE:
-        return True
     return (u.dtype == torch.float32 and A.shape[1] == 1 and u.shape[2] > _lib.SCAN_CHUNK and u.shape[2] % 16 == 0
             and u.shape[1] // B.shape[1] <= 4)
 
