@@ -58,7 +58,9 @@ VMASR_API const char *vmasr_last_error(void);
  *   dA (dim,dstate), dD, ddelta_bias (dim,) : float, ACCUMULATED INTO (caller zero-fills, like
  *                                     selective_scan.cpp:321-327)
  *   dB, dC                          : (batch, ngroups, dstate, seqlen) float contiguous, accumulated into
- *                                     (caller zero-fills; the reference casts them to io_dtype afterwards, :347)
+ *                                     (caller zero-fills -- or lets the FORWARD call clear them through zero_ptr / zero_bytes
+ *                                     below, or sets VMASR_SCAN_DBDC_STORE where the plan allows it; the reference casts
+ *                                     them to io_dtype afterwards, :347)
  *   workspace                       : carry-exchange area for the cross-chunk look-back.  At least
  *                                     vmasr_scan_workspace_bytes() bytes, ZERO-FILLED ONCE when allocated and
  *                                     then reused call after call (kernels recycle it themselves, so a
